@@ -1,0 +1,252 @@
+"""Synthetic SemanticKITTI-shaped chunks and maps.
+
+The reference never ships data; its hot loop (`pipeline/run_pipeline.py:160-195`) consumes
+25 m map chunks voxelised at 0.35 m (`pipeline/config.py:55-57`, `dataset_utils.py:534`).
+This module fabricates inputs of that shape, seeded and deterministic, for the parity tests and
+for `bench.py`.  numpy/scipy only: it runs on the GPU box as well as in the build container.
+
+Nothing here is on the product compute path; it only makes inputs.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+from scipy.spatial import cKDTree
+from scipy.sparse import coo_matrix
+from scipy.sparse.csgraph import connected_components
+
+MAJOR_VOXEL = 0.35          # config.py:56
+CHUNK_EDGE = 25.0           # config.py:57
+PROXIMITY = 1.0             # config.py:65
+
+# gains / thresholds exactly as config.py:6-37
+CONFIGS = {
+    "spatial": dict(alpha=1.0, theta=0.0, gamma=0.0, beta=0.0, T=0.075),
+    "tarl_spatial": dict(alpha=1.0, theta=0.5, gamma=0.0, beta=0.0, T=0.03),
+    "tarl_spatial_dino": dict(alpha=1.0, theta=0.5, gamma=0.1, beta=0.0, T=0.005),
+}
+
+
+@dataclass
+class Chunk:
+    """One chunk at the 0.35 m ("major") resolution, the N points NCuts sees."""
+    chunk_id: int
+    points: np.ndarray                  # (N,3) float64, float32-representable
+    instance: np.ndarray                # (N,) int32 ground-truth instance id (>=1)
+    tarl: np.ndarray | None = None      # (N,96) float64 from float32, 5 % zero rows
+    dino: np.ndarray | None = None      # (N,384) float64 from float32, 30 % zero rows
+    center: np.ndarray = field(default_factory=lambda: np.zeros(3))
+
+    @property
+    def n(self) -> int:
+        return int(self.points.shape[0])
+
+
+def voxel_centroid_downsample(points: np.ndarray, voxel: float, payload: np.ndarray | None = None):
+    """Centroid per occupied voxel, like Open3D `voxel_down_sample` used at
+    `dataset_utils.py:534`.  Returns centroids (and the payload of the first point per voxel)."""
+    origin = points.min(axis=0) - 0.5 * voxel
+    key = np.floor((points - origin) / voxel).astype(np.int64)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.reshape(-1)
+    cent = np.zeros((cnt.shape[0], 3))
+    np.add.at(cent, inv, points)
+    cent /= cnt[:, None]
+    if payload is None:
+        return cent
+    first = np.full(cnt.shape[0], -1, dtype=np.int64)
+    order = np.arange(points.shape[0])[::-1]
+    first[inv[order]] = order           # smallest source index wins
+    return cent, payload[first]
+
+
+def _box_surface(rng, size, n):
+    """n points on the faces of an axis-aligned box of the given size, centred at 0."""
+    sx, sy, sz = size
+    areas = np.array([sy * sz, sy * sz, sx * sz, sx * sz, sx * sy, sx * sy])
+    face = rng.choice(6, size=n, p=areas / areas.sum())
+    u = rng.uniform(-0.5, 0.5, size=(n, 3)) * np.array(size)
+    axis = face // 2
+    sign = np.where(face % 2 == 0, -0.5, 0.5)
+    u[np.arange(n), axis] = sign * np.array(size)[axis]
+    return u
+
+
+def _rotz(rng):
+    a = rng.uniform(0, 2 * np.pi)
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+
+
+def _make_object(rng, kind):
+    n = int(rng.integers(3000, 8000))
+    if kind == "facade":
+        w, h = rng.uniform(10, 25), rng.uniform(4, 8)
+        p = np.stack([rng.uniform(-w / 2, w / 2, n), rng.normal(0, 0.03, n),
+                      rng.uniform(0, h, n)], axis=1)
+    elif kind == "car":
+        p = _box_surface(rng, (4.0, 1.8, 1.5), n) + np.array([0, 0, 0.75])
+    elif kind == "pole":
+        p = _box_surface(rng, (0.3, 0.3, 6.0), n) + np.array([0, 0, 3.0])
+    else:  # vegetation blob
+        p = rng.normal(0, 1.0, size=(n, 3)) * np.array([0.65, 0.65, 0.55]) + np.array([0, 0, 1.5])
+    return p @ _rotz(rng).T
+
+
+def _components(points, radius):
+    tree = cKDTree(points)
+    pairs = tree.query_pairs(radius, output_type="ndarray")
+    n = points.shape[0]
+    g = coo_matrix((np.ones(len(pairs)), (pairs[:, 0], pairs[:, 1])), shape=(n, n))
+    return connected_components(g, directed=False)
+
+
+def _aabb_gap(lo_a, hi_a, lo_b, hi_b):
+    """Euclidean distance between two axis-aligned boxes (0 if they intersect)."""
+    d = np.maximum(0.0, np.maximum(lo_a - hi_b, lo_b - hi_a))
+    return float(np.sqrt((d * d).sum()))
+
+
+def make_chunk(chunk_id: int = 0, n_target: int = 8192, features: str = "tarl_dino",
+               clutter: int = 0, min_component_frac: float = 0.0125, attach_prob: float = 0.25,
+               center=(0.0, 0.0, 0.0), seed_base: int = 1234) -> Chunk:
+    """Seeded chunk with about `n_target` major points.
+
+    Objects are dropped into the 25 m cube with their (inflated) bounding boxes kept apart, except
+    that a fraction `attach_prob` is parked 0.5–0.9 m from an earlier object so the proximity
+    graph gets weak links that NCuts has to cut.
+    clutter == 0: every connected component of the 1 m proximity graph holds more than
+    `min_component_frac`·N points, so the reference's 1 % `split_lim` rule
+    (`normalized_cut.py:39-40`) never meets a disconnected leaf and the unpinned reference agrees
+    with itself.  clutter > 0 adds that many 2–12 voxel fragments.
+    """
+    rng = np.random.default_rng(seed_base + chunk_id)
+    half = CHUNK_EDGE / 2
+    kinds = ["facade", "car", "car", "veg", "car", "veg", "pole", "car"]
+    per_kind = {"facade": 900.0, "car": 285.0, "veg": 520.0, "pole": 72.0}   # mean major voxels
+    pts, inst, boxes = [], [], []
+    total_est, o = 0.0, 0
+    while total_est < 0.85 * n_target and o < 4096:
+        kind = kinds[o % len(kinds)]
+        o += 1
+        p = _make_object(rng, kind)
+        lo0, hi0 = p.min(0), p.max(0)
+        placed = False
+        attach = bool(boxes) and rng.random() < attach_prob
+        for _ in range(60):
+            if attach:
+                hl, hh = boxes[int(rng.integers(len(boxes)))]
+                ax = int(rng.integers(2))
+                gap = rng.uniform(0.5, 0.9)
+                shift = np.zeros(3)
+                side = rng.random() < 0.5
+                shift[ax] = (hh[ax] + gap - lo0[ax]) if side else (hl[ax] - gap - hi0[ax])
+                oa = 1 - ax
+                a, b = hl[oa] - hi0[oa] + 0.5, hh[oa] - lo0[oa] - 0.5
+                shift[oa] = rng.uniform(min(a, b), max(a, b))
+                shift[2] = hl[2] - lo0[2]
+            else:
+                shift = rng.uniform(-half + 0.5, half - 0.5, size=3) - (lo0 + hi0) / 2
+                shift[2] = rng.uniform(-half + 0.3, half - 0.3 - (hi0[2] - lo0[2])) - lo0[2]
+            lo, hi = lo0 + shift, hi0 + shift
+            if np.any(lo < -half) or np.any(hi > half):
+                continue
+            gaps = [_aabb_gap(lo, hi, bl, bh) for bl, bh in boxes]
+            if attach:
+                ok = sum(g < 1.3 for g in gaps) == 1 and min(gaps) >= 0.45
+            else:
+                ok = all(g > 1.3 for g in gaps)
+            if ok:
+                placed = True
+                break
+        if not placed:
+            continue
+        boxes.append((lo, hi))
+        pts.append(p + shift)
+        inst.append(np.full(p.shape[0], len(boxes), dtype=np.int32))
+        total_est += per_kind[kind]
+    pts = np.concatenate(pts)
+    inst = np.concatenate(inst)
+    pm, im = voxel_centroid_downsample(pts, MAJOR_VOXEL, inst)
+
+    if clutter == 0:
+        while True:                                            # drop small components
+            ncomp, lab = _components(pm, PROXIMITY)
+            size = np.bincount(lab, minlength=ncomp)
+            keep = size[lab] > min_component_frac * pm.shape[0]
+            if keep.all():
+                break
+            pm, im = pm[keep], im[keep]
+    else:
+        frag_pts, frag_inst = [], []
+        next_id = int(im.max()) + 1
+        for f in range(clutter):
+            k = int(rng.integers(2, 13))
+            c = rng.uniform(-half + 1, half - 1, size=3)
+            q = c + rng.uniform(-0.5, 0.5, size=(k, 3))
+            frag_pts.append(q)
+            frag_inst.append(np.full(k, next_id + f, dtype=np.int32))
+        pm = np.concatenate([pm] + frag_pts)
+        im = np.concatenate([im] + frag_inst)
+
+    # shuffle so that index order carries no spatial structure (Open3D's voxel hash order is arbitrary)
+    perm = rng.permutation(pm.shape[0])
+    pm, im = pm[perm], im[perm]
+    # float32-representable coordinates, stored as float64 (the oracle reads float64)
+    pm = (pm + np.asarray(center, dtype=np.float64)).astype(np.float32).astype(np.float64)
+    ch = Chunk(chunk_id=chunk_id, points=pm, instance=im, center=np.asarray(center, dtype=np.float64))
+    n = ch.n
+    n_inst = int(im.max()) + 1
+    if "tarl" in features:
+        proto = rng.normal(0, 1, size=(n_inst, 96))
+        t = (proto[im] + 0.3 * rng.normal(0, 1, size=(n, 96))).astype(np.float32)
+        t[rng.random(n) < 0.05] = 0.0                          # no scan point within 0.175 m
+        ch.tarl = t.astype(np.float64)
+    if "dino" in features:
+        proto = rng.normal(0, 1, size=(n_inst, 384))
+        g = (proto[im] + 0.3 * rng.normal(0, 1, size=(n, 384))).astype(np.float32)
+        g[rng.random(n) < 0.30] = 0.0                          # never visible in camera 0
+        ch.dino = g.astype(np.float64)
+    return ch
+
+
+def make_map(n_chunks: int = 40, n_range=(3000, 12000), features: str = "tarl",
+             seed: int = 77, clutter: int = 0) -> list[Chunk]:
+    """Synthetic "first map": chunks along a gently curving path, 22 m apart
+    (`chunk_generation.py:123-125`), N_major drawn from n_range."""
+    rng = np.random.default_rng(seed)
+    chunks = []
+    pos = np.zeros(3)
+    heading = 0.0
+    for c in range(n_chunks):
+        n_t = int(rng.integers(n_range[0], n_range[1]))
+        chunks.append(make_chunk(chunk_id=c, n_target=n_t, features=features, clutter=clutter,
+                                 center=pos.copy(), seed_base=seed * 1000))
+        heading += rng.normal(0, 0.08)
+        pos = pos + 22.0 * np.array([np.cos(heading), np.sin(heading), 0.0])
+    return chunks
+
+
+def small_chunk(seed: int, n_obj: int = 4, pts_per_obj: int = 400, features: str = "tarl_dino"):
+    """Small chunk (N in the hundreds) of box-surface objects: golden fixtures and smoke tests."""
+    rng = np.random.default_rng(seed)
+    pts, inst = [], []
+    for o in range(n_obj):
+        size = rng.uniform([0.8, 0.8, 0.6], [4.0, 4.0, 2.5])
+        p = _box_surface(rng, size, pts_per_obj) @ _rotz(rng).T + rng.uniform(-4.5, 4.5, size=3)
+        pts.append(p)
+        inst.append(np.full(pts_per_obj, o + 1, dtype=np.int32))
+    pm, im = voxel_centroid_downsample(np.concatenate(pts), MAJOR_VOXEL, np.concatenate(inst))
+    pm = pm.astype(np.float32).astype(np.float64)
+    ch = Chunk(chunk_id=seed, points=pm, instance=im)
+    n, n_inst = ch.n, int(im.max()) + 1
+    if "tarl" in features:
+        t = (rng.normal(0, 1, (n_inst, 96))[im] + 0.3 * rng.normal(0, 1, (n, 96))).astype(np.float32)
+        t[rng.random(n) < 0.05] = 0.0
+        ch.tarl = t.astype(np.float64)
+    if "dino" in features:
+        g = (rng.normal(0, 1, (n_inst, 384))[im] + 0.3 * rng.normal(0, 1, (n, 384))).astype(np.float32)
+        g[rng.random(n) < 0.30] = 0.0
+        ch.dino = g.astype(np.float64)
+    return ch
