@@ -1,0 +1,427 @@
+"""Array-level Python API over the C ABI.
+
+PyTorch is used only for device memory and streams; every computation happens in
+libautoinst_ncuts.so.  The reference-facing call surface (`ncuts.ncuts_utils.ncuts_chunk`,
+`ncuts.normalized_cut.normalized_cut`) is in the top-level `ncuts` package and calls into here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import NodeStat, Params, check
+
+STAGES = ("affinity", "degree", "matvec", "reorth", "scan", "partition")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+class Handle:
+    """One library handle (device workspace, counters) per CUDA device."""
+    _cache: dict[int, "Handle"] = {}
+
+    def __init__(self, device: int):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("autoinst_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = int(device)
+        self.h = C.c_void_p()
+        check(self.lib.ancuts_create(self.device, C.byref(self.h)))
+
+    @classmethod
+    def get(cls, device=None) -> "Handle":
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if isinstance(device, torch.device):
+            device = device.index if device.index is not None else torch.cuda.current_device()
+        device = int(device)
+        if device not in cls._cache:
+            cls._cache[device] = Handle(device)
+        return cls._cache[device]
+
+    def launch_count(self, reset=False) -> int:
+        return int(self.lib.ancuts_launch_count(self.h, 1 if reset else 0))
+
+    def set_stage_timing(self, on: bool):
+        check(self.lib.ancuts_set_stage_timing(self.h, 1 if on else 0))
+
+    def accounting(self) -> dict:
+        b = (C.c_double * 6)()
+        m = (C.c_double * 6)()
+        l = (C.c_int64 * 6)()
+        check(self.lib.ancuts_last_accounting(self.h, b, m, l))
+        return {s: dict(bytes=b[i], ms=m[i], launches=int(l[i])) for i, s in enumerate(STAGES)}
+
+
+def make_params(alpha=1.0, theta=0.0, gamma=0.0, T=0.01, proximity=1.0, split_lim=0.01, beta=0.0,
+                tarl_dim=0, dino_dim=0, max_steps=0, check_every=0, tol=0.0, affinity_impl=0) -> Params:
+    if beta:
+        # SAM term, ncuts_utils.py:115-123; beta = 0.0 in every shipped config (config.py:12,23,34,45)
+        raise NotImplementedError("beta != 0 (SAM label term) is not supported by the B200 path")
+    return Params(float(alpha or 0.0), float(theta or 0.0), float(gamma or 0.0), float(proximity), float(T),
+                  float(split_lim), int(tarl_dim), int(dino_dim), int(max_steps), int(check_every),
+                  float(tol), int(affinity_impl))
+
+
+def _dev(device):
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    d = torch.device(device)
+    if d.index is None:
+        d = torch.device("cuda", torch.cuda.current_device())
+    return d
+
+
+def _as_dev(x, dtype, device):
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(device)
+
+
+def padded_ld(n: int) -> int:
+    return (int(n) + 31) // 32 * 32
+
+
+def alloc_matrix(n, device):
+    """n x ld float32 storage and its n x n view."""
+    ld = padded_ld(n)
+    buf = torch.empty((n, ld), dtype=torch.float32, device=device)
+    return buf, buf[:, :n]
+
+
+# ------------------------------------------------------------------------------------------------
+# stage entry points
+# ------------------------------------------------------------------------------------------------
+def affinity(points, tarl=None, dino=None, *, alpha=1.0, theta=0.0, gamma=0.0, proximity=1.0, impl=0,
+             device=None, return_rowsum=False):
+    """Stage 1: dense float32 affinity (ncuts_utils.py:60-156).  Returns the n x n view of an n x ld buffer."""
+    device = _dev(device)
+    hd = Handle.get(device)
+    pts = _as_dev(points, torch.float64, device)
+    n = pts.shape[0]
+    t = _as_dev(tarl, torch.float32, device) if theta else None
+    g = _as_dev(dino, torch.float32, device) if gamma else None
+    if theta and t is None:
+        raise ValueError("theta != 0 needs TARL features")
+    if gamma and g is None:
+        raise ValueError("The length should be longer than 0!")       # ncuts_utils.py:126-127
+    p = make_params(alpha, theta, gamma, 0.0, proximity, tarl_dim=t.shape[1] if t is not None else 0,
+                    dino_dim=g.shape[1] if g is not None else 0, affinity_impl=impl)
+    buf, view = alloc_matrix(n, device)
+    rs = torch.empty(n, dtype=torch.float64, device=device) if return_rowsum else None
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_affinity_f32(hd.h, n, _ptr(pts), _ptr(t), _ptr(g), C.byref(p), _ptr(buf), buf.stride(0),
+                                         _ptr(rs), _stream(device)))
+    return (view, rs) if return_rowsum else view
+
+
+def _matrix_args(W):
+    if W.dtype != torch.float32 or W.dim() != 2 or W.stride(1) != 1 or W.stride(0) % 4 or W.data_ptr() % 16:
+        n = W.shape[0]
+        buf, view = alloc_matrix(n, W.device)
+        view.copy_(W)
+        W = view
+    return W, W.stride(0)
+
+
+def degree_normalize(W, return_normalized=False):
+    """Stage 2: d = (w + I).sum(0) in float64; optionally M = D^-1/2 (w+I) D^-1/2 (normalized_cut.py:38-47)."""
+    W, ld = _matrix_args(W)
+    device = W.device
+    hd = Handle.get(device)
+    n = W.shape[0]
+    deg = torch.empty(n, dtype=torch.float64, device=device)
+    Mbuf = Mv = None
+    if return_normalized:
+        Mbuf, Mv = alloc_matrix(n, device)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_degree_normalize_f32(hd.h, n, _ptr(W), ld, _ptr(deg), _ptr(Mbuf),
+                                                 Mbuf.stride(0) if Mbuf is not None else 0, _stream(device)))
+    return (deg, Mv) if return_normalized else deg
+
+
+def _node_arrays(node_off, node_n):
+    off = np.ascontiguousarray(node_off, dtype=np.int32)
+    nn = np.ascontiguousarray(node_n, dtype=np.int32)
+    return off, nn, off.ctypes.data_as(C.POINTER(C.c_int32)), nn.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def lanczos_fiedler(W, node_off, node_n, *, max_steps=0, check_every=0, tol=0.0):
+    """Stage 3: Fiedler vector of every diagonal block (normalized_cut.py:49-53).
+    Returns (ev float64 [n_total] on device, lambda2, steps, converged)."""
+    W, ld = _matrix_args(W)
+    device = W.device
+    hd = Handle.get(device)
+    n = W.shape[0]
+    off, nn, poff, pn = _node_arrays(node_off, node_n)
+    k = len(off)
+    ev = torch.zeros(n, dtype=torch.float64, device=device)
+    lam = np.zeros(k)
+    steps = np.zeros(k, dtype=np.int32)
+    conv = np.zeros(k, dtype=np.int32)
+    p = make_params(T=0.0, max_steps=max_steps, check_every=check_every, tol=tol)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_lanczos_fiedler_batched(
+            hd.h, n, _ptr(W), ld, k, poff, pn, C.byref(p), _ptr(ev), lam.ctypes.data_as(C.POINTER(C.c_double)),
+            steps.ctypes.data_as(C.POINTER(C.c_int32)), conv.ctypes.data_as(C.POINTER(C.c_int32)), _stream(device)))
+    return ev, lam, steps, conv
+
+
+def ncut_scan(W, node_off, node_n, ev):
+    """Stage 4a: best of the ten threshold cuts per node (normalized_cut.py:13-34).
+    Returns (best_k, mcut, costs [k,10], mask uint8 [n_total] on device; 1 where ev > threshold)."""
+    W, ld = _matrix_args(W)
+    device = W.device
+    hd = Handle.get(device)
+    n = W.shape[0]
+    off, nn, poff, pn = _node_arrays(node_off, node_n)
+    k = len(off)
+    evd = _as_dev(ev, torch.float64, device)
+    best = np.zeros(k, dtype=np.int32)
+    mcut = np.zeros(k)
+    costs = np.zeros((k, _lib.NUM_CUTS))
+    side = torch.zeros(n, dtype=torch.uint8, device=device)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_ncut_scan_batched(
+            hd.h, n, _ptr(W), ld, k, poff, pn, _ptr(evd), best.ctypes.data_as(C.POINTER(C.c_int32)),
+            mcut.ctypes.data_as(C.POINTER(C.c_double)), costs.ctypes.data_as(C.POINTER(C.c_double)), _ptr(side),
+            _stream(device)))
+    return best, mcut, costs, side
+
+
+def partition(W, node_off, node_n, mask, split_components=True):
+    """Stage 4b: stable partition (mask side first) + connected components + block gather
+    (normalized_cut.py:57-58).  Returns (W_out view, perm [new]->old on device, child_off, child_n)."""
+    W, ld = _matrix_args(W)
+    device = W.device
+    hd = Handle.get(device)
+    n = W.shape[0]
+    off, nn, poff, pn = _node_arrays(node_off, node_n)
+    k = len(off)
+    m = _as_dev(mask, torch.uint8, device)
+    obuf = torch.zeros((n, ld), dtype=torch.float32, device=device)
+    perm = torch.zeros(n, dtype=torch.int32, device=device)
+    cnt = C.c_int32(0)
+    coff = np.zeros(n, dtype=np.int32)
+    cn = np.zeros(n, dtype=np.int32)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_partition_batched(
+            hd.h, n, _ptr(W), _ptr(obuf), ld, k, poff, pn, _ptr(m), 1 if split_components else 0, _ptr(perm),
+            C.byref(cnt), coff.ctypes.data_as(C.POINTER(C.c_int32)), cn.ctypes.data_as(C.POINTER(C.c_int32)),
+            _stream(device)))
+    c = cnt.value
+    return obuf[:, :n], perm, coff[:c].copy(), cn[:c].copy()
+
+
+# ------------------------------------------------------------------------------------------------
+# whole path
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SegmentResult:
+    labels: list            # one int32 numpy array per chunk
+    num_segments: np.ndarray
+    stats: np.ndarray | None   # structured array of ancuts_node_stat rows (all chunks of the call)
+
+
+_STAT_DTYPE = np.dtype([("chunk", "<i4"), ("n", "<i4"), ("steps", "<i4"), ("converged", "<i4"), ("best_k", "<i4"),
+                        ("split", "<i4"), ("level", "<i4"), ("n_side", "<i4"), ("lambda2", "<f8"), ("mcut", "<f8")])
+
+
+def workspace_bytes(sizes, max_steps=0) -> int:
+    lib = _lib.load()
+    arr = np.ascontiguousarray(sizes, dtype=np.int32)
+    return int(lib.ancuts_segment_workspace_bytes(len(arr), arr.ctypes.data_as(C.POINTER(C.c_int32)), int(max_steps)))
+
+
+def plan_batches(sizes, budget_bytes, max_steps=0):
+    """Greedy split of chunk indices (in order) into batches whose workspace fits the budget."""
+    batches, cur = [], []
+    for i, n in enumerate(sizes):
+        trial = cur + [i]
+        if cur and workspace_bytes([sizes[j] for j in trial], max_steps) > budget_bytes:
+            batches.append(cur)
+            cur = [i]
+        else:
+            cur = trial
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+def _pack_host(points_list, tarl_list, dino_list, use_t, use_d, pin=True):
+    sizes = [int(np.asarray(p).shape[0]) for p in points_list]
+    off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    total = int(off[-1])
+
+    def mk(shape, dtype):
+        t = torch.empty(shape, dtype=dtype)
+        return t.pin_memory() if pin else t
+    hp = mk((total, 3), torch.float64)
+    ht = mk((total, np.asarray(tarl_list[0]).shape[1]), torch.float32) if use_t else None
+    hd_ = mk((total, np.asarray(dino_list[0]).shape[1]), torch.float32) if use_d else None
+    for c, (a, b) in enumerate(zip(off[:-1], off[1:])):
+        hp[a:b] = torch.as_tensor(np.asarray(points_list[c], dtype=np.float64))
+        if use_t:
+            ht[a:b] = torch.as_tensor(np.asarray(tarl_list[c], dtype=np.float32))
+        if use_d:
+            hd_[a:b] = torch.as_tensor(np.asarray(dino_list[c], dtype=np.float32))
+    return sizes, off, hp, ht, hd_
+
+
+class PackedChunks:
+    """Inputs of a batch of chunks packed once into pinned host buffers (what a data loader hands over)."""
+
+    def __init__(self, points_list, tarl_list=None, dino_list=None, *, theta=0.0, gamma=0.0, pin=True):
+        self.use_t = bool(theta) and tarl_list is not None
+        self.use_d = bool(gamma) and dino_list is not None
+        if theta and tarl_list is None:
+            raise ValueError("theta != 0 needs TARL features")
+        if gamma and dino_list is None:
+            raise ValueError("The length should be longer than 0!")
+        self.sizes, self.off, self.points, self.tarl, self.dino = _pack_host(
+            points_list, tarl_list, dino_list, self.use_t, self.use_d, pin)
+        self.labels = torch.empty(int(self.off[-1]), dtype=torch.int32)
+        if pin:
+            self.labels = self.labels.pin_memory()
+        self.tarl_dim = self.tarl.shape[1] if self.use_t else 0
+        self.dino_dim = self.dino.shape[1] if self.use_d else 0
+
+    def h2d_bytes(self):
+        b = self.points.numel() * 8
+        if self.use_t:
+            b += self.tarl.numel() * 4
+        if self.use_d:
+            b += self.dino.numel() * 4
+        return b
+
+    def d2h_bytes(self):
+        return self.labels.numel() * 4
+
+    def to_device(self, device):
+        device = _dev(device)
+        return DeviceChunks(self, device)
+
+
+class DeviceChunks:
+    def __init__(self, packed: PackedChunks, device):
+        self.packed = packed
+        self.device = device
+        self.points = packed.points.to(device, non_blocking=True)
+        self.tarl = packed.tarl.to(device, non_blocking=True) if packed.use_t else None
+        self.dino = packed.dino.to(device, non_blocking=True) if packed.use_d else None
+        self.labels = torch.empty(int(packed.off[-1]), dtype=torch.int32, device=device)
+
+
+def _run_segment(hd, fn_host, packed, dev_chunks, p, want_stats, device):
+    B = len(packed.sizes)
+    off = np.ascontiguousarray(packed.off, dtype=np.int64)
+    nseg = np.zeros(B, dtype=np.int32)
+    cap = 128 * B + 64 if want_stats else 0
+    stats = np.zeros(max(cap, 1), dtype=_STAT_DTYPE)
+    nstats = C.c_int32(0)
+    sp = stats.ctypes.data_as(C.POINTER(NodeStat)) if want_stats else None
+    with torch.cuda.device(device):
+        if fn_host:
+            check(hd.lib.ancuts_segment_chunks_host(
+                hd.h, B, off.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(packed.points), _ptr(packed.tarl),
+                _ptr(packed.dino), C.byref(p), _ptr(packed.labels), nseg.ctypes.data_as(C.POINTER(C.c_int32)),
+                sp, cap, C.byref(nstats), _stream(device)))
+        else:
+            check(hd.lib.ancuts_segment_chunks(
+                hd.h, B, off.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(dev_chunks.points), _ptr(dev_chunks.tarl),
+                _ptr(dev_chunks.dino), C.byref(p), _ptr(dev_chunks.labels), nseg.ctypes.data_as(C.POINTER(C.c_int32)),
+                sp, cap, C.byref(nstats), _stream(device)))
+    return nseg, (stats[:nstats.value].copy() if want_stats else None)
+
+
+def segment_packed(packed: PackedChunks, *, alpha=1.0, theta=0.0, gamma=0.0, T=0.01, proximity=1.0, split_lim=0.01,
+                   device=None, dev_chunks: DeviceChunks | None = None, want_stats=False, max_steps=0,
+                   check_every=0, tol=0.0, affinity_impl=0) -> SegmentResult:
+    """Segment a packed batch.  With `dev_chunks` the inputs are already resident in HBM (labels stay on
+    the device in dev_chunks.labels); otherwise host buffers go through ancuts_segment_chunks_host."""
+    device = _dev(device if dev_chunks is None else dev_chunks.device)
+    hd = Handle.get(device)
+    p = make_params(alpha, theta if packed.use_t else 0.0, gamma if packed.use_d else 0.0, T, proximity, split_lim,
+                    tarl_dim=packed.tarl_dim, dino_dim=packed.dino_dim, max_steps=max_steps, check_every=check_every,
+                    tol=tol, affinity_impl=affinity_impl)
+    nseg, stats = _run_segment(hd, dev_chunks is None, packed, dev_chunks, p, want_stats, device)
+    src = packed.labels if dev_chunks is None else dev_chunks.labels
+    labels = None
+    if dev_chunks is None:
+        arr = src.numpy()
+        labels = [arr[a:b].copy() for a, b in zip(packed.off[:-1], packed.off[1:])]
+    return SegmentResult(labels=labels, num_segments=nseg, stats=stats)
+
+
+def segment_chunks(points_list, tarl_list=None, dino_list=None, *, alpha=1.0, theta=0.0, gamma=0.0, T=0.01,
+                   proximity=1.0, split_lim=0.01, device=None, want_stats=False, memory_budget=None,
+                   **kw) -> SegmentResult:
+    """Segment a list of chunks (host arrays in, host labels out), batched to fit device memory."""
+    device = _dev(device)
+    sizes = [int(np.asarray(p).shape[0]) for p in points_list]
+    if memory_budget is None:
+        free, _total = torch.cuda.mem_get_info(device)
+        memory_budget = int(free * 0.7)
+    batches = plan_batches(sizes, memory_budget, kw.get("max_steps", 0))
+    labels = [None] * len(sizes)
+    nseg = np.zeros(len(sizes), dtype=np.int32)
+    stats_all = []
+    for batch in batches:
+        pk = PackedChunks([points_list[i] for i in batch],
+                          [tarl_list[i] for i in batch] if tarl_list is not None else None,
+                          [dino_list[i] for i in batch] if dino_list is not None else None,
+                          theta=theta, gamma=gamma, pin=False)
+        res = segment_packed(pk, alpha=alpha, theta=theta, gamma=gamma, T=T, proximity=proximity,
+                             split_lim=split_lim, device=device, want_stats=want_stats, **kw)
+        for j, i in enumerate(batch):
+            labels[i] = res.labels[j]
+            nseg[i] = res.num_segments[j]
+        if want_stats and res.stats is not None:
+            st = res.stats.copy()
+            st["chunk"] = np.asarray(batch, dtype=np.int32)[st["chunk"]]
+            stats_all.append(st)
+    stats = np.concatenate(stats_all) if stats_all else None
+    return SegmentResult(labels=labels, num_segments=nseg, stats=stats)
+
+
+def segment_chunk(points, tarl=None, dino=None, **kw):
+    """One chunk: int32 label per point (ncuts_utils.py:56-183 without the Open3D glue)."""
+    res = segment_chunks([points], [tarl] if tarl is not None else None, [dino] if dino is not None else None, **kw)
+    return res.labels[0]
+
+
+def segment_dense(W, num_points_orig=None, *, T=0.01, split_lim=0.01, want_stats=False, max_steps=0, tol=0.0):
+    """normalized_cut(w, num_points_orig, labels, T, split_lim) (normalized_cut.py:37) for a dense float32
+    copy of w on the device.  Returns int32 labels (numpy), and stats if requested."""
+    W, ld = _matrix_args(W)
+    device = W.device
+    hd = Handle.get(device)
+    n = W.shape[0]
+    p = make_params(T=T, split_lim=split_lim, max_steps=max_steps, tol=tol)
+    labels = torch.empty(n, dtype=torch.int32, device=device)
+    nseg = np.zeros(1, dtype=np.int32)
+    cap = 4096 if want_stats else 0
+    stats = np.zeros(max(cap, 1), dtype=_STAT_DTYPE)
+    nstats = C.c_int32(0)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_segment_dense_f32(
+            hd.h, n, _ptr(W), ld, int(num_points_orig if num_points_orig is not None else n), C.byref(p), _ptr(labels),
+            nseg.ctypes.data_as(C.POINTER(C.c_int32)), stats.ctypes.data_as(C.POINTER(NodeStat)) if want_stats else None,
+            cap, C.byref(nstats), _stream(device)))
+    out = labels.cpu().numpy()
+    return (out, stats[:nstats.value].copy()) if want_stats else out

@@ -1,0 +1,1020 @@
+// engine.cu — host side of libautoinst_ncuts: workspace planning, the level loop that drives the
+// recursion of normalized_cut.py:37-63 breadth-first on the device, and the C ABI of
+// include/autoinst_ncuts.h.  All decisions (costs, mcut < T, stop rules, child tables) are taken
+// by kernels; the host only reads back a few counters per level to size the next grids.
+#include <cub/cub.cuh>
+#include <stdarg.h>
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels_graph.cuh"
+#include "kernels_lanczos.cuh"
+#include "kernels_ncut.cuh"
+
+namespace ancuts {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// affinity_tc.cu
+int launch_affinity_tc(int n, const double* pts, const float* tarl, int tdim, const float* dino, int ddim,
+                       const uint8_t* tarl_zero, double alpha, double theta, double gamma, double prox,
+                       float* W, long long ld, void* scratch, size_t scratch_bytes, cudaStream_t st);
+size_t affinity_tc_scratch_bytes(int n, int tdim, int ddim);
+
+struct TimedLaunch { int stage; cudaEvent_t a, b; };
+
+}  // namespace ancuts
+
+using namespace ancuts;
+
+struct ancuts_handle {
+    int device = 0;
+    char* ws = nullptr;
+    size_t ws_bytes = 0;
+    int* h_ctr = nullptr;                    // pinned, 8 ints
+    unsigned long long* h_acct = nullptr;    // pinned, SG_COUNT
+    int64_t launches_total = 0;
+    int64_t stage_launches[SG_COUNT] = {0};
+    double stage_bytes[SG_COUNT] = {0};
+    double stage_ms[SG_COUNT] = {0};
+    bool stage_timing = false;
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> pool;
+    size_t pool_used = 0;
+    bool attrs_set = false;
+};
+
+namespace ancuts {
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct Arena {
+    char* base;
+    size_t off = 0;
+    template <typename T> T* take(size_t count) {
+        off = align_up(off, 256);
+        T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+struct Plan {
+    int B = 0;
+    int P = 0;
+    int kmax = KMAX_DEFAULT;
+    int KS = KMAX_DEFAULT + 2;
+    int active_cap = 0;
+    int cslot_cap = 0;
+    bool own_w0 = true, own_w1 = true;
+    std::vector<int> n, ld, base, norig;
+    size_t cub_bytes = 0;
+    // device pointers handed out by the arena
+    int *c_base, *c_n, *c_ld, *c_norig;
+    float **c_W0, **c_W1;
+    std::vector<float*> hW0, hW1;
+    int* labels_scratch;
+    int* nseg;
+    uint8_t* tarl_zero;
+    void* cub_tmp;
+    void* tc_scratch; size_t tc_scratch_bytes = 0;
+    ancuts_node_stat* stats;
+    Eng e;
+};
+
+static size_t cub_temp_bytes(int P) {
+    size_t a = 0, b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                    (int*)nullptr, (int*)nullptr, P, 0, 64);
+    cub::DeviceScan::InclusiveSum(nullptr, b, (int*)nullptr, (int*)nullptr, P);
+    return std::max(a, b) + 256;
+}
+
+// lay out every buffer; with base == nullptr only the size is computed
+static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bool need_tc) {
+    Arena ar{base};
+    const int B = pl.B, P = pl.P, KS = pl.KS;
+    Eng& e = pl.e;
+    pl.c_base = ar.take<int>(B); pl.c_n = ar.take<int>(B); pl.c_ld = ar.take<int>(B); pl.c_norig = ar.take<int>(B);
+    pl.c_W0 = ar.take<float*>(B); pl.c_W1 = ar.take<float*>(B);
+    e.r_start = ar.take<int>(P + 1); e.r_n = ar.take<int>(P + 1); e.r_chunk = ar.take<int>(P + 1);
+    e.r_status = ar.take<int>(P + 1); e.r_level = ar.take<int>(P + 1);
+    e.q_start = ar.take<int>(P + 1); e.q_n = ar.take<int>(P + 1); e.q_chunk = ar.take<int>(P + 1);
+    e.q_status = ar.take<int>(P + 1); e.q_level = ar.take<int>(P + 1);
+    e.r_pass = ar.take<int>(2 * (size_t)P + 2); e.r_slot = nullptr;
+    e.rid = ar.take<int>(P); e.rid2 = ar.take<int>(P); e.perm = ar.take<int>(P); e.perm2 = ar.take<int>(P);
+    e.deg = ar.take<double>(P); e.sinv = ar.take<double>(P); e.wbuf = ar.take<double>(P);
+    e.ybuf = ar.take<double>(P); e.ev = ar.take<double>(P);
+    e.bucket = ar.take<uint8_t>(P); e.side = ar.take<uint8_t>(P);
+    e.parent = ar.take<int>(P); e.croot = ar.take<int>(P);
+    e.key = ar.take<unsigned long long>(P); e.key2 = ar.take<unsigned long long>(P);
+    e.val = ar.take<int>(P); e.val2 = ar.take<int>(P); e.flag = ar.take<int>(P); e.incl = ar.take<int>(P);
+    e.V = ar.take<double>((size_t)KS * P);
+    const int A = pl.active_cap;
+    e.split_ids = ar.take<int>(A);
+    e.a_rid = ar.take<int>(A); e.a_k = ar.take<int>(A); e.a_kcap = ar.take<int>(A); e.a_done = ar.take<int>(A);
+    e.a_conv = ar.take<int>(A); e.a_slot0 = ar.take<int>(A); e.a_nch = ar.take<int>(A);
+    e.a_alpha = ar.take<double>((size_t)A * KS); e.a_beta = ar.take<double>((size_t)A * KS);
+    e.a_y = ar.take<double>((size_t)A * KS);
+    e.a_bprev = ar.take<double>(A); e.a_h1 = ar.take<double>(A); e.a_h2 = ar.take<double>(A);
+    e.a_theta = ar.take<double>(2 * (size_t)A); e.a_thr = ar.take<double>((size_t)A * NCUT);
+    e.a_sign = ar.take<double>(A); e.a_nocut = ar.take<int>(A);
+    e.a_diff = ar.take<unsigned long long>((size_t)A * (NB + 1)); e.a_cnt = ar.take<int>((size_t)A * NB);
+    e.a_bestk = ar.take<int>(A); e.a_mcut = ar.take<double>(A); e.a_costs = ar.take<double>((size_t)A * NCUT);
+    const int C = pl.cslot_cap;
+    e.p_dot = ar.take<double>((size_t)C * KS); e.p_dot2 = ar.take<double>((size_t)C * KS);
+    e.p_norm = ar.take<double>(C); e.p_stat = ar.take<double>((size_t)C * 4); e.p_vol = ar.take<double>((size_t)C * NB);
+    e.ctr = ar.take<int>(8);
+    e.acct = ar.take<unsigned long long>(SG_COUNT);
+    pl.stats = ar.take<ancuts_node_stat>(std::max(stats_cap, 1));
+    pl.labels_scratch = ar.take<int>(P);
+    pl.nseg = ar.take<int>(B);
+    pl.tarl_zero = ar.take<uint8_t>(P);
+    pl.cub_tmp = ar.take<char>(pl.cub_bytes);
+    pl.tc_scratch_bytes = 0;
+    pl.tc_scratch = nullptr;
+    if (need_tc) {
+        int nmax = 0;
+        for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
+        pl.tc_scratch_bytes = affinity_tc_scratch_bytes(nmax, tdim, ddim);
+        pl.tc_scratch = ar.take<char>(pl.tc_scratch_bytes);
+    }
+    pl.hW0.assign(B, nullptr); pl.hW1.assign(B, nullptr);
+    for (int c = 0; c < B; ++c) {
+        size_t elems = (size_t)pl.n[c] * pl.ld[c];
+        if (pl.own_w0) pl.hW0[c] = ar.take<float>(elems);
+        if (pl.own_w1) pl.hW1[c] = ar.take<float>(elems);
+    }
+    return align_up(ar.off, 256);
+}
+
+static void make_plan(Plan& pl, int B, const int* n, const int* norig, const int64_t* ld_user, int kmax,
+                      int extra_active) {
+    pl.B = B;
+    pl.n.assign(n, n + B);
+    pl.norig.resize(B); pl.ld.resize(B); pl.base.resize(B);
+    long long P = 0;
+    for (int c = 0; c < B; ++c) {
+        pl.base[c] = (int)P;
+        pl.norig[c] = norig ? norig[c] : n[c];
+        pl.ld[c] = ld_user ? (int)ld_user[c] : (int)align_up((size_t)n[c], 32);
+        P += n[c];
+    }
+    pl.P = (int)P;
+    pl.kmax = kmax;
+    pl.KS = kmax + 2;
+    pl.active_cap = std::max(101 * B + 1, extra_active + 1);
+    pl.active_cap = std::min(pl.active_cap, pl.P + 1);
+    pl.cslot_cap = pl.P / CH + pl.active_cap + 1;
+    pl.cub_bytes = cub_temp_bytes(pl.P);
+}
+
+static int ensure_ws(ancuts_handle* h, size_t bytes) {
+    if (bytes <= h->ws_bytes) return ANCUTS_OK;
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    cudaError_t err = cudaMalloc((void**)&h->ws, bytes);
+    if (err != cudaSuccess) {
+        set_error("workspace cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+        cudaGetLastError();
+        return ANCUTS_ENOMEM;
+    }
+    h->ws_bytes = bytes;
+    return ANCUTS_OK;
+}
+
+// --- launch bookkeeping ------------------------------------------------------------------------
+static cudaEvent_t take_event(ancuts_handle* h) {
+    if (h->pool_used == h->pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        h->pool.push_back(ev);
+    }
+    return h->pool[h->pool_used++];
+}
+
+struct LaunchScope {
+    ancuts_handle* h; int stage; cudaStream_t st; cudaEvent_t b = nullptr;
+    LaunchScope(ancuts_handle* h_, int stage_, cudaStream_t st_) : h(h_), stage(stage_), st(st_) {
+        h->launches_total++;
+        h->stage_launches[stage]++;
+        if (h->stage_timing) {
+            cudaEvent_t a = take_event(h);
+            b = take_event(h);
+            cudaEventRecord(a, st);
+            h->timed.push_back({stage, a, b});
+        }
+    }
+    ~LaunchScope() { if (b) cudaEventRecord(b, st); }
+};
+#define LAUNCH(stage, ...) do { LaunchScope _ls(h, stage, st); __VA_ARGS__; } while (0)
+
+static void begin_accounting(ancuts_handle* h) {
+    for (int i = 0; i < SG_COUNT; ++i) { h->stage_launches[i] = 0; h->stage_bytes[i] = 0; h->stage_ms[i] = 0; }
+    h->timed.clear();
+    h->pool_used = 0;
+}
+
+static int end_accounting(ancuts_handle* h, const Eng& e, cudaStream_t st) {
+    ANCUTS_CUDA(cudaMemcpyAsync(h->h_acct, e.acct, SG_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaStreamSynchronize(st));
+    for (int i = 0; i < SG_COUNT; ++i) h->stage_bytes[i] += (double)h->h_acct[i];
+    for (auto& t : h->timed) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) h->stage_ms[t.stage] += ms;
+    }
+    h->timed.clear();
+    return ANCUTS_OK;
+}
+
+static int set_attrs(ancuts_handle* h, int KS) {
+    if (h->attrs_set) return ANCUTS_OK;
+    ANCUTS_CUDA(cudaFuncSetAttribute(k_matvec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (ZT + 8) * 8));
+    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_check, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (KMAX_LIMIT + 2) * 68 + 64));
+    (void)KS;
+    h->attrs_set = true;
+    return ANCUTS_OK;
+}
+
+static int read_ctr(ancuts_handle* h, const Eng& e, cudaStream_t st) {
+    ANCUTS_CUDA(cudaMemcpyAsync(h->h_ctr, e.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaStreamSynchronize(st));
+    return ANCUTS_OK;
+}
+
+// --- engine pieces -------------------------------------------------------------------------------
+__global__ void k_init_roots(Eng e, double split_lim, double T) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < e.B) {
+        int c = g;
+        int n = e.c_n[c];
+        e.r_start[c] = e.c_base[c];
+        e.r_n[c] = n;
+        e.r_chunk[c] = c;
+        e.r_level[c] = 0;
+        double frac = (double)n / ((double)e.c_norig[c] + 1e-8);
+        bool pass = (n > 2) && (frac > split_lim) && (T > 0.0);     // normalized_cut.py:39-40
+        e.r_status[c] = pass ? ST_SPLIT : ST_LEAF;
+        e.r_pass[2 * c] = 1;
+        e.r_pass[2 * c + 1] = 1;
+        if (pass) {
+            int s = atomicAdd(&e.ctr[5], 1);
+            e.split_ids[s] = c;
+            atomicMax(&e.ctr[7], n);
+        }
+    }
+    if (g < e.P) e.side[g] = 0;
+}
+
+__global__ void k_init_positions(Eng e) {
+    int c = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e.c_n[c]) {
+        int g = e.c_base[c] + i;
+        e.rid[g] = c;
+        e.perm[g] = i;
+    }
+}
+
+static int upload_tables(Plan& pl, cudaStream_t st) {
+    const int B = pl.B;
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.c_base, pl.base.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.c_n, pl.n.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.c_ld, pl.ld.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.c_norig, pl.norig.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.c_W0, pl.hW0.data(), B * sizeof(float*), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.c_W1, pl.hW1.data(), B * sizeof(float*), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaStreamSynchronize(st));      // host vectors may go away
+    Eng& e = pl.e;
+    e.P = pl.P; e.B = B; e.KS = pl.KS; e.kmax = pl.kmax;
+    e.c_base = pl.c_base; e.c_n = pl.c_n; e.c_ld = pl.c_ld; e.c_norig = pl.c_norig;
+    e.c_W0 = pl.c_W0; e.c_W1 = pl.c_W1;
+    return ANCUTS_OK;
+}
+
+static void fill_params(Eng& e, const ancuts_params* p, int kmax) {
+    e.kmax = kmax;
+    e.KS = kmax + 2;
+    e.check_every = p->lanczos_check_every > 0 ? p->lanczos_check_every : CHECK_DEFAULT;
+    e.tol = p->lanczos_tol > 0 ? p->lanczos_tol : TOL_DEFAULT;
+    e.T = p->T;
+}
+
+static int resolve_kmax(const ancuts_params* p) {
+    int k = p->lanczos_max_steps > 0 ? p->lanczos_max_steps : KMAX_DEFAULT;
+    return std::min(std::max(k, 2), KMAX_LIMIT);
+}
+
+static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, const float* tarl, const float* dino,
+                        const ancuts_params* p, float* W, long long ld, uint8_t* tarl_zero, cudaStream_t st) {
+    const bool use_tarl = p->theta != 0.0 && tarl != nullptr;
+    const bool use_dino = p->gamma != 0.0 && dino != nullptr;
+    if (p->theta != 0.0 && tarl == nullptr) { set_error("theta != 0 but no TARL features"); return ANCUTS_EINVAL; }
+    if (p->gamma != 0.0 && dino == nullptr) {
+        set_error("The length should be longer than 0!");      // ncuts_utils.py:126-127
+        return ANCUTS_EINVAL;
+    }
+    if ((use_tarl && (p->tarl_dim <= 0 || p->tarl_dim % 4)) || (use_dino && (p->dino_dim <= 0 || p->dino_dim % 4))) {
+        set_error("feature dimensions must be positive multiples of 4 (got %d, %d)", p->tarl_dim, p->dino_dim);
+        return ANCUTS_EUNSUPPORTED;
+    }
+    if (use_tarl)
+        LAUNCH(SG_AFFINITY, k_zero_rows<<<(n + 7) / 8, 256, 0, st>>>(n, tarl, p->tarl_dim, tarl_zero));
+    if (p->affinity_impl == 1 && (use_tarl || use_dino)) {
+        h->launches_total++; h->stage_launches[SG_AFFINITY]++;
+        int rc = launch_affinity_tc(n, pts, use_tarl ? tarl : nullptr, p->tarl_dim, use_dino ? dino : nullptr,
+                                    p->dino_dim, tarl_zero, p->alpha, p->theta, p->gamma, p->proximity, W, ld,
+                                    pl.tc_scratch, pl.tc_scratch_bytes, st);
+        if (rc != ANCUTS_OK) return rc;
+    } else {
+        dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
+        LAUNCH(SG_AFFINITY, k_affinity_exact<<<grid, 256, 0, st>>>(n, pts, use_tarl ? tarl : nullptr, p->tarl_dim,
+                                                                   use_dino ? dino : nullptr, p->dino_dim, tarl_zero,
+                                                                   p->alpha, p->theta, p->gamma, p->proximity, W, ld));
+    }
+    ANCUTS_CUDA(cudaGetLastError());
+    return ANCUTS_OK;
+}
+
+// Lanczos for all active nodes of the current table (degrees must be set)
+static int run_lanczos(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n, cudaStream_t st) {
+    const int KS = e.KS;
+    LAUNCH(SG_REORTH, k_lanczos_init<<<num_active, 256, 0, st>>>(e));
+    const int nch_max = (max_n + CH - 1) / CH;
+    const int zt = std::min(ZT, (int)align_up((size_t)max_n + 4, 4));
+    const size_t mv_smem = (size_t)(zt + 8) * 8;
+    const size_t up_smem = (size_t)(KS + CH + 8) * 8;
+    const size_t ck_smem = (size_t)KS * 8 * 8 + (size_t)KS * 4 + 64;
+    const int kcap_max = std::min(e.kmax, std::max(max_n - 1, 1));
+    int step = 0;
+    while (true) {
+        int burst = std::min(e.check_every, kcap_max - step);
+        for (int s = 0; s < burst; ++s, ++step) {
+            dim3 gmv((max_n + 31) / 32, num_active);
+            LAUNCH(SG_MATVEC, k_matvec<4><<<gmv, 256, mv_smem, st>>>(e, cur, zt));
+            dim3 gd(nch_max, (step + 2 + 31) / 32, num_active);
+            LAUNCH(SG_REORTH, k_dots<<<gd, 256, 0, st>>>(e));
+            dim3 gu(nch_max, num_active);
+            LAUNCH(SG_REORTH, k_update<1><<<gu, 256, up_smem, st>>>(e));
+            LAUNCH(SG_REORTH, k_update<2><<<gu, 256, up_smem, st>>>(e));
+            LAUNCH(SG_REORTH, k_lanczos_finalize<<<(num_active + 127) / 128, 128, 0, st>>>(e, num_active));
+        }
+        bool last = step >= kcap_max;
+        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 4, 0, sizeof(int), st));
+        LAUNCH(SG_REORTH, k_lanczos_check<<<num_active, 128, ck_smem, st>>>(e, last ? 1 : 0));
+        ANCUTS_CUDA(cudaGetLastError());
+        int rc = read_ctr(h, e, st);
+        if (rc) return rc;
+        if (h->h_ctr[4] == 0 || last) break;
+    }
+    return ANCUTS_OK;
+}
+
+// Ritz vector, sign, thresholds, buckets, cut scan, decision, side flags
+static int run_cut(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n, bool ritz, cudaStream_t st) {
+    const int nch_max = (max_n + CH - 1) / CH;
+    dim3 gc(nch_max, num_active);
+    if (ritz) {
+        LAUNCH(SG_REORTH, k_ritz<<<gc, 256, (size_t)(e.KS + 32) * 8, st>>>(e));
+    }
+    LAUNCH(SG_SCAN, k_ev_final<<<(num_active + 127) / 128, 128, 0, st>>>(e, num_active));
+    LAUNCH(SG_SCAN, k_bucket<<<gc, 256, 0, st>>>(e));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 5, 0, sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 7, 0, sizeof(int), st));
+    dim3 gs((max_n + 7) / 8, num_active);
+    LAUNCH(SG_SCAN, k_scan<<<gs, 256, 0, st>>>(e, cur));
+    LAUNCH(SG_SCAN, k_decide<<<(num_active + 127) / 128, 128, 0, st>>>(e, num_active));
+    LAUNCH(SG_SCAN, k_sides<<<gc, 256, 0, st>>>(e));
+    ANCUTS_CUDA(cudaGetLastError());
+    return ANCUTS_OK;
+}
+
+__global__ void k_add_scalar(int n, double* x, double v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += v;
+}
+
+// ABI side flags (1 = the reference's mask, ev > t) <-> internal side (0 = mask side, sorted first)
+__global__ void k_mask_from_side(Eng e, uint8_t* __restrict__ out) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= e.P) return;
+    int r = e.rid[g];
+    out[g] = (e.r_status[r] == ST_SPLIT && e.side[g] == 0) ? 1 : 0;
+}
+__global__ void k_side_from_mask(Eng e, const uint8_t* __restrict__ mask) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < e.P) e.side[g] = mask[g] ? 0 : 1;
+}
+
+// chunk-level statistics for stand-alone ev input (stage 4a entry point): sum/min/max/sumsq partials
+__global__ void __launch_bounds__(256)
+k_ev_stats(Eng e) {
+    __shared__ double red[32];
+    int a = blockIdx.y;
+    int nch = e.a_nch[a];
+    int ch = blockIdx.x;
+    if (ch >= nch) return;
+    int r = e.a_rid[a];
+    int start = e.r_start[r], n = e.r_n[r];
+    int c0 = ch * CH + threadIdx.x, c1 = c0 + 256;
+    double x0 = c0 < n ? e.ev[start + c0] : 0.0, x1 = c1 < n ? e.ev[start + c1] : 0.0;
+    double s = x0 + x1;
+    double mn = fmin(c0 < n ? x0 : 1e300, c1 < n ? x1 : 1e300);
+    double mx = fmax(c0 < n ? x0 : -1e300, c1 < n ? x1 : -1e300);
+    double q = x0 * x0 + x1 * x1;
+    s = warp_sum(s); mn = warp_min(mn); mx = warp_max(mx); q = warp_sum(q);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[w] = s; red[8 + w] = mn; red[16 + w] = mx; red[24 + w] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tmn = 1e300, tmx = -1e300, tq = 0.0;
+        for (int i = 0; i < 8; ++i) { ts += red[i]; tmn = fmin(tmn, red[8 + i]); tmx = fmax(tmx, red[16 + i]); tq += red[24 + i]; }
+        double* o = e.p_stat + (size_t)(e.a_slot0[a] + ch) * 4;
+        o[0] = ts; o[1] = tmn; o[2] = tmx; o[3] = tq;
+    }
+}
+
+// split phase: components, sort, new table, gather.  Returns new counts through h->h_ctr.
+static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int max_split_n, bool components,
+                       cudaStream_t st) {
+    Eng& e = pl.e;
+    const int P = e.P;
+    const int tb = 256, gP = (P + tb - 1) / tb;
+    LAUNCH(SG_PARTITION, k_cc_init<<<gP, tb, 0, st>>>(e));
+    if (components && num_split > 0) {
+        dim3 g((max_split_n + 7) / 8, num_split);
+        LAUNCH(SG_PARTITION, k_cc_union<<<g, 256, 0, st>>>(e, cur, e.split_ids));
+    }
+    LAUNCH(SG_PARTITION, k_cc_flatten<<<gP, tb, 0, st>>>(e));
+    LAUNCH(SG_PARTITION, k_build_keys<<<gP, tb, 0, st>>>(e));
+    int pbits = 1;
+    while ((1ll << pbits) < (long long)P + 1) ++pbits;
+    size_t tmp = pl.cub_bytes;
+    h->launches_total += 2; h->stage_launches[SG_PARTITION] += 2;
+    ANCUTS_CUDA(cub::DeviceRadixSort::SortPairs(pl.cub_tmp, tmp, e.key, e.key2, e.val, e.val2, P, 0, 32 + pbits, st));
+    LAUNCH(SG_PARTITION, k_boundaries<<<gP, tb, 0, st>>>(e));
+    tmp = pl.cub_bytes;
+    ANCUTS_CUDA(cub::DeviceScan::InclusiveSum(pl.cub_tmp, tmp, e.flag, e.incl, P, st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 4 * sizeof(int), st));
+    LAUNCH(SG_PARTITION, k_new_ranges<<<gP, tb, 0, st>>>(e));
+    ANCUTS_CUDA(cudaGetLastError());
+    int rc = read_ctr(h, e, st);
+    if (rc) return rc;
+    int num_ranges = h->h_ctr[0];
+    LAUNCH(SG_PARTITION, k_finish_ranges<<<(num_ranges + tb - 1) / tb, tb, 0, st>>>(e, num_ranges));
+    ANCUTS_CUDA(cudaGetLastError());
+    rc = read_ctr(h, e, st);
+    if (rc) return rc;
+    int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
+    if (num_active > pl.active_cap || h->h_ctr[3] > pl.cslot_cap) {
+        set_error("internal: active table overflow (%d nodes, %d chunk slots)", num_active, h->h_ctr[3]);
+        return ANCUTS_EINVAL;
+    }
+    // the rebuilt table becomes current
+    std::swap(e.r_start, e.q_start); std::swap(e.r_n, e.q_n); std::swap(e.r_chunk, e.q_chunk);
+    std::swap(e.r_status, e.q_status); std::swap(e.r_level, e.q_level);
+    std::swap(e.rid, e.rid2); std::swap(e.perm, e.perm2);
+    if (num_active > 0) {
+        dim3 g((max_n + 255) / 256, (max_n + 15) / 16, num_active);
+        LAUNCH(SG_PARTITION, k_gather_blocks_cur<<<g, 256, 0, st>>>(e, cur));
+        ANCUTS_CUDA(cudaGetLastError());
+        cur ^= 1;
+    }
+    return ANCUTS_OK;
+}
+
+// the whole recursion for the chunks described by the plan; W of every chunk is in buffer `cur`
+static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cur, int32_t* d_labels,
+                      int32_t* h_num_segments, cudaStream_t st) {
+    Eng& e = pl.e;
+    const int P = e.P, B = e.B;
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 8 * sizeof(int), st));
+    {
+        int nmax = 0;
+        for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
+        dim3 g((nmax + 255) / 256, B);
+        LAUNCH(SG_PARTITION, k_init_positions<<<g, 256, 0, st>>>(e));
+        int m = std::max(P, B);
+        LAUNCH(SG_PARTITION, k_init_roots<<<(m + 255) / 256, 256, 0, st>>>(e, p->split_lim, p->T));
+    }
+    int rc = read_ctr(h, e, st);
+    if (rc) return rc;
+    int num_split = h->h_ctr[5], max_split_n = h->h_ctr[7];
+    int guard = 0;
+    while (num_split > 0) {
+        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st);
+        if (rc) return rc;
+        int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
+        if (num_active == 0) break;
+        dim3 gdeg((max_n + 7) / 8, num_active);
+        LAUNCH(SG_DEGREE, k_degree<<<gdeg, 256, 0, st>>>(e, cur));
+        rc = run_lanczos(h, e, cur, num_active, max_n, st);
+        if (rc) return rc;
+        rc = run_cut(h, e, cur, num_active, max_n, true, st);
+        if (rc) return rc;
+        rc = read_ctr(h, e, st);
+        if (rc) return rc;
+        num_split = h->h_ctr[5];
+        max_split_n = h->h_ctr[7];
+        if (++guard > 100000) { set_error("internal: recursion did not terminate"); return ANCUTS_EINVAL; }
+    }
+    LAUNCH(SG_PARTITION, k_emit_labels<<<(P + 255) / 256, 256, 0, st>>>(e, d_labels, pl.nseg));
+    ANCUTS_CUDA(cudaGetLastError());
+    if (h_num_segments) {
+        ANCUTS_CUDA(cudaMemcpyAsync(h_num_segments, pl.nseg, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    ANCUTS_CUDA(cudaStreamSynchronize(st));
+    return ANCUTS_OK;
+}
+
+static int copy_stats(ancuts_handle* h, Plan& pl, ancuts_node_stat* h_stats, int stats_cap, int32_t* h_num_stats,
+                      cudaStream_t st) {
+    int rc = read_ctr(h, pl.e, st);
+    if (rc) return rc;
+    int cnt = std::min(h->h_ctr[6], stats_cap);
+    if (h_num_stats) *h_num_stats = cnt;
+    if (h_stats && cnt > 0) {
+        ANCUTS_CUDA(cudaMemcpyAsync(h_stats, pl.stats, (size_t)cnt * sizeof(ancuts_node_stat), cudaMemcpyDeviceToHost, st));
+        ANCUTS_CUDA(cudaStreamSynchronize(st));
+    }
+    return ANCUTS_OK;
+}
+
+static int check_params(const ancuts_params* p) {
+    if (!p) { set_error("params is NULL"); return ANCUTS_EINVAL; }
+    if (!(p->proximity >= 0.0)) { set_error("proximity must be >= 0"); return ANCUTS_EINVAL; }
+    return ANCUTS_OK;
+}
+
+}  // namespace ancuts
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int ancuts_version(void) { return 100; }
+
+const char* ancuts_last_error(void) { return g_err; }
+
+int ancuts_create(int device, ancuts_handle** out) {
+    if (!out) { set_error("out is NULL"); return ANCUTS_EINVAL; }
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0) {
+        set_error("no CUDA device available (%s); libautoinst_ncuts has no CPU fallback",
+                  err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+        cudaGetLastError();
+        return ANCUTS_ECUDA;
+    }
+    if (device < 0 || device >= count) { set_error("device %d out of range (0..%d)", device, count - 1); return ANCUTS_EINVAL; }
+    ANCUTS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    ANCUTS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return ANCUTS_EUNSUPPORTED;
+    }
+    ancuts_handle* h = new ancuts_handle();
+    h->device = device;
+    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_ctr, 8 * sizeof(int)));
+    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_acct, SG_COUNT * sizeof(unsigned long long)));
+    *out = h;
+    return ANCUTS_OK;
+}
+
+int ancuts_destroy(ancuts_handle* h) {
+    if (!h) return ANCUTS_OK;
+    cudaSetDevice(h->device);
+    if (h->ws) cudaFree(h->ws);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->h_acct) cudaFreeHost(h->h_acct);
+    for (auto ev : h->pool) cudaEventDestroy(ev);
+    delete h;
+    return ANCUTS_OK;
+}
+
+int64_t ancuts_segment_workspace_bytes(int num_chunks, const int32_t* h_chunk_n, int lanczos_max_steps) {
+    if (num_chunks <= 0 || !h_chunk_n) return -1;
+    Plan pl;
+    int kmax = lanczos_max_steps > 0 ? lanczos_max_steps : KMAX_DEFAULT;
+    make_plan(pl, num_chunks, h_chunk_n, nullptr, nullptr, kmax, 0);
+    return (int64_t)layout(pl, nullptr, 1 << 16, 96, 384, true);
+}
+
+int64_t ancuts_launch_count(ancuts_handle* h, int reset) {
+    if (!h) return -1;
+    int64_t v = h->launches_total;
+    if (reset) h->launches_total = 0;
+    return v;
+}
+
+int ancuts_set_stage_timing(ancuts_handle* h, int on) {
+    if (!h) return ANCUTS_EINVAL;
+    h->stage_timing = on != 0;
+    return ANCUTS_OK;
+}
+
+int ancuts_last_accounting(ancuts_handle* h, double* bytes6, double* ms6, int64_t* launches6) {
+    if (!h) return ANCUTS_EINVAL;
+    for (int i = 0; i < SG_COUNT; ++i) {
+        if (bytes6) bytes6[i] = h->stage_bytes[i];
+        if (ms6) ms6[i] = h->stage_ms[i];
+        if (launches6) launches6[i] = h->stage_launches[i];
+    }
+    return ANCUTS_OK;
+}
+
+int ancuts_affinity_f32(ancuts_handle* h, int n, const double* d_points, const float* d_tarl, const float* d_dino,
+                        const ancuts_params* p, float* d_W, int64_t ld, double* d_rowsum, void* stream) {
+    if (!h || n <= 0 || !d_points || !d_W || ld < n || (ld % 4)) { set_error("bad argument to ancuts_affinity_f32"); return ANCUTS_EINVAL; }
+    int rc = check_params(p);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    Plan pl;
+    size_t tcb = (p->affinity_impl == 1) ? affinity_tc_scratch_bytes(n, p->tarl_dim, p->dino_dim) : 0;
+    size_t need = align_up((size_t)n, 256) + 256 + tcb + 256;
+    rc = ensure_ws(h, need);
+    if (rc) return rc;
+    uint8_t* tz = (uint8_t*)h->ws;
+    pl.tc_scratch = h->ws + align_up((size_t)n, 256) + 256;
+    pl.tc_scratch_bytes = tcb;
+    begin_accounting(h);
+    rc = run_affinity(h, pl, n, d_points, d_tarl, d_dino, p, d_W, ld, tz, st);
+    if (rc) return rc;
+    if (d_rowsum) {
+        LAUNCH(SG_DEGREE, k_degree_dense<<<(n + 7) / 8, 256, 0, st>>>(n, d_W, ld, d_rowsum));
+        LAUNCH(SG_DEGREE, k_add_scalar<<<(n + 255) / 256, 256, 0, st>>>(n, d_rowsum, -1.0));
+    }
+    ANCUTS_CUDA(cudaGetLastError());
+    if (h->stage_timing) {
+        ANCUTS_CUDA(cudaStreamSynchronize(st));
+        for (auto& t : h->timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) h->stage_ms[t.stage] += ms; }
+        h->timed.clear();
+        h->stage_bytes[SG_AFFINITY] = 4.0 * n * (double)n + 4.0 * n * (3 + (p->theta != 0 ? p->tarl_dim : 0) + (p->gamma != 0 ? p->dino_dim : 0));
+    }
+    return ANCUTS_OK;
+}
+
+int ancuts_degree_normalize_f32(ancuts_handle* h, int n, const float* d_W, int64_t ld, double* d_deg, float* d_M,
+                                int64_t ldm, void* stream) {
+    if (!h || n <= 0 || !d_W || !d_deg || ld < n || (ld % 4) || (d_M && (ldm < n || (ldm % 4)))) {
+        set_error("bad argument to ancuts_degree_normalize_f32");
+        return ANCUTS_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    begin_accounting(h);
+    LAUNCH(SG_DEGREE, k_degree_dense<<<(n + 7) / 8, 256, 0, st>>>(n, d_W, ld, d_deg));
+    if (d_M) {
+        dim3 g((n + 1023) / 1024, n);
+        LAUNCH(SG_DEGREE, k_normalize_dense<<<g, 256, 0, st>>>(n, d_W, ld, d_deg, d_M, ldm));
+    }
+    ANCUTS_CUDA(cudaGetLastError());
+    if (h->stage_timing) {
+        ANCUTS_CUDA(cudaStreamSynchronize(st));
+        for (auto& t : h->timed) { float ms = 0.f; if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) h->stage_ms[t.stage] += ms; }
+        h->timed.clear();
+        h->stage_bytes[SG_DEGREE] = (d_M ? 12.0 : 4.0) * n * (double)n;
+    }
+    return ANCUTS_OK;
+}
+
+// common set-up for the stage entry points that take explicit node lists on one dense matrix
+static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float* W1, int64_t ld, int num_nodes,
+                       const int32_t* h_off, const int32_t* h_n, const ancuts_params* p, int status,
+                       cudaStream_t st, int* max_n_out) {
+    if (!h || n_total <= 0 || !W0 || ld < n_total || (ld % 4) || num_nodes <= 0 || !h_off || !h_n) {
+        set_error("bad argument (n_total=%d ld=%lld num_nodes=%d)", n_total, (long long)ld, num_nodes);
+        return ANCUTS_EINVAL;
+    }
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    int kmax = resolve_kmax(p);
+    int nn = n_total;
+    int64_t ldu = ld;
+    make_plan(pl, 1, &nn, nullptr, &ldu, kmax, num_nodes + 2 * n_total / 3 + 8);
+    pl.own_w0 = false; pl.own_w1 = false;
+    size_t bytes = layout(pl, nullptr, 1, 0, 0, false);
+    int rc = ensure_ws(h, bytes);
+    if (rc) return rc;
+    layout(pl, h->ws, 1, 0, 0, false);
+    pl.hW0[0] = W0; pl.hW1[0] = W1 ? W1 : W0;
+    rc = upload_tables(pl, st);
+    if (rc) return rc;
+    fill_params(pl.e, p, kmax);
+    pl.e.stats = nullptr; pl.e.stats_cap = 0;
+    rc = set_attrs(h, pl.KS);
+    if (rc) return rc;
+    // host-built range table: the given nodes plus filler leaves so that ranges tile [0, n_total)
+    std::vector<int> rs, rn, rst, aid, anch, aslot;
+    std::vector<std::pair<int, int>> nodes;
+    for (int i = 0; i < num_nodes; ++i) {
+        if (h_n[i] <= 0 || h_off[i] < 0 || h_off[i] + h_n[i] > n_total) { set_error("node %d out of range", i); return ANCUTS_EINVAL; }
+        nodes.push_back({h_off[i], i});
+    }
+    std::sort(nodes.begin(), nodes.end());
+    int pos = 0, maxn = 0, cslots = 0;
+    for (auto& pr : nodes) {
+        int i = pr.second;
+        if (h_off[i] < pos) { set_error("nodes overlap"); return ANCUTS_EINVAL; }
+        if (h_off[i] > pos) { rs.push_back(pos); rn.push_back(h_off[i] - pos); rst.push_back(ST_LEAF); }
+        rs.push_back(h_off[i]); rn.push_back(h_n[i]); rst.push_back(status);
+        pos = h_off[i] + h_n[i];
+        maxn = std::max(maxn, h_n[i]);
+    }
+    if (pos < n_total) { rs.push_back(pos); rn.push_back(n_total - pos); rst.push_back(ST_LEAF); }
+    int R = (int)rs.size();
+    std::vector<int> rid(n_total), chunk(R, 0), level(R, 0), pass(2 * R, 1), perm(n_total);
+    // active slots in the caller's node order
+    aid.resize(num_nodes); anch.resize(num_nodes); aslot.resize(num_nodes);
+    for (int r = 0; r < R; ++r) for (int i = 0; i < rn[r]; ++i) rid[rs[r] + i] = r;
+    for (int i = 0; i < num_nodes; ++i) {
+        aid[i] = rid[h_off[i]];
+        anch[i] = (h_n[i] + CH - 1) / CH;
+        aslot[i] = cslots;
+        cslots += anch[i];
+    }
+    for (int i = 0; i < n_total; ++i) perm[i] = i;
+    Eng& e = pl.e;
+    ANCUTS_CUDA(cudaMemcpyAsync(e.r_start, rs.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.r_n, rn.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.r_status, rst.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.r_chunk, chunk.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.r_level, level.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.r_pass, pass.data(), 2 * R * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.rid, rid.data(), n_total * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.perm, perm.data(), n_total * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.a_rid, aid.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.split_ids, aid.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.a_nch, anch.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(e.a_slot0, aslot.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 8 * sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.acct, 0, SG_COUNT * sizeof(unsigned long long), st));
+    ANCUTS_CUDA(cudaStreamSynchronize(st));
+    *max_n_out = maxn;
+    return ANCUTS_OK;
+}
+
+int ancuts_lanczos_fiedler_batched(ancuts_handle* h, int n_total, const float* d_W, int64_t ld, int num_nodes,
+                                   const int32_t* h_node_off, const int32_t* h_node_n, const ancuts_params* p,
+                                   double* d_ev, double* h_lambda2, int32_t* h_steps, int32_t* h_converged,
+                                   void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    Plan pl;
+    int max_n = 0;
+    begin_accounting(h);
+    rc = setup_nodes(h, pl, n_total, const_cast<float*>(d_W), nullptr, ld, num_nodes, h_node_off, h_node_n, p,
+                     ST_ACTIVE, st, &max_n);
+    if (rc) return rc;
+    Eng& e = pl.e;
+    dim3 gdeg((max_n + 7) / 8, num_nodes);
+    LAUNCH(SG_DEGREE, k_degree<<<gdeg, 256, 0, st>>>(e, 0));
+    rc = run_lanczos(h, e, 0, num_nodes, max_n, st);
+    if (rc) return rc;
+    dim3 gc((max_n + CH - 1) / CH, num_nodes);
+    LAUNCH(SG_REORTH, k_ritz<<<gc, 256, (size_t)(e.KS + 32) * 8, st>>>(e));
+    LAUNCH(SG_SCAN, k_ev_final<<<(num_nodes + 127) / 128, 128, 0, st>>>(e, num_nodes));
+    LAUNCH(SG_SCAN, k_bucket<<<gc, 256, 0, st>>>(e));          // applies sign and unit norm to ev
+    ANCUTS_CUDA(cudaGetLastError());
+    if (d_ev) ANCUTS_CUDA(cudaMemcpyAsync(d_ev, e.ev, (size_t)n_total * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    std::vector<double> th(2 * (size_t)num_nodes);
+    std::vector<int> kk(num_nodes), cv(num_nodes);
+    ANCUTS_CUDA(cudaMemcpyAsync(th.data(), e.a_theta, th.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(kk.data(), e.a_k, num_nodes * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(cv.data(), e.a_conv, num_nodes * sizeof(int), cudaMemcpyDeviceToHost, st));
+    rc = end_accounting(h, e, st);
+    if (rc) return rc;
+    for (int i = 0; i < num_nodes; ++i) {
+        if (h_lambda2) h_lambda2[i] = 1.0 - th[2 * i];
+        if (h_steps) h_steps[i] = kk[i];
+        if (h_converged) h_converged[i] = cv[i];
+    }
+    return ANCUTS_OK;
+}
+
+int ancuts_ncut_scan_batched(ancuts_handle* h, int n_total, const float* d_W, int64_t ld, int num_nodes,
+                             const int32_t* h_node_off, const int32_t* h_node_n, const double* d_ev,
+                             int32_t* h_best_k, double* h_mcut, double* h_costs, uint8_t* d_side, void* stream) {
+    if (!d_ev) { set_error("d_ev is NULL"); return ANCUTS_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ancuts_params p;
+    memset(&p, 0, sizeof(p));
+    p.T = 1e300;                // every node "splits": the caller wants the best cut and its side flags
+    p.proximity = 1.0;
+    Plan pl;
+    int max_n = 0;
+    begin_accounting(h);
+    int rc = setup_nodes(h, pl, n_total, const_cast<float*>(d_W), nullptr, ld, num_nodes, h_node_off, h_node_n, &p,
+                         ST_ACTIVE, st, &max_n);
+    if (rc) return rc;
+    Eng& e = pl.e;
+    ANCUTS_CUDA(cudaMemcpyAsync(e.ev, d_ev, (size_t)n_total * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.side, 0, n_total, st));
+    dim3 gdeg((max_n + 7) / 8, num_nodes);
+    LAUNCH(SG_DEGREE, k_degree<<<gdeg, 256, 0, st>>>(e, 0));
+    dim3 gc((max_n + CH - 1) / CH, num_nodes);
+    LAUNCH(SG_SCAN, k_ev_stats<<<gc, 256, 0, st>>>(e));
+    ANCUTS_CUDA(cudaMemsetAsync(e.a_k, 0, num_nodes * sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.a_conv, 0, num_nodes * sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.a_theta, 0, 2 * num_nodes * sizeof(double), st));
+    rc = run_cut(h, e, 0, num_nodes, max_n, false, st);
+    if (rc) return rc;
+    // the reference's mask is ev > t: side kernel stores 0 for the mask side; the ABI returns 1 there
+    std::vector<int> bk(num_nodes);
+    std::vector<double> mc(num_nodes), cs((size_t)num_nodes * NCUT);
+    ANCUTS_CUDA(cudaMemcpyAsync(bk.data(), e.a_bestk, num_nodes * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(mc.data(), e.a_mcut, num_nodes * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(cs.data(), e.a_costs, cs.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (d_side) {
+        LAUNCH(SG_SCAN, k_mask_from_side<<<(n_total + 255) / 256, 256, 0, st>>>(e, d_side));
+    }
+    rc = end_accounting(h, e, st);
+    if (rc) return rc;
+    for (int i = 0; i < num_nodes; ++i) {
+        if (h_best_k) h_best_k[i] = bk[i];
+        if (h_mcut) h_mcut[i] = mc[i];
+    }
+    if (h_costs) memcpy(h_costs, cs.data(), cs.size() * sizeof(double));
+    return ANCUTS_OK;
+}
+
+int ancuts_partition_batched(ancuts_handle* h, int n_total, const float* d_W_in, float* d_W_out, int64_t ld,
+                             int num_nodes, const int32_t* h_node_off, const int32_t* h_node_n,
+                             const uint8_t* d_side, int split_components, int32_t* d_perm_out,
+                             int32_t* h_num_children, int32_t* h_child_off, int32_t* h_child_n, void* stream) {
+    if (!d_W_out || !d_side) { set_error("d_W_out / d_side is NULL"); return ANCUTS_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ancuts_params p;
+    memset(&p, 0, sizeof(p));
+    p.T = 1.0;
+    Plan pl;
+    int max_n = 0;
+    begin_accounting(h);
+    int rc = setup_nodes(h, pl, n_total, const_cast<float*>(d_W_in), d_W_out, ld, num_nodes, h_node_off, h_node_n, &p,
+                         ST_SPLIT, st, &max_n);
+    if (rc) return rc;
+    Eng& e = pl.e;
+    // ABI: side 1 = mask (goes first); internal: 0 = mask side
+    LAUNCH(SG_PARTITION, k_side_from_mask<<<(n_total + 255) / 256, 256, 0, st>>>(e, d_side));
+    // stop rule off for this entry point: every child is kept as an ACTIVE range so it gets gathered
+    std::vector<int> big(1, 1);
+    ANCUTS_CUDA(cudaMemcpyAsync(const_cast<int*>(e.c_norig), big.data(), sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaStreamSynchronize(st));
+    if (!split_components)       // sides stay whole: no component roots in the sort key
+        ANCUTS_CUDA(cudaMemsetAsync(e.r_pass, 0, 2 * (size_t)(n_total + 1) * sizeof(int), st));
+    int cur = 0;
+    rc = run_rebuild(h, pl, cur, num_nodes, max_n, split_components != 0, st);
+    if (rc) return rc;
+    int num_ranges = h->h_ctr[0];
+    std::vector<int> rs(num_ranges), rn(num_ranges), rst(num_ranges);
+    ANCUTS_CUDA(cudaMemcpyAsync(rs.data(), e.r_start, num_ranges * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(rn.data(), e.r_n, num_ranges * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(rst.data(), e.r_status, num_ranges * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (d_perm_out) {
+        // perm2 holds the previous (identity) permutation after the swap; val2 = old position per new position
+        ANCUTS_CUDA(cudaMemcpyAsync(d_perm_out, e.val2, (size_t)n_total * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
+    rc = end_accounting(h, e, st);
+    if (rc) return rc;
+    int cnt = 0;
+    for (int r = 0; r < num_ranges; ++r) {
+        // children of the given nodes only (filler leaves are skipped)
+        bool inside = false;
+        for (int i = 0; i < num_nodes && !inside; ++i)
+            inside = rs[r] >= h_node_off[i] && rs[r] < h_node_off[i] + h_node_n[i];
+        if (!inside) continue;
+        if (h_child_off) h_child_off[cnt] = rs[r];
+        if (h_child_n) h_child_n[cnt] = rn[r];
+        ++cnt;
+    }
+    if (h_num_children) *h_num_children = cnt;
+    return ANCUTS_OK;
+}
+
+static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off, const double* d_points,
+                          const float* d_tarl, const float* d_dino, const float* d_W_dense, int64_t ld_dense,
+                          int num_points_orig, const ancuts_params* p, int32_t* d_labels, int32_t* h_num_segments,
+                          ancuts_node_stat* h_stats, int32_t stats_cap, int32_t* h_num_stats, cudaStream_t st) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (!h || num_chunks <= 0 || !h_chunk_off || !d_labels) { set_error("bad argument to segment"); return ANCUTS_EINVAL; }
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    std::vector<int> n(num_chunks), norig(num_chunks);
+    for (int c = 0; c < num_chunks; ++c) {
+        int64_t d = h_chunk_off[c + 1] - h_chunk_off[c];
+        if (d <= 0 || d > (1 << 28)) { set_error("chunk %d has %lld points", c, (long long)d); return ANCUTS_EINVAL; }
+        n[c] = (int)d;
+        norig[c] = (d_W_dense && num_points_orig > 0) ? num_points_orig : (int)d;
+    }
+    if (h_chunk_off[num_chunks] - h_chunk_off[0] > 0x7fffffffLL / 4) { set_error("batch too large"); return ANCUTS_EINVAL; }
+    const int kmax = resolve_kmax(p);
+    Plan pl;
+    make_plan(pl, num_chunks, n.data(), norig.data(), nullptr, kmax, 0);
+    if (stats_cap < 0) stats_cap = 0;
+    const bool need_tc = (p->affinity_impl == 1) && !d_W_dense;
+    size_t bytes = layout(pl, nullptr, stats_cap, p->tarl_dim, p->dino_dim, need_tc);
+    rc = ensure_ws(h, bytes);
+    if (rc) return rc;
+    layout(pl, h->ws, stats_cap, p->tarl_dim, p->dino_dim, need_tc);
+    rc = upload_tables(pl, st);
+    if (rc) return rc;
+    fill_params(pl.e, p, kmax);
+    pl.e.stats = (h_stats && stats_cap > 0) ? pl.stats : nullptr;
+    pl.e.stats_cap = stats_cap;
+    rc = set_attrs(h, pl.KS);
+    if (rc) return rc;
+    begin_accounting(h);
+    ANCUTS_CUDA(cudaMemsetAsync(pl.e.acct, 0, SG_COUNT * sizeof(unsigned long long), st));
+    const int64_t off0 = h_chunk_off[0];
+    if (d_W_dense) {
+        ANCUTS_CUDA(cudaMemcpy2DAsync(pl.hW0[0], (size_t)pl.ld[0] * 4, d_W_dense, (size_t)ld_dense * 4, (size_t)n[0] * 4,
+                                      n[0], cudaMemcpyDeviceToDevice, st));
+    } else {
+        double aff_bytes = 0.0;
+        for (int c = 0; c < num_chunks; ++c) {
+            int64_t o = h_chunk_off[c] - off0;
+            const float* tz = d_tarl ? d_tarl + (size_t)(h_chunk_off[c]) * p->tarl_dim : nullptr;
+            const float* dz = d_dino ? d_dino + (size_t)(h_chunk_off[c]) * p->dino_dim : nullptr;
+            rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
+                              pl.tarl_zero + o, st);
+            if (rc) return rc;
+            aff_bytes += 4.0 * n[c] * (double)n[c] +
+                         4.0 * n[c] * (3 + (p->theta != 0 ? p->tarl_dim : 0) + (p->gamma != 0 ? p->dino_dim : 0));
+        }
+        h->stage_bytes[SG_AFFINITY] = aff_bytes;
+    }
+    rc = run_levels(h, pl, p, 0, d_labels, h_num_segments, st);
+    if (rc) return rc;
+    rc = copy_stats(h, pl, h_stats, stats_cap, h_num_stats, st);
+    if (rc) return rc;
+    return end_accounting(h, pl.e, st);
+}
+
+int ancuts_segment_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off, const double* d_points,
+                          const float* d_tarl, const float* d_dino, const ancuts_params* p, int32_t* d_labels,
+                          int32_t* h_num_segments, ancuts_node_stat* h_stats, int32_t stats_cap,
+                          int32_t* h_num_stats, void* stream) {
+    if (!d_points) { set_error("d_points is NULL"); return ANCUTS_EINVAL; }
+    if (h_chunk_off && h_chunk_off[0] != 0) { set_error("h_chunk_off[0] must be 0"); return ANCUTS_EINVAL; }
+    return segment_common(h, num_chunks, h_chunk_off, d_points, d_tarl, d_dino, nullptr, 0, 0, p, d_labels,
+                          h_num_segments, h_stats, stats_cap, h_num_stats, (cudaStream_t)stream);
+}
+
+int ancuts_segment_dense_f32(ancuts_handle* h, int n, const float* d_W, int64_t ld, int num_points_orig,
+                             const ancuts_params* p, int32_t* d_labels, int32_t* h_num_segments,
+                             ancuts_node_stat* h_stats, int32_t stats_cap, int32_t* h_num_stats, void* stream) {
+    if (!d_W || n <= 0 || ld < n) { set_error("bad argument to ancuts_segment_dense_f32"); return ANCUTS_EINVAL; }
+    int64_t off[2] = {0, n};
+    return segment_common(h, 1, off, nullptr, nullptr, nullptr, d_W, ld, num_points_orig, p, d_labels,
+                          h_num_segments, h_stats, stats_cap, h_num_stats, (cudaStream_t)stream);
+}
+
+int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off, const double* h_points,
+                               const float* h_tarl, const float* h_dino, const ancuts_params* p, int32_t* h_labels,
+                               int32_t* h_num_segments, ancuts_node_stat* h_stats, int32_t stats_cap,
+                               int32_t* h_num_stats, void* stream) {
+    if (!h || !h_points || !h_labels || !h_chunk_off || num_chunks <= 0 || !p) { set_error("bad argument to ancuts_segment_chunks_host"); return ANCUTS_EINVAL; }
+    if (h_chunk_off[0] != 0) { set_error("h_chunk_off[0] must be 0"); return ANCUTS_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    const size_t P = (size_t)h_chunk_off[num_chunks];
+    const bool use_t = h_tarl && p->theta != 0.0, use_d = h_dino && p->gamma != 0.0;
+    size_t bp = P * 3 * sizeof(double), bt = use_t ? P * p->tarl_dim * sizeof(float) : 0,
+           bd = use_d ? P * p->dino_dim * sizeof(float) : 0, bl = P * sizeof(int32_t);
+    char* stage = nullptr;
+    size_t total = align_up(bp, 256) + align_up(bt, 256) + align_up(bd, 256) + align_up(bl, 256);
+    ANCUTS_CUDA(cudaMalloc((void**)&stage, total));
+    double* d_points = (double*)stage;
+    float* d_tarl = use_t ? (float*)(stage + align_up(bp, 256)) : nullptr;
+    float* d_dino = use_d ? (float*)(stage + align_up(bp, 256) + align_up(bt, 256)) : nullptr;
+    int32_t* d_labels = (int32_t*)(stage + align_up(bp, 256) + align_up(bt, 256) + align_up(bd, 256));
+    int rc = ANCUTS_OK;
+    cudaError_t ce = cudaMemcpyAsync(d_points, h_points, bp, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess && use_t) ce = cudaMemcpyAsync(d_tarl, h_tarl, bt, cudaMemcpyHostToDevice, st);
+    if (ce == cudaSuccess && use_d) ce = cudaMemcpyAsync(d_dino, h_dino, bd, cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(ce)); rc = ANCUTS_ECUDA; }
+    if (rc == ANCUTS_OK)
+        rc = segment_common(h, num_chunks, h_chunk_off, d_points, d_tarl, d_dino, nullptr, 0, 0, p, d_labels,
+                            h_num_segments, h_stats, stats_cap, h_num_stats, st);
+    if (rc == ANCUTS_OK) {
+        ce = cudaMemcpyAsync(h_labels, d_labels, bl, cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(ce)); rc = ANCUTS_ECUDA; }
+    }
+    cudaFree(stage);
+    return rc;
+}
+
+}  // extern "C"

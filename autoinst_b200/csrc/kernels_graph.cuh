@@ -1,0 +1,404 @@
+// kernels_graph.cuh — affinity (exact CUDA-core tile kernel), degrees, connected components,
+// range-table rebuild and block gather.  Reference lines are cited per kernel.
+#pragma once
+#include "common.cuh"
+
+namespace ancuts {
+
+struct NodeView {
+    int start;      // global position of the first point
+    int n;
+    int chunk;
+    int ro;         // chunk-local offset = row/column of the block inside the chunk's matrix
+    int ld;
+    const float* W; // chunk matrix in the current buffer
+};
+
+__device__ __forceinline__ NodeView node_view(const Eng& e, int r, int cur) {
+    NodeView v;
+    v.start = e.r_start[r];
+    v.n = e.r_n[r];
+    v.chunk = e.r_chunk[r];
+    v.ro = v.start - e.c_base[v.chunk];
+    v.ld = e.c_ld[v.chunk];
+    v.W = cur ? e.c_W1[v.chunk] : e.c_W0[v.chunk];
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1 (exact): A_ij = [sd_ij <= prox] * exp(-(alpha*sd_ij + theta*td_ij + gamma*dd_ij))
+//   ncuts_utils.py:60-66 (spatial, float64 compare), :135-149 (TARL, zero rows neutralised),
+//   :125-133 (DINOv2, zero rows NOT neutralised), :151-156 (product).
+// One 64x64 tile per CTA.  Pass 1 evaluates the float64 spatial test for every pair; pairs inside
+// the mask are queued in shared memory.  Pass 2 spreads the queued pairs over 8-lane groups which
+// evaluate the feature distances by direct differences (float32 inputs, float64 accumulation).
+// ---------------------------------------------------------------------------------------------
+constexpr int AT = 64;
+
+__global__ void __launch_bounds__(256)
+k_zero_rows(int n, const float* __restrict__ f, int dim, uint8_t* __restrict__ zero) {
+    int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    bool any = false;
+    for (int k = lane; k < dim; k += 32) any |= (f[(size_t)row * dim + k] != 0.0f);
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) zero[row] = any ? 0 : 1;          // ~tarl.any(1), ncuts_utils.py:143
+}
+
+__device__ __forceinline__ double feat_dist8(const float* __restrict__ a, const float* __restrict__ b,
+                                             int dim, int lane8) {
+    double s = 0.0;
+    for (int k = lane8 * 4; k < dim; k += 32) {
+        float4 x = *reinterpret_cast<const float4*>(a + k);
+        float4 y = *reinterpret_cast<const float4*>(b + k);
+        double d0 = (double)x.x - (double)y.x, d1 = (double)x.y - (double)y.y;
+        double d2 = (double)x.z - (double)y.z, d3 = (double)x.w - (double)y.w;
+        s += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    return sqrt(s);
+}
+
+__global__ void __launch_bounds__(256)
+k_affinity_exact(int n, const double* __restrict__ pts, const float* __restrict__ tarl, int tdim,
+                 const float* __restrict__ dino, int ddim, const uint8_t* __restrict__ tarl_zero,
+                 double alpha, double theta, double gamma, double prox,
+                 float* __restrict__ W, long long ld) {
+    __shared__ double pr[AT][3];
+    __shared__ double pc[AT][3];
+    __shared__ __align__(16) float tile[AT][AT];
+    __shared__ unsigned short queue[AT * AT];
+    __shared__ int qn;
+
+    const int row0 = blockIdx.y * AT, col0 = blockIdx.x * AT;
+    const int tid = threadIdx.x;
+    if (tid == 0) qn = 0;
+    for (int i = tid; i < AT * 3; i += 256) {
+        int p = i / 3, k = i % 3;
+        int gr = row0 + p, gc = col0 + p;
+        pr[p][k] = gr < n ? pts[(size_t)gr * 3 + k] : 0.0;
+        pc[p][k] = gc < n ? pts[(size_t)gc * 3 + k] : 0.0;
+    }
+    __syncthreads();
+
+    const bool feats = (theta != 0.0 && tarl != nullptr) || (gamma != 0.0 && dino != nullptr);
+    const int cg = (tid & 15) * 4, rg = tid >> 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int r = rg + 16 * k;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            int c = cg + c4;
+            float out = 0.0f;
+            if (row0 + r < n && col0 + c < n) {
+                double dx = pr[r][0] - pc[c][0], dy = pr[r][1] - pc[c][1], dz = pr[r][2] - pc[c][2];
+                // cdist accumulates the squares one after another in float64 without contraction
+                double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                double sd = __dsqrt_rn(s);
+                if (sd <= prox) {                                    // ncuts_utils.py:61, inclusive
+                    double a = alpha != 0.0 ? alpha * sd : 0.0;      // :63-66
+                    if (feats) {
+                        out = (float)a;
+                        int q = atomicAdd(&qn, 1);
+                        queue[q] = (unsigned short)(r * AT + c);
+                    } else {
+                        out = (float)exp(-a);
+                    }
+                }
+            }
+            tile[r][c] = out;
+        }
+    }
+    __syncthreads();
+
+    if (feats) {
+        const int total = qn;
+        const int grp = tid >> 3, lane8 = tid & 7;
+        const int rounds = (total + 31) / 32;
+        for (int it = 0; it < rounds; ++it) {
+            int q = it * 32 + grp;
+            bool live = q < total;
+            int idx = live ? queue[q] : 0;
+            int r = idx / AT, c = idx % AT;
+            int gi = row0 + r, gj = col0 + c;
+            if (!live) { gi = 0; gj = 0; }                            // keep the 8-lane shuffles uniform
+            double arg = 0.0;
+            if (theta != 0.0 && tarl != nullptr) {
+                double td = feat_dist8(tarl + (size_t)gi * tdim, tarl + (size_t)gj * tdim, tdim, lane8);
+                if (tarl_zero[gi] | tarl_zero[gj]) td = 0.0;          // ncuts_utils.py:145-146
+                arg += theta * td;
+            }
+            if (gamma != 0.0 && dino != nullptr) {
+                double dd = feat_dist8(dino + (size_t)gi * ddim, dino + (size_t)gj * ddim, ddim, lane8);
+                arg += gamma * dd;                                    // :129-133
+            }
+            if (live && lane8 == 0) tile[r][c] = (float)exp(-((double)tile[r][c] + arg));
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int r = rg + 16 * k;
+        int gr = row0 + r, gc = col0 + cg;
+        if (gr < n && gc < ld) {
+            float4 v = *reinterpret_cast<const float4*>(&tile[r][cg]);
+            *reinterpret_cast<float4*>(W + (size_t)gr * ld + gc) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 2: degrees of W = w + I for every active node:  d_i = 1 + sum_j w_ij  (float64)
+//   normalized_cut.py:38,42-43.  One warp per row, aligned 128-bit window loads.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double row_sum_window(const float* __restrict__ rowp, int c_lo, int c_hi, int lane) {
+    double acc = 0.0;
+    int a0 = c_lo & ~3;
+    for (int c = a0 + lane * 4; c < c_hi; c += 128) {
+        float4 w = ld_stream4(rowp + c);
+        double s = 0.0;
+        if (c >= c_lo && c + 3 < c_hi) {
+            s = ((double)w.x + (double)w.y) + ((double)w.z + (double)w.w);
+        } else {
+            if (c >= c_lo && c < c_hi) s += (double)w.x;
+            if (c + 1 >= c_lo && c + 1 < c_hi) s += (double)w.y;
+            if (c + 2 >= c_lo && c + 2 < c_hi) s += (double)w.z;
+            if (c + 3 >= c_lo && c + 3 < c_hi) s += (double)w.w;
+        }
+        acc += s;
+    }
+    return warp_sum(acc);
+}
+
+__global__ void __launch_bounds__(256)
+k_degree(Eng e, int cur) {
+    int a = blockIdx.y;
+    NodeView v = node_view(e, e.a_rid[a], cur);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int row = blockIdx.x * 8 + warp;
+    if (row >= v.n) return;
+    const float* rowp = v.W + (size_t)(v.ro + row) * v.ld;
+    double s = row_sum_window(rowp, v.ro, v.ro + v.n, lane);
+    if (lane == 0) {
+        double d = 1.0 + s;                         // + identity (normalized_cut.py:38)
+        e.deg[v.start + row] = d;
+        e.sinv[v.start + row] = 1.0 / sqrt(d);      // :43
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&e.acct[SG_DEGREE], 4ull * v.n * v.n);
+}
+
+// plain dense version for the stage-2 entry point (optionally writes M = D^-1/2 (w+I) D^-1/2)
+__global__ void __launch_bounds__(256)
+k_degree_dense(int n, const float* __restrict__ W, long long ld, double* __restrict__ deg) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int row = blockIdx.x * 8 + warp;
+    if (row >= n) return;
+    double s = row_sum_window(W + (size_t)row * ld, 0, n, lane);
+    if (lane == 0) deg[row] = 1.0 + s;
+}
+
+__global__ void __launch_bounds__(256)
+k_normalize_dense(int n, const float* __restrict__ W, long long ld, const double* __restrict__ deg,
+                  float* __restrict__ M, long long ldm) {
+    int row = blockIdx.y;
+    int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+    if (c >= n) return;
+    double si = rsqrt(deg[row]);
+    float4 w = *reinterpret_cast<const float4*>(W + (size_t)row * ld + c);
+    float in[4] = {w.x, w.y, w.z, w.w};
+    float out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        int cc = c + k;
+        double x = 0.0;
+        if (cc < n) x = ((double)in[k] + (cc == row ? 1.0 : 0.0)) * si * rsqrt(deg[cc]);
+        out[k] = (float)x;
+    }
+    *reinterpret_cast<float4*>(M + (size_t)row * ldm + c) = make_float4(out[0], out[1], out[2], out[3]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Connected components of each side of every SPLIT range (lock-free union-find; the larger root
+// is hooked under the smaller one, so the final root of a component is its smallest position and
+// the result does not depend on scheduling).
+//   Replaces the reference's null-space splits of disconnected nodes (normalized_cut.py:49-58 with
+//   lambda_2 = 0); see DESIGN.md "degenerate nodes".
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_load(const int* parent, int x) {
+    return __ldcg(parent + x);
+}
+__device__ __forceinline__ int uf_find(int* parent, int x) {
+    int p = uf_load(parent, x);
+    while (p != x) {
+        int gp = uf_load(parent, p);
+        if (gp != p) parent[x] = gp;     // path halving; only ever points to an ancestor
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }       // a > b: hook a under b
+        if (atomicCAS(parent + a, a, b) == a) return;
+    }
+}
+
+__global__ void k_cc_init(Eng e) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < e.P) e.parent[g] = g;
+}
+
+// grid: (row blocks of 8 rows, split list).  split list = ranges with ST_SPLIT, ids in a_rid-like list
+__global__ void __launch_bounds__(256)
+k_cc_union(Eng e, int cur, const int* __restrict__ split_ids) {
+    int r = split_ids[blockIdx.y];
+    NodeView v = node_view(e, r, cur);
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int row = blockIdx.x * 8 + warp;
+    if (row >= v.n) return;
+    int gi = v.start + row;
+    int si = e.side[gi];
+    if (!e.r_pass[2 * r + si]) return;             // a side at or below the size limit stays whole
+    const float* rowp = v.W + (size_t)(v.ro + row) * v.ld;
+    int c_lo = v.ro + row + 1, c_hi = v.ro + v.n;  // upper triangle only (w is symmetric)
+    int a0 = c_lo & ~3;
+    for (int c = a0 + lane * 4; c < c_hi; c += 128) {
+        float4 w = ld_stream4(rowp + c);
+        float in[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int cc = c + k;
+            if (cc >= c_lo && cc < c_hi && in[k] != 0.0f) {
+                int gj = v.start + (cc - v.ro);
+                if (e.side[gj] == si) uf_union(e.parent, gi, gj);
+            }
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&e.acct[SG_PARTITION], 2ull * v.n * v.n);
+}
+
+__global__ void k_cc_flatten(Eng e) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g < e.P) e.croot[g] = uf_find(e.parent, g);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Range-table rebuild.  Sort key = (range start << 32) | (side << 30 | component root + 1);
+// leaves keep key low = 0 so the stable sort leaves them in place.  Mask side first
+// (normalized_cut.py:57-59).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_build_keys(Eng e) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= e.P) return;
+    int r = e.rid[g];
+    unsigned int lo = 0;
+    int start = e.r_start[r];
+    if (e.r_status[r] == ST_SPLIT) {
+        int s = e.side[g];
+        lo = ((unsigned int)s << 30);
+        if (e.r_pass[2 * r + s]) lo |= (unsigned int)(e.croot[g] - start + 1);
+    }
+    e.key[g] = ((unsigned long long)(unsigned int)start << 32) | lo;
+    e.val[g] = g;
+}
+
+__global__ void k_boundaries(Eng e) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= e.P) return;
+    e.flag[p] = (p == 0 || e.key2[p] != e.key2[p - 1]) ? 1 : 0;
+}
+
+// after the inclusive scan of flag -> incl
+__global__ void k_new_ranges(Eng e) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= e.P) return;
+    int nr = e.incl[p] - 1;
+    e.rid2[p] = nr;
+    e.perm2[p] = e.perm[e.val2[p]];
+    if (e.flag[p]) {
+        int oldr = e.rid[e.val2[p]];
+        e.q_start[nr] = p;
+        e.q_chunk[nr] = e.r_chunk[oldr];
+        // provisional: remember whether the parent range was being split; level of the child
+        e.q_status[nr] = (e.r_status[oldr] == ST_SPLIT) ? ST_ACTIVE : ST_LEAF;
+        e.q_level[nr] = e.r_level[oldr] + ((e.r_status[oldr] == ST_SPLIT) ? 1 : 0);
+    }
+    if (p == e.P - 1) e.ctr[0] = nr + 1;
+}
+
+// sizes, stop rule (normalized_cut.py:39-40 with the child default 0.01), active slots
+__global__ void k_finish_ranges(Eng e, int num_ranges) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= num_ranges) return;
+    int start = e.q_start[r];
+    int end = (r + 1 < num_ranges) ? e.q_start[r + 1] : e.P;
+    int n = end - start;
+    e.q_n[r] = n;
+    int st = e.q_status[r];
+    if (st == ST_ACTIVE) {
+        int c = e.q_chunk[r];
+        double frac = (double)n / ((double)e.c_norig[c] + 1e-8);
+        bool pass = (n > 2) && (frac > CHILD_SPLIT_LIM);
+        if (!pass) st = ST_LEAF;
+    }
+    e.q_status[r] = st;
+    if (st == ST_ACTIVE) {
+        int a = atomicAdd(&e.ctr[1], 1);
+        int nch = (n + CH - 1) / CH;
+        e.a_rid[a] = r;
+        e.a_nch[a] = nch;
+        e.a_slot0[a] = atomicAdd(&e.ctr[3], nch);
+        atomicMax(&e.ctr[2], n);
+    }
+}
+
+// gather the blocks of the new ACTIVE ranges from the old buffer into the other one:
+//   w[mask][:, mask] etc. (normalized_cut.py:57-58).  Called after the rebuilt table became current;
+//   val2[new position] = old position.  grid: (col tiles of 256, row tiles of 16, active)
+__global__ void __launch_bounds__(256)
+k_gather_blocks_cur(Eng e, int cur /* source buffer */) {
+    int a = blockIdx.z;
+    int r = e.a_rid[a];
+    int start = e.r_start[r], n = e.r_n[r], c = e.r_chunk[r];
+    int col = blockIdx.x * 256 + threadIdx.x;
+    int row0 = blockIdx.y * 16;
+    if (row0 >= n) return;
+    int base = e.c_base[c], ld = e.c_ld[c];
+    const float* src = cur ? e.c_W1[c] : e.c_W0[c];
+    float* dst = cur ? e.c_W0[c] : e.c_W1[c];
+    int ro = start - base;
+    if (col < n) {
+        int sc = e.val2[start + col] - base;
+        int rows = min(16, n - row0);
+        for (int i = 0; i < rows; ++i) {
+            int sr = e.val2[start + row0 + i] - base;
+            dst[(size_t)(ro + row0 + i) * ld + ro + col] = __ldg(src + (size_t)sr * ld + sc);
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        atomicAdd(&e.acct[SG_PARTITION], 8ull * n * n);
+}
+
+// final labels: label = range index relative to the chunk's first range (ncuts_utils.py:177-183)
+__global__ void k_emit_labels(Eng e, int* __restrict__ labels, int* __restrict__ nseg) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= e.P) return;
+    int r = e.rid[p];
+    int c = e.r_chunk[r];
+    int base = e.c_base[c];
+    int first = e.rid[base];
+    labels[base + e.perm[p]] = r - first;
+    if (p == base + e.c_n[c] - 1) nseg[c] = r - first + 1;
+}
+
+}  // namespace ancuts

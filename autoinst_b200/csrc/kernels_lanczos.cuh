@@ -1,0 +1,465 @@
+// kernels_lanczos.cuh — stage 3: batched Lanczos for the Fiedler vector of every active node.
+//   Replaces eigsh(A, 2, sigma=1e-10, which='LM') + argsort (normalized_cut.py:49-53).
+// Operator: M = S (w + I) S with S = D^-1/2; the Fiedler vector of L = I - M is the eigenvector
+// of the second largest eigenvalue of M.  The largest (1, vector D^1/2 1) is deflated by keeping
+// it as row 0 of the basis V and re-orthogonalising against it like any Lanczos vector.
+// W is read as float32; every vector and every sum is float64.
+#pragma once
+#include "common.cuh"
+#include "kernels_graph.cuh"
+
+namespace ancuts {
+
+__device__ __forceinline__ double start_value(int i) {
+    // same integer hash as oracle/device_model.py::start_vector
+    unsigned long long x = ((unsigned long long)i + 1ull) * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+// One CTA per active node: u1 = sqrt(d)/||sqrt(d)|| -> V row 0; w0 = start - u1 (u1.start) -> wbuf,
+// ||w0|| -> a_bprev.  Also resets the per-node Lanczos state.
+__global__ void __launch_bounds__(256)
+k_lanczos_init(Eng e) {
+    __shared__ double red[8];
+    int a = blockIdx.x;
+    int r = e.a_rid[a];
+    int start = e.r_start[r], n = e.r_n[r];
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) s += e.deg[start + i];
+    double vol = block_sum_256(s, red);
+    double inv = 1.0 / sqrt(vol);
+    double dot = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        double u = sqrt(e.deg[start + i]) * inv;
+        e.V[start + i] = u;                                   // row 0
+        dot += u * start_value(i);
+    }
+    dot = block_sum_256(dot, red);
+    double nn = 0.0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        double x = start_value(i) - dot * e.V[start + i];
+        e.wbuf[start + i] = x;
+        nn += x * x;
+    }
+    nn = block_sum_256(nn, red);
+    if (threadIdx.x == 0) {
+        e.a_bprev[a] = sqrt(nn);
+        e.a_k[a] = 0;
+        int kcap = min(e.kmax, n - 1);
+        e.a_kcap[a] = kcap;
+        e.a_done[a] = DONE_NO;
+        e.a_conv[a] = 0;
+    }
+}
+
+// y = S (w+I) S v  with v = wbuf / bprev (the normalisation of the previous step is folded in
+// here; the rows of this block also store v into V row k+1).
+// grid: (row blocks of 8*R rows, active).  z = S v is staged in shared memory as float64 in
+// tiles of at most ZT columns, laid out on the 16-byte window of the matrix row.
+template <int R>
+__global__ void __launch_bounds__(256)
+k_matvec(Eng e, int cur, int zt) {
+    extern __shared__ double zs[];      // zt + 8 doubles
+    int a = blockIdx.y;
+    if (e.a_done[a] != DONE_NO) return;
+    NodeView v = node_view(e, e.a_rid[a], cur);
+    const int rows_per_block = 8 * R;
+    int row0 = blockIdx.x * rows_per_block;
+    if (row0 >= v.n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double invb = 1.0 / e.a_bprev[a];
+    const int k = e.a_k[a];
+    double acc[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) acc[rr] = 0.0;
+    const int myrow0 = row0 + warp * R;
+
+    for (int t0 = 0; t0 < v.n; t0 += zt) {
+        int tn = min(zt, v.n - t0);
+        int c_lo = v.ro + t0, c_hi = c_lo + tn;
+        int a0 = c_lo & ~3;
+        int pad = c_lo - a0;
+        int span = ((c_hi - a0) + 3) & ~3;
+        if (t0 > 0) __syncthreads();
+        for (int j = threadIdx.x; j < span; j += 256) {
+            int jj = j - pad;
+            double z = 0.0;
+            if (jj >= 0 && jj < tn) {
+                int g = v.start + t0 + jj;
+                z = e.sinv[g] * e.wbuf[g] * invb;
+            }
+            zs[j] = z;
+        }
+        __syncthreads();
+        for (int j = lane * 4; j < span; j += 128) {
+            int c = a0 + j;
+            double2 za = *reinterpret_cast<const double2*>(&zs[j]);
+            double2 zb = *reinterpret_cast<const double2*>(&zs[j + 2]);
+            bool v0 = (c >= c_lo) & (c < c_hi), v1 = (c + 1 >= c_lo) & (c + 1 < c_hi);
+            bool v2 = (c + 2 >= c_lo) & (c + 2 < c_hi), v3 = (c + 3 >= c_lo) & (c + 3 < c_hi);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                int row = myrow0 + rr;
+                if (row < v.n) {
+                    float4 w = ld_stream4(v.W + (size_t)(v.ro + row) * v.ld + c);
+                    // entries outside the block belong to other nodes or are uninitialised
+                    double w0 = v0 ? (double)w.x : 0.0, w1 = v1 ? (double)w.y : 0.0;
+                    double w2 = v2 ? (double)w.z : 0.0, w3 = v3 ? (double)w.w : 0.0;
+                    acc[rr] += w0 * za.x + w1 * za.y + w2 * zb.x + w3 * zb.y;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+        double s = warp_sum(acc[rr]);
+        int row = myrow0 + rr;
+        if (lane == 0 && row < v.n) {
+            int g = v.start + row;
+            double vi = e.wbuf[g] * invb;
+            double si = e.sinv[g];
+            e.ybuf[g] = si * (s + si * vi);                       // (w + I) z, z_i = s_i v_i
+            e.V[(size_t)(k + 1) * e.P + g] = vi;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&e.acct[SG_MATVEC], 4ull * v.n * v.n + 8ull * v.n);
+}
+
+// partial dots of ybuf with basis rows 0..k+1 over one CH-column chunk.
+// grid: (chunks, row tiles of 32 basis rows, active)
+__global__ void __launch_bounds__(256)
+k_dots(Eng e) {
+    int a = blockIdx.z;
+    if (e.a_done[a] != DONE_NO) return;
+    int nch = e.a_nch[a];
+    int ch = blockIdx.x;
+    if (ch >= nch) return;
+    int rows = e.a_k[a] + 2;
+    int j0 = blockIdx.y * 32;
+    if (j0 >= rows) return;
+    int r = e.a_rid[a];
+    int start = e.r_start[r], n = e.r_n[r];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cbase = ch * CH;
+    double yr[CH / 32];
+#pragma unroll
+    for (int m = 0; m < CH / 32; ++m) {
+        int c = cbase + lane + 32 * m;
+        yr[m] = c < n ? e.ybuf[start + c] : 0.0;
+    }
+    double* out = e.p_dot + (size_t)(e.a_slot0[a] + ch) * e.KS;
+    for (int j = j0 + warp; j < min(j0 + 32, rows); j += 8) {
+        const double* vr = e.V + (size_t)j * e.P + start;
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < CH / 32; ++m) {
+            int c = cbase + lane + 32 * m;
+            if (c < n) s += vr[c] * yr[m];
+        }
+        s = warp_sum(s);
+        if (lane == 0) out[j] = s;
+    }
+}
+
+// y -= V^T h over one chunk; pass 1 then computes the partial dots of the updated y (second
+// Gram-Schmidt pass), pass 2 writes wbuf and the partial squared norm.
+// grid: (chunks, active)
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_update(Eng e) {
+    extern __shared__ double sm[];          // hs[KS] | ych[CH] | red[8]
+    double* hs = sm;
+    double* ych = sm + e.KS;
+    double* red = ych + CH;
+    int a = blockIdx.y;
+    if (e.a_done[a] != DONE_NO) return;
+    int nch = e.a_nch[a];
+    int ch = blockIdx.x;
+    if (ch >= nch) return;
+    int rows = e.a_k[a] + 2;
+    int r = e.a_rid[a];
+    int start = e.r_start[r], n = e.r_n[r];
+    const double* pd = (PASS == 1 ? e.p_dot : e.p_dot2) + (size_t)e.a_slot0[a] * e.KS;
+    for (int j = threadIdx.x; j < rows; j += 256) {
+        double h = 0.0;
+        for (int c = 0; c < nch; ++c) h += pd[(size_t)c * e.KS + j];     // fixed order
+        hs[j] = h;
+    }
+    __syncthreads();
+    if (ch == 0 && threadIdx.x == 0) {
+        if (PASS == 1) e.a_h1[a] = hs[rows - 1]; else e.a_h2[a] = hs[rows - 1];
+    }
+    int c0 = ch * CH + threadIdx.x, c1 = c0 + 256;
+    double y0 = c0 < n ? e.ybuf[start + c0] : 0.0;
+    double y1 = c1 < n ? e.ybuf[start + c1] : 0.0;
+    const double* vb = e.V + start;
+#pragma unroll 4
+    for (int j = 0; j < rows; ++j) {
+        const double* vr = vb + (size_t)j * e.P;
+        double h = hs[j];
+        if (c0 < n) y0 -= h * vr[c0];
+        if (c1 < n) y1 -= h * vr[c1];
+    }
+    if (PASS == 1) {
+        if (c0 < n) e.ybuf[start + c0] = y0;
+        if (c1 < n) e.ybuf[start + c1] = y1;
+        ych[threadIdx.x] = y0;
+        ych[threadIdx.x + 256] = y1;
+        __syncthreads();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        double yr[CH / 32];
+#pragma unroll
+        for (int m = 0; m < CH / 32; ++m) yr[m] = ych[lane + 32 * m];
+        // other CTAs of this node may still be reading the pass-1 partials: pass 2 has its own buffer
+        double* out = e.p_dot2 + (size_t)(e.a_slot0[a] + ch) * e.KS;
+        for (int j = warp; j < rows; j += 8) {
+            const double* vr = vb + (size_t)j * e.P;
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < CH / 32; ++m) {
+                int c = ch * CH + lane + 32 * m;
+                if (c < n) s += vr[c] * yr[m];
+            }
+            s = warp_sum(s);
+            if (lane == 0) out[j] = s;
+        }
+    } else {
+        if (c0 < n) e.wbuf[start + c0] = y0;
+        if (c1 < n) e.wbuf[start + c1] = y1;
+        double nn = block_sum_256(y0 * y0 + y1 * y1, red);
+        if (threadIdx.x == 0) e.p_norm[e.a_slot0[a] + ch] = nn;
+    }
+}
+
+// alpha_k, beta_k, step counter.  One thread per active node.
+__global__ void k_lanczos_finalize(Eng e, int num_active) {
+    int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= num_active) return;
+    if (e.a_done[a] != DONE_NO) return;
+    int k = e.a_k[a];
+    double nn = 0.0;
+    int s0 = e.a_slot0[a], nch = e.a_nch[a];
+    for (int c = 0; c < nch; ++c) nn += e.p_norm[s0 + c];
+    double beta = sqrt(nn);
+    e.a_alpha[(size_t)a * e.KS + k] = e.a_h1[a] + e.a_h2[a];
+    e.a_beta[(size_t)a * e.KS + k] = beta;
+    e.a_bprev[a] = beta;
+    k += 1;
+    e.a_k[a] = k;
+    // breakdown (invariant subspace) or Krylov space exhausted: wait for the check kernel
+    if (beta < 1e-13 || k >= e.a_kcap[a]) e.a_done[a] = DONE_HOLD;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Convergence check: two largest eigenvalues of the k x k tridiagonal by Sturm-count
+// multisection (128 shifts per round), eigenvector of the largest by inverse iteration with a
+// pivoted tridiagonal LU, residual = beta_{k-1} |y_{k-1}|.
+// One CTA of 128 threads per active node.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sturm_count(const double* al, const double* be2, int k, double x, double pivmin) {
+    int cnt = 0;
+    double q = al[0] - x;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += (q < 0.0);
+    for (int i = 1; i < k; ++i) {
+        q = al[i] - x - be2[i - 1] / q;
+        if (fabs(q) < pivmin) q = -pivmin;
+        cnt += (q < 0.0);
+    }
+    return cnt;     // number of eigenvalues < x
+}
+
+// whole CTA: eigenvalue with ascending index m of the k x k tridiagonal, to full float64 resolution
+__device__ double tridiag_bisect(const double* al, const double* be2, int k, int m, double glo, double ghi,
+                                 double pivmin, int* cnts, double* bounds) {
+    const int tid = threadIdx.x;
+    double lo = glo, hi = ghi;
+    for (int round = 0; round < 10; ++round) {
+        double x = lo + (hi - lo) * ((double)(tid + 1) / 129.0);
+        cnts[tid] = sturm_count(al, be2, k, x, pivmin);
+        __syncthreads();
+        if (tid == 0) {
+            // eigenvalue m lies in (x_t, x_{t+1}] with count(x_t) <= m < count(x_{t+1})
+            int t = -1;
+            for (int i = 0; i < 128; ++i) if (cnts[i] <= m) t = i;
+            bounds[0] = (t >= 0) ? lo + (hi - lo) * ((double)(t + 1) / 129.0) : lo;
+            bounds[1] = (t < 127) ? lo + (hi - lo) * ((double)(t + 2) / 129.0) : hi;
+        }
+        __syncthreads();
+        lo = bounds[0];
+        hi = bounds[1];
+        __syncthreads();
+    }
+    return 0.5 * (lo + hi);
+}
+
+__global__ void __launch_bounds__(128)
+k_lanczos_check(Eng e, int force) {
+    extern __shared__ double sm[];
+    const int KS = e.KS;
+    double* al = sm;             // alpha
+    double* be = al + KS;        // beta (off-diagonals)
+    double* be2 = be + KS;       // beta^2
+    double* dd = be2 + KS;       // LU diagonal
+    double* du = dd + KS;        // LU first super-diagonal
+    double* du2 = du + KS;       // LU second super-diagonal
+    double* dl = du2 + KS;       // LU multipliers
+    double* yv = dl + KS;        // inverse-iteration vector
+    int* swp = reinterpret_cast<int*>(yv + KS);   // row interchange flags
+    __shared__ int cnts[128];
+    __shared__ double bounds[2];
+    __shared__ double gb[3];
+
+    int a = blockIdx.x;
+    int done = e.a_done[a];
+    if (done == DONE_YES) return;
+    int k = e.a_k[a];
+    bool due = (done == DONE_HOLD) || force || (k > 0 && (k % e.check_every) == 0);
+    if (!due || k == 0) {
+        if (threadIdx.x == 0 && done == DONE_NO) atomicAdd(&e.ctr[4], 1);
+        return;
+    }
+    const int tid = threadIdx.x;
+    for (int i = tid; i < k; i += 128) {
+        al[i] = e.a_alpha[(size_t)a * KS + i];
+        double b = e.a_beta[(size_t)a * KS + i];
+        be[i] = b;
+        be2[i] = b * b;
+    }
+    __syncthreads();
+    if (tid == 0) {                     // Gershgorin interval and pivmin
+        double lo = 1e300, hi = -1e300, bmax = 0.0;
+        for (int i = 0; i < k; ++i) {
+            double rad = (i > 0 ? fabs(be[i - 1]) : 0.0) + (i < k - 1 ? fabs(be[i]) : 0.0);
+            lo = fmin(lo, al[i] - rad);
+            hi = fmax(hi, al[i] + rad);
+            if (i < k - 1) bmax = fmax(bmax, be2[i]);
+        }
+        double w = fmax(fmax(fabs(lo), fabs(hi)), 1e-300);
+        gb[0] = lo - 1e-10 * w;
+        gb[1] = hi + 1e-10 * w;
+        gb[2] = fmax(bmax, 1.0) * 1.0020841800044864e-292;      // safmin / eps
+    }
+    __syncthreads();
+    const double glo = gb[0], ghi = gb[1], pivmin = gb[2];
+    double th1 = tridiag_bisect(al, be2, k, k - 1, glo, ghi, pivmin, cnts, bounds);
+    double th2 = (k > 1) ? tridiag_bisect(al, be2, k, k - 2, glo, ghi, pivmin, cnts, bounds) : -1e300;
+    if (tid == 0) {
+        // inverse iteration for the eigenvector of th1: pivoted LU of (T - th1 I) (as LAPACK dgttrf/dgtts2)
+        double tnorm = fmax(fmax(fabs(glo), fabs(ghi)), 1e-300);
+        double eps_piv = 2.220446049250313e-16 * tnorm;
+        for (int i = 0; i < k; ++i) {
+            dd[i] = al[i] - th1;
+            du[i] = (i < k - 1) ? be[i] : 0.0;
+            du2[i] = 0.0;
+            dl[i] = (i < k - 1) ? be[i] : 0.0;
+            swp[i] = 0;
+        }
+        for (int i = 0; i < k - 1; ++i) {
+            if (fabs(dd[i]) >= fabs(dl[i])) {
+                if (fabs(dd[i]) < eps_piv) dd[i] = (dd[i] < 0.0) ? -eps_piv : eps_piv;
+                double f = dl[i] / dd[i];
+                dl[i] = f;
+                dd[i + 1] -= f * du[i];
+            } else {
+                double f = dd[i] / dl[i];
+                dd[i] = dl[i];
+                dl[i] = f;
+                double tmp = du[i];
+                du[i] = dd[i + 1];
+                dd[i + 1] = tmp - f * du[i];
+                if (i < k - 2) { du2[i] = du[i + 1]; du[i + 1] = -f * du2[i]; }
+                swp[i] = 1;
+            }
+        }
+        if (fabs(dd[k - 1]) < eps_piv) dd[k - 1] = (dd[k - 1] < 0.0) ? -eps_piv : eps_piv;
+        for (int i = 0; i < k; ++i) yv[i] = (i & 1) ? 1.0 : 0.9;
+        for (int iter = 0; iter < 4; ++iter) {
+            for (int i = 0; i < k - 1; ++i) {
+                if (!swp[i]) {
+                    yv[i + 1] -= dl[i] * yv[i];
+                } else {
+                    double t = yv[i];
+                    yv[i] = yv[i + 1];
+                    yv[i + 1] = t - dl[i] * yv[i];
+                }
+            }
+            yv[k - 1] /= dd[k - 1];
+            if (k > 1) yv[k - 2] = (yv[k - 2] - du[k - 2] * yv[k - 1]) / dd[k - 2];
+            for (int i = k - 3; i >= 0; --i)
+                yv[i] = (yv[i] - du[i] * yv[i + 1] - du2[i] * yv[i + 2]) / dd[i];
+            double big = 0.0;
+            for (int i = 0; i < k; ++i) big = fmax(big, fabs(yv[i]));
+            double sc = 1.0 / big;                     // avoid overflow in the squared norm
+            double nn = 0.0;
+            for (int i = 0; i < k; ++i) { yv[i] *= sc; nn += yv[i] * yv[i]; }
+            double inv = 1.0 / sqrt(nn);
+            for (int i = 0; i < k; ++i) yv[i] *= inv;
+        }
+        double res = fabs(be[k - 1] * yv[k - 1]);
+        double gap = fmax(th1 - th2, 1e-300);
+        int n = e.r_n[e.a_rid[a]];
+        bool exhausted = (k >= n - 1);
+        bool breakdown = be[k - 1] < 1e-13;
+        bool conv = exhausted || breakdown || (res <= e.tol * gap);
+        bool stop = conv || (k >= e.a_kcap[a]) || force;
+        e.a_theta[2 * a] = th1;
+        e.a_theta[2 * a + 1] = th2;
+        if (stop) {
+            for (int i = 0; i < k; ++i) e.a_y[(size_t)a * KS + i] = yv[i];
+            e.a_conv[a] = conv ? 1 : 0;
+            e.a_done[a] = DONE_YES;
+        } else {
+            atomicAdd(&e.ctr[4], 1);
+        }
+    }
+}
+
+// ev = sum_j y_j V[j+1] over one chunk, plus per-chunk (sum, min, max).  grid: (chunks, active)
+__global__ void __launch_bounds__(256)
+k_ritz(Eng e) {
+    extern __shared__ double sm[];      // y[KS] | red[3*8]
+    double* ys = sm;
+    double* red = sm + e.KS;
+    int a = blockIdx.y;
+    int nch = e.a_nch[a];
+    int ch = blockIdx.x;
+    if (ch >= nch) return;
+    int k = e.a_k[a];
+    int r = e.a_rid[a];
+    int start = e.r_start[r], n = e.r_n[r];
+    for (int j = threadIdx.x; j < k; j += 256) ys[j] = e.a_y[(size_t)a * e.KS + j];
+    __syncthreads();
+    int c0 = ch * CH + threadIdx.x, c1 = c0 + 256;
+    double x0 = 0.0, x1 = 0.0;
+    const double* vb = e.V + start + (size_t)e.P;     // row 1
+#pragma unroll 4
+    for (int j = 0; j < k; ++j) {
+        const double* vr = vb + (size_t)j * e.P;
+        double y = ys[j];
+        if (c0 < n) x0 += y * vr[c0];
+        if (c1 < n) x1 += y * vr[c1];
+    }
+    if (c0 < n) e.ev[start + c0] = x0;
+    if (c1 < n) e.ev[start + c1] = x1;
+    double s = (c0 < n ? x0 : 0.0) + (c1 < n ? x1 : 0.0);
+    double mn = fmin(c0 < n ? x0 : 1e300, c1 < n ? x1 : 1e300);
+    double mx = fmax(c0 < n ? x0 : -1e300, c1 < n ? x1 : -1e300);
+    double q = (c0 < n ? x0 * x0 : 0.0) + (c1 < n ? x1 * x1 : 0.0);
+    s = warp_sum(s); mn = warp_min(mn); mx = warp_max(mx); q = warp_sum(q);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { red[w] = s; red[8 + w] = mn; red[16 + w] = mx; red[24 + w] = q; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ts = 0.0, tmn = 1e300, tmx = -1e300, tq = 0.0;
+        for (int i = 0; i < 8; ++i) { ts += red[i]; tmn = fmin(tmn, red[8 + i]); tmx = fmax(tmx, red[16 + i]); tq += red[24 + i]; }
+        double* o = e.p_stat + (size_t)(e.a_slot0[a] + ch) * 4;   // sum, min, max, sum of squares
+        o[0] = ts; o[1] = tmn; o[2] = tmx; o[3] = tq;
+    }
+}
+
+}  // namespace ancuts

@@ -1,0 +1,158 @@
+/*
+ * autoinst_ncuts.h — C ABI of libautoinst_ncuts.so, the B200 (sm_100a) implementation of the
+ * chunk-level normalized-cuts path of artonson/autoinst (reference: pipeline/ncuts/).
+ *
+ * The reference is pure Python and has no FFI; its boundary for this path is two imports
+ * (pipeline/run_pipeline.py:14-17, pipeline/ncuts/ncuts_utils.py:22).  The entry points below are
+ * what a ctypes binding inside those two modules calls; each one names the
+ * reference lines it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative ANCUTS_E* code; ancuts_last_error() gives a
+ *    thread-local message for the last failure on the calling thread;
+ *  - pointers named d_* are device pointers on the handle's device, h_* are host pointers;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream); device-pointer entry
+ *    points are asynchronous on it unless they return data through host pointers;
+ *  - one handle per (device, host thread); a handle owns a growable device workspace.
+ *  - dense matrices are row-major float32 with leading dimension ld (elements), ld % 4 == 0 and a
+ *    16-byte aligned base.
+ */
+#ifndef AUTOINST_NCUTS_H
+#define AUTOINST_NCUTS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANCUTS_OK            0
+#define ANCUTS_EINVAL       -1   /* bad argument */
+#define ANCUTS_ECUDA        -2   /* CUDA runtime error (message holds cudaGetErrorString) */
+#define ANCUTS_ENOMEM       -3   /* workspace allocation failed */
+#define ANCUTS_ENOTCONV     -4   /* reserved: non-convergence is reported per node, not as an error */
+#define ANCUTS_EUNSUPPORTED -5   /* e.g. beta != 0 (SAM term, ncuts_utils.py:115-123) */
+
+#define ANCUTS_NUM_CUTS 10       /* normalized_cut.py:54 calls get_min_ncut(ev, D, w, 10) */
+
+typedef struct ancuts_handle ancuts_handle;
+
+/* Gains and thresholds of one run: pipeline/config.py:6-37 (alpha, theta, gamma, T) and
+ * config.py:61,65 (SPLIT_LIM, PROXIMITY_THRESHOLD). */
+typedef struct ancuts_params {
+    double alpha;        /* spatial gain  (ncuts_utils.py:63-66);  0 -> term is the mask        */
+    double theta;        /* TARL gain     (ncuts_utils.py:135-149); 0 -> term is the mask        */
+    double gamma;        /* DINOv2 gain   (ncuts_utils.py:125-133); 0 -> term is the mask        */
+    double proximity;    /* PROXIMITY_THRESHOLD, inclusive (ncuts_utils.py:61)                   */
+    double T;            /* N-cut stopping threshold, strict '<' (normalized_cut.py:56)          */
+    double split_lim;    /* size limit at the root (normalized_cut.py:39-40); children use 0.01  */
+    int    tarl_dim;     /* 96  (0 when d_tarl is NULL) */
+    int    dino_dim;     /* 384 (0 when d_dino is NULL) */
+    int    lanczos_max_steps;   /* 0 -> default (1024) */
+    int    lanczos_check_every; /* 0 -> default (16)   */
+    double lanczos_tol;         /* 0 -> default (1e-10): residual <= tol * (theta1 - theta2) */
+    int    affinity_impl;       /* 0 = exact CUDA-core tile kernel, 1 = tcgen05 Gram GEMM */
+} ancuts_params;
+
+/* One row per recursion node that reached the eigensolver (debug / accounting). */
+typedef struct ancuts_node_stat {
+    int32_t chunk;       /* chunk index within the call */
+    int32_t n;           /* node size */
+    int32_t steps;       /* Lanczos steps taken */
+    int32_t converged;   /* 1 = residual test met or Krylov space exhausted */
+    int32_t best_k;      /* index of the chosen threshold, -1 = none (allclose) */
+    int32_t split;       /* 1 = mcut < T */
+    int32_t level;       /* recursion level */
+    int32_t n_side;      /* points on the mask side of the chosen cut */
+    double  lambda2;     /* second smallest eigenvalue of the normalised Laplacian */
+    double  mcut;        /* N-cut value of the chosen cut */
+} ancuts_node_stat;
+
+int         ancuts_version(void);
+const char* ancuts_last_error(void);
+int         ancuts_create(int device, ancuts_handle** out);
+int         ancuts_destroy(ancuts_handle* h);
+/* bytes of device workspace a segment call over these chunk sizes needs (for batch planning) */
+int64_t     ancuts_segment_workspace_bytes(int num_chunks, const int32_t* h_chunk_n, int lanczos_max_steps);
+
+/* Stage 1 — replaces ncuts_utils.py:60-66,125-133,135-156 (3x cdist + mask + exp + product).
+ * d_points: n x 3 float64; d_tarl: n x tarl_dim float32 or NULL; d_dino: n x dino_dim float32 or NULL.
+ * Writes the dense n x n float32 affinity (zeros outside the proximity mask, 1 on the diagonal)
+ * and, if d_rowsum != NULL, float64 row sums. */
+int ancuts_affinity_f32(ancuts_handle* h, int n, const double* d_points, const float* d_tarl,
+                        const float* d_dino, const ancuts_params* p, float* d_W, int64_t ld,
+                        double* d_rowsum, void* stream);
+
+/* Stage 2 — replaces normalized_cut.py:38,42-47 (W = w + I, d = W.sum(0), D^-1/2 W D^-1/2).
+ * d_deg[i] = 1 + sum_j w_ij (float64).  If d_M != NULL also writes M = D^-1/2 (w+I) D^-1/2 in
+ * float32 (the pipeline itself applies the scaling inside the matvec and never materialises M). */
+int ancuts_degree_normalize_f32(ancuts_handle* h, int n, const float* d_W, int64_t ld,
+                                double* d_deg, float* d_M, int64_t ldm, void* stream);
+
+/* Stage 3 — replaces normalized_cut.py:49-53 (eigsh(A, 2, sigma=1e-10) + argsort).
+ * Nodes are diagonal blocks [off, off+n) of the dense matrix.  For each node writes the unit-norm
+ * Fiedler vector with sum >= 0 into d_ev[off .. off+n), and per node lambda2 / steps / converged
+ * to the host arrays.  Blocks until done. */
+int ancuts_lanczos_fiedler_batched(ancuts_handle* h, int n_total, const float* d_W, int64_t ld,
+                                   int num_nodes, const int32_t* h_node_off, const int32_t* h_node_n,
+                                   const ancuts_params* p, double* d_ev, double* h_lambda2,
+                                   int32_t* h_steps, int32_t* h_converged, void* stream);
+
+/* Stage 4a — replaces get_min_ncut / ncut_cost / cut_cost (normalized_cut.py:4-34): all ten
+ * threshold cuts from one pass over each block.  d_ev as produced by stage 3.
+ * h_best_k[node] = -1 when min and max of ev are allclose; d_side[i] = 1 where ev > threshold
+ * (the reference's mask) for the chosen cut, 0 elsewhere.  Blocks until done. */
+int ancuts_ncut_scan_batched(ancuts_handle* h, int n_total, const float* d_W, int64_t ld,
+                             int num_nodes, const int32_t* h_node_off, const int32_t* h_node_n,
+                             const double* d_ev, int32_t* h_best_k, double* h_mcut,
+                             double* h_costs /* num_nodes x 10 or NULL */, uint8_t* d_side, void* stream);
+
+/* Stage 4b — replaces w[mask][:, mask], w[~mask][:, ~mask], labels[mask] (normalized_cut.py:57-58):
+ * stable partition of every node (mask side first), each side further split into the connected
+ * components of its sub-graph, blocks gathered into d_W_out.  d_perm_out[new position] = old
+ * position; child ranges are returned through the host arrays (capacity n_total). Blocks. */
+int ancuts_partition_batched(ancuts_handle* h, int n_total, const float* d_W_in, float* d_W_out,
+                             int64_t ld, int num_nodes, const int32_t* h_node_off,
+                             const int32_t* h_node_n, const uint8_t* d_side, int split_components,
+                             int32_t* d_perm_out, int32_t* h_num_children, int32_t* h_child_off,
+                             int32_t* h_child_n, void* stream);
+
+/* Whole path on the device for a batch of chunks — replaces ncuts_utils.py:56-174 per chunk
+ * (affinity -> remove_isolated_points (no-op) -> normalized_cut -> labels, :177-183).
+ * Chunk c owns points [h_chunk_off[c], h_chunk_off[c+1]) of the concatenated inputs.
+ * d_labels[i] = segment id of point i within its chunk (0 .. h_num_segments[c]-1).
+ * h_stats/h_num_stats: optional per-node log (capacity stats_cap).  Blocks until done. */
+int ancuts_segment_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off,
+                          const double* d_points, const float* d_tarl, const float* d_dino,
+                          const ancuts_params* p, int32_t* d_labels, int32_t* h_num_segments,
+                          ancuts_node_stat* h_stats, int32_t stats_cap, int32_t* h_num_stats,
+                          void* stream);
+
+/* Same with HOST buffers (pinned memory recommended): copies inputs to the device, runs, copies
+ * labels back.  This is the call ncuts_chunk() makes (ncuts_utils.py:28-204). */
+int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off,
+                               const double* h_points, const float* h_tarl, const float* h_dino,
+                               const ancuts_params* p, int32_t* h_labels, int32_t* h_num_segments,
+                               ancuts_node_stat* h_stats, int32_t stats_cap, int32_t* h_num_stats,
+                               void* stream);
+
+/* normalized_cut(w, num_points_orig, labels, T, split_lim) (normalized_cut.py:37) on a dense
+ * float32 copy of w already on the device (n x n, unit diagonal, symmetric). Blocks. */
+int ancuts_segment_dense_f32(ancuts_handle* h, int n, const float* d_W, int64_t ld,
+                             int num_points_orig, const ancuts_params* p, int32_t* d_labels,
+                             int32_t* h_num_segments, ancuts_node_stat* h_stats, int32_t stats_cap,
+                             int32_t* h_num_stats, void* stream);
+
+/* Counters for bench.py: kernels launched by this handle since the last reset, and the per-kernel
+ * CUDA-event time of the kernels named by ancuts_timing_select(). */
+int64_t ancuts_launch_count(ancuts_handle* h, int reset);
+/* Accounting of the last segment call: algorithmic bytes and event-timed
+ * milliseconds per stage: [0]=affinity [1]=degree [2]=matvec [3]=reorth [4]=scan [5]=cc+partition */
+int ancuts_last_accounting(ancuts_handle* h, double* bytes6, double* ms6, int64_t* launches6);
+/* 1 = time each stage with CUDA events (adds stream syncs; for profiling runs), 0 = off */
+int ancuts_set_stage_timing(ancuts_handle* h, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUTOINST_NCUTS_H */

@@ -1,0 +1,196 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (run in the build container only).
+
+    python -m oracle.make_golden            # needs /root/reference, never runs on the GPU box
+
+What it pins (SURVEY.md §8c — the reference has no tests of its own for this path):
+
+1. affinity: the reference's `ncuts_chunk` (`pipeline/ncuts/ncuts_utils.py:28-174`) is imported with
+   stub `open3d` / `matplotlib` modules and driven up to its `normalized_cut(...)` call, which is
+   intercepted to capture the affinity matrix the reference actually builds.  The feature fetchers
+   outside the hot path (`tarl_features_per_patch`, `image_based_features_per_patch`) are replaced
+   by the synthetic arrays; `dinov2_mean` is the reference's own.  `oracle.affinity_ref` must
+   reproduce that matrix bit for bit, else this script fails.
+2. recursion: the reference's `normalized_cut` (`pipeline/ncuts/normalized_cut.py:37-63`) is run on
+   that matrix with the eigsh pin of `oracle.ncut_ref.pinned_eigsh`; `oracle.ncut_ref` must return
+   the same groups in the same order, else this script fails.
+3. the captured matrices and groups are written as fixtures for the CPU and GPU test suites.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import scipy.sparse as sp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference/pipeline"
+OUT = os.path.join(REPO, "tests", "golden")
+
+
+class _Captured(Exception):
+    pass
+
+
+class _FakeCloud:
+    def __init__(self, pts):
+        self.points = np.asarray(pts, dtype=np.float64)
+
+    def select_by_index(self, idx):
+        return _FakeCloud(self.points[np.asarray(idx)])
+
+
+def import_reference():
+    """Import ncuts.ncuts_utils and ncuts.normalized_cut from the reference tree."""
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tree not found: golden vectors can only be generated in the build container")
+    for name in ["open3d", "open3d.geometry", "open3d.utility", "open3d.io", "open3d.pipelines",
+                 "open3d.pipelines.registration", "matplotlib", "matplotlib.pyplot"]:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["open3d"].geometry = sys.modules["open3d.geometry"]
+    sys.modules["open3d"].utility = sys.modules["open3d.utility"]
+    sys.modules["open3d"].io = sys.modules["open3d.io"]
+    sys.modules["open3d"].pipelines = sys.modules["open3d.pipelines"]
+    sys.modules["open3d.pipelines"].registration = sys.modules["open3d.pipelines.registration"]
+    plt = sys.modules["matplotlib.pyplot"]
+    plt.cm = types.SimpleNamespace(viridis=lambda x: np.zeros((len(x), 4)))
+    sys.modules["matplotlib"].pyplot = plt
+    cwd = os.getcwd()
+    os.chdir(REF)                       # config.py:79 opens "utils/semantic-kitti.yaml" relative to cwd
+    saved = [m for m in ("ncuts", "ncuts.ncuts_utils", "ncuts.normalized_cut", "config") if m in sys.modules]
+    stash = {m: sys.modules.pop(m) for m in saved}
+    sys.path.insert(0, REF)
+    try:
+        import ncuts.ncuts_utils as nu
+        import ncuts.normalized_cut as nc
+        import config as cfg
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+    ref = dict(nu=nu, nc=nc, cfg=cfg)
+    # leave the reference modules out of sys.modules so the repo's own `ncuts` package stays importable
+    for m in [k for k in sys.modules if k == "ncuts" or k.startswith("ncuts.") or k == "config"
+              or k == "utils" or k.startswith("utils.")]:
+        sys.modules.pop(m)
+    sys.modules.update(stash)
+    return ref
+
+
+def reference_affinity(ref, chunk, config_name):
+    """Drive the reference's ncuts_chunk up to its normalized_cut call and return what it passes."""
+    nu, cfg = ref["nu"], ref["cfg"]
+    nu.CONFIG = getattr(cfg, "config_" + config_name)
+    got = {}
+
+    def capture(A, num_points, labels, T=None, split_lim=None):
+        got.update(A=A, n=num_points, labels=labels, T=T, split_lim=split_lim)
+        raise _Captured()
+
+    def fake_tarl(dataset, chunk_major, T_pcd, center_position, tarl_indices_global):
+        return chunk.tarl
+
+    def fake_image(dataset, pcd_nonground_minor, chunk_indices, chunk_major, T_pcd, cam_indices_global,
+                   sam=False, dino=False, pcd_chunk=None):
+        assert dino and not sam
+        return [chunk.dino[:, None, :]], None           # one camera, one view
+
+    nu.normalized_cut = capture
+    nu.tarl_features_per_patch = fake_tarl
+    nu.image_based_features_per_patch = fake_image
+    major = _FakeCloud(chunk.points)
+    d = {
+        "center_ids": [5], "center_positions": [np.zeros(3)], "indices": [np.arange(chunk.n)],
+        "pcd_nonground_chunks": [major], "pcd_ground_chunks": [major],
+        "pcd_nonground_chunks_major_downsampling": [major],
+        "kitti_labels": {"ground": {"instance": [np.zeros(1)], "semantic": [np.zeros(1)]}},
+    }
+    try:
+        nu.ncuts_chunk(None, d, None, np.eye(4), list(range(0, 40)), sequence=0, patchwise_indices=[[5]])
+    except _Captured:
+        pass
+    else:
+        raise RuntimeError("reference ncuts_chunk returned without calling normalized_cut")
+    return got
+
+
+def known_answer_cases():
+    """Hand-checkable inputs: returns name -> dense float64 w."""
+    cases = {}
+    # two 6-cliques joined by one weak edge: the cut must separate them
+    w = np.zeros((12, 12))
+    w[:6, :6] = 0.9
+    w[6:, 6:] = 0.8
+    w[5, 6] = w[6, 5] = 0.01
+    np.fill_diagonal(w, 1.0)
+    cases["two_cliques"] = w
+    # single clique: Fiedler space is degenerate, every cut is expensive -> one segment at T = 0.03
+    w = np.full((8, 8), 0.7)
+    np.fill_diagonal(w, 1.0)
+    cases["one_clique"] = w
+    # path graph with one weak link in the middle
+    w = np.eye(10)
+    for i in range(9):
+        w[i, i + 1] = w[i + 1, i] = 0.05 if i == 4 else 0.6
+    cases["weak_path"] = w
+    return cases
+
+
+def main():
+    sys.path.insert(0, REPO)
+    from autoinst_b200.synthetic import CONFIGS, small_chunk
+    from oracle import ncut_ref as R
+    from oracle.affinity_ref import affinity_ref
+
+    os.makedirs(OUT, exist_ok=True)
+    ref = import_reference()
+    ref_nc = ref["nc"].normalized_cut
+
+    for seed, n_obj, ppo in [(11, 3, 250), (12, 4, 300), (13, 5, 350)]:
+        ch = small_chunk(seed, n_obj=n_obj, pts_per_obj=ppo)
+        np.savez_compressed(os.path.join(OUT, f"chunk_s{seed}_inputs.npz"), points=ch.points,
+                            tarl=ch.tarl.astype(np.float32), dino=ch.dino.astype(np.float32), instance=ch.instance)
+        for name, cfg in CONFIGS.items():
+            got = reference_affinity(ref, ch, name)
+            A_ref = got["A"].toarray()
+            A_or = affinity_ref(ch.points, ch.tarl, ch.dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
+            if not np.array_equal(A_ref, A_or):
+                raise SystemExit(f"oracle affinity differs from the reference (seed {seed}, {name}): "
+                                 f"max abs diff {np.abs(A_ref - A_or).max()}")
+            assert got["n"] == ch.n and got["T"] == cfg["T"] and got["split_lim"] == 0.01
+            w = got["A"]
+            with R.pinned_eigsh():
+                g_ref = ref_nc(w, ch.n, np.arange(ch.n), T=cfg["T"], split_lim=0.01)
+                g_or = R.normalized_cut_ref(w, ch.n, np.arange(ch.n), T=cfg["T"], split_lim=0.01, faithful=True)
+                g_fast = R.normalized_cut_ref(w, ch.n, np.arange(ch.n), T=cfg["T"], split_lim=0.01, faithful=False)
+            with R.pinned_eigsh("random", 3):
+                g_alt = ref_nc(w, ch.n, np.arange(ch.n), T=cfg["T"], split_lim=0.01)
+            for g in (g_or, g_fast):
+                if len(g) != len(g_ref) or any(not np.array_equal(a, b) for a, b in zip(g, g_ref)):
+                    raise SystemExit(f"oracle normalized_cut differs from the reference (seed {seed}, {name})")
+            lab = R.labels_from_groups(g_ref, ch.n)
+            stable = R.same_partition(lab, R.labels_from_groups(g_alt, ch.n))
+            csr = sp.csr_matrix(w)
+            path = os.path.join(OUT, f"chunk_s{seed}_{name}.npz")
+            np.savez_compressed(
+                path, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"], T=cfg["T"],
+                A_data=csr.data, A_indices=csr.indices, A_indptr=csr.indptr, labels=lab,
+                group_sizes=np.array([len(g) for g in g_ref]), oracle_stable=stable)
+            print(f"{os.path.basename(path)}: N={ch.n} nnz={csr.nnz} segments={len(g_ref)} stable={stable}")
+
+    kat = {}
+    for name, w in known_answer_cases().items():
+        for T in (0.03, 0.5):
+            with R.pinned_eigsh():
+                g_ref = ref_nc(sp.csr_matrix(w), w.shape[0], np.arange(w.shape[0]), T=T, split_lim=0.01)
+                g_or = R.normalized_cut_ref(sp.csr_matrix(w), w.shape[0], np.arange(w.shape[0]), T=T, split_lim=0.01)
+            assert len(g_ref) == len(g_or) and all(np.array_equal(a, b) for a, b in zip(g_ref, g_or)), name
+            kat[f"{name}_T{T}_w"] = w
+            kat[f"{name}_T{T}_labels"] = R.labels_from_groups(g_ref, w.shape[0])
+            print(f"KAT {name} T={T}: {[list(map(int, g)) for g in g_ref]}")
+    np.savez_compressed(os.path.join(OUT, "known_answers.npz"), **kat)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,112 @@
+"""CPU tests: the oracle against the golden vectors generated from the unmodified reference
+(oracle/make_golden.py), and the numpy model of the device algorithm against the oracle."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from conftest import CONFIG_NAMES, GOLDEN, GOLDEN_SEEDS, load_golden
+from autoinst_b200.synthetic import CONFIGS, make_chunk, small_chunk
+from oracle import ncut_ref as R
+from oracle.affinity_ref import affinity_ref, drop_isolated
+from oracle.device_model import lanczos_fiedler, scan_cuts, segment_model
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_affinity_ref_matches_reference_bitwise(seed, name):
+    inp, out, A = load_golden(seed, name)
+    got = affinity_ref(inp["points"], inp["tarl"].astype(np.float64), inp["dino"].astype(np.float64),
+                       alpha=float(out["alpha"]), theta=float(out["theta"]), gamma=float(out["gamma"]))
+    assert np.array_equal(got, A.toarray())
+    keep, sub = drop_isolated(got)
+    assert len(keep) == got.shape[0]          # A_ii = 1: nothing is ever isolated (point_cloud_utils.py:189-195)
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+@pytest.mark.parametrize("faithful", [True, False])
+def test_normalized_cut_ref_matches_reference(seed, name, faithful):
+    inp, out, A = load_golden(seed, name)
+    n = A.shape[0]
+    with R.pinned_eigsh():
+        groups = R.normalized_cut_ref(A, n, np.arange(n), T=float(out["T"]), split_lim=0.01, faithful=faithful)
+    assert np.array_equal([len(g) for g in groups], out["group_sizes"])     # same DFS order as the reference
+    assert np.array_equal(R.labels_from_groups(groups, n), out["labels"])
+
+
+def test_known_answers():
+    kat = np.load(f"{GOLDEN}/known_answers.npz")
+    names = sorted({k[:-2] for k in kat.files if k.endswith("_w")})
+    assert names
+    for nm in names:
+        w, lab = kat[nm + "_w"], kat[nm + "_labels"]
+        T = float(nm.split("_T")[1])
+        with R.pinned_eigsh():
+            g = R.normalized_cut_ref(sp.csr_matrix(w), w.shape[0], np.arange(w.shape[0]), T=T)
+        assert np.array_equal(R.labels_from_groups(g, w.shape[0]), lab)
+    # two cliques joined by a weak edge: hand-computed N-cut of the separating cut (normalized_cut.py:4-11)
+    w = kat["two_cliques_T0.03_w"]
+    d = 1.0 + w.sum(0)
+    side = np.arange(12) >= 6
+    cut = w[np.ix_(side, ~side)].sum()
+    expect = cut / d[side].sum() + cut / d[~side].sum()
+    assert abs(cut - 0.01) < 1e-15
+    D = sp.diags(d)
+    ev = np.where(side, 1.0, -1.0)
+    mask, cost = R.best_threshold_cut(ev, D, d, sp.csr_matrix(w))
+    assert np.array_equal(mask, side) and abs(cost - expect) < 1e-15
+
+
+def test_stop_rules():
+    # n <= 2 and n/N <= split_lim are leaves (normalized_cut.py:39-40)
+    w = sp.csr_matrix(np.array([[1.0, 0.0], [0.0, 1.0]]))
+    assert len(R.normalized_cut_ref(w, 2, np.arange(2), T=1.0)) == 1
+    w3 = sp.csr_matrix(np.eye(3))
+    assert len(R.normalized_cut_ref(w3, 1000, np.arange(3), T=1.0)) == 1
+
+
+def test_inclusive_threshold_and_zero_rows():
+    pts = np.array([[0, 0, 0], [1.0, 0, 0], [2.0000001, 0, 0]])
+    A = affinity_ref(pts, alpha=1.0)
+    assert A[0, 1] == np.exp(-1.0) and A[1, 2] == 0.0             # <= 1.0 inclusive, ncuts_utils.py:61
+    tarl = np.zeros((3, 96)); tarl[1] = 1.0
+    B = affinity_ref(pts, tarl, alpha=1.0, theta=0.5)
+    assert B[0, 1] == np.exp(-1.0)                                 # zero row neutralised, :145-146
+    dino = np.zeros((3, 384)); dino[1] = 1.0
+    Cm = affinity_ref(pts, None, dino, alpha=1.0, gamma=0.1)
+    assert np.isclose(Cm[0, 1], np.exp(-1.0 - 0.1 * np.sqrt(384)))  # DINO zero rows are not, :129-133
+    with pytest.raises(ValueError):
+        affinity_ref(pts, None, None, gamma=0.1)
+
+
+@pytest.mark.parametrize("seed", GOLDEN_SEEDS)
+@pytest.mark.parametrize("name", CONFIG_NAMES)
+def test_device_model_matches_reference_on_golden(seed, name):
+    inp, out, A = load_golden(seed, name)
+    lab = segment_model(A.toarray().astype(np.float32), float(out["T"]))
+    assert R.same_partition(lab, out["labels"])
+
+
+def test_device_model_stage_parity():
+    """Lanczos vs ARPACK shift-invert, bucket scan vs ten ncut_cost calls, on one connected block."""
+    ch = small_chunk(21, n_obj=1, pts_per_obj=500, features="tarl")
+    A = affinity_ref(ch.points, ch.tarl, alpha=1.0, theta=0.5)
+    w = sp.csr_matrix(A)
+    with R.pinned_eigsh():
+        d, D, ev_ref, vals = R.fiedler_of_block(w)
+    ev, lam2 = lanczos_fiedler(A.astype(np.float32), 1.0 + A.astype(np.float32).astype(np.float64).sum(1))
+    assert abs(lam2 - vals[1]) < 1e-6
+    assert np.abs(ev - R.canonical_sign(ev_ref)).max() < 1e-5      # float32 W vs float64 W
+    side_ref, cost_ref = R.best_threshold_cut(ev, D, d, w)
+    k, cost, bucket = scan_cuts(A.astype(np.float32), d, ev)
+    assert np.array_equal(bucket > k, side_ref) and abs(cost - cost_ref) < 1e-6
+
+
+def test_device_model_matches_oracle_on_a_chunk():
+    ch = make_chunk(3, n_target=1500, features="tarl")
+    cfg = CONFIGS["tarl_spatial"]
+    A = affinity_ref(ch.points, ch.tarl, alpha=cfg["alpha"], theta=cfg["theta"])
+    with R.pinned_eigsh():
+        g = R.normalized_cut_ref(sp.csr_matrix(A), ch.n, np.arange(ch.n), T=cfg["T"])
+    lab = segment_model(A.astype(np.float32), cfg["T"])
+    assert R.same_partition(lab, R.labels_from_groups(g, ch.n))
