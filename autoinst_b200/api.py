@@ -54,8 +54,9 @@ class Handle:
     def launch_count(self, reset=False) -> int:
         return int(self.lib.ancuts_launch_count(self.h, 1 if reset else 0))
 
-    def set_stage_timing(self, on: bool):
-        check(self.lib.ancuts_set_stage_timing(self.h, 1 if on else 0))
+    def set_stage_timing(self, mode: int):
+        """0 = off, 1 = CUDA events around every launch, 2 = around the matvec launches only."""
+        check(self.lib.ancuts_set_stage_timing(self.h, int(mode)))
 
     def accounting(self) -> dict:
         b = (C.c_double * 6)()

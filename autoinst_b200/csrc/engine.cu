@@ -44,7 +44,7 @@ struct ancuts_handle {
     int64_t stage_launches[SG_COUNT] = {0};
     double stage_bytes[SG_COUNT] = {0};
     double stage_ms[SG_COUNT] = {0};
-    bool stage_timing = false;
+    int stage_timing = 0;                    // 0 off, 1 every launch, 2 matvec launches only
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
@@ -206,7 +206,7 @@ struct LaunchScope {
     LaunchScope(ancuts_handle* h_, int stage_, cudaStream_t st_) : h(h_), stage(stage_), st(st_) {
         h->launches_total++;
         h->stage_launches[stage]++;
-        if (h->stage_timing) {
+        if (h->stage_timing == 1 || (h->stage_timing == 2 && stage == SG_MATVEC)) {
             cudaEvent_t a = take_event(h);
             b = take_event(h);
             cudaEventRecord(a, st);
@@ -620,7 +620,7 @@ int64_t ancuts_launch_count(ancuts_handle* h, int reset) {
 
 int ancuts_set_stage_timing(ancuts_handle* h, int on) {
     if (!h) return ANCUTS_EINVAL;
-    h->stage_timing = on != 0;
+    h->stage_timing = on;
     return ANCUTS_OK;
 }
 

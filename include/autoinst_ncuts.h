@@ -149,7 +149,8 @@ int64_t ancuts_launch_count(ancuts_handle* h, int reset);
 /* Accounting of the last segment call: algorithmic bytes and event-timed
  * milliseconds per stage: [0]=affinity [1]=degree [2]=matvec [3]=reorth [4]=scan [5]=cc+partition */
 int ancuts_last_accounting(ancuts_handle* h, double* bytes6, double* ms6, int64_t* launches6);
-/* 1 = time each stage with CUDA events (adds stream syncs; for profiling runs), 0 = off */
+/* CUDA-event timing of the library's own launches, summed per stage and read back with
+ * ancuts_last_accounting: 0 = off, 1 = every launch, 2 = only the matvec launches (dominant kernel) */
 int ancuts_set_stage_timing(ancuts_handle* h, int on);
 
 #ifdef __cplusplus

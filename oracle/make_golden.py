@@ -59,13 +59,19 @@ def import_reference():
     sys.modules["matplotlib"].pyplot = plt
     cwd = os.getcwd()
     os.chdir(REF)                       # config.py:79 opens "utils/semantic-kitti.yaml" relative to cwd
-    saved = [m for m in ("ncuts", "ncuts.ncuts_utils", "ncuts.normalized_cut", "config") if m in sys.modules]
-    stash = {m: sys.modules.pop(m) for m in saved}
+    mine = [k for k in sys.modules if k == "ncuts" or k.startswith("ncuts.") or k == "config"]
+    stash = {m: sys.modules.pop(m) for m in mine}
+    # the reference's ncuts/ has no __init__.py; this repo's own `ncuts` package would shadow it, so the
+    # name is bound to the reference directory explicitly while its modules are imported
+    pkg = types.ModuleType("ncuts")
+    pkg.__path__ = [os.path.join(REF, "ncuts")]
+    sys.modules["ncuts"] = pkg
     sys.path.insert(0, REF)
     try:
         import ncuts.ncuts_utils as nu
         import ncuts.normalized_cut as nc
         import config as cfg
+        assert nu.__file__.startswith(REF) and nc.__file__.startswith(REF)
     finally:
         os.chdir(cwd)
         sys.path.remove(REF)
@@ -129,10 +135,11 @@ def known_answer_cases():
     w = np.full((8, 8), 0.7)
     np.fill_diagonal(w, 1.0)
     cases["one_clique"] = w
-    # path graph with one weak link in the middle
+    # path graph with one weak link in the middle; unequal weights so that no Fiedler vector is
+    # antisymmetric (a symmetric path makes the chosen cut depend on the arbitrary eigenvector sign)
     w = np.eye(10)
-    for i in range(9):
-        w[i, i + 1] = w[i + 1, i] = 0.05 if i == 4 else 0.6
+    for i, v in enumerate([0.6, 0.5, 0.7, 0.4, 0.05, 0.65, 0.45, 0.55, 0.75]):
+        w[i, i + 1] = w[i + 1, i] = v
     cases["weak_path"] = w
     return cases
 
@@ -186,6 +193,10 @@ def main():
                 g_ref = ref_nc(sp.csr_matrix(w), w.shape[0], np.arange(w.shape[0]), T=T, split_lim=0.01)
                 g_or = R.normalized_cut_ref(sp.csr_matrix(w), w.shape[0], np.arange(w.shape[0]), T=T, split_lim=0.01)
             assert len(g_ref) == len(g_or) and all(np.array_equal(a, b) for a, b in zip(g_ref, g_or)), name
+            with R.pinned_eigsh(flip=True):
+                g_flip = ref_nc(sp.csr_matrix(w), w.shape[0], np.arange(w.shape[0]), T=T, split_lim=0.01)
+            assert R.same_partition(R.labels_from_groups(g_ref, w.shape[0]), R.labels_from_groups(g_flip, w.shape[0])), \
+                f"KAT {name} T={T} depends on the eigenvector sign"
             kat[f"{name}_T{T}_w"] = w
             kat[f"{name}_T{T}_labels"] = R.labels_from_groups(g_ref, w.shape[0])
             print(f"KAT {name} T={T}: {[list(map(int, g)) for g in g_ref]}")

@@ -106,7 +106,7 @@ def canonical_sign(v):
 
 
 @contextlib.contextmanager
-def pinned_eigsh(v0_kind="ones", seed=0):
+def pinned_eigsh(v0_kind="ones", seed=0, flip=False):
     """Make `scipy.sparse.linalg.eigsh` deterministic for the duration of the block:
     fixed ARPACK start vector and a canonical sign for every returned vector.  Works on the
     reference module too because it resolves `sparse.linalg.eigsh` at call time."""
@@ -121,7 +121,7 @@ def pinned_eigsh(v0_kind="ones", seed=0):
                 kw["v0"] = np.random.default_rng(seed + n).standard_normal(n)
         vals, vecs = orig(A, k, **kw)
         vecs = np.stack([canonical_sign(vecs[:, j]) for j in range(vecs.shape[1])], axis=1)
-        return vals, vecs
+        return vals, (-vecs if flip else vecs)      # flip=True: the opposite sign, to probe sign sensitivity
 
     sla.eigsh = wrapped                     # sla IS scipy.sparse.linalg: one attribute, seen by all callers
     try:

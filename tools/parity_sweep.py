@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Label parity at scale (north_star level 2): GPU labels vs the pinned CPU oracle on many seeded
+chunks, oracle runs spread over the host cores.  Writes a JSON summary.
+
+    python tools/parity_sweep.py --config tarl_spatial --chunks 64 --n-target 4096 --out gpurun_out/parity.json
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def oracle_job(a):
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    seed, n_target, name = a
+    import scipy.sparse as sp
+    from autoinst_b200.synthetic import CONFIGS, make_chunk
+    from oracle import ncut_ref as R
+    from oracle.affinity_ref import affinity_ref
+    cfg = CONFIGS[name]
+    ch = make_chunk(seed, n_target=n_target, features="tarl_dino" if cfg["gamma"] else "tarl")
+    A = affinity_ref(ch.points, ch.tarl, ch.dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
+    w = sp.csr_matrix(A)
+    out = []
+    for kind, sd in (("ones", 0), ("random", 11)):
+        with R.pinned_eigsh(kind, sd):
+            g = R.normalized_cut_ref(w, ch.n, np.arange(ch.n), T=cfg["T"])
+        out.append(R.labels_from_groups(g, ch.n))
+    return seed, out[0], R.same_partition(out[0], out[1])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="tarl_spatial")
+    ap.add_argument("--chunks", type=int, default=64)
+    ap.add_argument("--n-target", type=int, default=4096)
+    ap.add_argument("--seed", type=int, default=5000)
+    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--out", default="gpurun_out/parity.json")
+    args = ap.parse_args()
+    import torch
+    from autoinst_b200 import api
+    from autoinst_b200.synthetic import CONFIGS, make_chunk
+    from oracle import ncut_ref as R
+    cfg = CONFIGS[args.config]
+    feats = "tarl_dino" if cfg["gamma"] else "tarl"
+    seeds = [args.seed + i for i in range(args.chunks)]
+    workers = args.workers or min(os.cpu_count() or 1, 32, args.chunks)
+    t0 = time.time()
+    with mp.get_context("spawn").Pool(workers) as pool:
+        async_res = pool.map_async(oracle_job, [(s, args.n_target, args.config) for s in seeds])
+        chunks = [make_chunk(s, n_target=args.n_target, features=feats) for s in seeds]
+        t1 = time.time()
+        res = api.segment_chunks([c.points for c in chunks], [c.tarl for c in chunks],
+                                 [c.dino for c in chunks] if cfg["gamma"] else None, alpha=cfg["alpha"],
+                                 theta=cfg["theta"], gamma=cfg["gamma"], T=cfg["T"], want_stats=True)
+        torch.cuda.synchronize()
+        t_gpu = time.time() - t1
+        oracle = {s: (lab, st) for s, lab, st in async_res.get()}
+    t_all = time.time() - t0
+    stable = matched = 0
+    bad = []
+    for s, ch, lab in zip(seeds, chunks, res.labels):
+        ref, st = oracle[s]
+        if not st:
+            continue
+        stable += 1
+        if R.same_partition(lab, ref):
+            matched += 1
+        else:
+            bad.append(dict(seed=s, n=ch.n, segs_gpu=int(lab.max() + 1), segs_ref=int(ref.max() + 1),
+                            moved=int((lab != ref).sum())))
+    st = res.stats
+    summary = dict(config=args.config, chunks=args.chunks, n_target=args.n_target, oracle_stable=stable, matched=matched,
+                   match_rate=matched / max(stable, 1), oracle_unstable=args.chunks - stable, mismatches=bad,
+                   gpu_seconds_incl_h2d=t_gpu, wall_seconds=t_all, oracle_workers=workers,
+                   eig_nodes=int(len(st)), unconverged=int((st["converged"] == 0).sum()),
+                   steps_max=int(st["steps"].max()), steps_mean=float(st["steps"].mean()),
+                   points=int(sum(c.n for c in chunks)))
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    json.dump(summary, open(args.out, "w"), indent=1)
+    print(json.dumps(summary))
+
+
+if __name__ == "__main__":
+    main()
