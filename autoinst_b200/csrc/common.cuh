@@ -84,7 +84,7 @@ struct Eng {
     // sizes
     int P;            // total points in the batch
     int B;            // chunks
-    int KS;           // stride of per-node Krylov arrays = kmax + 2
+    int KS;           // stride of per-node Krylov arrays = kmax + 4
     int kmax;
     int check_every;
     double tol;
@@ -104,6 +104,7 @@ struct Eng {
     // per position
     int* rid; int* rid2; int* perm; int* perm2;
     double* deg; double* sinv; double* wbuf; double* ybuf; double* ev;
+    double* zbuf;           // S wbuf (input of the matvec), P + 4 entries
     uint8_t* bucket; uint8_t* side;
     int* parent; int* croot;
     unsigned long long* key; unsigned long long* key2; int* val; int* val2; int* flag; int* incl;
@@ -113,7 +114,7 @@ struct Eng {
     int* a_rid; int* a_k; int* a_kcap; int* a_done; int* a_conv; int* a_slot0; int* a_nch;
     double* a_alpha; double* a_beta;     // [slot][KS]
     double* a_y;                         // [slot][KS]
-    double* a_bprev; double* a_h1; double* a_h2;
+    double* a_bprev; double* a_h1; double* a_h2; int* a_need2;
     double* a_theta;                     // [slot][2]
     double* a_thr;                       // [slot][NCUT]
     double* a_sign; int* a_nocut;

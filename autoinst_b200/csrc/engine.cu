@@ -38,6 +38,8 @@ struct ancuts_handle {
     int device = 0;
     char* ws = nullptr;
     size_t ws_bytes = 0;
+    char* stage = nullptr;                   // device staging of host inputs / labels (host entry point)
+    size_t stage_cap = 0;
     int* h_ctr = nullptr;                    // pinned, 8 ints
     unsigned long long* h_acct = nullptr;    // pinned, SG_COUNT
     int64_t launches_total = 0;
@@ -70,7 +72,7 @@ struct Plan {
     int B = 0;
     int P = 0;
     int kmax = KMAX_DEFAULT;
-    int KS = KMAX_DEFAULT + 2;
+    int KS = KMAX_DEFAULT + 4;
     int active_cap = 0;
     int cslot_cap = 0;
     bool own_w0 = true, own_w1 = true;
@@ -111,7 +113,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     e.r_pass = ar.take<int>(2 * (size_t)P + 2); e.r_slot = nullptr;
     e.rid = ar.take<int>(P); e.rid2 = ar.take<int>(P); e.perm = ar.take<int>(P); e.perm2 = ar.take<int>(P);
     e.deg = ar.take<double>(P); e.sinv = ar.take<double>(P); e.wbuf = ar.take<double>(P);
-    e.ybuf = ar.take<double>(P); e.ev = ar.take<double>(P);
+    e.ybuf = ar.take<double>(P); e.ev = ar.take<double>(P); e.zbuf = ar.take<double>(P + 4);
     e.bucket = ar.take<uint8_t>(P); e.side = ar.take<uint8_t>(P);
     e.parent = ar.take<int>(P); e.croot = ar.take<int>(P);
     e.key = ar.take<unsigned long long>(P); e.key2 = ar.take<unsigned long long>(P);
@@ -123,7 +125,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     e.a_conv = ar.take<int>(A); e.a_slot0 = ar.take<int>(A); e.a_nch = ar.take<int>(A);
     e.a_alpha = ar.take<double>((size_t)A * KS); e.a_beta = ar.take<double>((size_t)A * KS);
     e.a_y = ar.take<double>((size_t)A * KS);
-    e.a_bprev = ar.take<double>(A); e.a_h1 = ar.take<double>(A); e.a_h2 = ar.take<double>(A);
+    e.a_bprev = ar.take<double>(A); e.a_h1 = ar.take<double>(A); e.a_h2 = ar.take<double>(A); e.a_need2 = ar.take<int>(A);
     e.a_theta = ar.take<double>(2 * (size_t)A); e.a_thr = ar.take<double>((size_t)A * NCUT);
     e.a_sign = ar.take<double>(A); e.a_nocut = ar.take<int>(A);
     e.a_diff = ar.take<unsigned long long>((size_t)A * (NB + 1)); e.a_cnt = ar.take<int>((size_t)A * NB);
@@ -169,7 +171,7 @@ static void make_plan(Plan& pl, int B, const int* n, const int* norig, const int
     }
     pl.P = (int)P;
     pl.kmax = kmax;
-    pl.KS = kmax + 2;
+    pl.KS = kmax + 4;
     pl.active_cap = std::max(101 * B + 1, extra_active + 1);
     pl.active_cap = std::min(pl.active_cap, pl.P + 1);
     pl.cslot_cap = pl.P / CH + pl.active_cap + 1;
@@ -237,9 +239,8 @@ static int end_accounting(ancuts_handle* h, const Eng& e, cudaStream_t st) {
 
 static int set_attrs(ancuts_handle* h, int KS) {
     if (h->attrs_set) return ANCUTS_OK;
-    ANCUTS_CUDA(cudaFuncSetAttribute(k_matvec<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (ZT + 8) * 8));
     ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_check, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (KMAX_LIMIT + 2) * 68 + 64));
+                                     (KMAX_LIMIT + 4) * 68 + 64));
     (void)KS;
     h->attrs_set = true;
     return ANCUTS_OK;
@@ -303,7 +304,7 @@ static int upload_tables(Plan& pl, cudaStream_t st) {
 
 static void fill_params(Eng& e, const ancuts_params* p, int kmax) {
     e.kmax = kmax;
-    e.KS = kmax + 2;
+    e.KS = kmax + 4;
     e.check_every = p->lanczos_check_every > 0 ? p->lanczos_check_every : CHECK_DEFAULT;
     e.tol = p->lanczos_tol > 0 ? p->lanczos_tol : TOL_DEFAULT;
     e.T = p->T;
@@ -350,8 +351,6 @@ static int run_lanczos(ancuts_handle* h, Eng& e, int cur, int num_active, int ma
     const int KS = e.KS;
     LAUNCH(SG_REORTH, k_lanczos_init<<<num_active, 256, 0, st>>>(e));
     const int nch_max = (max_n + CH - 1) / CH;
-    const int zt = std::min(ZT, (int)align_up((size_t)max_n + 4, 4));
-    const size_t mv_smem = (size_t)(zt + 8) * 8;
     const size_t up_smem = (size_t)(KS + CH + 8) * 8;
     const size_t ck_smem = (size_t)KS * 8 * 8 + (size_t)KS * 4 + 64;
     const int kcap_max = std::min(e.kmax, std::max(max_n - 1, 1));
@@ -360,7 +359,7 @@ static int run_lanczos(ancuts_handle* h, Eng& e, int cur, int num_active, int ma
         int burst = std::min(e.check_every, kcap_max - step);
         for (int s = 0; s < burst; ++s, ++step) {
             dim3 gmv((max_n + 31) / 32, num_active);
-            LAUNCH(SG_MATVEC, k_matvec<4><<<gmv, 256, mv_smem, st>>>(e, cur, zt));
+            LAUNCH(SG_MATVEC, k_matvec<4><<<gmv, 256, 0, st>>>(e, cur));
             dim3 gd(nch_max, (step + 2 + 31) / 32, num_active);
             LAUNCH(SG_REORTH, k_dots<<<gd, 256, 0, st>>>(e));
             dim3 gu(nch_max, num_active);
@@ -596,6 +595,7 @@ int ancuts_destroy(ancuts_handle* h) {
     if (!h) return ANCUTS_OK;
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
+    if (h->stage) cudaFree(h->stage);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_acct) cudaFreeHost(h->h_acct);
     for (auto ev : h->pool) cudaEventDestroy(ev);
@@ -993,9 +993,16 @@ int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* 
     const bool use_t = h_tarl && p->theta != 0.0, use_d = h_dino && p->gamma != 0.0;
     size_t bp = P * 3 * sizeof(double), bt = use_t ? P * p->tarl_dim * sizeof(float) : 0,
            bd = use_d ? P * p->dino_dim * sizeof(float) : 0, bl = P * sizeof(int32_t);
-    char* stage = nullptr;
     size_t total = align_up(bp, 256) + align_up(bt, 256) + align_up(bd, 256) + align_up(bl, 256);
-    ANCUTS_CUDA(cudaMalloc((void**)&stage, total));
+    if (total > h->stage_cap) {
+        if (h->stage) cudaFree(h->stage);
+        h->stage = nullptr;
+        h->stage_cap = 0;
+        cudaError_t me = cudaMalloc((void**)&h->stage, total);
+        if (me != cudaSuccess) { set_error("staging cudaMalloc(%zu) failed: %s", total, cudaGetErrorString(me)); cudaGetLastError(); return ANCUTS_ENOMEM; }
+        h->stage_cap = total;
+    }
+    char* stage = h->stage;
     double* d_points = (double*)stage;
     float* d_tarl = use_t ? (float*)(stage + align_up(bp, 256)) : nullptr;
     float* d_dino = use_d ? (float*)(stage + align_up(bp, 256) + align_up(bt, 256)) : nullptr;
@@ -1013,7 +1020,6 @@ int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* 
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) { set_error("D2H copy failed: %s", cudaGetErrorString(ce)); rc = ANCUTS_ECUDA; }
     }
-    cudaFree(stage);
     return rc;
 }
 

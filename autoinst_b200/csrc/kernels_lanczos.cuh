@@ -42,6 +42,7 @@ k_lanczos_init(Eng e) {
     for (int i = threadIdx.x; i < n; i += 256) {
         double x = start_value(i) - dot * e.V[start + i];
         e.wbuf[start + i] = x;
+        e.zbuf[start + i] = e.sinv[start + i] * x;
         nn += x * x;
     }
     nn = block_sum_256(nn, red);
@@ -56,61 +57,60 @@ k_lanczos_init(Eng e) {
 }
 
 // y = S (w+I) S v  with v = wbuf / bprev (the normalisation of the previous step is folded in
-// here; the rows of this block also store v into V row k+1).
-// grid: (row blocks of 8*R rows, active).  z = S v is staged in shared memory as float64 in
-// tiles of at most ZT columns, laid out on the 16-byte window of the matrix row.
+// here; every row also stores its entry of v into V row k+1).  zbuf = S wbuf is written by the
+// producer of wbuf, so  y_i = s_i/bprev * (sum_j w_ij zbuf_j + zbuf_i).
+// grid: (row blocks of 8*R rows, active).  One warp owns R rows and walks the 16-byte window of the
+// block's columns 256 columns at a time: all 2R 128-bit loads of W are issued before the first use.
 template <int R>
 __global__ void __launch_bounds__(256)
-k_matvec(Eng e, int cur, int zt) {
-    extern __shared__ double zs[];      // zt + 8 doubles
+k_matvec(Eng e, int cur) {
     int a = blockIdx.y;
     if (e.a_done[a] != DONE_NO) return;
     NodeView v = node_view(e, e.a_rid[a], cur);
-    const int rows_per_block = 8 * R;
-    int row0 = blockIdx.x * rows_per_block;
+    int row0 = blockIdx.x * (8 * R);
     if (row0 >= v.n) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int myrow0 = row0 + warp * R;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(&e.acct[SG_MATVEC], 4ull * v.n * v.n + 8ull * v.n);
+    if (myrow0 >= v.n) return;
     const double invb = 1.0 / e.a_bprev[a];
     const int k = e.a_k[a];
+    const double* __restrict__ z = e.zbuf + (v.start - v.ro);      // indexed by chunk-local column
+    const float* rp[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+        rp[rr] = v.W + (size_t)(v.ro + min(myrow0 + rr, v.n - 1)) * v.ld;
     double acc[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) acc[rr] = 0.0;
-    const int myrow0 = row0 + warp * R;
-
-    for (int t0 = 0; t0 < v.n; t0 += zt) {
-        int tn = min(zt, v.n - t0);
-        int c_lo = v.ro + t0, c_hi = c_lo + tn;
-        int a0 = c_lo & ~3;
-        int pad = c_lo - a0;
-        int span = ((c_hi - a0) + 3) & ~3;
-        if (t0 > 0) __syncthreads();
-        for (int j = threadIdx.x; j < span; j += 256) {
-            int jj = j - pad;
-            double z = 0.0;
-            if (jj >= 0 && jj < tn) {
-                int g = v.start + t0 + jj;
-                z = e.sinv[g] * e.wbuf[g] * invb;
-            }
-            zs[j] = z;
-        }
-        __syncthreads();
-        for (int j = lane * 4; j < span; j += 128) {
-            int c = a0 + j;
-            double2 za = *reinterpret_cast<const double2*>(&zs[j]);
-            double2 zb = *reinterpret_cast<const double2*>(&zs[j + 2]);
-            bool v0 = (c >= c_lo) & (c < c_hi), v1 = (c + 1 >= c_lo) & (c + 1 < c_hi);
-            bool v2 = (c + 2 >= c_lo) & (c + 2 < c_hi), v3 = (c + 3 >= c_lo) & (c + 3 < c_hi);
+    const int c_lo = v.ro, c_hi = v.ro + v.n;
+    const int a0 = c_lo & ~3;
+    for (int c = a0 + lane * 4; c < c_hi; c += 256) {
+        const int cb = c + 128;
+        const bool hasb = cb < c_hi;
+        float4 wa[R], wb[R];
 #pragma unroll
-            for (int rr = 0; rr < R; ++rr) {
-                int row = myrow0 + rr;
-                if (row < v.n) {
-                    float4 w = ld_stream4(v.W + (size_t)(v.ro + row) * v.ld + c);
-                    // entries outside the block belong to other nodes or are uninitialised
-                    double w0 = v0 ? (double)w.x : 0.0, w1 = v1 ? (double)w.y : 0.0;
-                    double w2 = v2 ? (double)w.z : 0.0, w3 = v3 ? (double)w.w : 0.0;
-                    acc[rr] += w0 * za.x + w1 * za.y + w2 * zb.x + w3 * zb.y;
-                }
-            }
+        for (int rr = 0; rr < R; ++rr) wa[rr] = ld_stream4(rp[rr] + c);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) wb[rr] = hasb ? ld_stream4(rp[rr] + cb) : make_float4(0.f, 0.f, 0.f, 0.f);
+        double za[4], zb[4];
+        bool va[4], vb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            va[q] = (c + q >= c_lo) & (c + q < c_hi);
+            vb[q] = hasb & (cb + q < c_hi);
+            za[q] = va[q] ? __ldg(z + c + q) : 0.0;
+            zb[q] = vb[q] ? __ldg(z + cb + q) : 0.0;
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            // entries outside the block belong to other nodes or are uninitialised: select, do not multiply
+            double s0 = (va[0] ? (double)wa[rr].x : 0.0) * za[0] + (va[1] ? (double)wa[rr].y : 0.0) * za[1];
+            double s1 = (va[2] ? (double)wa[rr].z : 0.0) * za[2] + (va[3] ? (double)wa[rr].w : 0.0) * za[3];
+            double s2 = (vb[0] ? (double)wb[rr].x : 0.0) * zb[0] + (vb[1] ? (double)wb[rr].y : 0.0) * zb[1];
+            double s3 = (vb[2] ? (double)wb[rr].z : 0.0) * zb[2] + (vb[3] ? (double)wb[rr].w : 0.0) * zb[3];
+            acc[rr] += (s0 + s1) + (s2 + s3);
         }
     }
 #pragma unroll
@@ -119,14 +119,11 @@ k_matvec(Eng e, int cur, int zt) {
         int row = myrow0 + rr;
         if (lane == 0 && row < v.n) {
             int g = v.start + row;
-            double vi = e.wbuf[g] * invb;
             double si = e.sinv[g];
-            e.ybuf[g] = si * (s + si * vi);                       // (w + I) z, z_i = s_i v_i
-            e.V[(size_t)(k + 1) * e.P + g] = vi;
+            e.ybuf[g] = si * invb * (s + e.zbuf[g]);              // (w + I) z
+            e.V[(size_t)(k + 1) * e.P + g] = e.wbuf[g] * invb;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(&e.acct[SG_MATVEC], 4ull * v.n * v.n + 8ull * v.n);
 }
 
 // partial dots of ybuf with basis rows 0..k+1 over one CH-column chunk.
@@ -163,11 +160,20 @@ k_dots(Eng e) {
         s = warp_sum(s);
         if (lane == 0) out[j] = s;
     }
+    if (blockIdx.y == 0 && warp == 0) {          // |y|^2 over the chunk, stored behind the last basis row
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < CH / 32; ++m) s += yr[m] * yr[m];
+        s = warp_sum(s);
+        if (lane == 0) out[rows] = s;
+    }
 }
 
-// y -= V^T h over one chunk; pass 1 then computes the partial dots of the updated y (second
-// Gram-Schmidt pass), pass 2 writes wbuf and the partial squared norm.
-// grid: (chunks, active)
+// y -= V^T h over one chunk (classical Gram-Schmidt against u1 and every Lanczos vector).
+// Pass 1 decides, from |y|^2 and |h|^2, whether a second pass is needed (DGKS test as in ARPACK:
+// |y - V h| < 0.717 |y|); if not, it finishes the step (wbuf, zbuf, partial squared norm); if so,
+// it leaves the partial dots of the updated y for pass 2, which exits at once for nodes that
+// do not need it.   grid: (chunks, active)
 template <int PASS>
 __global__ void __launch_bounds__(256)
 k_update(Eng e) {
@@ -177,6 +183,7 @@ k_update(Eng e) {
     double* red = ych + CH;
     int a = blockIdx.y;
     if (e.a_done[a] != DONE_NO) return;
+    if (PASS == 2 && !e.a_need2[a]) return;
     int nch = e.a_nch[a];
     int ch = blockIdx.x;
     if (ch >= nch) return;
@@ -184,27 +191,50 @@ k_update(Eng e) {
     int r = e.a_rid[a];
     int start = e.r_start[r], n = e.r_n[r];
     const double* pd = (PASS == 1 ? e.p_dot : e.p_dot2) + (size_t)e.a_slot0[a] * e.KS;
+    double hh = 0.0;
     for (int j = threadIdx.x; j < rows; j += 256) {
         double h = 0.0;
         for (int c = 0; c < nch; ++c) h += pd[(size_t)c * e.KS + j];     // fixed order
         hs[j] = h;
+        hh += h * h;
+    }
+    bool second = false;
+    if (PASS == 1) {
+        hh = block_sum_256(hh, red);
+        double yy = 0.0;
+        for (int c = 0; c < nch; ++c) yy += pd[(size_t)c * e.KS + rows];
+        second = (yy - hh) < 0.5 * yy;                                    // eta^2 = 1/2
     }
     __syncthreads();
     if (ch == 0 && threadIdx.x == 0) {
-        if (PASS == 1) e.a_h1[a] = hs[rows - 1]; else e.a_h2[a] = hs[rows - 1];
+        if (PASS == 1) { e.a_h1[a] = hs[rows - 1]; e.a_h2[a] = 0.0; e.a_need2[a] = second ? 1 : 0; }
+        else e.a_h2[a] = hs[rows - 1];
     }
     int c0 = ch * CH + threadIdx.x, c1 = c0 + 256;
     double y0 = c0 < n ? e.ybuf[start + c0] : 0.0;
     double y1 = c1 < n ? e.ybuf[start + c1] : 0.0;
     const double* vb = e.V + start;
-#pragma unroll 4
-    for (int j = 0; j < rows; ++j) {
-        const double* vr = vb + (size_t)j * e.P;
-        double h = hs[j];
-        if (c0 < n) y0 -= h * vr[c0];
-        if (c1 < n) y1 -= h * vr[c1];
+    const int cc0 = min(c0, n - 1), cc1 = min(c1, n - 1);                 // clamped: loads are always legal
+    int j = 0;
+    for (; j + 8 <= rows; j += 8) {
+        double t0[8], t1[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const double* vr = vb + (size_t)(j + u) * e.P;
+            t0[u] = vr[cc0];
+            t1[u] = vr[cc1];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { y0 -= hs[j + u] * t0[u]; y1 -= hs[j + u] * t1[u]; }
     }
-    if (PASS == 1) {
+    for (; j < rows; ++j) {
+        const double* vr = vb + (size_t)j * e.P;
+        y0 -= hs[j] * vr[cc0];
+        y1 -= hs[j] * vr[cc1];
+    }
+    if (c0 >= n) y0 = 0.0;
+    if (c1 >= n) y1 = 0.0;
+    if (PASS == 1 && second) {
         if (c0 < n) e.ybuf[start + c0] = y0;
         if (c1 < n) e.ybuf[start + c1] = y1;
         ych[threadIdx.x] = y0;
@@ -216,8 +246,8 @@ k_update(Eng e) {
         for (int m = 0; m < CH / 32; ++m) yr[m] = ych[lane + 32 * m];
         // other CTAs of this node may still be reading the pass-1 partials: pass 2 has its own buffer
         double* out = e.p_dot2 + (size_t)(e.a_slot0[a] + ch) * e.KS;
-        for (int j = warp; j < rows; j += 8) {
-            const double* vr = vb + (size_t)j * e.P;
+        for (int jj = warp; jj < rows; jj += 8) {
+            const double* vr = vb + (size_t)jj * e.P;
             double s = 0.0;
 #pragma unroll
             for (int m = 0; m < CH / 32; ++m) {
@@ -225,11 +255,11 @@ k_update(Eng e) {
                 if (c < n) s += vr[c] * yr[m];
             }
             s = warp_sum(s);
-            if (lane == 0) out[j] = s;
+            if (lane == 0) out[jj] = s;
         }
     } else {
-        if (c0 < n) e.wbuf[start + c0] = y0;
-        if (c1 < n) e.wbuf[start + c1] = y1;
+        if (c0 < n) { e.wbuf[start + c0] = y0; e.zbuf[start + c0] = e.sinv[start + c0] * y0; }
+        if (c1 < n) { e.wbuf[start + c1] = y1; e.zbuf[start + c1] = e.sinv[start + c1] * y1; }
         double nn = block_sum_256(y0 * y0 + y1 * y1, red);
         if (threadIdx.x == 0) e.p_norm[e.a_slot0[a] + ch] = nn;
     }
@@ -273,28 +303,32 @@ __device__ __forceinline__ int sturm_count(const double* al, const double* be2, 
     return cnt;     // number of eigenvalues < x
 }
 
-// whole CTA: eigenvalue with ascending index m of the k x k tridiagonal, to full float64 resolution
-__device__ double tridiag_bisect(const double* al, const double* be2, int k, int m, double glo, double ghi,
-                                 double pivmin, int* cnts, double* bounds) {
+// whole CTA (128 threads): the two largest eigenvalues of the k x k tridiagonal at once, 64 shifts per
+// eigenvalue and round (65^10 > 2^60: full float64 resolution of the Gershgorin bracket in 10 rounds).
+__device__ void tridiag_top2_bisect(const double* al, const double* be2, int k, double glo, double ghi,
+                                    double pivmin, int* cnts, double* bounds, double* th1, double* th2) {
     const int tid = threadIdx.x;
+    const int which = tid >> 6, t64 = tid & 63;      // 0: largest, 1: second largest
+    const int m = k - 1 - which;
     double lo = glo, hi = ghi;
     for (int round = 0; round < 10; ++round) {
-        double x = lo + (hi - lo) * ((double)(tid + 1) / 129.0);
-        cnts[tid] = sturm_count(al, be2, k, x, pivmin);
+        double x = lo + (hi - lo) * ((double)(t64 + 1) / 65.0);
+        cnts[tid] = (m >= 0) ? sturm_count(al, be2, k, x, pivmin) : 0;
         __syncthreads();
-        if (tid == 0) {
+        if (t64 == 0) {
             // eigenvalue m lies in (x_t, x_{t+1}] with count(x_t) <= m < count(x_{t+1})
             int t = -1;
-            for (int i = 0; i < 128; ++i) if (cnts[i] <= m) t = i;
-            bounds[0] = (t >= 0) ? lo + (hi - lo) * ((double)(t + 1) / 129.0) : lo;
-            bounds[1] = (t < 127) ? lo + (hi - lo) * ((double)(t + 2) / 129.0) : hi;
+            for (int i = 0; i < 64; ++i) if (cnts[which * 64 + i] <= m) t = i;
+            bounds[2 * which] = (t >= 0) ? lo + (hi - lo) * ((double)(t + 1) / 65.0) : lo;
+            bounds[2 * which + 1] = (t < 63) ? lo + (hi - lo) * ((double)(t + 2) / 65.0) : hi;
         }
         __syncthreads();
-        lo = bounds[0];
-        hi = bounds[1];
+        lo = bounds[2 * which];
+        hi = bounds[2 * which + 1];
         __syncthreads();
     }
-    return 0.5 * (lo + hi);
+    *th1 = 0.5 * (bounds[0] + bounds[1]);
+    *th2 = (k > 1) ? 0.5 * (bounds[2] + bounds[3]) : -1e300;
 }
 
 __global__ void __launch_bounds__(128)
@@ -311,7 +345,7 @@ k_lanczos_check(Eng e, int force) {
     double* yv = dl + KS;        // inverse-iteration vector
     int* swp = reinterpret_cast<int*>(yv + KS);   // row interchange flags
     __shared__ int cnts[128];
-    __shared__ double bounds[2];
+    __shared__ double bounds[4];
     __shared__ double gb[3];
 
     int a = blockIdx.x;
@@ -346,8 +380,8 @@ k_lanczos_check(Eng e, int force) {
     }
     __syncthreads();
     const double glo = gb[0], ghi = gb[1], pivmin = gb[2];
-    double th1 = tridiag_bisect(al, be2, k, k - 1, glo, ghi, pivmin, cnts, bounds);
-    double th2 = (k > 1) ? tridiag_bisect(al, be2, k, k - 2, glo, ghi, pivmin, cnts, bounds) : -1e300;
+    double th1, th2;
+    tridiag_top2_bisect(al, be2, k, glo, ghi, pivmin, cnts, bounds, &th1, &th2);
     if (tid == 0) {
         // inverse iteration for the eigenvector of th1: pivoted LU of (T - th1 I) (as LAPACK dgttrf/dgtts2)
         double tnorm = fmax(fmax(fabs(glo), fabs(ghi)), 1e-300);
@@ -378,7 +412,7 @@ k_lanczos_check(Eng e, int force) {
         }
         if (fabs(dd[k - 1]) < eps_piv) dd[k - 1] = (dd[k - 1] < 0.0) ? -eps_piv : eps_piv;
         for (int i = 0; i < k; ++i) yv[i] = (i & 1) ? 1.0 : 0.9;
-        for (int iter = 0; iter < 4; ++iter) {
+        for (int iter = 0; iter < 3; ++iter) {
             for (int i = 0; i < k - 1; ++i) {
                 if (!swp[i]) {
                     yv[i + 1] -= dl[i] * yv[i];
