@@ -31,7 +31,7 @@ class Params(C.Structure):
         ("proximity", C.c_double), ("T", C.c_double), ("split_lim", C.c_double),
         ("tarl_dim", C.c_int), ("dino_dim", C.c_int),
         ("lanczos_max_steps", C.c_int), ("lanczos_check_every", C.c_int),
-        ("lanczos_tol", C.c_double), ("affinity_impl", C.c_int),
+        ("lanczos_tol", C.c_double), ("affinity_impl", C.c_int), ("lanczos_impl", C.c_int),
     ]
 
 

@@ -67,13 +67,14 @@ class Handle:
 
 
 def make_params(alpha=1.0, theta=0.0, gamma=0.0, T=0.01, proximity=1.0, split_lim=0.01, beta=0.0,
-                tarl_dim=0, dino_dim=0, max_steps=0, check_every=0, tol=0.0, affinity_impl=0) -> Params:
+                tarl_dim=0, dino_dim=0, max_steps=0, check_every=0, tol=0.0, affinity_impl=0,
+                lanczos_impl=0) -> Params:
     if beta:
         # SAM term, ncuts_utils.py:115-123; beta = 0.0 in every shipped config (config.py:12,23,34,45)
         raise NotImplementedError("beta != 0 (SAM label term) is not supported by the B200 path")
     return Params(float(alpha or 0.0), float(theta or 0.0), float(gamma or 0.0), float(proximity), float(T),
                   float(split_lim), int(tarl_dim), int(dino_dim), int(max_steps), int(check_every),
-                  float(tol), int(affinity_impl))
+                  float(tol), int(affinity_impl), int(lanczos_impl))
 
 
 def _dev(device):
@@ -161,7 +162,7 @@ def _node_arrays(node_off, node_n):
     return off, nn, off.ctypes.data_as(C.POINTER(C.c_int32)), nn.ctypes.data_as(C.POINTER(C.c_int32))
 
 
-def lanczos_fiedler(W, node_off, node_n, *, max_steps=0, check_every=0, tol=0.0):
+def lanczos_fiedler(W, node_off, node_n, *, max_steps=0, check_every=0, tol=0.0, lanczos_impl=0):
     """Stage 3: Fiedler vector of every diagonal block (normalized_cut.py:49-53).
     Returns (ev float64 [n_total] on device, lambda2, steps, converged)."""
     W, ld = _matrix_args(W)
@@ -174,7 +175,7 @@ def lanczos_fiedler(W, node_off, node_n, *, max_steps=0, check_every=0, tol=0.0)
     lam = np.zeros(k)
     steps = np.zeros(k, dtype=np.int32)
     conv = np.zeros(k, dtype=np.int32)
-    p = make_params(T=0.0, max_steps=max_steps, check_every=check_every, tol=tol)
+    p = make_params(T=0.0, max_steps=max_steps, check_every=check_every, tol=tol, lanczos_impl=lanczos_impl)
     with torch.cuda.device(device):
         check(hd.lib.ancuts_lanczos_fiedler_batched(
             hd.h, n, _ptr(W), ld, k, poff, pn, C.byref(p), _ptr(ev), lam.ctypes.data_as(C.POINTER(C.c_double)),
@@ -352,14 +353,14 @@ def _run_segment(hd, fn_host, packed, dev_chunks, p, want_stats, device):
 
 def segment_packed(packed: PackedChunks, *, alpha=1.0, theta=0.0, gamma=0.0, T=0.01, proximity=1.0, split_lim=0.01,
                    device=None, dev_chunks: DeviceChunks | None = None, want_stats=False, max_steps=0,
-                   check_every=0, tol=0.0, affinity_impl=0) -> SegmentResult:
+                   check_every=0, tol=0.0, affinity_impl=0, lanczos_impl=0) -> SegmentResult:
     """Segment a packed batch.  With `dev_chunks` the inputs are already resident in HBM (labels stay on
     the device in dev_chunks.labels); otherwise host buffers go through ancuts_segment_chunks_host."""
     device = _dev(device if dev_chunks is None else dev_chunks.device)
     hd = Handle.get(device)
     p = make_params(alpha, theta if packed.use_t else 0.0, gamma if packed.use_d else 0.0, T, proximity, split_lim,
                     tarl_dim=packed.tarl_dim, dino_dim=packed.dino_dim, max_steps=max_steps, check_every=check_every,
-                    tol=tol, affinity_impl=affinity_impl)
+                    tol=tol, affinity_impl=affinity_impl, lanczos_impl=lanczos_impl)
     nseg, stats = _run_segment(hd, dev_chunks is None, packed, dev_chunks, p, want_stats, device)
     src = packed.labels if dev_chunks is None else dev_chunks.labels
     labels = None

@@ -112,6 +112,9 @@ struct Eng {
     // per active slot
     int* split_ids;       // ranges that split at this level (input of the next rebuild)
     int* a_rid; int* a_k; int* a_kcap; int* a_done; int* a_conv; int* a_slot0; int* a_nch;
+    int* a_path;          // 1 = multi-launch Lanczos path (k_ritz needed), 0 = finished by the cluster kernel
+    int* cl_ids;          // [class][active_cap] active slots per cluster-size class
+    int active_cap;
     double* a_alpha; double* a_beta;     // [slot][KS]
     double* a_y;                         // [slot][KS]
     double* a_bprev; double* a_h1; double* a_h2; int* a_need2;
@@ -128,7 +131,7 @@ struct Eng {
     double* p_stat;       // [cslot][4]  sum, min, max, sum of squares
     double* p_vol;        // [cslot][NB]
     // counters (device)
-    int* ctr;             // [0]=numRanges [1]=numActive [2]=maxActiveN [3]=cslots [4]=notDone [5]=numSplit [6]=statCount [7]=maxSplitN
+    int* ctr;             // 16 ints: [8..12]=nodes per cluster class [13]=nodes for the multi-launch path; [0]=numRanges [1]=numActive [2]=maxActiveN [3]=cslots [4]=notDone [5]=numSplit [6]=statCount [7]=maxSplitN
     unsigned long long* acct;   // [SG_COUNT] algorithmic bytes
     ancuts_node_stat* stats; int stats_cap;
 };

@@ -10,6 +10,7 @@
 #include "kernels_graph.cuh"
 #include "kernels_lanczos.cuh"
 #include "kernels_ncut.cuh"
+#include "kernels_cluster.cuh"
 
 namespace ancuts {
 
@@ -40,7 +41,11 @@ struct ancuts_handle {
     size_t ws_bytes = 0;
     char* stage = nullptr;                   // device staging of host inputs / labels (host entry point)
     size_t stage_cap = 0;
-    int* h_ctr = nullptr;                    // pinned, 8 ints
+    int* h_ctr = nullptr;                    // pinned, 16 ints
+    cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per cluster-size class
+    cudaEvent_t ev_fork = nullptr;
+    cudaEvent_t ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool cluster16_ok = true;
     unsigned long long* h_acct = nullptr;    // pinned, SG_COUNT
     int64_t launches_total = 0;
     int64_t stage_launches[SG_COUNT] = {0};
@@ -133,7 +138,10 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     const int C = pl.cslot_cap;
     e.p_dot = ar.take<double>((size_t)C * KS); e.p_dot2 = ar.take<double>((size_t)C * KS);
     e.p_norm = ar.take<double>(C); e.p_stat = ar.take<double>((size_t)C * 4); e.p_vol = ar.take<double>((size_t)C * NB);
-    e.ctr = ar.take<int>(8);
+    e.ctr = ar.take<int>(16);
+    e.a_path = ar.take<int>(A);
+    e.cl_ids = ar.take<int>((size_t)CL_CLASSES * A);
+    e.active_cap = A;
     e.acct = ar.take<unsigned long long>(SG_COUNT);
     pl.stats = ar.take<ancuts_node_stat>(std::max(stats_cap, 1));
     pl.labels_scratch = ar.take<int>(P);
@@ -218,6 +226,7 @@ struct LaunchScope {
     ~LaunchScope() { if (b) cudaEventRecord(b, st); }
 };
 #define LAUNCH(stage, ...) do { LaunchScope _ls(h, stage, st); __VA_ARGS__; } while (0)
+#define LAUNCH_ON(stream, stage, ...) do { LaunchScope _ls(h, stage, stream); __VA_ARGS__; } while (0)
 
 static void begin_accounting(ancuts_handle* h) {
     for (int i = 0; i < SG_COUNT; ++i) { h->stage_launches[i] = 0; h->stage_bytes[i] = 0; h->stage_ms[i] = 0; }
@@ -242,12 +251,22 @@ static int set_attrs(ancuts_handle* h, int KS) {
     ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_check, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (KMAX_LIMIT + 4) * 68 + 64));
     (void)KS;
+    const int cl_smem = CL_DYN_SMEM;
+    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
+    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
+    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
+    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
+    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
+    if (cudaFuncSetAttribute(k_lanczos_cluster<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        h->cluster16_ok = false;
+    }
     h->attrs_set = true;
     return ANCUTS_OK;
 }
 
 static int read_ctr(ancuts_handle* h, const Eng& e, cudaStream_t st) {
-    ANCUTS_CUDA(cudaMemcpyAsync(h->h_ctr, e.ctr, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(h->h_ctr, e.ctr, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
     ANCUTS_CUDA(cudaStreamSynchronize(st));
     return ANCUTS_OK;
 }
@@ -378,6 +397,69 @@ static int run_lanczos(ancuts_handle* h, Eng& e, int cur, int num_active, int ma
     return ANCUTS_OK;
 }
 
+template <int C>
+static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)count * C, 1, 1);
+    cfg.blockDim = dim3(CL_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = CL_DYN_SMEM;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (C > 1) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_lanczos_cluster<C>, e, cur, ids, (int)(CL_DYN_SMEM / 8));
+}
+
+// Lanczos for every active node: persistent cluster kernels (one stream per cluster size, running
+// concurrently) for nodes up to CL_NMAX points, then the grid-wide multi-launch path for larger
+// nodes and for nodes the cluster kernel could not finish in CL_KMAX steps.
+static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n, const int* class_cnt,
+                           int big_cnt, cudaStream_t st) {
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 4, 0, sizeof(int), st));
+    ANCUTS_CUDA(cudaEventRecord(h->ev_fork, st));
+    bool any = false, launch_failed = false;
+    for (int cls = CL_CLASSES - 1; cls >= 0; --cls) {          // largest clusters first
+        int cnt = class_cnt[cls];
+        if (cnt <= 0) continue;
+        if (cls == 4 && !h->cluster16_ok) { launch_failed = true; continue; }
+        cudaStream_t s = h->side[cls];
+        ANCUTS_CUDA(cudaStreamWaitEvent(s, h->ev_fork, 0));
+        const int* ids = e.cl_ids + (size_t)cls * e.active_cap;
+        cudaError_t err = cudaSuccess;
+        {
+            LaunchScope ls(h, SG_MATVEC, s);
+            switch (cls) {
+                case 0: err = launch_cluster<1>(e, cur, ids, cnt, s); break;
+                case 1: err = launch_cluster<2>(e, cur, ids, cnt, s); break;
+                case 2: err = launch_cluster<4>(e, cur, ids, cnt, s); break;
+                case 3: err = launch_cluster<8>(e, cur, ids, cnt, s); break;
+                default: err = launch_cluster<16>(e, cur, ids, cnt, s); break;
+            }
+        }
+        if (err != cudaSuccess) {                               // e.g. cluster size not schedulable: multi-launch path
+            cudaGetLastError();
+            launch_failed = true;
+            if (cls == 4) h->cluster16_ok = false;
+        }
+        ANCUTS_CUDA(cudaEventRecord(h->ev_join[cls], s));
+        ANCUTS_CUDA(cudaStreamWaitEvent(st, h->ev_join[cls], 0));
+        any = true;
+    }
+    int rest = big_cnt;
+    if (any || launch_failed) {
+        int rc = read_ctr(h, e, st);
+        if (rc) return rc;
+        rest += h->h_ctr[4];
+    }
+    if (rest > 0 || launch_failed) return run_lanczos(h, e, cur, num_active, max_n, st);
+    return ANCUTS_OK;
+}
+
 // Ritz vector, sign, thresholds, buckets, cut scan, decision, side flags
 static int run_cut(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n, bool ritz, cudaStream_t st) {
     const int nch_max = (max_n + CH - 1) / CH;
@@ -444,7 +526,7 @@ k_ev_stats(Eng e) {
 
 // split phase: components, sort, new table, gather.  Returns new counts through h->h_ctr.
 static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int max_split_n, bool components,
-                       cudaStream_t st) {
+                       cudaStream_t st, int* class_cnt = nullptr, int* big_cnt = nullptr) {
     Eng& e = pl.e;
     const int P = e.P;
     const int tb = 256, gP = (P + tb - 1) / tb;
@@ -464,6 +546,7 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
     tmp = pl.cub_bytes;
     ANCUTS_CUDA(cub::DeviceScan::InclusiveSum(pl.cub_tmp, tmp, e.flag, e.incl, P, st));
     ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 4 * sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 8, 0, 8 * sizeof(int), st));
     LAUNCH(SG_PARTITION, k_new_ranges<<<gP, tb, 0, st>>>(e));
     ANCUTS_CUDA(cudaGetLastError());
     int rc = read_ctr(h, e, st);
@@ -474,6 +557,8 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
     rc = read_ctr(h, e, st);
     if (rc) return rc;
     int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
+    if (class_cnt) for (int i = 0; i < CL_CLASSES; ++i) class_cnt[i] = h->h_ctr[8 + i];
+    if (big_cnt) *big_cnt = h->h_ctr[13];
     if (num_active > pl.active_cap || h->h_ctr[3] > pl.cslot_cap) {
         set_error("internal: active table overflow (%d nodes, %d chunk slots)", num_active, h->h_ctr[3]);
         return ANCUTS_EINVAL;
@@ -496,7 +581,7 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
                       int32_t* h_num_segments, cudaStream_t st) {
     Eng& e = pl.e;
     const int P = e.P, B = e.B;
-    ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 8 * sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 16 * sizeof(int), st));
     {
         int nmax = 0;
         for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
@@ -510,13 +595,15 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
     int num_split = h->h_ctr[5], max_split_n = h->h_ctr[7];
     int guard = 0;
     while (num_split > 0) {
-        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st);
+        int class_cnt[CL_CLASSES] = {0, 0, 0, 0, 0}, big_cnt = 0;
+        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt);
         if (rc) return rc;
         int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
         if (num_active == 0) break;
         dim3 gdeg((max_n + 7) / 8, num_active);
         LAUNCH(SG_DEGREE, k_degree<<<gdeg, 256, 0, st>>>(e, cur));
-        rc = run_lanczos(h, e, cur, num_active, max_n, st);
+        if (p->lanczos_impl == 1) rc = run_lanczos(h, e, cur, num_active, max_n, st);
+        else rc = run_lanczos_all(h, e, cur, num_active, max_n, class_cnt, big_cnt, st);
         if (rc) return rc;
         rc = run_cut(h, e, cur, num_active, max_n, true, st);
         if (rc) return rc;
@@ -585,7 +672,12 @@ int ancuts_create(int device, ancuts_handle** out) {
     }
     ancuts_handle* h = new ancuts_handle();
     h->device = device;
-    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_ctr, 8 * sizeof(int)));
+    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_ctr, 16 * sizeof(int)));
+    for (int i = 0; i < 5; ++i) {
+        ANCUTS_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
+        ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
+    ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ANCUTS_CUDA(cudaMallocHost((void**)&h->h_acct, SG_COUNT * sizeof(unsigned long long)));
     *out = h;
     return ANCUTS_OK;
@@ -599,6 +691,8 @@ int ancuts_destroy(ancuts_handle* h) {
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_acct) cudaFreeHost(h->h_acct);
     for (auto ev : h->pool) cudaEventDestroy(ev);
+    for (int i = 0; i < 5; ++i) { if (h->side[i]) cudaStreamDestroy(h->side[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return ANCUTS_OK;
 }
@@ -746,6 +840,21 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
     }
     for (int i = 0; i < n_total; ++i) perm[i] = i;
     Eng& e = pl.e;
+    {   // Lanczos bookkeeping the rebuild kernels would have written
+        std::vector<int> zeros(num_nodes, DONE_NO), ones(num_nodes, 1);
+        std::vector<int> cl((size_t)CL_CLASSES * pl.active_cap, 0);
+        int cnt[16] = {0};
+        for (int i = 0; i < num_nodes; ++i) {
+            int cls = (p->lanczos_impl == 1) ? -1 : cluster_class(h_n[i]);
+            if (cls >= 0) cl[(size_t)cls * pl.active_cap + cnt[8 + cls]++] = i; else cnt[13]++;
+        }
+        ANCUTS_CUDA(cudaMemcpyAsync(e.a_done, zeros.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+        ANCUTS_CUDA(cudaMemcpyAsync(e.a_path, ones.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+        ANCUTS_CUDA(cudaMemcpyAsync(e.cl_ids, cl.data(), cl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        ANCUTS_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < CL_CLASSES; ++i) h->h_ctr[8 + i] = cnt[8 + i];
+        h->h_ctr[13] = cnt[13];
+    }
     ANCUTS_CUDA(cudaMemcpyAsync(e.r_start, rs.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
     ANCUTS_CUDA(cudaMemcpyAsync(e.r_n, rn.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
     ANCUTS_CUDA(cudaMemcpyAsync(e.r_status, rst.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -772,6 +881,8 @@ int ancuts_lanczos_fiedler_batched(ancuts_handle* h, int n_total, const float* d
     int rc = check_params(p);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < num_nodes; ++i)
+        if (h_node_n && h_node_n[i] < 3) { set_error("node %d has %d points; the eigensolver needs n >= 3", i, h_node_n[i]); return ANCUTS_EINVAL; }
     Plan pl;
     int max_n = 0;
     begin_accounting(h);
@@ -781,8 +892,12 @@ int ancuts_lanczos_fiedler_batched(ancuts_handle* h, int n_total, const float* d
     Eng& e = pl.e;
     dim3 gdeg((max_n + 7) / 8, num_nodes);
     LAUNCH(SG_DEGREE, k_degree<<<gdeg, 256, 0, st>>>(e, 0));
-    rc = run_lanczos(h, e, 0, num_nodes, max_n, st);
-    if (rc) return rc;
+    {
+        int class_cnt[CL_CLASSES], big_cnt = h->h_ctr[13];
+        for (int i = 0; i < CL_CLASSES; ++i) class_cnt[i] = h->h_ctr[8 + i];
+        rc = run_lanczos_all(h, e, 0, num_nodes, max_n, class_cnt, big_cnt, st);
+        if (rc) return rc;
+    }
     dim3 gc((max_n + CH - 1) / CH, num_nodes);
     LAUNCH(SG_REORTH, k_ritz<<<gc, 256, (size_t)(e.KS + 32) * 8, st>>>(e));
     LAUNCH(SG_SCAN, k_ev_final<<<(num_nodes + 127) / 128, 128, 0, st>>>(e, num_nodes));

@@ -1,0 +1,454 @@
+// kernels_cluster.cuh — stage 3, persistent variant: ONE thread-block cluster runs the whole Lanczos
+// iteration of ONE node (init, matvec, re-orthogonalisation, convergence checks, Ritz vector) without
+// returning to the host.  Replaces eigsh(A, 2, sigma=1e-10) + argsort (normalized_cut.py:49-53) for
+// nodes of up to CL_NMAX points; larger nodes keep the grid-wide multi-launch path (kernels_lanczos.cuh).
+//
+// The C CTAs of a cluster own C row slices of the node's block.  Per step:
+//   matvec of the slice (W streamed from L2/HBM, z = S v for the whole node in shared memory),
+//   classical Gram-Schmidt twice against u1 = D^1/2 1 and every Lanczos vector: each CTA forms the
+//   partial dots over its slice, the partials are exchanged through distributed shared memory
+//   (cluster barrier, then every CTA sums the C partials in rank order, so all CTAs hold bit-identical
+//   alpha/beta and take identical decisions), three cluster barriers per step.
+// Every sum is float64 and evaluated in a fixed order: results do not depend on scheduling.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "kernels_graph.cuh"
+#include "kernels_lanczos.cuh"
+
+namespace ancuts {
+namespace cg = cooperative_groups;
+
+constexpr int CL_KMAX = 256;             // steps the cluster kernel can take; nodes needing more fall back
+constexpr int CL_KS = CL_KMAX + 4;
+constexpr int CL_RPMAX = 384;            // rows per CTA
+constexpr int CL_NMAX = 4096;            // largest node handled here (16 CTAs x 256 rows)
+constexpr int CL_THREADS = 512;
+constexpr int CL_CLASSES = 5;            // cluster sizes 1, 2, 4, 8, 16
+constexpr int CL_DYN_SMEM = 192 * 1024;  // z for the whole node + as many basis rows of the slice as fit
+
+struct ClusterShared {
+    double hpart[2][CL_KS];      // this CTA's partial dots (pass 1 / pass 2), read by the peers
+    double npart[2];             // partial squared norm of the slice
+    double spart[4];             // at the end: partial (sum, min, max, sum of squares) of the Ritz vector
+    double hs[CL_KS];            // reduced projection coefficients
+    double alpha[CL_KS], beta[CL_KS];
+    double be2[CL_KS], dd[CL_KS], du[CL_KS], du2[CL_KS], dl[CL_KS], yv[CL_KS];
+    double ysl[CL_RPMAX];        // this CTA's slice of the current vector
+    double sv[CL_RPMAX];         // D^-1/2 of the slice
+    double red[16];
+    double bounds[4];
+    double gb[3];
+    int swp[CL_KS];
+    int cnts[CL_THREADS];
+};
+
+__device__ __forceinline__ double block_sum_512(double v, double* red) {
+    v = warp_sum(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) t += red[i];
+    return t;
+}
+__device__ __forceinline__ double block_min_512(double v, double* red) {
+    v = warp_min(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) red[w] = v;
+    __syncthreads();
+    double t = red[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) t = fmin(t, red[i]);
+    return t;
+}
+
+// tridiagonal analysis by the whole CTA (512 threads): top two eigenvalues by multisection with 256
+// shifts each (257^8 > 2^64), eigenvector of the largest by inverse iteration (thread 0).
+// Returns the residual estimate beta_{k-1} |y_{k-1}|; th[0], th[1] = eigenvalues; S.yv = eigenvector.
+__device__ double cluster_tridiag(ClusterShared& S, int k, double* th) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < k; i += CL_THREADS) S.be2[i] = S.beta[i] * S.beta[i];
+    __syncthreads();
+    if (tid == 0) {
+        double lo = 1e300, hi = -1e300, bmax = 0.0;
+        for (int i = 0; i < k; ++i) {
+            double rad = (i > 0 ? fabs(S.beta[i - 1]) : 0.0) + (i < k - 1 ? fabs(S.beta[i]) : 0.0);
+            lo = fmin(lo, S.alpha[i] - rad);
+            hi = fmax(hi, S.alpha[i] + rad);
+            if (i < k - 1) bmax = fmax(bmax, S.be2[i]);
+        }
+        double w = fmax(fmax(fabs(lo), fabs(hi)), 1e-300);
+        S.gb[0] = lo - 1e-10 * w;
+        S.gb[1] = hi + 1e-10 * w;
+        S.gb[2] = fmax(bmax, 1.0) * 1.0020841800044864e-292;
+    }
+    __syncthreads();
+    const double glo = S.gb[0], ghi = S.gb[1], pivmin = S.gb[2];
+    {
+        const int which = tid >> 8, t256 = tid & 255;
+        const int m = k - 1 - which;
+        double lo = glo, hi = ghi;
+        for (int round = 0; round < 8; ++round) {
+            double x = lo + (hi - lo) * ((double)(t256 + 1) / 257.0);
+            S.cnts[tid] = (m >= 0) ? sturm_count(S.alpha, S.be2, k, x, pivmin) : 0;
+            __syncthreads();
+            if (t256 < 32) {                 // one warp per eigenvalue finds the last shift with count <= m
+                int best = -1;
+                for (int i = t256; i < 256; i += 32) if (S.cnts[which * 256 + i] <= m) best = max(best, i);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+                if (t256 == 0) {
+                    S.bounds[2 * which] = (best >= 0) ? lo + (hi - lo) * ((double)(best + 1) / 257.0) : lo;
+                    S.bounds[2 * which + 1] = (best < 255) ? lo + (hi - lo) * ((double)(best + 2) / 257.0) : hi;
+                }
+            }
+            __syncthreads();
+            lo = S.bounds[2 * which];
+            hi = S.bounds[2 * which + 1];
+            __syncthreads();
+        }
+    }
+    const double th1 = 0.5 * (S.bounds[0] + S.bounds[1]);
+    const double th2 = (k > 1) ? 0.5 * (S.bounds[2] + S.bounds[3]) : -1e300;
+    if (tid == 0) {
+        double tnorm = fmax(fmax(fabs(glo), fabs(ghi)), 1e-300);
+        double eps_piv = 2.220446049250313e-16 * tnorm;
+        for (int i = 0; i < k; ++i) {
+            S.dd[i] = S.alpha[i] - th1;
+            S.du[i] = (i < k - 1) ? S.beta[i] : 0.0;
+            S.du2[i] = 0.0;
+            S.dl[i] = (i < k - 1) ? S.beta[i] : 0.0;
+            S.swp[i] = 0;
+        }
+        for (int i = 0; i < k - 1; ++i) {
+            if (fabs(S.dd[i]) >= fabs(S.dl[i])) {
+                if (fabs(S.dd[i]) < eps_piv) S.dd[i] = (S.dd[i] < 0.0) ? -eps_piv : eps_piv;
+                double f = S.dl[i] / S.dd[i];
+                S.dl[i] = f;
+                S.dd[i + 1] -= f * S.du[i];
+            } else {
+                double f = S.dd[i] / S.dl[i];
+                S.dd[i] = S.dl[i];
+                S.dl[i] = f;
+                double tmp = S.du[i];
+                S.du[i] = S.dd[i + 1];
+                S.dd[i + 1] = tmp - f * S.du[i];
+                if (i < k - 2) { S.du2[i] = S.du[i + 1]; S.du[i + 1] = -f * S.du2[i]; }
+                S.swp[i] = 1;
+            }
+        }
+        if (fabs(S.dd[k - 1]) < eps_piv) S.dd[k - 1] = (S.dd[k - 1] < 0.0) ? -eps_piv : eps_piv;
+        for (int i = 0; i < k; ++i) S.yv[i] = (i & 1) ? 1.0 : 0.9;
+        for (int iter = 0; iter < 3; ++iter) {
+            for (int i = 0; i < k - 1; ++i) {
+                if (!S.swp[i]) {
+                    S.yv[i + 1] -= S.dl[i] * S.yv[i];
+                } else {
+                    double t = S.yv[i];
+                    S.yv[i] = S.yv[i + 1];
+                    S.yv[i + 1] = t - S.dl[i] * S.yv[i];
+                }
+            }
+            S.yv[k - 1] /= S.dd[k - 1];
+            if (k > 1) S.yv[k - 2] = (S.yv[k - 2] - S.du[k - 2] * S.yv[k - 1]) / S.dd[k - 2];
+            for (int i = k - 3; i >= 0; --i)
+                S.yv[i] = (S.yv[i] - S.du[i] * S.yv[i + 1] - S.du2[i] * S.yv[i + 2]) / S.dd[i];
+            double big = 0.0;
+            for (int i = 0; i < k; ++i) big = fmax(big, fabs(S.yv[i]));
+            double sc = 1.0 / big, nn = 0.0;
+            for (int i = 0; i < k; ++i) { S.yv[i] *= sc; nn += S.yv[i] * S.yv[i]; }
+            double inv = 1.0 / sqrt(nn);
+            for (int i = 0; i < k; ++i) S.yv[i] *= inv;
+        }
+        S.gb[0] = fabs(S.beta[k - 1] * S.yv[k - 1]);
+    }
+    __syncthreads();
+    th[0] = th1;
+    th[1] = th2;
+    return S.gb[0];
+}
+
+template <int C>
+__device__ __forceinline__ void cl_sync(cg::cluster_group& cl) {
+    if (C > 1) cl.sync(); else __syncthreads();
+}
+
+// Basis rows restricted to this CTA's slice: the first rows_s rows live in shared memory, later rows
+// (long runs) spill to the global basis V.
+struct SliceBasis {
+    double* smem;          // rows_s rows of stride nrp
+    double* glob;          // e.V + first global position of the slice; row stride P
+    size_t P;
+    int rows_s;
+    int nrp;
+    __device__ __forceinline__ double* row(int j) const {
+        return (j < rows_s) ? smem + (size_t)j * nrp : glob + (size_t)j * P;
+    }
+};
+
+// partial dots of the slice vector with basis rows [0, rows): S.hpart[buf][j].  One warp per row,
+// up to 10 loads per lane in flight (nr <= CL_RPMAX = 10 * 32 + ...).
+__device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const SliceBasis& B, int rows, int nr, int buf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int M = (CL_RPMAX + 31) / 32;
+    double yr[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { int i = lane + 32 * m; yr[m] = (i < nr) ? S.ysl[i] : 0.0; }
+    for (int j = warp; j < rows; j += CL_THREADS / 32) {
+        const double* vr = B.row(j);
+        double t[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { int i = lane + 32 * m; t[m] = (i < nr) ? vr[i] : 0.0; }
+        double s = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) s += t[m] * yr[m];
+        s = warp_sum(s);
+        if (lane == 0) S.hpart[buf][j] = s;
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void cl_reduce_h(cg::cluster_group& cl, ClusterShared& S, int rows, int buf) {
+    for (int j = threadIdx.x; j < rows; j += CL_THREADS) {
+        double h = 0.0;
+        if (C > 1) {
+#pragma unroll
+            for (int r = 0; r < C; ++r) h += cl.map_shared_rank(&S.hpart[buf][0], r)[j];     // rank order
+        } else {
+            h = S.hpart[buf][j];
+        }
+        S.hs[j] = h;
+    }
+    __syncthreads();
+}
+
+// slice -= sum_j hs[j] V[j][slice]
+__device__ __forceinline__ void cl_update(ClusterShared& S, const SliceBasis& B, int rows, int nr) {
+    const int i = threadIdx.x;
+    if (i < nr) {
+        double y = S.ysl[i];
+        int j = 0;
+        for (; j + 8 <= rows; j += 8) {
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = B.row(j + u)[i];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) y -= S.hs[j + u] * t[u];
+        }
+        for (; j < rows; ++j) y -= S.hs[j] * B.row(j)[i];
+        S.ysl[i] = y;
+    }
+    __syncthreads();
+}
+
+// grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot
+template <int C>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) {
+    extern __shared__ __align__(16) double zs[];   // z = S v for the whole node on the 16-byte window of W's columns;
+                                                   // behind it: the first rows of the basis, restricted to this CTA's slice
+    __shared__ ClusterShared S;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (C > 1) ? (int)cl.block_rank() : 0;
+    const int a = ids[blockIdx.x / C];
+    const NodeView v = node_view(e, e.a_rid[a], cur);
+    const int n = v.n;
+    const int rp = (n + C - 1) / C;
+    const int r0 = min(n, rank * rp), r1 = min(n, r0 + rp);
+    const int nr = r1 - r0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t P = (size_t)e.P;
+    const int g0 = v.start + r0;                       // global position of the slice
+    const int pad = v.ro & 3;                          // zs[j + pad] <-> column v.ro + j
+    SliceBasis B;
+    {
+        const int nz = (n + 8 + 3) & ~3;               // doubles used by zs
+        B.nrp = (max(nr, 1) + 3) & ~3;
+        B.smem = zs + nz;
+        B.rows_s = max(0, (dyn_doubles - nz) / B.nrp);
+        B.glob = e.V + g0;
+        B.P = P;
+    }
+    const int kcap = min(min(CL_KMAX, e.kmax), n - 1);
+
+    // ---- init (every CTA redundantly: bit-identical scalars, no exchange needed) ----
+    double s = 0.0;
+    for (int i = tid; i < n; i += CL_THREADS) s += e.deg[v.start + i];
+    const double vol = block_sum_512(s, S.red);
+    const double ivol = 1.0 / sqrt(vol);
+    s = 0.0;
+    for (int i = tid; i < n; i += CL_THREADS) s += sqrt(e.deg[v.start + i]) * ivol * start_value(i);
+    const double dot = block_sum_512(s, S.red);
+    s = 0.0;
+    for (int i = tid; i < n + 8; i += CL_THREADS) {
+        int j = i - pad;
+        double z = 0.0;
+        if (j >= 0 && j < n) {
+            double u = sqrt(e.deg[v.start + j]) * ivol;
+            double x = start_value(j) - dot * u;
+            z = e.sinv[v.start + j] * x;
+            s += x * x;
+        }
+        zs[i] = z;
+    }
+    double bprev = sqrt(block_sum_512(s, S.red));
+    if (tid < nr) {
+        int j = r0 + tid;
+        double u = sqrt(e.deg[v.start + j]) * ivol;
+        B.row(0)[tid] = u;                               // basis row 0 = u1
+        S.ysl[tid] = start_value(j) - dot * u;
+        S.sv[tid] = e.sinv[v.start + j];
+    }
+    __syncthreads();
+
+    int k = 0;
+    int conv = 0;
+    double th[2] = {0.0, 0.0};
+    while (true) {
+        const double invb = 1.0 / bprev;
+        // basis row k+1 = current vector (slice)
+        if (tid < nr) B.row(k + 1)[tid] = S.ysl[tid] * invb;
+        __syncthreads();
+        // ---- matvec of the slice: 4 rows per warp, 256 columns per iteration, loads issued first ----
+        {
+            const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
+            for (int rb = warp * 4; rb < nr; rb += (CL_THREADS / 32) * 4) {
+                const float* rpt[4];
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr)
+                    rpt[rr] = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld;
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int c = a0 + lane * 4; c < c_hi; c += 256) {
+                    const int cb = c + 128;
+                    const bool hasb = cb < c_hi;
+                    float4 wa[4], wb[4];
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) wa[rr] = ld_stream4(rpt[rr] + c);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) wb[rr] = hasb ? ld_stream4(rpt[rr] + cb) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const double2 za0 = *reinterpret_cast<const double2*>(&zs[c - a0]);
+                    const double2 za1 = *reinterpret_cast<const double2*>(&zs[c - a0 + 2]);
+                    double2 zb0 = make_double2(0.0, 0.0), zb1 = make_double2(0.0, 0.0);
+                    if (hasb) {
+                        zb0 = *reinterpret_cast<const double2*>(&zs[cb - a0]);
+                        zb1 = *reinterpret_cast<const double2*>(&zs[cb - a0 + 2]);
+                    }
+                    const bool va0 = (c >= c_lo) & (c < c_hi), va1 = (c + 1 >= c_lo) & (c + 1 < c_hi);
+                    const bool va2 = (c + 2 >= c_lo) & (c + 2 < c_hi), va3 = (c + 3 >= c_lo) & (c + 3 < c_hi);
+                    const bool vb0 = hasb, vb1 = hasb & (cb + 1 < c_hi), vb2 = hasb & (cb + 2 < c_hi), vb3 = hasb & (cb + 3 < c_hi);
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        // entries outside the block belong to other nodes or are uninitialised: select them away
+                        double q0 = (va0 ? (double)wa[rr].x : 0.0) * za0.x + (va1 ? (double)wa[rr].y : 0.0) * za0.y;
+                        double q1 = (va2 ? (double)wa[rr].z : 0.0) * za1.x + (va3 ? (double)wa[rr].w : 0.0) * za1.y;
+                        double q2 = (vb0 ? (double)wb[rr].x : 0.0) * zb0.x + (vb1 ? (double)wb[rr].y : 0.0) * zb0.y;
+                        double q3 = (vb2 ? (double)wb[rr].z : 0.0) * zb1.x + (vb3 ? (double)wb[rr].w : 0.0) * zb1.y;
+                        acc[rr] += (q0 + q1) + (q2 + q3);
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    double t = warp_sum(acc[rr]);
+                    int i = rb + rr;
+                    if (lane == 0 && i < nr) S.ysl[i] = S.sv[i] * invb * (t + zs[r0 + i + pad]);   // (w + I) z
+                }
+            }
+        }
+        __syncthreads();
+        const int rows = k + 2;
+        // ---- classical Gram-Schmidt, pass 1 ----
+        cl_partial_dots(S, B, rows, nr, 0);
+        __syncthreads();
+        cl_sync<C>(cl);
+        cl_reduce_h<C>(cl, S, rows, 0);
+        const double a1 = S.hs[rows - 1];
+        __syncthreads();
+        cl_update(S, B, rows, nr);
+        // ---- pass 2 ----
+        cl_partial_dots(S, B, rows, nr, 1);
+        __syncthreads();
+        cl_sync<C>(cl);
+        cl_reduce_h<C>(cl, S, rows, 1);
+        const double a2 = S.hs[rows - 1];
+        __syncthreads();
+        cl_update(S, B, rows, nr);
+        // ---- norm, publication of z = S y for the next matvec ----
+        double q = (tid < nr) ? S.ysl[tid] * S.ysl[tid] : 0.0;
+        q = block_sum_512(q, S.red);
+        if (tid == 0) S.npart[0] = q;
+        if (C > 1 && tid < nr) e.zbuf[g0 + tid] = S.sv[tid] * S.ysl[tid];
+        __syncthreads();
+        cl_sync<C>(cl);
+        double nn = 0.0;
+        if (C > 1) {
+#pragma unroll
+            for (int r = 0; r < C; ++r) nn += cl.map_shared_rank(&S.npart[0], r)[0];
+        } else {
+            nn = S.npart[0];
+        }
+        const double beta = sqrt(nn);
+        if (tid == 0) { S.alpha[k] = a1 + a2; S.beta[k] = beta; }
+        bprev = beta;
+        k += 1;
+        // refill z for the whole node
+        if (C > 1) {
+            for (int i = tid; i < n; i += CL_THREADS) zs[i + pad] = __ldcg(e.zbuf + v.start + i);
+        } else {
+            if (tid < nr) zs[tid + pad] = S.sv[tid] * S.ysl[tid];
+        }
+        __syncthreads();
+        const bool breakdown = beta < 1e-13;
+        if (breakdown || k >= kcap || (k % e.check_every) == 0) {
+            double res = cluster_tridiag(S, k, th);
+            double gap = fmax(th[0] - th[1], 1e-300);
+            bool c1 = (k >= n - 1) || breakdown || (res <= e.tol * gap);
+            if (c1) { conv = 1; break; }
+            if (k >= kcap) break;
+        }
+    }
+    // ---- Ritz vector of the slice, statistics for the cut kernels ----
+    if (conv) {
+        double x = 0.0;
+        if (tid < nr) {
+            for (int j = 0; j < k; ++j) x += S.yv[j] * B.row(j + 1)[tid];
+            e.ev[g0 + tid] = x;
+        }
+        double sm_ = block_sum_512(tid < nr ? x : 0.0, S.red);
+        double sq = block_sum_512(tid < nr ? x * x : 0.0, S.red);
+        double mn = block_min_512(tid < nr ? x : 1e300, S.red);
+        double mx = -block_min_512(tid < nr ? -x : 1e300, S.red);
+        if (tid == 0) { S.spart[0] = sm_; S.spart[1] = mn; S.spart[2] = mx; S.spart[3] = sq; }
+        __syncthreads();
+        cl_sync<C>(cl);
+        if (rank == 0 && tid == 0) {
+            double ts = 0.0, tmn = 1e300, tmx = -1e300, tq = 0.0;
+            for (int r = 0; r < C; ++r) {
+                const double* np_ = (C > 1) ? cl.map_shared_rank(&S.spart[0], r) : &S.spart[0];
+                ts += np_[0]; tmn = fmin(tmn, np_[1]); tmx = fmax(tmx, np_[2]); tq += np_[3];
+            }
+            const int s0 = e.a_slot0[a], nch = e.a_nch[a];
+            double* o = e.p_stat + (size_t)s0 * 4;
+            o[0] = ts; o[1] = tmn; o[2] = tmx; o[3] = tq;
+            for (int c = 1; c < nch; ++c) { double* oc = e.p_stat + (size_t)(s0 + c) * 4; oc[0] = 0.0; oc[1] = 1e300; oc[2] = -1e300; oc[3] = 0.0; }
+            e.a_k[a] = k;
+            e.a_kcap[a] = kcap;
+            e.a_conv[a] = 1;
+            e.a_theta[2 * a] = th[0];
+            e.a_theta[2 * a + 1] = th[1];
+            e.a_done[a] = DONE_YES;
+            e.a_path[a] = 0;                    // Ritz vector and statistics are already in place
+            atomicAdd(&e.acct[SG_MATVEC], (unsigned long long)k * (4ull * n * n + 8ull * n));
+        }
+    } else if (rank == 0 && tid == 0) {
+        e.a_done[a] = DONE_NO;                  // left for the multi-launch path (more steps)
+        e.a_path[a] = 1;
+        atomicAdd(&e.ctr[4], 1);
+    }
+    cl_sync<C>(cl);                             // peers may still be reading this CTA's shared memory
+}
+
+}  // namespace ancuts

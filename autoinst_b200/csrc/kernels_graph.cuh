@@ -5,6 +5,16 @@
 
 namespace ancuts {
 
+// cluster-size class of a node for the persistent Lanczos kernel (kernels_cluster.cuh); -1 = too large
+__host__ __device__ inline int cluster_class(int n) {
+    if (n <= 320) return 0;              // 1 CTA
+    if (n <= 640) return 1;              // 2
+    if (n <= 1024) return 2;             // 4
+    if (n <= 1536) return 3;             // 8
+    if (n <= 4096) return 4;             // 16
+    return -1;
+}
+
 struct NodeView {
     int start;      // global position of the first point
     int n;
@@ -359,6 +369,11 @@ __global__ void k_finish_ranges(Eng e, int num_ranges) {
         e.a_nch[a] = nch;
         e.a_slot0[a] = atomicAdd(&e.ctr[3], nch);
         atomicMax(&e.ctr[2], n);
+        e.a_done[a] = DONE_NO;
+        e.a_path[a] = 1;
+        int cls = cluster_class(n);
+        if (cls >= 0) e.cl_ids[cls * e.active_cap + atomicAdd(&e.ctr[8 + cls], 1)] = a;
+        else atomicAdd(&e.ctr[13], 1);
     }
 }
 

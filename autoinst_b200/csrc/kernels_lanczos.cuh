@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256)
 k_lanczos_init(Eng e) {
     __shared__ double red[8];
     int a = blockIdx.x;
+    if (e.a_done[a] != DONE_NO) return;          // already finished by the cluster kernel
     int r = e.a_rid[a];
     int start = e.r_start[r], n = e.r_n[r];
     double s = 0.0;
@@ -460,6 +461,7 @@ k_ritz(Eng e) {
     double* ys = sm;
     double* red = sm + e.KS;
     int a = blockIdx.y;
+    if (e.a_path[a] == 0) return;                // the cluster kernel already wrote ev and its statistics
     int nch = e.a_nch[a];
     int ch = blockIdx.x;
     if (ch >= nch) return;

@@ -52,6 +52,8 @@ typedef struct ancuts_params {
     int    lanczos_check_every; /* 0 -> default (16)   */
     double lanczos_tol;         /* 0 -> default (1e-10): residual <= tol * (theta1 - theta2) */
     int    affinity_impl;       /* 0 = exact CUDA-core tile kernel, 1 = tcgen05 Gram GEMM */
+    int    lanczos_impl;        /* 0 = persistent cluster kernel for nodes <= 4096 points, grid-wide
+                                   multi-launch path above; 1 = multi-launch path for every node */
 } ancuts_params;
 
 /* One row per recursion node that reached the eigensolver (debug / accounting). */

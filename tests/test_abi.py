@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_struct_layout_matches_header():
-    assert ctypes.sizeof(_lib.Params) == 6 * 8 + 4 * 4 + 8 + 8      # 6 doubles, 4 ints, double, int (+pad)
+    assert ctypes.sizeof(_lib.Params) == 6 * 8 + 4 * 4 + 8 + 8      # 6 doubles, 4 ints, double, 2 ints
     assert ctypes.sizeof(_lib.NodeStat) == 8 * 4 + 2 * 8
 
 

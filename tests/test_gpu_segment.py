@@ -70,6 +70,20 @@ def test_labels_match_oracle_batched(cuda_device, name):
     assert stable >= 3 and matched == stable
 
 
+def test_multi_launch_path_gives_the_same_labels(cuda_device):
+    """lanczos_impl=1 (grid-wide kernels for every node) against the default persistent cluster kernels."""
+    cfg = CONFIGS["tarl_spatial"]
+    from autoinst_b200 import api
+    chunks = [make_chunk(400 + i, n_target=1500, features="tarl") for i in range(2)]
+    pk = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], theta=cfg["theta"], pin=False)
+    kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"], device=cuda_device, want_stats=True)
+    a = api.segment_packed(pk, lanczos_impl=0, **kw)
+    b = api.segment_packed(pk, lanczos_impl=1, **kw)
+    for la, lb in zip(a.labels, b.labels):
+        assert R.same_partition(la, lb)
+    assert a.stats["converged"].all() and b.stats["converged"].all()
+
+
 def test_batched_equals_single(cuda_device):
     cfg = CONFIGS["tarl_spatial"]
     chunks = [make_chunk(200 + i, n_target=900 + 200 * i, features="tarl") for i in range(3)]

@@ -98,9 +98,10 @@ def _blocks(cuda_device, seeds=(31, 32, 33), ppo=450):
     return api, Wd, W, mats, offs, ns
 
 
-def test_lanczos_fiedler_matches_arpack(cuda_device):
+@pytest.mark.parametrize("impl", [0, 1])        # 0: persistent cluster kernel, 1: grid-wide multi-launch path
+def test_lanczos_fiedler_matches_arpack(cuda_device, impl):
     api, Wd, W, mats, offs, ns = _blocks(cuda_device)
-    ev, lam2, steps, conv = api.lanczos_fiedler(Wd, offs, ns)
+    ev, lam2, steps, conv = api.lanczos_fiedler(Wd, offs, ns, lanczos_impl=impl)
     ev = ev.cpu().numpy()
     for A32, o, n, l2, k, c in zip(mats, offs, ns, lam2, steps, conv):
         w = sp.csr_matrix(A32.astype(np.float64))
@@ -113,7 +114,40 @@ def test_lanczos_fiedler_matches_arpack(cuda_device):
         assert np.abs(got - R.canonical_sign(ev_ref)).max() < 1e-8, np.abs(got - R.canonical_sign(ev_ref)).max()
 
 
-def test_lanczos_tiny_nodes(cuda_device):
+def test_lanczos_cluster_sizes(cuda_device):
+    """One connected block per cluster-size class (1, 2, 4, 8, 16 CTAs) plus one above the cluster limit."""
+    api = _api()
+    from autoinst_b200.synthetic import make_chunk
+    import scipy.sparse.csgraph as csg
+    ch = make_chunk(41, n_target=9000, features="tarl")
+    A = affinity_ref(ch.points, ch.tarl, alpha=1.0, theta=0.5)
+    ncomp, lab = csg.connected_components(sp.csr_matrix(A))
+    sizes = np.bincount(lab)
+    picks = {}
+    for c in np.argsort(-sizes):
+        n = int(sizes[c])
+        cls = 0 if n <= 320 else 1 if n <= 640 else 2 if n <= 1024 else 3 if n <= 1536 else 4
+        picks.setdefault(cls, c)
+    assert len(picks) >= 3
+    mats, offs, ns = [], [], []
+    off = 1
+    for cls, c in sorted(picks.items()):
+        idx = np.where(lab == c)[0]
+        mats.append(A[np.ix_(idx, idx)].astype(np.float32)); offs.append(off); ns.append(len(idx)); off += len(idx) + 3
+    W = np.zeros((off, off), dtype=np.float32)
+    for B, o, n in zip(mats, offs, ns):
+        W[o:o + n, o:o + n] = B
+    ev, lam2, steps, conv = api.lanczos_fiedler(torch.as_tensor(W, device=cuda_device), offs, ns)
+    ev = ev.cpu().numpy()
+    for B, o, n, l2, c in zip(mats, offs, ns, lam2, conv):
+        with R.pinned_eigsh():
+            d, D, ev_ref, vals = R.fiedler_of_block(sp.csr_matrix(B.astype(np.float64)))
+        assert c == 1 and abs(l2 - vals[1]) < 1e-9
+        assert np.abs(ev[o:o + n] - R.canonical_sign(ev_ref)).max() < 1e-7
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_lanczos_tiny_nodes(cuda_device, impl):
     """n = 3 .. 6: the Krylov space is exhausted after n-1 steps and the result is exact."""
     api = _api()
     rng = np.random.default_rng(0)
@@ -125,7 +159,7 @@ def test_lanczos_tiny_nodes(cuda_device):
     W = np.zeros((off, off), dtype=np.float32)
     for B, o, n in zip(mats, offs, ns):
         W[o:o + n, o:o + n] = B
-    ev, lam2, steps, conv = api.lanczos_fiedler(torch.as_tensor(W, device=cuda_device), offs, ns)
+    ev, lam2, steps, conv = api.lanczos_fiedler(torch.as_tensor(W, device=cuda_device), offs, ns, lanczos_impl=impl)
     ev = ev.cpu().numpy()
     for B, o, n, l2 in zip(mats, offs, ns, lam2):
         Wf = B.astype(np.float64) + np.eye(n)
