@@ -47,9 +47,9 @@ def gather_labels(local_ids, local_labels, num_chunks: int, group=None, device=N
     for j, (i, lab) in enumerate(zip(local_ids, local_labels)):
         meta[j, 0] = i
         meta[j, 1] = len(lab)
-    metas = torch.empty((world,) + tuple(meta.shape), dtype=torch.int64, device=device)
+    metas = torch.empty((world * meta.shape[0], 2), dtype=torch.int64, device=device)      # concatenated form
     dist.all_gather_into_tensor(metas, meta, group=group)
-    metas_h = metas.cpu().numpy()
+    metas_h = metas.cpu().numpy().reshape(world, meta.shape[0], 2)
     totals = [int(m[m[:, 0] >= 0, 1].sum()) for m in metas_h]
     pad = max(max(totals), 1)
     flat = torch.zeros(pad, dtype=torch.int32, device=device)
@@ -58,9 +58,9 @@ def gather_labels(local_ids, local_labels, num_chunks: int, group=None, device=N
         t = lab if isinstance(lab, torch.Tensor) else torch.as_tensor(np.asarray(lab, dtype=np.int32))
         flat[o:o + len(t)] = t.to(device=device, dtype=torch.int32)
         o += len(t)
-    allflat = torch.empty((world, pad), dtype=torch.int32, device=device)
+    allflat = torch.empty(world * pad, dtype=torch.int32, device=device)
     dist.all_gather_into_tensor(allflat, flat, group=group)
-    allflat_h = allflat.cpu().numpy()
+    allflat_h = allflat.cpu().numpy().reshape(world, pad)
     out = [None] * num_chunks
     for r in range(world):
         o = 0
