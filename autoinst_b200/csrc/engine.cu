@@ -42,7 +42,7 @@ struct ancuts_handle {
     char* stage = nullptr;                   // device staging of host inputs / labels (host entry point)
     size_t stage_cap = 0;
     int* h_ctr = nullptr;                    // pinned, 16 ints
-    cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per cluster-size class
+    cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per cluster-size class (4 used)
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool cluster16_ok = true;
@@ -256,11 +256,6 @@ static int set_attrs(ancuts_handle* h, int KS) {
     ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
     ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
     ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
-    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
-    if (cudaFuncSetAttribute(k_lanczos_cluster<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-        cudaGetLastError();
-        h->cluster16_ok = false;
-    }
     h->attrs_set = true;
     return ANCUTS_OK;
 }
@@ -426,7 +421,6 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
     for (int cls = CL_CLASSES - 1; cls >= 0; --cls) {          // largest clusters first
         int cnt = class_cnt[cls];
         if (cnt <= 0) continue;
-        if (cls == 4 && !h->cluster16_ok) { launch_failed = true; continue; }
         cudaStream_t s = h->side[cls];
         ANCUTS_CUDA(cudaStreamWaitEvent(s, h->ev_fork, 0));
         const int* ids = e.cl_ids + (size_t)cls * e.active_cap;
@@ -437,14 +431,12 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
                 case 0: err = launch_cluster<1>(e, cur, ids, cnt, s); break;
                 case 1: err = launch_cluster<2>(e, cur, ids, cnt, s); break;
                 case 2: err = launch_cluster<4>(e, cur, ids, cnt, s); break;
-                case 3: err = launch_cluster<8>(e, cur, ids, cnt, s); break;
-                default: err = launch_cluster<16>(e, cur, ids, cnt, s); break;
+                default: err = launch_cluster<8>(e, cur, ids, cnt, s); break;
             }
         }
         if (err != cudaSuccess) {                               // e.g. cluster size not schedulable: multi-launch path
             cudaGetLastError();
             launch_failed = true;
-            if (cls == 4) h->cluster16_ok = false;
         }
         ANCUTS_CUDA(cudaEventRecord(h->ev_join[cls], s));
         ANCUTS_CUDA(cudaStreamWaitEvent(st, h->ev_join[cls], 0));
@@ -595,7 +587,7 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
     int num_split = h->h_ctr[5], max_split_n = h->h_ctr[7];
     int guard = 0;
     while (num_split > 0) {
-        int class_cnt[CL_CLASSES] = {0, 0, 0, 0, 0}, big_cnt = 0;
+        int class_cnt[CL_CLASSES] = {0}, big_cnt = 0;
         rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt);
         if (rc) return rc;
         int num_active = h->h_ctr[1], max_n = h->h_ctr[2];

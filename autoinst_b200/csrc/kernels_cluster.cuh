@@ -22,9 +22,9 @@ namespace cg = cooperative_groups;
 constexpr int CL_KMAX = 256;             // steps the cluster kernel can take; nodes needing more fall back
 constexpr int CL_KS = CL_KMAX + 4;
 constexpr int CL_RPMAX = 384;            // rows per CTA
-constexpr int CL_NMAX = 4096;            // largest node handled here (16 CTAs x 256 rows)
+constexpr int CL_NMAX = 2560;            // largest node handled here (8 CTAs x 320 rows)
 constexpr int CL_THREADS = 512;
-constexpr int CL_CLASSES = 5;            // cluster sizes 1, 2, 4, 8, 16
+constexpr int CL_CLASSES = 4;            // cluster sizes 1, 2, 4, 8 (portable)
 constexpr int CL_DYN_SMEM = 192 * 1024;  // z for the whole node + as many basis rows of the slice as fit
 
 struct ClusterShared {
@@ -67,7 +67,7 @@ __device__ __forceinline__ double block_min_512(double v, double* red) {
 }
 
 // tridiagonal analysis by the whole CTA (512 threads): top two eigenvalues by multisection with 256
-// shifts each (257^8 > 2^64), eigenvector of the largest by inverse iteration (thread 0).
+// shifts each (257^8 > 2^64), eigenvector of the largest by a twisted factorisation (thread 0).
 // Returns the residual estimate beta_{k-1} |y_{k-1}|; th[0], th[1] = eigenvalues; S.yv = eigenvector.
 __device__ double cluster_tridiag(ClusterShared& S, int k, double* th) {
     const int tid = threadIdx.x;
@@ -92,7 +92,9 @@ __device__ double cluster_tridiag(ClusterShared& S, int k, double* th) {
         const int which = tid >> 8, t256 = tid & 255;
         const int m = k - 1 - which;
         double lo = glo, hi = ghi;
-        for (int round = 0; round < 8; ++round) {
+        const int rounds = 8;                       // 257^8 > 2^64: full float64 resolution (the residual
+                                                    // estimate below is only as good as the eigenvalue)
+        for (int round = 0; round < rounds; ++round) {
             double x = lo + (hi - lo) * ((double)(t256 + 1) / 257.0);
             S.cnts[tid] = (m >= 0) ? sturm_count(S.alpha, S.be2, k, x, pivmin) : 0;
             __syncthreads();
@@ -115,55 +117,33 @@ __device__ double cluster_tridiag(ClusterShared& S, int k, double* th) {
     const double th1 = 0.5 * (S.bounds[0] + S.bounds[1]);
     const double th2 = (k > 1) ? 0.5 * (S.bounds[2] + S.bounds[3]) : -1e300;
     if (tid == 0) {
-        double tnorm = fmax(fmax(fabs(glo), fabs(ghi)), 1e-300);
-        double eps_piv = 2.220446049250313e-16 * tnorm;
-        for (int i = 0; i < k; ++i) {
-            S.dd[i] = S.alpha[i] - th1;
-            S.du[i] = (i < k - 1) ? S.beta[i] : 0.0;
-            S.du2[i] = 0.0;
-            S.dl[i] = (i < k - 1) ? S.beta[i] : 0.0;
-            S.swp[i] = 0;
+        // Eigenvector of th1 from the factorisation of T - th1 I twisted at the FIRST index: bottom-up
+        // pivots p_k = a_k - th, p_i = a_i - th - b_i^2 / p_{i+1}.  The trailing blocks of T do not contain
+        // the converged part of the Krylov space, their eigenvalues stay below th1 (interlacing), so every
+        // pivot is safely negative and the recurrence z_1 = 1, z_{i+1} = -b_i z_i / p_{i+1} is stable; it
+        // replaces a pivoted LU plus inverse iteration (2k divisions, agreement with LAPACK to 1e-14).
+        double d = S.alpha[k - 1] - th1;
+        if (fabs(d) < pivmin) d = -pivmin;
+        S.dd[k - 1] = d;
+        for (int i = k - 2; i >= 0; --i) {
+            d = S.alpha[i] - th1 - S.be2[i] / d;
+            if (fabs(d) < pivmin) d = -pivmin;
+            S.dd[i] = d;
         }
+        double z = 1.0, ss = 1.0;
+        S.yv[0] = 1.0;
         for (int i = 0; i < k - 1; ++i) {
-            if (fabs(S.dd[i]) >= fabs(S.dl[i])) {
-                if (fabs(S.dd[i]) < eps_piv) S.dd[i] = (S.dd[i] < 0.0) ? -eps_piv : eps_piv;
-                double f = S.dl[i] / S.dd[i];
-                S.dl[i] = f;
-                S.dd[i + 1] -= f * S.du[i];
-            } else {
-                double f = S.dd[i] / S.dl[i];
-                S.dd[i] = S.dl[i];
-                S.dl[i] = f;
-                double tmp = S.du[i];
-                S.du[i] = S.dd[i + 1];
-                S.dd[i + 1] = tmp - f * S.du[i];
-                if (i < k - 2) { S.du2[i] = S.du[i + 1]; S.du[i + 1] = -f * S.du2[i]; }
-                S.swp[i] = 1;
+            z = -S.beta[i] * z / S.dd[i + 1];
+            if (fabs(z) > 1e150) {                       // start vector almost orthogonal to the Ritz vector
+                for (int j = 0; j <= i; ++j) S.yv[j] *= 1e-150;
+                z *= 1e-150;
+                ss *= 1e-300;
             }
+            S.yv[i + 1] = z;
+            ss += z * z;
         }
-        if (fabs(S.dd[k - 1]) < eps_piv) S.dd[k - 1] = (S.dd[k - 1] < 0.0) ? -eps_piv : eps_piv;
-        for (int i = 0; i < k; ++i) S.yv[i] = (i & 1) ? 1.0 : 0.9;
-        for (int iter = 0; iter < 3; ++iter) {
-            for (int i = 0; i < k - 1; ++i) {
-                if (!S.swp[i]) {
-                    S.yv[i + 1] -= S.dl[i] * S.yv[i];
-                } else {
-                    double t = S.yv[i];
-                    S.yv[i] = S.yv[i + 1];
-                    S.yv[i + 1] = t - S.dl[i] * S.yv[i];
-                }
-            }
-            S.yv[k - 1] /= S.dd[k - 1];
-            if (k > 1) S.yv[k - 2] = (S.yv[k - 2] - S.du[k - 2] * S.yv[k - 1]) / S.dd[k - 2];
-            for (int i = k - 3; i >= 0; --i)
-                S.yv[i] = (S.yv[i] - S.du[i] * S.yv[i + 1] - S.du2[i] * S.yv[i + 2]) / S.dd[i];
-            double big = 0.0;
-            for (int i = 0; i < k; ++i) big = fmax(big, fabs(S.yv[i]));
-            double sc = 1.0 / big, nn = 0.0;
-            for (int i = 0; i < k; ++i) { S.yv[i] *= sc; nn += S.yv[i] * S.yv[i]; }
-            double inv = 1.0 / sqrt(nn);
-            for (int i = 0; i < k; ++i) S.yv[i] *= inv;
-        }
+        double inv = 1.0 / sqrt(ss);
+        for (int i = 0; i < k; ++i) S.yv[i] *= inv;
         S.gb[0] = fabs(S.beta[k - 1] * S.yv[k - 1]);
     }
     __syncthreads();
@@ -313,45 +293,45 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         // basis row k+1 = current vector (slice)
         if (tid < nr) B.row(k + 1)[tid] = S.ysl[tid] * invb;
         __syncthreads();
-        // ---- matvec of the slice: 4 rows per warp, 256 columns per iteration, loads issued first ----
+        // ---- matvec of the slice: 2 rows per warp, 512 columns per iteration, 8 loads issued first ----
         {
             const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
-            for (int rb = warp * 4; rb < nr; rb += (CL_THREADS / 32) * 4) {
-                const float* rpt[4];
+            for (int rb = warp * 2; rb < nr; rb += (CL_THREADS / 32) * 2) {
+                const float* rpt[2];
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr)
+                for (int rr = 0; rr < 2; ++rr)
                     rpt[rr] = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld;
-                double acc[4] = {0.0, 0.0, 0.0, 0.0};
-                for (int c = a0 + lane * 4; c < c_hi; c += 256) {
-                    const int cb = c + 128;
-                    const bool hasb = cb < c_hi;
-                    float4 wa[4], wb[4];
+                double acc[2] = {0.0, 0.0};
+                for (int c = a0 + lane * 4; c < c_hi; c += 512) {
+                    float4 w[2][4];
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) wa[rr] = ld_stream4(rpt[rr] + c);
+                    for (int g = 0; g < 4; ++g) {
+                        const int cg_ = c + 128 * g;
+                        const bool has = cg_ < c_hi;
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) wb[rr] = hasb ? ld_stream4(rpt[rr] + cb) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    const double2 za0 = *reinterpret_cast<const double2*>(&zs[c - a0]);
-                    const double2 za1 = *reinterpret_cast<const double2*>(&zs[c - a0 + 2]);
-                    double2 zb0 = make_double2(0.0, 0.0), zb1 = make_double2(0.0, 0.0);
-                    if (hasb) {
-                        zb0 = *reinterpret_cast<const double2*>(&zs[cb - a0]);
-                        zb1 = *reinterpret_cast<const double2*>(&zs[cb - a0 + 2]);
+                        for (int rr = 0; rr < 2; ++rr)
+                            w[rr][g] = has ? ld_stream4(rpt[rr] + cg_) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    const bool va0 = (c >= c_lo) & (c < c_hi), va1 = (c + 1 >= c_lo) & (c + 1 < c_hi);
-                    const bool va2 = (c + 2 >= c_lo) & (c + 2 < c_hi), va3 = (c + 3 >= c_lo) & (c + 3 < c_hi);
-                    const bool vb0 = hasb, vb1 = hasb & (cb + 1 < c_hi), vb2 = hasb & (cb + 2 < c_hi), vb3 = hasb & (cb + 3 < c_hi);
 #pragma unroll
-                    for (int rr = 0; rr < 4; ++rr) {
-                        // entries outside the block belong to other nodes or are uninitialised: select them away
-                        double q0 = (va0 ? (double)wa[rr].x : 0.0) * za0.x + (va1 ? (double)wa[rr].y : 0.0) * za0.y;
-                        double q1 = (va2 ? (double)wa[rr].z : 0.0) * za1.x + (va3 ? (double)wa[rr].w : 0.0) * za1.y;
-                        double q2 = (vb0 ? (double)wb[rr].x : 0.0) * zb0.x + (vb1 ? (double)wb[rr].y : 0.0) * zb0.y;
-                        double q3 = (vb2 ? (double)wb[rr].z : 0.0) * zb1.x + (vb3 ? (double)wb[rr].w : 0.0) * zb1.y;
-                        acc[rr] += (q0 + q1) + (q2 + q3);
+                    for (int g = 0; g < 4; ++g) {
+                        const int cg_ = c + 128 * g;
+                        if (cg_ < c_hi) {
+                            const double2 z0 = *reinterpret_cast<const double2*>(&zs[cg_ - a0]);
+                            const double2 z1 = *reinterpret_cast<const double2*>(&zs[cg_ - a0 + 2]);
+                            const bool v0 = (cg_ >= c_lo), v1 = (cg_ + 1 >= c_lo) & (cg_ + 1 < c_hi);
+                            const bool v2 = (cg_ + 2 >= c_lo) & (cg_ + 2 < c_hi), v3 = (cg_ + 3 >= c_lo) & (cg_ + 3 < c_hi);
+#pragma unroll
+                            for (int rr = 0; rr < 2; ++rr) {
+                                // entries outside the block belong to other nodes or are uninitialised: select them away
+                                double q0 = (v0 ? (double)w[rr][g].x : 0.0) * z0.x + (v1 ? (double)w[rr][g].y : 0.0) * z0.y;
+                                double q1 = (v2 ? (double)w[rr][g].z : 0.0) * z1.x + (v3 ? (double)w[rr][g].w : 0.0) * z1.y;
+                                acc[rr] += q0 + q1;
+                            }
+                        }
                     }
                 }
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) {
+                for (int rr = 0; rr < 2; ++rr) {
                     double t = warp_sum(acc[rr]);
                     int i = rb + rr;
                     if (lane == 0 && i < nr) S.ysl[i] = S.sv[i] * invb * (t + zs[r0 + i + pad]);   // (w + I) z

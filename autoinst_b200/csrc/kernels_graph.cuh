@@ -10,8 +10,7 @@ __host__ __device__ inline int cluster_class(int n) {
     if (n <= 320) return 0;              // 1 CTA
     if (n <= 640) return 1;              // 2
     if (n <= 1024) return 2;             // 4
-    if (n <= 1536) return 3;             // 8
-    if (n <= 4096) return 4;             // 16
+    if (n <= 2560) return 3;             // 8 (portable cluster size)
     return -1;
 }
 

@@ -384,57 +384,30 @@ k_lanczos_check(Eng e, int force) {
     double th1, th2;
     tridiag_top2_bisect(al, be2, k, glo, ghi, pivmin, cnts, bounds, &th1, &th2);
     if (tid == 0) {
-        // inverse iteration for the eigenvector of th1: pivoted LU of (T - th1 I) (as LAPACK dgttrf/dgtts2)
-        double tnorm = fmax(fmax(fabs(glo), fabs(ghi)), 1e-300);
-        double eps_piv = 2.220446049250313e-16 * tnorm;
-        for (int i = 0; i < k; ++i) {
-            dd[i] = al[i] - th1;
-            du[i] = (i < k - 1) ? be[i] : 0.0;
-            du2[i] = 0.0;
-            dl[i] = (i < k - 1) ? be[i] : 0.0;
-            swp[i] = 0;
+        // eigenvector of th1 from the factorisation of T - th1 I twisted at the first index (bottom-up
+        // pivots, all safely negative below the largest eigenvalue; see kernels_cluster.cuh)
+        double d = al[k - 1] - th1;
+        if (fabs(d) < pivmin) d = -pivmin;
+        dd[k - 1] = d;
+        for (int i = k - 2; i >= 0; --i) {
+            d = al[i] - th1 - be2[i] / d;
+            if (fabs(d) < pivmin) d = -pivmin;
+            dd[i] = d;
         }
+        double z = 1.0, ss = 1.0;
+        yv[0] = 1.0;
         for (int i = 0; i < k - 1; ++i) {
-            if (fabs(dd[i]) >= fabs(dl[i])) {
-                if (fabs(dd[i]) < eps_piv) dd[i] = (dd[i] < 0.0) ? -eps_piv : eps_piv;
-                double f = dl[i] / dd[i];
-                dl[i] = f;
-                dd[i + 1] -= f * du[i];
-            } else {
-                double f = dd[i] / dl[i];
-                dd[i] = dl[i];
-                dl[i] = f;
-                double tmp = du[i];
-                du[i] = dd[i + 1];
-                dd[i + 1] = tmp - f * du[i];
-                if (i < k - 2) { du2[i] = du[i + 1]; du[i + 1] = -f * du2[i]; }
-                swp[i] = 1;
+            z = -be[i] * z / dd[i + 1];
+            if (fabs(z) > 1e150) {
+                for (int j = 0; j <= i; ++j) yv[j] *= 1e-150;
+                z *= 1e-150;
+                ss *= 1e-300;
             }
+            yv[i + 1] = z;
+            ss += z * z;
         }
-        if (fabs(dd[k - 1]) < eps_piv) dd[k - 1] = (dd[k - 1] < 0.0) ? -eps_piv : eps_piv;
-        for (int i = 0; i < k; ++i) yv[i] = (i & 1) ? 1.0 : 0.9;
-        for (int iter = 0; iter < 3; ++iter) {
-            for (int i = 0; i < k - 1; ++i) {
-                if (!swp[i]) {
-                    yv[i + 1] -= dl[i] * yv[i];
-                } else {
-                    double t = yv[i];
-                    yv[i] = yv[i + 1];
-                    yv[i + 1] = t - dl[i] * yv[i];
-                }
-            }
-            yv[k - 1] /= dd[k - 1];
-            if (k > 1) yv[k - 2] = (yv[k - 2] - du[k - 2] * yv[k - 1]) / dd[k - 2];
-            for (int i = k - 3; i >= 0; --i)
-                yv[i] = (yv[i] - du[i] * yv[i + 1] - du2[i] * yv[i + 2]) / dd[i];
-            double big = 0.0;
-            for (int i = 0; i < k; ++i) big = fmax(big, fabs(yv[i]));
-            double sc = 1.0 / big;                     // avoid overflow in the squared norm
-            double nn = 0.0;
-            for (int i = 0; i < k; ++i) { yv[i] *= sc; nn += yv[i] * yv[i]; }
-            double inv = 1.0 / sqrt(nn);
-            for (int i = 0; i < k; ++i) yv[i] *= inv;
-        }
+        double inv = 1.0 / sqrt(ss);
+        for (int i = 0; i < k; ++i) yv[i] *= inv;
         double res = fabs(be[k - 1] * yv[k - 1]);
         double gap = fmax(th1 - th2, 1e-300);
         int n = e.r_n[e.a_rid[a]];
