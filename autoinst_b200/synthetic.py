@@ -211,20 +211,82 @@ def make_chunk(chunk_id: int = 0, n_target: int = 8192, features: str = "tarl_di
     return ch
 
 
-def make_map(n_chunks: int = 40, n_range=(3000, 12000), features: str = "tarl",
-             seed: int = 77, clutter: int = 0) -> list[Chunk]:
-    """Synthetic "first map": chunks along a gently curving path, 22 m apart
-    (`chunk_generation.py:123-125`), N_major drawn from n_range."""
+def make_map(n_chunks: int = 8, n_per_chunk: int = 4096, features: str = "tarl", seed: int = 77,
+             background_facades: bool = True) -> list[Chunk]:
+    """Synthetic "first map": ONE scene along a straight 25 m wide corridor, voxelised once at 0.35 m, then
+    cut into 25 m cubes every 22 m (`chunk_generation.py:123-137`, OVERLAP = 3 m, `config.py:58`), so that
+    neighbouring chunks share instances and, in the 3 m overlap, exactly the same points — what the
+    reference's merge relies on (`point_cloud_utils.py:387-491`).
+    Facades are "stuff": their GT instance id is 0 (background) when background_facades is set, like
+    buildings in SemanticKITTI; they exercise `remove_semantics`.
+    Chunk.instance holds the map-level GT instance id (0 = background)."""
     rng = np.random.default_rng(seed)
+    half = CHUNK_EDGE / 2
+    length = 22.0 * (n_chunks - 1) + CHUNK_EDGE
+    kinds = ["facade", "car", "car", "veg", "car", "veg", "car", "car"]
+    per_kind = {"facade": 900.0, "car": 285.0, "veg": 520.0}
+    target = n_per_chunk * length / CHUNK_EDGE
+    pts, inst, boxes, is_bg = [], [], [], []
+    total, o = 0.0, 0
+    while total < 0.9 * target and o < 100000:
+        kind = kinds[o % len(kinds)]
+        o += 1
+        p = _make_object(rng, kind)
+        lo0, hi0 = p.min(0), p.max(0)
+        for _ in range(40):
+            shift = np.array([rng.uniform(0.5, length - 0.5), rng.uniform(-half + 0.5, half - 0.5),
+                              rng.uniform(-half + 0.3, half - 0.3)]) - (lo0 + hi0) / 2
+            shift[2] = rng.uniform(-half + 0.3, half - 0.3 - (hi0[2] - lo0[2])) - lo0[2]
+            lo, hi = lo0 + shift, hi0 + shift
+            if lo[0] < 0 or hi[0] > length or lo[1] < -half or hi[1] > half:
+                continue
+            if all(_aabb_gap(lo, hi, bl, bh) > 1.3 for bl, bh in boxes):
+                boxes.append((lo, hi))
+                pts.append(p + shift)
+                inst.append(np.full(p.shape[0], len(boxes), dtype=np.int32))
+                is_bg.append(kind == "facade" and background_facades)
+                total += per_kind[kind]
+                break
+    pts = np.concatenate(pts)
+    inst = np.concatenate(inst)
+    pm, im = voxel_centroid_downsample(pts, MAJOR_VOXEL, inst)
+    while True:                                                 # every component well above the 1 % size limit
+        ncomp, lab = _components(pm, PROXIMITY)
+        size = np.bincount(lab, minlength=ncomp)
+        keep = size[lab] > 0.03 * n_per_chunk
+        if keep.all():
+            break
+        pm, im = pm[keep], im[keep]
+    pm = pm.astype(np.float32).astype(np.float64)
+    gt = im.copy()
+    for k, bg in enumerate(is_bg):
+        if bg:
+            gt[im == k + 1] = 0
+    n_inst = int(im.max()) + 1
+    proto_t = rng.normal(0, 1, size=(n_inst, 96))
+    tarl_all = (proto_t[im] + 0.3 * rng.normal(0, 1, size=(pm.shape[0], 96))).astype(np.float32)
+    tarl_all[rng.random(pm.shape[0]) < 0.05] = 0.0
+    dino_all = None
+    if "dino" in features:
+        proto_d = rng.normal(0, 1, size=(n_inst, 384))
+        dino_all = (proto_d[im] + 0.3 * rng.normal(0, 1, size=(pm.shape[0], 384))).astype(np.float32)
+        dino_all[rng.random(pm.shape[0]) < 0.30] = 0.0
     chunks = []
-    pos = np.zeros(3)
-    heading = 0.0
     for c in range(n_chunks):
-        n_t = int(rng.integers(n_range[0], n_range[1]))
-        chunks.append(make_chunk(chunk_id=c, n_target=n_t, features=features, clutter=clutter,
-                                 center=pos.copy(), seed_base=seed * 1000))
-        heading += rng.normal(0, 0.08)
-        pos = pos + 22.0 * np.array([np.cos(heading), np.sin(heading), 0.0])
+        cx = half + 22.0 * c
+        sel = np.where((pm[:, 0] > cx - half) & (pm[:, 0] < cx + half))[0]      # strictly inside (:131-137)
+        while True:                                             # objects sliced by the cube faces leave fragments:
+            ncomp, lab = _components(pm[sel], PROXIMITY)        # keep the chunk free of components near the 1 % limit
+            size = np.bincount(lab, minlength=ncomp)
+            keep = size[lab] > 0.02 * sel.shape[0]
+            if keep.all():
+                break
+            sel = sel[keep]
+        sel = sel[rng.permutation(sel.shape[0])]
+        ch = Chunk(chunk_id=c, points=pm[sel], instance=gt[sel], center=np.array([cx, 0.0, 0.0]))
+        ch.tarl = tarl_all[sel].astype(np.float64) if "tarl" in features else None
+        ch.dino = dino_all[sel].astype(np.float64) if dino_all is not None else None
+        chunks.append(ch)
     return chunks
 
 

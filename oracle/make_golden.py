@@ -201,6 +201,56 @@ def main():
             kat[f"{name}_T{T}_labels"] = R.labels_from_groups(g_ref, w.shape[0])
             print(f"KAT {name} T={T}: {[list(map(int, g)) for g in g_ref]}")
     np.savez_compressed(os.path.join(OUT, "known_answers.npz"), **kat)
+    golden_metrics()
+
+
+def golden_metrics():
+    """Run the reference's own Metrics class (`pipeline/metrics/metrics_class.py`) on seeded label arrays and
+    check oracle.metrics_ref against it; store inputs + reference outputs in tests/golden/metrics.npz."""
+    from oracle.metrics_ref import instance_metrics
+    cwd = os.getcwd()
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    stash = {m: sys.modules.pop(m) for m in [k for k in sys.modules if k == "config" or k == "metrics" or k.startswith("metrics.")]}
+    try:
+        import metrics.metrics_class as mc
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+    out = {}
+    rng = np.random.default_rng(42)
+    for case in range(4):
+        n = 6000
+        n_gt = 6 + case
+        gt = rng.integers(0, n_gt + 1, size=n)
+        gt = np.sort(gt)                                        # contiguous instances
+        pred = gt.copy()
+        # perturb: split some instances, merge others, add noise and a background-heavy prediction
+        pred[(gt == 2) & (rng.random(n) < 0.5)] = n_gt + 5
+        pred[gt == 4] = 3
+        noise = rng.random(n) < (0.03 + 0.02 * case)
+        pred[noise] = rng.integers(0, n_gt + 8, size=int(noise.sum()))
+        allp = pred.copy()
+        pred2 = pred.copy()
+        pred2[pred2 == 1] = 0                                   # what remove_semantics would do
+        for mp in (200, 20):
+            m = mc.Metrics(name=f"golden{case}", min_points=mp)
+            ref_out, ref_ap = m.update_stats(allp.copy(), pred2.copy(), gt.copy())
+            ref = {"p": ref_out["precision"], "r": ref_out["recall"], "f1": ref_out["fScore"], "ap": ref_ap["ap"],
+                   "ap0.25": ref_ap["0.25"], "ap0.5": ref_ap["0.5"], "S_assoc": ref_ap["lstq"]}
+            mine = instance_metrics(allp, pred2, gt, min_points=mp)
+            for k in ref:
+                if not np.isclose(ref[k], mine[k], rtol=0, atol=1e-12):
+                    raise SystemExit(f"oracle metrics differ from the reference: case {case} min_points {mp} {k}: {ref[k]} vs {mine[k]}")
+            out[f"c{case}_mp{mp}_ref"] = np.array([ref[k] for k in ("p", "r", "f1", "ap", "ap0.25", "ap0.5", "S_assoc")])
+            print(f"metrics case {case} min_points {mp}:", {k: round(float(v), 4) for k, v in ref.items()})
+        out[f"c{case}_all"] = allp
+        out[f"c{case}_pred"] = pred2
+        out[f"c{case}_gt"] = gt
+    for m_ in [k for k in sys.modules if k == "config" or k == "metrics" or k.startswith("metrics.")]:
+        sys.modules.pop(m_)
+    sys.modules.update(stash)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
 
 
 if __name__ == "__main__":

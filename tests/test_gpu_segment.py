@@ -108,3 +108,31 @@ def test_edge_cases(cuda_device):
     assert lab.shape == (chc.n,) and lab.min() == 0 and len(set(lab.tolist())) == lab.max() + 1
     with pytest.raises(NotImplementedError):
         api.make_params(beta=0.5)
+
+
+def test_map_level_metrics_match_oracle(cuda_device):
+    """north_star level 3: AP, P/R/F1, S_assoc from GPU labels vs oracle labels, both through the same merge
+    (oracle.merge_ref) and the same metrics (oracle.metrics_ref, pinned to the reference's Metrics class)."""
+    from autoinst_b200.synthetic import make_map
+    from oracle import merge_ref as M
+    from oracle.metrics_ref import instance_metrics
+    cfg = CONFIGS["tarl_spatial"]
+    chunks = make_map(5, 2000, seed=9)
+    res = _api().segment_chunks([c.points for c in chunks], [c.tarl for c in chunks], alpha=cfg["alpha"],
+                                theta=cfg["theta"], T=cfg["T"], device=cuda_device)
+    gt_pts, gt_lab = M.merge_unite_gt([(c.points, c.instance) for c in chunks])
+    gt = M.compact_labels(gt_lab)
+
+    def evaluate(per_chunk_labels):
+        parts = [(c.points, M.globally_unique(c.chunk_id, lab)) for c, lab in zip(chunks, per_chunk_labels)]
+        pts, lab = M.merge_chunks_unite_instances(parts)
+        assert np.array_equal(pts, gt_pts)
+        allp = M.compact_labels(lab)
+        inst = M.remove_semantics(gt, allp.copy())
+        return instance_metrics(allp, inst, gt, min_points=20)      # major-level evaluation (SURVEY Appendix A item 10)
+
+    got = evaluate(res.labels)
+    ref = evaluate([oracle_labels(c, cfg) for c in chunks])
+    for k in ("p", "r", "f1", "ap", "ap0.25", "ap0.5", "S_assoc"):
+        assert abs(got[k] - ref[k]) <= 1e-3, (k, got[k], ref[k])    # 0.1 points
+    assert ref["S_assoc"] > 0.3 and ref["ap0.25"] > 0.2              # the comparison is not vacuous

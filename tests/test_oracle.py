@@ -110,3 +110,34 @@ def test_device_model_matches_oracle_on_a_chunk():
         g = R.normalized_cut_ref(sp.csr_matrix(A), ch.n, np.arange(ch.n), T=cfg["T"])
     lab = segment_model(A.astype(np.float32), cfg["T"])
     assert R.same_partition(lab, R.labels_from_groups(g, ch.n))
+
+
+def test_metrics_ref_matches_reference_golden():
+    """oracle.metrics_ref against the outputs of the reference's own Metrics class (tests/golden/metrics.npz)."""
+    from oracle.metrics_ref import instance_metrics
+    g = np.load(f"{GOLDEN}/metrics.npz")
+    keys = ("p", "r", "f1", "ap", "ap0.25", "ap0.5", "S_assoc")
+    for case in range(4):
+        for mp in (200, 20):
+            got = instance_metrics(g[f"c{case}_all"], g[f"c{case}_pred"], g[f"c{case}_gt"], min_points=mp)
+            assert np.allclose([got[k] for k in keys], g[f"c{case}_mp{mp}_ref"], rtol=0, atol=1e-12)
+
+
+def test_merge_ref_unites_instances_across_overlapping_chunks():
+    from autoinst_b200.synthetic import make_map
+    from oracle import merge_ref as M
+    chunks = make_map(4, 1500, seed=5)
+    # GT labels as "predictions": every instance seen by two chunks must end up with ONE merged label
+    parts = [(c.points, M.globally_unique(c.chunk_id, c.instance) * (c.instance != 0)) for c in chunks]
+    pts, lab = M.merge_chunks_unite_instances(parts)
+    gpts, glab = M.merge_unite_gt([(c.points, c.instance) for c in chunks])
+    assert pts.shape == gpts.shape and np.array_equal(pts, gpts)          # same de-duplicated map
+    assert len(pts) < sum(c.n for c in chunks)                            # the 3 m overlaps were de-duplicated
+    for g in np.unique(glab):
+        if g == 0:
+            continue
+        assert len(np.unique(lab[glab == g])) == 1, g
+    pred = M.compact_labels(lab)
+    assert pred.min() == 0 and (pred == 0).sum() == (glab == 0).sum()
+    cleaned = M.remove_semantics(M.compact_labels(glab), pred)
+    assert np.array_equal(cleaned, pred)                                   # nothing sits on GT background here
