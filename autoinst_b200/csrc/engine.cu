@@ -416,6 +416,9 @@ static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int cou
 static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n, const int* class_cnt,
                            int big_cnt, cudaStream_t st) {
     ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 4, 0, sizeof(int), st));
+    // one timed "launch" per level: the concurrent cluster kernels from fork to join on the launching stream
+    cudaEvent_t t_a = nullptr, t_b = nullptr;
+    if (h->stage_timing) { t_a = take_event(h); t_b = take_event(h); cudaEventRecord(t_a, st); }
     ANCUTS_CUDA(cudaEventRecord(h->ev_fork, st));
     bool any = false, launch_failed = false;
     for (int cls = CL_CLASSES - 1; cls >= 0; --cls) {          // largest clusters first
@@ -426,7 +429,7 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
         const int* ids = e.cl_ids + (size_t)cls * e.active_cap;
         cudaError_t err = cudaSuccess;
         {
-            LaunchScope ls(h, SG_MATVEC, s);
+            h->launches_total++;
             switch (cls) {
                 case 0: err = launch_cluster<1>(e, cur, ids, cnt, s); break;
                 case 1: err = launch_cluster<2>(e, cur, ids, cnt, s); break;
@@ -441,6 +444,10 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
         ANCUTS_CUDA(cudaEventRecord(h->ev_join[cls], s));
         ANCUTS_CUDA(cudaStreamWaitEvent(st, h->ev_join[cls], 0));
         any = true;
+    }
+    if (any) {
+        h->stage_launches[SG_MATVEC]++;
+        if (t_b) { cudaEventRecord(t_b, st); h->timed.push_back({SG_MATVEC, t_a, t_b}); }
     }
     int rest = big_cnt;
     if (any || launch_failed) {
@@ -763,7 +770,7 @@ int ancuts_degree_normalize_f32(ancuts_handle* h, int n, const float* d_W, int64
     begin_accounting(h);
     LAUNCH(SG_DEGREE, k_degree_dense<<<(n + 7) / 8, 256, 0, st>>>(n, d_W, ld, d_deg));
     if (d_M) {
-        dim3 g((n + 1023) / 1024, n);
+        dim3 g((n + 1023) / 1024, (n + 15) / 16);
         LAUNCH(SG_DEGREE, k_normalize_dense<<<g, 256, 0, st>>>(n, d_W, ld, d_deg, d_M, ldm));
     }
     ANCUTS_CUDA(cudaGetLastError());

@@ -78,6 +78,8 @@ k_affinity_exact(int n, const double* __restrict__ pts, const float* __restrict_
                  float* __restrict__ W, long long ld) {
     __shared__ double pr[AT][3];
     __shared__ double pc[AT][3];
+    __shared__ float pr32[AT][3];           // coordinates relative to the tile's first row point: float32 pre-filter
+    __shared__ float pc32[AT][3];
     __shared__ __align__(16) float tile[AT][AT];
     __shared__ unsigned short queue[AT * AT];
     __shared__ int qn;
@@ -88,10 +90,19 @@ k_affinity_exact(int n, const double* __restrict__ pts, const float* __restrict_
     for (int i = tid; i < AT * 3; i += 256) {
         int p = i / 3, k = i % 3;
         int gr = row0 + p, gc = col0 + p;
-        pr[p][k] = gr < n ? pts[(size_t)gr * 3 + k] : 0.0;
-        pc[p][k] = gc < n ? pts[(size_t)gc * 3 + k] : 0.0;
+        double org = pts[(size_t)min(row0, n - 1) * 3 + k];
+        double a = gr < n ? pts[(size_t)gr * 3 + k] : 0.0;
+        double b = gc < n ? pts[(size_t)gc * 3 + k] : 0.0;
+        pr[p][k] = a;
+        pc[p][k] = b;
+        pr32[p][k] = (float)(a - org);
+        pc32[p][k] = (float)(b - org);
     }
     __syncthreads();
+    // pairs whose float32 distance exceeds prox by more than this margin are outside for certain (the
+    // float32 error of the relative coordinates is orders of magnitude smaller); every pair that might be
+    // inside still takes the exact float64 test below, so the result is unchanged
+    const float lim32 = (float)((prox + 1e-2) * (prox + 1e-2) * 1.001);
 
     const bool feats = (theta != 0.0 && tarl != nullptr) || (gamma != 0.0 && dino != nullptr);
     const int cg = (tid & 15) * 4, rg = tid >> 4;
@@ -102,7 +113,8 @@ k_affinity_exact(int n, const double* __restrict__ pts, const float* __restrict_
         for (int c4 = 0; c4 < 4; ++c4) {
             int c = cg + c4;
             float out = 0.0f;
-            if (row0 + r < n && col0 + c < n) {
+            float fx = pr32[r][0] - pc32[c][0], fy = pr32[r][1] - pc32[c][1], fz = pr32[r][2] - pc32[c][2];
+            if (row0 + r < n && col0 + c < n && !(fx * fx + fy * fy + fz * fz > lim32)) {
                 double dx = pr[r][0] - pc[c][0], dy = pr[r][1] - pc[c][1], dz = pr[r][2] - pc[c][2];
                 // cdist accumulates the squares one after another in float64 without contraction
                 double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
@@ -214,21 +226,30 @@ k_degree_dense(int n, const float* __restrict__ W, long long ld, double* __restr
 __global__ void __launch_bounds__(256)
 k_normalize_dense(int n, const float* __restrict__ W, long long ld, const double* __restrict__ deg,
                   float* __restrict__ M, long long ldm) {
-    int row = blockIdx.y;
     int c = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (c >= n) return;
-    double si = rsqrt(deg[row]);
-    float4 w = *reinterpret_cast<const float4*>(W + (size_t)row * ld + c);
-    float in[4] = {w.x, w.y, w.z, w.w};
-    float out[4];
+    double sc[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        int cc = c + k;
-        double x = 0.0;
-        if (cc < n) x = ((double)in[k] + (cc == row ? 1.0 : 0.0)) * si * rsqrt(deg[cc]);
-        out[k] = (float)x;
+    for (int k = 0; k < 4; ++k) sc[k] = (c + k < n) ? rsqrt(deg[c + k]) : 0.0;
+    int r0 = blockIdx.y * 16;
+    float4 w[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+        if (r0 + r < n) w[r] = ld_stream4(W + (size_t)(r0 + r) * ld + c);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        int row = r0 + r;
+        if (row >= n) break;
+        double si = rsqrt(deg[row]);
+        float in[4] = {w[r].x, w[r].y, w[r].z, w[r].w};
+        float out[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int cc = c + k;
+            out[k] = (cc < n) ? (float)(((double)in[k] + (cc == row ? 1.0 : 0.0)) * si * sc[k]) : 0.0f;
+        }
+        *reinterpret_cast<float4*>(M + (size_t)row * ldm + c) = make_float4(out[0], out[1], out[2], out[3]);
     }
-    *reinterpret_cast<float4*>(M + (size_t)row * ldm + c) = make_float4(out[0], out[1], out[2], out[3]);
 }
 
 // ---------------------------------------------------------------------------------------------

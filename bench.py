@@ -97,7 +97,7 @@ def host_workers(n_target):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -111,11 +111,13 @@ class ClockSampler:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "50", "-i", str(self.gpu_index)], stdout=f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock over the samples taken inside [t_begin, t_end] (wall clock); all samples if none fall inside."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -124,24 +126,31 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 p = [x.strip() for x in line.split(",")]
                 if len(p) < 9:
                     continue
                 try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
+                    ts = datetime.datetime.strptime(p[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    rows.append((ts, float(p[1]), float(p[2]), float(p[3]) if p[3].replace(".", "").isdigit() else 0.0, p[5:9]))
                 except ValueError:
                     continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if t_begin is not None and t_begin - 0.05 <= r[0] <= t_end + 0.05]
+        use = inside if inside else rows
+        reasons = set()
+        for r in use:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if use:
+            out.update(sm_mhz=float(np.median([r[1] for r in use])), sm_max_mhz=float(max(r[2] for r in use)),
+                       reasons=sorted(reasons), samples=len(use), samples_in_timed_region=len(inside),
+                       power_w_max=float(max(r[3] for r in use)))
         return out
 
 
@@ -173,10 +182,30 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL banner, torchrun) may write to fd 1; the contract is ONE JSON line on stdout.
+    fd 1 is pointed at stderr for the whole run and the line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -253,14 +282,14 @@ def main():
             ms = float(t.item())
         return ms
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                 # nvidia-smi needs ~1 s before its first sample: start before the warm-up
     # warm-up (also sizes the workspace)
     for _ in range(args.warmup):
         step_resident()
     step_e2e()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    t_begin = time.time()
     # timed region 1: inputs resident in HBM.  CUDA events around every matvec launch (timing mode 2)
     # give the roofline of the dominant kernel over exactly this region.
     hd.set_stage_timing(2)
@@ -282,7 +311,8 @@ def main():
     hd.set_stage_timing(0)
     # timed region 2: the same steps through the host-buffer entry point
     ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
 
     # parity spot check + node statistics outside the timed regions
     res = api.segment_packed(packed, device=dev, want_stats=True, **kw)
@@ -333,7 +363,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
