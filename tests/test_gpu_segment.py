@@ -84,6 +84,18 @@ def test_multi_launch_path_gives_the_same_labels(cuda_device):
     assert a.stats["converged"].all() and b.stats["converged"].all()
 
 
+def test_tensor_core_affinity_gives_the_same_labels(cuda_device):
+    cfg = CONFIGS["tarl_spatial"]
+    from autoinst_b200 import api
+    chunks = [make_chunk(500 + i, n_target=1500, features="tarl") for i in range(2)]
+    pk = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], theta=cfg["theta"], pin=False)
+    kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"], device=cuda_device)
+    a = api.segment_packed(pk, affinity_impl=0, **kw)
+    b = api.segment_packed(pk, affinity_impl=1, **kw)
+    for la, lb in zip(a.labels, b.labels):
+        assert R.same_partition(la, lb)
+
+
 def test_batched_equals_single(cuda_device):
     cfg = CONFIGS["tarl_spatial"]
     chunks = [make_chunk(200 + i, n_target=900 + 200 * i, features="tarl") for i in range(3)]

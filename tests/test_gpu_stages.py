@@ -245,3 +245,31 @@ def test_partition_matches_fancy_indexing(cuda_device):
             idx = o + np.where(sel)[0]
             expected += sp.csgraph.connected_components(sp.csr_matrix(W[np.ix_(idx, idx)] != 0))[0]
     assert len(coff) == expected
+
+
+@pytest.mark.parametrize("name", ["tarl_spatial", "tarl_spatial_dino"])
+def test_affinity_tensor_core_path(cuda_device, name):
+    """affinity_impl=1: TARL Gram matrix by tcgen05 (3xTF32, TMA-fed) must meet the same level-1 gate."""
+    cfg = CONFIGS[name]
+    api = _api()
+    for seed in GOLDEN_SEEDS:
+        inp, out, A = load_golden(seed, name)
+        W = api.affinity(inp["points"], inp["tarl"], inp["dino"], alpha=float(out["alpha"]), theta=float(out["theta"]),
+                         gamma=float(out["gamma"]), device=cuda_device, impl=1)
+        affinity_check(W, A.toarray())
+    ch = make_chunk(5, n_target=2500, features="tarl_dino")
+    A = affinity_ref(ch.points, ch.tarl, ch.dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
+    W1 = api.affinity(ch.points, ch.tarl, ch.dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"],
+                      device=cuda_device, impl=1)
+    affinity_check(W1, A)
+    # identical feature rows (distance 0) and near-identical rows: the cancellation fallback must hold the gate
+    t2 = ch.tarl.copy()
+    t2[1] = t2[0]
+    t2[3] = t2[2] * (1 + 1e-6)
+    A2 = affinity_ref(ch.points, t2, None, alpha=1.0, theta=0.5)
+    W2 = api.affinity(ch.points, t2, None, alpha=1.0, theta=0.5, device=cuda_device, impl=1)
+    affinity_check(W2, A2)
+    # no feature term: nothing for the tensor cores to do, the exact tile kernel runs
+    affinity_check(api.affinity(ch.points, None, None, alpha=1.0, device=cuda_device, impl=1), affinity_ref(ch.points, alpha=1.0))
+    with pytest.raises(Exception):                                      # DINOv2 term without TARL: fails loudly
+        api.affinity(ch.points, None, ch.dino, alpha=1.0, gamma=0.1, device=cuda_device, impl=1)
