@@ -42,9 +42,9 @@ struct ancuts_handle {
     char* stage = nullptr;                   // device staging of host inputs / labels (host entry point)
     size_t stage_cap = 0;
     int* h_ctr = nullptr;                    // pinned, 16 ints
-    cudaStream_t side[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // one per cluster-size class (4 used)
+    cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per node size bin
     cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     bool cluster16_ok = true;
     unsigned long long* h_acct = nullptr;    // pinned, SG_COUNT
     int64_t launches_total = 0;
@@ -421,7 +421,15 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
     if (h->stage_timing) { t_a = take_event(h); t_b = take_event(h); cudaEventRecord(t_a, st); }
     ANCUTS_CUDA(cudaEventRecord(h->ev_fork, st));
     bool any = false, launch_failed = false;
-    for (int cls = CL_CLASSES - 1; cls >= 0; --cls) {          // largest clusters first
+    // bins <=320, <=512, <=640, <=1024, <=2048, <=4096 points.  Latency mapping (short critical path) when all
+    // clusters of the level are resident at once; otherwise the level is bound by SM time and fewer CTAs per
+    // node do the same work with fewer cluster barriers.
+    static const int c_latency[CL_CLASSES] = {1, 2, 2, 4, 8, 8};
+    static const int c_throughput[CL_CLASSES] = {1, 1, 2, 2, 4, 8};
+    int ctas = 0;
+    for (int b = 0; b < CL_CLASSES; ++b) ctas += class_cnt[b] * c_latency[b];
+    const int* cmap = (ctas <= 148) ? c_latency : c_throughput;
+    for (int cls = CL_CLASSES - 1; cls >= 0; --cls) {          // largest nodes first
         int cnt = class_cnt[cls];
         if (cnt <= 0) continue;
         cudaStream_t s = h->side[cls];
@@ -430,10 +438,10 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
         cudaError_t err = cudaSuccess;
         {
             h->launches_total++;
-            switch (cls) {
-                case 0: err = launch_cluster<1>(e, cur, ids, cnt, s); break;
-                case 1: err = launch_cluster<2>(e, cur, ids, cnt, s); break;
-                case 2: err = launch_cluster<4>(e, cur, ids, cnt, s); break;
+            switch (cmap[cls]) {
+                case 1: err = launch_cluster<1>(e, cur, ids, cnt, s); break;
+                case 2: err = launch_cluster<2>(e, cur, ids, cnt, s); break;
+                case 4: err = launch_cluster<4>(e, cur, ids, cnt, s); break;
                 default: err = launch_cluster<8>(e, cur, ids, cnt, s); break;
             }
         }
@@ -557,7 +565,7 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
     if (rc) return rc;
     int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
     if (class_cnt) for (int i = 0; i < CL_CLASSES; ++i) class_cnt[i] = h->h_ctr[8 + i];
-    if (big_cnt) *big_cnt = h->h_ctr[13];
+    if (big_cnt) *big_cnt = h->h_ctr[14];
     if (num_active > pl.active_cap || h->h_ctr[3] > pl.cslot_cap) {
         set_error("internal: active table overflow (%d nodes, %d chunk slots)", num_active, h->h_ctr[3]);
         return ANCUTS_EINVAL;
@@ -672,7 +680,7 @@ int ancuts_create(int device, ancuts_handle** out) {
     ancuts_handle* h = new ancuts_handle();
     h->device = device;
     ANCUTS_CUDA(cudaMallocHost((void**)&h->h_ctr, 16 * sizeof(int)));
-    for (int i = 0; i < 5; ++i) {
+    for (int i = 0; i < 6; ++i) {
         ANCUTS_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
         ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
     }
@@ -690,7 +698,7 @@ int ancuts_destroy(ancuts_handle* h) {
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_acct) cudaFreeHost(h->h_acct);
     for (auto ev : h->pool) cudaEventDestroy(ev);
-    for (int i = 0; i < 5; ++i) { if (h->side[i]) cudaStreamDestroy(h->side[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
+    for (int i = 0; i < 6; ++i) { if (h->side[i]) cudaStreamDestroy(h->side[i]); if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]); }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return ANCUTS_OK;
@@ -845,14 +853,14 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
         int cnt[16] = {0};
         for (int i = 0; i < num_nodes; ++i) {
             int cls = (p->lanczos_impl == 1) ? -1 : cluster_class(h_n[i]);
-            if (cls >= 0) cl[(size_t)cls * pl.active_cap + cnt[8 + cls]++] = i; else cnt[13]++;
+            if (cls >= 0) cl[(size_t)cls * pl.active_cap + cnt[8 + cls]++] = i; else cnt[14]++;
         }
         ANCUTS_CUDA(cudaMemcpyAsync(e.a_done, zeros.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
         ANCUTS_CUDA(cudaMemcpyAsync(e.a_path, ones.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
         ANCUTS_CUDA(cudaMemcpyAsync(e.cl_ids, cl.data(), cl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         ANCUTS_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < CL_CLASSES; ++i) h->h_ctr[8 + i] = cnt[8 + i];
-        h->h_ctr[13] = cnt[13];
+        h->h_ctr[14] = cnt[14];
     }
     ANCUTS_CUDA(cudaMemcpyAsync(e.r_start, rs.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
     ANCUTS_CUDA(cudaMemcpyAsync(e.r_n, rn.data(), R * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -892,7 +900,7 @@ int ancuts_lanczos_fiedler_batched(ancuts_handle* h, int n_total, const float* d
     dim3 gdeg((max_n + 7) / 8, num_nodes);
     LAUNCH(SG_DEGREE, k_degree<<<gdeg, 256, 0, st>>>(e, 0));
     {
-        int class_cnt[CL_CLASSES], big_cnt = h->h_ctr[13];
+        int class_cnt[CL_CLASSES], big_cnt = h->h_ctr[14];
         for (int i = 0; i < CL_CLASSES; ++i) class_cnt[i] = h->h_ctr[8 + i];
         rc = run_lanczos_all(h, e, 0, num_nodes, max_n, class_cnt, big_cnt, st);
         if (rc) return rc;

@@ -21,11 +21,14 @@ namespace cg = cooperative_groups;
 
 constexpr int CL_KMAX = 256;             // steps the cluster kernel can take; nodes needing more fall back
 constexpr int CL_KS = CL_KMAX + 4;
-constexpr int CL_RPMAX = 384;            // rows per CTA
-constexpr int CL_NMAX = 2560;            // largest node handled here (8 CTAs x 320 rows)
+constexpr int CL_RPMAX = 512;            // rows per CTA (two per thread)
+constexpr int CL_NMAX = 4096;            // largest node handled here (8 CTAs x 512 rows)
 constexpr int CL_THREADS = 512;
-constexpr int CL_CLASSES = 4;            // cluster sizes 1, 2, 4, 8 (portable)
-constexpr int CL_DYN_SMEM = 192 * 1024;  // z for the whole node + as many basis rows of the slice as fit
+constexpr int CL_WARPS = CL_THREADS / 32;
+constexpr int CL_HALF = CL_THREADS / 2;     // shifts per eigenvalue and bisection round
+constexpr int CL_CLASSES = 6;            // node size bins (kernels_graph.cuh::cluster_class); cluster sizes 1, 2, 4, 8
+constexpr int CL_DYN_SMEM = 190 * 1024;  // z for the whole node + as many basis rows of the slice as fit
+                                         // (one CTA per SM; 256 threads x 2 CTAs per SM measured 25 % slower)
 
 struct ClusterShared {
     double hpart[2][CL_KS];      // this CTA's partial dots (pass 1 / pass 2), read by the peers
@@ -51,7 +54,7 @@ __device__ __forceinline__ double block_sum_512(double v, double* red) {
     __syncthreads();
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) t += red[i];
+    for (int i = 0; i < CL_WARPS; ++i) t += red[i];
     return t;
 }
 __device__ __forceinline__ double block_min_512(double v, double* red) {
@@ -62,7 +65,7 @@ __device__ __forceinline__ double block_min_512(double v, double* red) {
     __syncthreads();
     double t = red[0];
 #pragma unroll
-    for (int i = 1; i < 16; ++i) t = fmin(t, red[i]);
+    for (int i = 1; i < CL_WARPS; ++i) t = fmin(t, red[i]);
     return t;
 }
 
@@ -89,23 +92,23 @@ __device__ double cluster_tridiag(ClusterShared& S, int k, double* th) {
     __syncthreads();
     const double glo = S.gb[0], ghi = S.gb[1], pivmin = S.gb[2];
     {
-        const int which = tid >> 8, t256 = tid & 255;
+        const int which = tid / CL_HALF, t256 = tid % CL_HALF;
         const int m = k - 1 - which;
         double lo = glo, hi = ghi;
         const int rounds = 8;                       // 257^8 > 2^64: full float64 resolution (the residual
                                                     // estimate below is only as good as the eigenvalue)
         for (int round = 0; round < rounds; ++round) {
-            double x = lo + (hi - lo) * ((double)(t256 + 1) / 257.0);
+            double x = lo + (hi - lo) * ((double)(t256 + 1) / (double)(CL_HALF + 1));
             S.cnts[tid] = (m >= 0) ? sturm_count(S.alpha, S.be2, k, x, pivmin) : 0;
             __syncthreads();
             if (t256 < 32) {                 // one warp per eigenvalue finds the last shift with count <= m
                 int best = -1;
-                for (int i = t256; i < 256; i += 32) if (S.cnts[which * 256 + i] <= m) best = max(best, i);
+                for (int i = t256; i < CL_HALF; i += 32) if (S.cnts[which * CL_HALF + i] <= m) best = max(best, i);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
                 if (t256 == 0) {
-                    S.bounds[2 * which] = (best >= 0) ? lo + (hi - lo) * ((double)(best + 1) / 257.0) : lo;
-                    S.bounds[2 * which + 1] = (best < 255) ? lo + (hi - lo) * ((double)(best + 2) / 257.0) : hi;
+                    S.bounds[2 * which] = (best >= 0) ? lo + (hi - lo) * ((double)(best + 1) / (double)(CL_HALF + 1)) : lo;
+                    S.bounds[2 * which + 1] = (best < CL_HALF - 1) ? lo + (hi - lo) * ((double)(best + 2) / (double)(CL_HALF + 1)) : hi;
                 }
             }
             __syncthreads();
@@ -208,8 +211,7 @@ __device__ __forceinline__ void cl_reduce_h(cg::cluster_group& cl, ClusterShared
 
 // slice -= sum_j hs[j] V[j][slice]
 __device__ __forceinline__ void cl_update(ClusterShared& S, const SliceBasis& B, int rows, int nr) {
-    const int i = threadIdx.x;
-    if (i < nr) {
+    for (int i = threadIdx.x; i < nr; i += CL_THREADS) {
         double y = S.ysl[i];
         int j = 0;
         for (; j + 8 <= rows; j += 8) {
@@ -276,12 +278,12 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         zs[i] = z;
     }
     double bprev = sqrt(block_sum_512(s, S.red));
-    if (tid < nr) {
-        int j = r0 + tid;
+    for (int i = tid; i < nr; i += CL_THREADS) {
+        int j = r0 + i;
         double u = sqrt(e.deg[v.start + j]) * ivol;
-        B.row(0)[tid] = u;                               // basis row 0 = u1
-        S.ysl[tid] = start_value(j) - dot * u;
-        S.sv[tid] = e.sinv[v.start + j];
+        B.row(0)[i] = u;                                 // basis row 0 = u1
+        S.ysl[i] = start_value(j) - dot * u;
+        S.sv[i] = e.sinv[v.start + j];
     }
     __syncthreads();
 
@@ -291,7 +293,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     while (true) {
         const double invb = 1.0 / bprev;
         // basis row k+1 = current vector (slice)
-        if (tid < nr) B.row(k + 1)[tid] = S.ysl[tid] * invb;
+        for (int i = tid; i < nr; i += CL_THREADS) B.row(k + 1)[i] = S.ysl[i] * invb;
         __syncthreads();
         // ---- matvec of the slice: 2 rows per warp, 512 columns per iteration, 8 loads issued first ----
         {
@@ -357,10 +359,11 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         __syncthreads();
         cl_update(S, B, rows, nr);
         // ---- norm, publication of z = S y for the next matvec ----
-        double q = (tid < nr) ? S.ysl[tid] * S.ysl[tid] : 0.0;
+        double q = 0.0;
+        for (int i = tid; i < nr; i += CL_THREADS) q += S.ysl[i] * S.ysl[i];
         q = block_sum_512(q, S.red);
         if (tid == 0) S.npart[0] = q;
-        if (C > 1 && tid < nr) e.zbuf[g0 + tid] = S.sv[tid] * S.ysl[tid];
+        if (C > 1) for (int i = tid; i < nr; i += CL_THREADS) e.zbuf[g0 + i] = S.sv[i] * S.ysl[i];
         __syncthreads();
         cl_sync<C>(cl);
         double nn = 0.0;
@@ -378,7 +381,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         if (C > 1) {
             for (int i = tid; i < n; i += CL_THREADS) zs[i + pad] = __ldcg(e.zbuf + v.start + i);
         } else {
-            if (tid < nr) zs[tid + pad] = S.sv[tid] * S.ysl[tid];
+            for (int i = tid; i < nr; i += CL_THREADS) zs[i + pad] = S.sv[i] * S.ysl[i];
         }
         __syncthreads();
         const bool breakdown = beta < 1e-13;
@@ -392,15 +395,17 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     }
     // ---- Ritz vector of the slice, statistics for the cut kernels ----
     if (conv) {
-        double x = 0.0;
-        if (tid < nr) {
-            for (int j = 0; j < k; ++j) x += S.yv[j] * B.row(j + 1)[tid];
-            e.ev[g0 + tid] = x;
+        double xs = 0.0, xq = 0.0, xmn = 1e300, xmx = -1e300;
+        for (int i = tid; i < nr; i += CL_THREADS) {
+            double x = 0.0;
+            for (int j = 0; j < k; ++j) x += S.yv[j] * B.row(j + 1)[i];
+            e.ev[g0 + i] = x;
+            xs += x; xq += x * x; xmn = fmin(xmn, x); xmx = fmax(xmx, x);
         }
-        double sm_ = block_sum_512(tid < nr ? x : 0.0, S.red);
-        double sq = block_sum_512(tid < nr ? x * x : 0.0, S.red);
-        double mn = block_min_512(tid < nr ? x : 1e300, S.red);
-        double mx = -block_min_512(tid < nr ? -x : 1e300, S.red);
+        double sm_ = block_sum_512(xs, S.red);
+        double sq = block_sum_512(xq, S.red);
+        double mn = block_min_512(xmn, S.red);
+        double mx = -block_min_512(-xmx, S.red);
         if (tid == 0) { S.spart[0] = sm_; S.spart[1] = mn; S.spart[2] = mx; S.spart[3] = sq; }
         __syncthreads();
         cl_sync<C>(cl);

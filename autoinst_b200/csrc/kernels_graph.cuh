@@ -5,12 +5,16 @@
 
 namespace ancuts {
 
-// cluster-size class of a node for the persistent Lanczos kernel (kernels_cluster.cuh); -1 = too large
+// size bin of a node for the persistent Lanczos kernel (kernels_cluster.cuh); -1 = too large.
+// The host maps bins to cluster sizes per level (engine.cu: latency mapping when the level fits one
+// wave of CTAs, throughput mapping with fewer CTAs per node otherwise).
 __host__ __device__ inline int cluster_class(int n) {
-    if (n <= 320) return 0;              // 1 CTA
-    if (n <= 640) return 1;              // 2
-    if (n <= 1024) return 2;             // 4
-    if (n <= 2560) return 3;             // 8 (portable cluster size)
+    if (n <= 320) return 0;
+    if (n <= 512) return 1;
+    if (n <= 640) return 2;
+    if (n <= 1024) return 3;
+    if (n <= 2048) return 4;
+    if (n <= 4096) return 5;
     return -1;
 }
 
@@ -393,7 +397,7 @@ __global__ void k_finish_ranges(Eng e, int num_ranges) {
         e.a_path[a] = 1;
         int cls = cluster_class(n);
         if (cls >= 0) e.cl_ids[cls * e.active_cap + atomicAdd(&e.ctr[8 + cls], 1)] = a;
-        else atomicAdd(&e.ctr[13], 1);
+        else atomicAdd(&e.ctr[14], 1);
     }
 }
 

@@ -126,7 +126,7 @@ def test_lanczos_cluster_sizes(cuda_device):
     picks = {}
     for c in np.argsort(-sizes):
         n = int(sizes[c])
-        cls = 0 if n <= 320 else 1 if n <= 640 else 2 if n <= 1024 else 3 if n <= 2560 else 4
+        cls = 0 if n <= 320 else 1 if n <= 512 else 2 if n <= 640 else 3 if n <= 1024 else 4 if n <= 2048 else 5
         picks.setdefault(cls, c)
     assert len(picks) >= 3
     mats, offs, ns = [], [], []
