@@ -212,7 +212,7 @@ def make_chunk(chunk_id: int = 0, n_target: int = 8192, features: str = "tarl_di
 
 
 def make_map(n_chunks: int = 8, n_per_chunk: int = 4096, features: str = "tarl", seed: int = 77,
-             background_facades: bool = True) -> list[Chunk]:
+             background_facades: bool = True, attach_prob: float = 0.4, feature_noise: float = 0.5) -> list[Chunk]:
     """Synthetic "first map": ONE scene along a straight 25 m wide corridor, voxelised once at 0.35 m, then
     cut into 25 m cubes every 22 m (`chunk_generation.py:123-137`, OVERLAP = 3 m, `config.py:58`), so that
     neighbouring chunks share instances and, in the 3 m overlap, exactly the same points — what the
@@ -226,25 +226,40 @@ def make_map(n_chunks: int = 8, n_per_chunk: int = 4096, features: str = "tarl",
     kinds = ["facade", "car", "car", "veg", "car", "veg", "car", "car"]
     per_kind = {"facade": 900.0, "car": 285.0, "veg": 520.0}
     target = n_per_chunk * length / CHUNK_EDGE
-    pts, inst, boxes, is_bg = [], [], [], []
+    pts, inst, boxes, is_bg, obj_kind = [], [], [], [], []
     total, o = 0.0, 0
     while total < 0.9 * target and o < 100000:
         kind = kinds[o % len(kinds)]
         o += 1
         p = _make_object(rng, kind)
         lo0, hi0 = p.min(0), p.max(0)
+        attach = bool(boxes) and rng.random() < attach_prob
         for _ in range(40):
-            shift = np.array([rng.uniform(0.5, length - 0.5), rng.uniform(-half + 0.5, half - 0.5),
-                              rng.uniform(-half + 0.3, half - 0.3)]) - (lo0 + hi0) / 2
-            shift[2] = rng.uniform(-half + 0.3, half - 0.3 - (hi0[2] - lo0[2])) - lo0[2]
+            if attach:                                  # parked 0.5-0.9 m from an earlier object: a weak link to cut
+                hl, hh = boxes[int(rng.integers(len(boxes)))]
+                ax = int(rng.integers(2))
+                gap = rng.uniform(0.5, 0.9)
+                shift = np.zeros(3)
+                shift[ax] = (hh[ax] + gap - lo0[ax]) if rng.random() < 0.5 else (hl[ax] - gap - hi0[ax])
+                oa = 1 - ax
+                a_, b_ = hl[oa] - hi0[oa] + 0.5, hh[oa] - lo0[oa] - 0.5
+                shift[oa] = rng.uniform(min(a_, b_), max(a_, b_))
+                shift[2] = hl[2] - lo0[2]
+            else:
+                shift = np.array([rng.uniform(0.5, length - 0.5), rng.uniform(-half + 0.5, half - 0.5),
+                                  rng.uniform(-half + 0.3, half - 0.3)]) - (lo0 + hi0) / 2
+                shift[2] = rng.uniform(-half + 0.3, half - 0.3 - (hi0[2] - lo0[2])) - lo0[2]
             lo, hi = lo0 + shift, hi0 + shift
-            if lo[0] < 0 or hi[0] > length or lo[1] < -half or hi[1] > half:
+            if lo[0] < 0 or hi[0] > length or lo[1] < -half or hi[1] > half or lo[2] < -half or hi[2] > half:
                 continue
-            if all(_aabb_gap(lo, hi, bl, bh) > 1.3 for bl, bh in boxes):
+            gaps = [_aabb_gap(lo, hi, bl, bh) for bl, bh in boxes]
+            if (attach and sum(g < 1.3 for g in gaps) == 1 and min(gaps) >= 0.45) or \
+                    (not attach and all(g > 1.3 for g in gaps)):
                 boxes.append((lo, hi))
                 pts.append(p + shift)
                 inst.append(np.full(p.shape[0], len(boxes), dtype=np.int32))
                 is_bg.append(kind == "facade" and background_facades)
+                obj_kind.append(kind)
                 total += per_kind[kind]
                 break
     pts = np.concatenate(pts)
@@ -263,8 +278,13 @@ def make_map(n_chunks: int = 8, n_per_chunk: int = 4096, features: str = "tarl",
         if bg:
             gt[im == k + 1] = 0
     n_inst = int(im.max()) + 1
-    proto_t = rng.normal(0, 1, size=(n_inst, 96))
-    tarl_all = (proto_t[im] + 0.3 * rng.normal(0, 1, size=(pm.shape[0], 96))).astype(np.float32)
+    # TARL-like features are class-driven: a prototype per object kind plus a smaller per-instance offset, so that
+    # neighbouring objects of one kind are hard to tell apart (the metrics are not trivially perfect)
+    kind_proto = {k: rng.normal(0, 1, size=96) for k in ("facade", "car", "veg")}
+    proto_t = np.zeros((n_inst, 96))
+    for k, kd in enumerate(obj_kind):
+        proto_t[k + 1] = kind_proto[kd] + 0.35 * rng.normal(0, 1, size=96)
+    tarl_all = (proto_t[im] + feature_noise * rng.normal(0, 1, size=(pm.shape[0], 96))).astype(np.float32)
     tarl_all[rng.random(pm.shape[0]) < 0.05] = 0.0
     dino_all = None
     if "dino" in features:
