@@ -85,6 +85,18 @@ def remove_semantics(gt_labels, preds, threshold=0.8):
     return out
 
 
+def canonical_labels(seg_labels):
+    """Relabel the segments of one chunk by first occurrence in point order.  The greedy rules downstream
+    (merge tie-breaks, AP's np.unique order, `metrics_class.py:181-235`) depend on label VALUES, which the
+    reference draws at random (colours); both sides of a comparison must number segments the same way
+    (last paragraph)."""
+    seg_labels = np.asarray(seg_labels)
+    _, first, inv = np.unique(seg_labels, return_index=True, return_inverse=True)
+    rank = np.empty(len(first), dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(len(first))
+    return rank[inv.reshape(-1)]
+
+
 def globally_unique(chunk_id, seg_labels):
     """Per-chunk segment ids -> ids unique across the map (the reference draws a random colour per segment)."""
     return (np.int64(chunk_id + 1) << 20) + np.asarray(seg_labels, dtype=np.int64) + 1

@@ -75,7 +75,7 @@ def main():
         gt = M.compact_labels(gt_lab)
 
         def evaluate(per_chunk):
-            parts = [(c.points, M.globally_unique(c.chunk_id, lab)) for c, lab in zip(chunks, per_chunk)]
+            parts = [(c.points, M.globally_unique(c.chunk_id, M.canonical_labels(lab))) for c, lab in zip(chunks, per_chunk)]
             pts, lab = M.merge_chunks_unite_instances(parts)
             allp = M.compact_labels(lab)
             return instance_metrics(allp, M.remove_semantics(gt, allp.copy()), gt, min_points=20)
