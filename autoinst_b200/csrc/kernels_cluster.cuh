@@ -342,7 +342,9 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         }
         __syncthreads();
         const int rows = k + 2;
-        // ---- classical Gram-Schmidt, pass 1 ----
+        // ---- classical Gram-Schmidt against u1 and every Lanczos vector, always twice ("twice is enough").
+        //      Measured: skipping the second pass under a DGKS-style test applied after the three-term part
+        //      loses orthogonality within a few dozen steps (Ritz values outside [-1, 1]). ----
         cl_partial_dots(S, B, rows, nr, 0);
         __syncthreads();
         cl_sync<C>(cl);
@@ -350,7 +352,6 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         const double a1 = S.hs[rows - 1];
         __syncthreads();
         cl_update(S, B, rows, nr);
-        // ---- pass 2 ----
         cl_partial_dots(S, B, rows, nr, 1);
         __syncthreads();
         cl_sync<C>(cl);

@@ -201,10 +201,11 @@ k_update(Eng e) {
     }
     bool second = false;
     if (PASS == 1) {
-        hh = block_sum_256(hh, red);
+        hh = block_sum_256(hh, red);          // includes a __syncthreads: hs[] is complete
         double yy = 0.0;
         for (int c = 0; c < nch; ++c) yy += pd[(size_t)c * e.KS + rows];
-        second = (yy - hh) < 0.5 * yy;                                    // eta^2 = 1/2
+        second = (yy - hh) < 0.5 * yy;        // DGKS test on the whole projection (eta^2 = 1/2): in Lanczos the
+                                              // three-term part alone usually trips it, i.e. two passes almost always
     }
     __syncthreads();
     if (ch == 0 && threadIdx.x == 0) {
