@@ -21,7 +21,7 @@ EXPORTS = [
     "ancuts_segment_workspace_bytes", "ancuts_affinity_f32", "ancuts_degree_normalize_f32",
     "ancuts_lanczos_fiedler_batched", "ancuts_ncut_scan_batched", "ancuts_partition_batched",
     "ancuts_segment_chunks", "ancuts_segment_chunks_host", "ancuts_segment_dense_f32",
-    "ancuts_launch_count", "ancuts_last_accounting", "ancuts_set_stage_timing",
+    "ancuts_launch_count", "ancuts_last_accounting", "ancuts_set_stage_timing", "ancuts_nn_reproject",
 ]
 
 
@@ -96,6 +96,7 @@ def load():
                                                C.c_int32, i32p, vp]
     lib.ancuts_segment_dense_f32.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int, pp, vp, i32p, sp,
                                              C.c_int32, i32p, vp]
+    lib.ancuts_nn_reproject.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_int32, vp, vp, vp]
     lib.ancuts_launch_count.argtypes = [vp, C.c_int]
     lib.ancuts_launch_count.restype = C.c_int64
     lib.ancuts_last_accounting.argtypes = [vp, dp, dp, i64p]

@@ -30,7 +30,7 @@ def _stream(device):
 
 class Handle:
     """One library handle (device workspace, counters) per CUDA device."""
-    _cache: dict[int, "Handle"] = {}
+    _cache: dict = {}
 
     def __init__(self, device: int):
         self.lib = _lib.load()
@@ -41,15 +41,16 @@ class Handle:
         check(self.lib.ancuts_create(self.device, C.byref(self.h)))
 
     @classmethod
-    def get(cls, device=None) -> "Handle":
+    def get(cls, device=None, lane: int = 0) -> "Handle":
+        """Handle of `device`; `lane` > 0 gives further independent handles (own workspace) for concurrent calls."""
         if device is None:
             device = torch.cuda.current_device() if torch.cuda.is_available() else 0
         if isinstance(device, torch.device):
             device = device.index if device.index is not None else torch.cuda.current_device()
-        device = int(device)
-        if device not in cls._cache:
-            cls._cache[device] = Handle(device)
-        return cls._cache[device]
+        key = (int(device), int(lane))
+        if key not in cls._cache:
+            cls._cache[key] = Handle(int(device))
+        return cls._cache[key]
 
     def launch_count(self, reset=False) -> int:
         return int(self.lib.ancuts_launch_count(self.h, 1 if reset else 0))
@@ -229,6 +230,23 @@ def partition(W, node_off, node_n, mask, split_components=True):
     return obuf[:, :n], perm, coff[:c].copy(), cn[:c].copy()
 
 
+def nn_reproject(query_points, source_points, source_labels=None, max_radius=None, no_label=-1, device=None):
+    """Label of the nearest source point for every query point (point_cloud_utils.py:144-174).
+    Returns (labels int32 [nq], index int32 [nq]) on the device."""
+    device = _dev(device)
+    hd = Handle.get(device)
+    q = _as_dev(query_points, torch.float64, device)
+    s = _as_dev(source_points, torch.float64, device)
+    lab = _as_dev(source_labels, torch.int32, device) if source_labels is not None else None
+    out = torch.empty(q.shape[0], dtype=torch.int32, device=device)
+    idx = torch.empty(q.shape[0], dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_nn_reproject(hd.h, q.shape[0], _ptr(q), s.shape[0], _ptr(s), _ptr(lab),
+                                         float(max_radius) if max_radius else 0.0, int(no_label), _ptr(out), _ptr(idx),
+                                         _stream(device)))
+    return out, idx
+
+
 # ------------------------------------------------------------------------------------------------
 # whole path
 # ------------------------------------------------------------------------------------------------
@@ -353,11 +371,11 @@ def _run_segment(hd, fn_host, packed, dev_chunks, p, want_stats, device):
 
 def segment_packed(packed: PackedChunks, *, alpha=1.0, theta=0.0, gamma=0.0, T=0.01, proximity=1.0, split_lim=0.01,
                    device=None, dev_chunks: DeviceChunks | None = None, want_stats=False, max_steps=0,
-                   check_every=0, tol=0.0, affinity_impl=0, lanczos_impl=0) -> SegmentResult:
+                   check_every=0, tol=0.0, affinity_impl=0, lanczos_impl=0, lane: int = 0) -> SegmentResult:
     """Segment a packed batch.  With `dev_chunks` the inputs are already resident in HBM (labels stay on
     the device in dev_chunks.labels); otherwise host buffers go through ancuts_segment_chunks_host."""
     device = _dev(device if dev_chunks is None else dev_chunks.device)
-    hd = Handle.get(device)
+    hd = Handle.get(device, lane)
     p = make_params(alpha, theta if packed.use_t else 0.0, gamma if packed.use_d else 0.0, T, proximity, split_lim,
                     tarl_dim=packed.tarl_dim, dino_dim=packed.dino_dim, max_steps=max_steps, check_every=check_every,
                     tol=tol, affinity_impl=affinity_impl, lanczos_impl=lanczos_impl)
@@ -368,6 +386,39 @@ def segment_packed(packed: PackedChunks, *, alpha=1.0, theta=0.0, gamma=0.0, T=0
         arr = src.numpy()
         labels = [arr[a:b].copy() for a, b in zip(packed.off[:-1], packed.off[1:])]
     return SegmentResult(labels=labels, num_segments=nseg, stats=stats)
+
+
+def segment_packed_lanes(packed_lanes, dev_lanes=None, **kw):
+    """Run several packed batches CONCURRENTLY on one device, one host thread + CUDA stream + library handle
+    per batch ("lane").  The recursion of one batch is level-synchronous and its later levels leave most SMs
+    idle (few, long-running nodes); a second batch fills them.  ctypes releases the GIL during the calls."""
+    import threading
+    n = len(packed_lanes)
+    device = _dev(kw.pop("device", None) if dev_lanes is None else dev_lanes[0].device)
+    out = [None] * n
+    err = [None] * n
+    streams = [torch.cuda.Stream(device=device) for _ in range(n)]
+    cur = torch.cuda.current_stream(device)
+
+    def work(i):
+        try:
+            with torch.cuda.device(device), torch.cuda.stream(streams[i]):
+                streams[i].wait_stream(cur)
+                out[i] = segment_packed(packed_lanes[i], device=device, dev_chunks=None if dev_lanes is None else dev_lanes[i],
+                                        lane=i, **kw)
+        except Exception as ex:          # re-raised in the caller
+            err[i] = ex
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for s in streams:
+        cur.wait_stream(s)
+    for ex in err:
+        if ex is not None:
+            raise ex
+    return out
 
 
 def segment_chunks(points_list, tarl_list=None, dino_list=None, *, alpha=1.0, theta=0.0, gamma=0.0, T=0.01,

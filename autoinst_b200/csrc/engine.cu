@@ -1025,6 +1025,21 @@ int ancuts_partition_batched(ancuts_handle* h, int n_total, const float* d_W_in,
     return ANCUTS_OK;
 }
 
+int ancuts_nn_reproject(ancuts_handle* h, int num_query, const double* d_query, int num_source,
+                        const double* d_source, const int32_t* d_source_label, double max_radius, int32_t no_label,
+                        int32_t* d_out_label, int32_t* d_out_index, void* stream) {
+    if (!h || num_query <= 0 || num_source <= 0 || !d_query || !d_source || !d_out_label) {
+        set_error("bad argument to ancuts_nn_reproject");
+        return ANCUTS_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    LAUNCH(SG_PARTITION, k_nn_reproject<<<(num_query + 255) / 256, 256, 0, st>>>(
+        num_query, d_query, num_source, d_source, d_source_label, max_radius, no_label, d_out_label, d_out_index));
+    ANCUTS_CUDA(cudaGetLastError());
+    return ANCUTS_OK;
+}
+
 static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off, const double* d_points,
                           const float* d_tarl, const float* d_dino, const float* d_W_dense, int64_t ld_dense,
                           int num_points_orig, const ancuts_params* p, int32_t* d_labels, int32_t* h_num_segments,

@@ -428,6 +428,48 @@ k_gather_blocks_cur(Eng e, int cur /* source buffer */) {
         atomicAdd(&e.acct[SG_PARTITION], 8ull * n * n);
 }
 
+// ---------------------------------------------------------------------------------------------
+// "Next" row N1: 1-nearest-neighbour re-projection of the 0.35 m labels onto the 5 cm points
+//   (kDTree_1NN_feature_reprojection, point_cloud_utils.py:144-174; call ncuts_utils.py:185-189).
+// Brute force: one thread per query point, the source points staged through shared memory in tiles
+// of 1024 (float64 squared distances, first minimum wins), instead of a KD-tree query per point in a
+// Python loop.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_nn_reproject(int nq, const double* __restrict__ q, int ns, const double* __restrict__ src,
+               const int* __restrict__ src_label, double max_radius, int no_label,
+               int* __restrict__ out_label, int* __restrict__ out_index) {
+    __shared__ double sx[1024], sy[1024], sz[1024];
+    int i = blockIdx.x * 256 + threadIdx.x;
+    double px = 0.0, py = 0.0, pz = 0.0;
+    if (i < nq) { px = q[(size_t)i * 3]; py = q[(size_t)i * 3 + 1]; pz = q[(size_t)i * 3 + 2]; }
+    double best = 1e300;
+    int bi = -1;
+    for (int t0 = 0; t0 < ns; t0 += 1024) {
+        int tn = min(1024, ns - t0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < tn; j += 256) {
+            sx[j] = src[(size_t)(t0 + j) * 3];
+            sy[j] = src[(size_t)(t0 + j) * 3 + 1];
+            sz[j] = src[(size_t)(t0 + j) * 3 + 2];
+        }
+        __syncthreads();
+        if (i < nq) {
+#pragma unroll 4
+            for (int j = 0; j < tn; ++j) {
+                double dx = px - sx[j], dy = py - sy[j], dz = pz - sz[j];
+                double d = dx * dx + dy * dy + dz * dz;
+                if (d < best) { best = d; bi = t0 + j; }
+            }
+        }
+    }
+    if (i < nq) {
+        bool far = (max_radius > 0.0) && (sqrt(best) > max_radius);       // point_cloud_utils.py:166-168
+        out_label[i] = (bi < 0 || far) ? no_label : (src_label ? src_label[bi] : bi);
+        if (out_index) out_index[i] = bi;
+    }
+}
+
 // final labels: label = range index relative to the chunk's first range (ncuts_utils.py:177-183)
 __global__ void k_emit_labels(Eng e, int* __restrict__ labels, int* __restrict__ nseg) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;

@@ -145,6 +145,14 @@ int ancuts_segment_dense_f32(ancuts_handle* h, int n, const float* d_W, int64_t 
                              int32_t* h_num_segments, ancuts_node_stat* h_stats, int32_t stats_cap,
                              int32_t* h_num_stats, void* stream);
 
+/* "Next" row N1 — replaces kDTree_1NN_feature_reprojection (point_cloud_utils.py:144-174, called at
+ * ncuts_utils.py:185-189): every query point (5 cm cloud) takes the label of its nearest source point
+ * (0.35 m cloud).  d_source_label may be NULL (the source index is returned as label).  max_radius <= 0
+ * disables the radius test; otherwise points farther than max_radius get no_label.  Asynchronous. */
+int ancuts_nn_reproject(ancuts_handle* h, int num_query, const double* d_query, int num_source,
+                        const double* d_source, const int32_t* d_source_label, double max_radius,
+                        int32_t no_label, int32_t* d_out_label, int32_t* d_out_index, void* stream);
+
 /* Counters for bench.py: kernels launched by this handle since the last reset, and the per-kernel
  * CUDA-event time of the kernels named by ancuts_timing_select(). */
 int64_t ancuts_launch_count(ancuts_handle* h, int reset);

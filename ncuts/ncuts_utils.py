@@ -2,8 +2,8 @@
 
 The affinity build and the recursive cut (`ncuts_utils.py:56-174`) run on the GPU through
 `autoinst_b200.api` (C ABI: `ancuts_segment_chunks_host`).  Everything around them — feature
-fetching from the dataset, colour coding, 1-NN re-projection to the 5 cm cloud, ground handling —
-stays the reference's own helper code under `utils/`, imported lazily so that this module also
+fetching from the dataset, colour coding, ground handling — stays the reference's own helper code under
+`utils/` (the 1-NN re-projection to the 5 cm cloud also runs on the GPU, `ancuts_nn_reproject`), imported lazily so that this module also
 loads where Open3D is absent (the array-level entry `segment_major_points` needs none of it).
 
 Configuration is read the way the reference reads it: module globals star-imported from `config`
@@ -59,8 +59,8 @@ def ncuts_chunk(dataset, chunk_downsample_dict, pcd_nonground_minor, T_pcd, samp
     """Same contract as the reference (`ncuts_utils.py:28-204`): returns
     (merged_chunk, pcd_chunk, cut_hight, inst_ground, seg_ground)."""
     import open3d as o3d
-    from utils.point_cloud.point_cloud_utils import (get_subpcd, get_statistical_inlier_indices,
-                                                     kDTree_1NN_feature_reprojection)
+    from utils.point_cloud.point_cloud_utils import get_subpcd, get_statistical_inlier_indices
+    from autoinst_b200 import api
     from utils.visualization_utils import generate_random_colors
     from utils.image.image_utils import dinov2_mean, image_based_features_per_patch
     from utils.point_cloud.chunk_generation import tarl_features_per_patch, get_indices_feature_reprojection
@@ -96,9 +96,10 @@ def ncuts_chunk(dataset, chunk_downsample_dict, pcd_nonground_minor, T_pcd, samp
     colour_major = np.zeros((pts.shape[0], 3))
     for s, idx in enumerate(groups):
         colour_major[idx] = np.array(palette[s]) / 255
-    pcd_chunk.paint_uniform_color([0, 0, 0])
-    pcd_chunk.colors = o3d.utility.Vector3dVector(
-        kDTree_1NN_feature_reprojection(np.asarray(pcd_chunk.colors), pcd_chunk, colour_major, major))
+    # kDTree_1NN_feature_reprojection (point_cloud_utils.py:144-174): every 5 cm point takes the colour of its
+    # nearest 0.35 m point; the nearest-neighbour search runs on the GPU (C ABI ancuts_nn_reproject)
+    _, nearest = api.nn_reproject(np.asarray(pcd_chunk.points), pts)
+    pcd_chunk.colors = o3d.utility.Vector3dVector(colour_major[nearest.cpu().numpy()])
 
     inl = get_statistical_inlier_indices(ground)
     g_in = get_subpcd(ground, inl)

@@ -273,3 +273,20 @@ def test_affinity_tensor_core_path(cuda_device, name):
     affinity_check(api.affinity(ch.points, None, None, alpha=1.0, device=cuda_device, impl=1), affinity_ref(ch.points, alpha=1.0))
     with pytest.raises(Exception):                                      # DINOv2 term without TARL: fails loudly
         api.affinity(ch.points, None, ch.dino, alpha=1.0, gamma=0.1, device=cuda_device, impl=1)
+
+
+def test_nn_reprojection_matches_kdtree(cuda_device):
+    """next-row N1: 1-NN label re-projection (point_cloud_utils.py:144-174) against scipy's KD-tree."""
+    from scipy.spatial import cKDTree
+    api = _api()
+    rng = np.random.default_rng(3)
+    src = rng.uniform(-12.5, 12.5, size=(3000, 3))
+    lab = rng.integers(0, 40, size=3000).astype(np.int32)
+    qry = src[rng.integers(0, 3000, size=20000)] + rng.normal(0, 0.2, size=(20000, 3))
+    dist, idx = cKDTree(src).query(qry, k=1)
+    out, gi = api.nn_reproject(qry, src, lab, device=cuda_device)
+    assert np.array_equal(gi.cpu().numpy(), idx)
+    assert np.array_equal(out.cpu().numpy(), lab[idx])
+    out_r, _ = api.nn_reproject(qry, src, lab, max_radius=0.3, no_label=-1, device=cuda_device)
+    expect = np.where(dist > 0.3, -1, lab[idx])
+    assert np.array_equal(out_r.cpu().numpy(), expect)
