@@ -22,6 +22,7 @@ EXPORTS = [
     "ancuts_lanczos_fiedler_batched", "ancuts_ncut_scan_batched", "ancuts_partition_batched",
     "ancuts_segment_chunks", "ancuts_segment_chunks_host", "ancuts_segment_dense_f32",
     "ancuts_launch_count", "ancuts_last_accounting", "ancuts_set_stage_timing", "ancuts_nn_reproject",
+    "ancuts_last_levels", "ancuts_debug_phases",
 ]
 
 
@@ -101,6 +102,8 @@ def load():
     lib.ancuts_launch_count.restype = C.c_int64
     lib.ancuts_last_accounting.argtypes = [vp, dp, dp, i64p]
     lib.ancuts_set_stage_timing.argtypes = [vp, C.c_int]
+    lib.ancuts_last_levels.argtypes = [vp, dp, C.c_int]
+    lib.ancuts_debug_phases.argtypes = [vp, dp, C.c_int]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("ancuts_version",):

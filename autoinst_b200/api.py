@@ -66,6 +66,21 @@ class Handle:
         check(self.lib.ancuts_last_accounting(self.h, b, m, l))
         return {s: dict(bytes=b[i], ms=m[i], launches=int(l[i])) for i, s in enumerate(STAGES)}
 
+    def debug_phases(self, reset=True) -> dict:
+        """Cycles per phase of the persistent Lanczos kernel (needs ANCUTS_PHASES=1 before the handle is created)."""
+        buf = (C.c_double * 32)()
+        check(self.lib.ancuts_debug_phases(self.h, buf, 1 if reset else 0))
+        names = ["basis", "matvec", "dots1", "update1", "dots2", "update2", "norm", "check"]
+        return {c: {nm: buf[8 * i + j] for j, nm in enumerate(names)} for i, c in enumerate((1, 2, 4, 8))}
+
+    def levels(self, cap: int = 256) -> list:
+        """Per-level trace of the last segment call made in timing mode 2 (ancuts_last_levels)."""
+        buf = (C.c_double * (16 * cap))()
+        n = min(int(self.lib.ancuts_last_levels(self.h, buf, cap)), cap)
+        return [dict(active=int(buf[16 * i]), big=int(buf[16 * i + 1]), ms=buf[16 * i + 2],
+                     bins=[int(buf[16 * i + 3 + b]) for b in range(6)],
+                     cluster=[int(buf[16 * i + 9 + b]) for b in range(6)]) for i in range(n)]
+
 
 def make_params(alpha=1.0, theta=0.0, gamma=0.0, T=0.01, proximity=1.0, split_lim=0.01, beta=0.0,
                 tarl_dim=0, dino_dim=0, max_steps=0, check_every=0, tol=0.0, affinity_impl=0,

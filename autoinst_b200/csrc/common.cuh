@@ -134,6 +134,9 @@ struct Eng {
     int* ctr;             // 16 ints: [8..12]=nodes per cluster class [13]=nodes for the multi-launch path; [0]=numRanges [1]=numActive [2]=maxActiveN [3]=cslots [4]=notDone [5]=numSplit [6]=statCount [7]=maxSplitN
     unsigned long long* acct;   // [SG_COUNT] algorithmic bytes
     ancuts_node_stat* stats; int stats_cap;
+    int xf;               // experiment flags (ANCUTS_X): 1 = matvec without out-of-block selects, 2 = integer float->double widening
+    unsigned long long* dbg;   // optional [4 cluster sizes][8] phase cycle sums of the cluster kernel (thread 0 of rank 0), or NULL
+    int w_guard;          // 1 = entries next to a block may be non-finite (caller-provided W without a gather)
 };
 
 }  // namespace ancuts

@@ -29,7 +29,9 @@ int launch_affinity_tc(int n, const double* pts, const float* tarl, int tdim, co
                        float* W, long long ld, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t affinity_tc_scratch_bytes(int n, int tdim, int ddim);
 
-struct TimedLaunch { int stage; cudaEvent_t a, b; };
+struct TimedLaunch { int stage; cudaEvent_t a, b; int level = -1; };
+// one record per recursion level (timing mode 2): node counts per size bin and the time of the cluster phase
+struct LevelRec { int num_active, big; int cls[6]; int cmap[6]; double ms; };
 
 }  // namespace ancuts
 
@@ -53,9 +55,12 @@ struct ancuts_handle {
     double stage_ms[SG_COUNT] = {0};
     int stage_timing = 0;                    // 0 off, 1 every launch, 2 matvec launches only
     std::vector<TimedLaunch> timed;
+    std::vector<LevelRec> levels;
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
     bool attrs_set = false;
+    int xflags = 0;                          // ANCUTS_X (experiments)
+    unsigned long long* dbg = nullptr;       // device, 32 entries: phase cycles of the cluster kernel (ANCUTS_PHASES=1)
 };
 
 namespace ancuts {
@@ -231,6 +236,7 @@ struct LaunchScope {
 static void begin_accounting(ancuts_handle* h) {
     for (int i = 0; i < SG_COUNT; ++i) { h->stage_launches[i] = 0; h->stage_bytes[i] = 0; h->stage_ms[i] = 0; }
     h->timed.clear();
+    h->levels.clear();
     h->pool_used = 0;
 }
 
@@ -240,7 +246,10 @@ static int end_accounting(ancuts_handle* h, const Eng& e, cudaStream_t st) {
     for (int i = 0; i < SG_COUNT; ++i) h->stage_bytes[i] += (double)h->h_acct[i];
     for (auto& t : h->timed) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) h->stage_ms[t.stage] += ms;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            h->stage_ms[t.stage] += ms;
+            if (t.level >= 0 && t.level < (int)h->levels.size()) h->levels[t.level].ms = ms;
+        }
     }
     h->timed.clear();
     return ANCUTS_OK;
@@ -252,10 +261,11 @@ static int set_attrs(ancuts_handle* h, int KS) {
                                      (KMAX_LIMIT + 4) * 68 + 64));
     (void)KS;
     const int cl_smem = CL_DYN_SMEM;
-    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
-    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
-    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
-    ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem));
+#define ANCUTS_CL_ATTR(C, M) ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem))
+    ANCUTS_CL_ATTR(1, 0); ANCUTS_CL_ATTR(2, 0); ANCUTS_CL_ATTR(4, 0); ANCUTS_CL_ATTR(8, 0);
+    ANCUTS_CL_ATTR(1, 1); ANCUTS_CL_ATTR(2, 1); ANCUTS_CL_ATTR(4, 1); ANCUTS_CL_ATTR(8, 1);
+    ANCUTS_CL_ATTR(1, 2); ANCUTS_CL_ATTR(2, 2); ANCUTS_CL_ATTR(4, 2); ANCUTS_CL_ATTR(8, 2);
+#undef ANCUTS_CL_ATTR
     h->attrs_set = true;
     return ANCUTS_OK;
 }
@@ -392,8 +402,8 @@ static int run_lanczos(ancuts_handle* h, Eng& e, int cur, int num_active, int ma
     return ANCUTS_OK;
 }
 
-template <int C>
-static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
+template <int C, int MODE>
+static cudaError_t launch_cluster_m(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)count * C, 1, 1);
@@ -407,7 +417,24 @@ static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int cou
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = (C > 1) ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_lanczos_cluster<C>, e, cur, ids, (int)(CL_DYN_SMEM / 8));
+    return cudaLaunchKernelEx(&cfg, k_lanczos_cluster<C, MODE>, e, cur, ids, (int)(CL_DYN_SMEM / 8));
+}
+
+// matvec variant: 0 = out-of-block entries selected away (W may hold anything next to a block),
+// 1 = no selects (the gather zeroed the fringe), 2 = additionally the integer float->double widening
+static inline int cluster_mode(const Eng& e) {
+    if (e.w_guard) return 0;
+    if ((e.xf & 2) && (e.xf & 1)) return 2;
+    return (e.xf & 1) ? 1 : 0;
+}
+
+template <int C>
+static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
+    switch (cluster_mode(e)) {
+        case 2: return launch_cluster_m<C, 2>(e, cur, ids, count, s);
+        case 1: return launch_cluster_m<C, 1>(e, cur, ids, count, s);
+        default: return launch_cluster_m<C, 0>(e, cur, ids, count, s);
+    }
 }
 
 // Lanczos for every active node: persistent cluster kernels (one stream per cluster size, running
@@ -455,7 +482,14 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
     }
     if (any) {
         h->stage_launches[SG_MATVEC]++;
-        if (t_b) { cudaEventRecord(t_b, st); h->timed.push_back({SG_MATVEC, t_a, t_b}); }
+        if (t_b) {
+            cudaEventRecord(t_b, st);
+            LevelRec lr;
+            lr.num_active = num_active; lr.big = big_cnt; lr.ms = 0.0;
+            for (int b = 0; b < CL_CLASSES; ++b) { lr.cls[b] = class_cnt[b]; lr.cmap[b] = cmap[b]; }
+            h->levels.push_back(lr);
+            h->timed.push_back({SG_MATVEC, t_a, t_b, (int)h->levels.size() - 1});
+        }
     }
     int rest = big_cnt;
     if (any || launch_failed) {
@@ -679,6 +713,10 @@ int ancuts_create(int device, ancuts_handle** out) {
     }
     ancuts_handle* h = new ancuts_handle();
     h->device = device;
+    if (const char* x = getenv("ANCUTS_X")) h->xflags = atoi(x);
+    if (const char* x = getenv("ANCUTS_PHASES")) {
+        if (atoi(x)) { ANCUTS_CUDA(cudaMalloc((void**)&h->dbg, 32 * sizeof(unsigned long long))); ANCUTS_CUDA(cudaMemset(h->dbg, 0, 32 * sizeof(unsigned long long))); }
+    }
     ANCUTS_CUDA(cudaMallocHost((void**)&h->h_ctr, 16 * sizeof(int)));
     for (int i = 0; i < 6; ++i) {
         ANCUTS_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
@@ -695,6 +733,7 @@ int ancuts_destroy(ancuts_handle* h) {
     cudaSetDevice(h->device);
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
+    if (h->dbg) cudaFree(h->dbg);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_acct) cudaFreeHost(h->h_acct);
     for (auto ev : h->pool) cudaEventDestroy(ev);
@@ -717,6 +756,28 @@ int64_t ancuts_launch_count(ancuts_handle* h, int reset) {
     int64_t v = h->launches_total;
     if (reset) h->launches_total = 0;
     return v;
+}
+
+int ancuts_last_levels(ancuts_handle* h, double* out, int cap_rows) {
+    if (!h) return ANCUTS_EINVAL;
+    int n = std::min((int)h->levels.size(), cap_rows);
+    for (int i = 0; i < n && out; ++i) {
+        const LevelRec& l = h->levels[i];
+        double* o = out + (size_t)i * 16;
+        o[0] = l.num_active; o[1] = l.big; o[2] = l.ms;
+        for (int b = 0; b < 6; ++b) { o[3 + b] = l.cls[b]; o[9 + b] = l.cmap[b]; }
+        o[15] = 0.0;
+    }
+    return (int)h->levels.size();
+}
+
+int ancuts_debug_phases(ancuts_handle* h, double* out32, int reset) {
+    if (!h || !h->dbg) return ANCUTS_EINVAL;
+    unsigned long long tmp[32];
+    ANCUTS_CUDA(cudaMemcpy(tmp, h->dbg, sizeof(tmp), cudaMemcpyDeviceToHost));
+    if (out32) for (int i = 0; i < 32; ++i) out32[i] = (double)tmp[i];
+    if (reset) ANCUTS_CUDA(cudaMemset(h->dbg, 0, sizeof(tmp)));
+    return ANCUTS_OK;
 }
 
 int ancuts_set_stage_timing(ancuts_handle* h, int on) {
@@ -778,7 +839,7 @@ int ancuts_degree_normalize_f32(ancuts_handle* h, int n, const float* d_W, int64
     begin_accounting(h);
     LAUNCH(SG_DEGREE, k_degree_dense<<<(n + 7) / 8, 256, 0, st>>>(n, d_W, ld, d_deg));
     if (d_M) {
-        dim3 g((n + 1023) / 1024, (n + 15) / 16);
+        dim3 g((n + 1023) / 1024, (n + NRM_ROWS - 1) / NRM_ROWS);
         LAUNCH(SG_DEGREE, k_normalize_dense<<<g, 256, 0, st>>>(n, d_W, ld, d_deg, d_M, ldm));
     }
     ANCUTS_CUDA(cudaGetLastError());
@@ -813,6 +874,7 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
     rc = upload_tables(pl, st);
     if (rc) return rc;
     fill_params(pl.e, p, kmax);
+    pl.e.xf = 0; pl.e.w_guard = 1; pl.e.dbg = nullptr;           // caller's W is read in place: anything may sit next to a block
     pl.e.stats = nullptr; pl.e.stats_cap = 0;
     rc = set_attrs(h, pl.KS);
     if (rc) return rc;
@@ -1068,6 +1130,9 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     rc = upload_tables(pl, st);
     if (rc) return rc;
     fill_params(pl.e, p, kmax);
+    pl.e.dbg = h->dbg;
+    pl.e.w_guard = 0;                         // every node block is written by k_gather_blocks_cur (fringe zeroed)
+    pl.e.xf = d_W_dense ? (h->xflags & ~2) : h->xflags;    // caller-provided weights may be negative or denormal
     pl.e.stats = (h_stats && stats_cap > 0) ? pl.stats : nullptr;
     pl.e.stats_cap = stats_cap;
     rc = set_attrs(h, pl.KS);

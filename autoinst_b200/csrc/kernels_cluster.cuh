@@ -227,8 +227,102 @@ __device__ __forceinline__ void cl_update(ClusterShared& S, const SliceBasis& B,
     __syncthreads();
 }
 
+// float -> double widening.  MODE 2: integer form for weights in {0} U [2^-126, 2): bits move 29 places, the
+// exponent is re-biased; +0 becomes 2^-127 (5.9e-39), which every later float64 sum absorbs exactly.
+template <int MODE>
+__device__ __forceinline__ double widen(float f) {
+    if (MODE == 2) {
+        const unsigned b = __float_as_uint(f);
+        return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
+    }
+    return (double)f;
+}
+
+// y_slice = S (w + I) z * invb for the rows [r0, r0+nr) of the node.  MODE 0: entries outside the block are
+// selected away (they may be uninitialised).  MODE 1/2: the caller guarantees that the <= 3 columns on either
+// side of the block hold finite values (k_gather_blocks_cur zeroes them) and zs is zero there.
+// L2 prefetch of one row segment (16-byte aligned, size a multiple of 16): one instruction, no registers, no barrier.
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
+
+// Rows of the passes [pass0, pass0 + npass) of this warp (2 rows per pass, CL_WARPS * 2 rows apart): lane l asks for
+// row l of that list.  Issued `pf` passes ahead of their use, so the matvec loads below find W in L2 although the
+// node blocks of a large batch stream from HBM (ncu, batch 64: L2 hit rate 12 %, long-scoreboard stalls on the loads).
+__device__ __forceinline__ void cl_prefetch_rows(const NodeView& v, int r0, int nr, int pass0, int npass) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane < 2 * npass) {
+        const int row = warp * 2 + (pass0 + (lane >> 1)) * (CL_WARPS * 2) + (lane & 1);
+        if (row < nr) {
+            const int a0 = v.ro & ~3;
+            const unsigned bytes = (unsigned)(((v.ro + v.n - a0) + 3) & ~3) * 4u;
+            l2_prefetch_bulk(v.W + (size_t)(v.ro + r0 + row) * v.ld + a0, bytes);
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, const NodeView& v, int r0, int nr,
+                                          int pad, double invb, int pf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = v.n;
+    const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
+    int pass = 0;
+    for (int rb = warp * 2; rb < nr; rb += (CL_THREADS / 32) * 2, ++pass) {
+        if (pf > 0) cl_prefetch_rows(v, r0, nr, pass + pf, 1);
+        const float* rpt[2];
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr)
+            rpt[rr] = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld;
+        double acc[2] = {0.0, 0.0};
+        for (int c = a0 + lane * 4; c < c_hi; c += 512) {
+            float4 w[2][4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int cg_ = c + 128 * g;
+                const bool has = cg_ < c_hi;
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+                    w[rr][g] = has ? ld_stream4(rpt[rr] + cg_) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                const int cg_ = c + 128 * g;
+                if (cg_ < c_hi) {
+                    const double2 z0 = *reinterpret_cast<const double2*>(&zs[cg_ - a0]);
+                    const double2 z1 = *reinterpret_cast<const double2*>(&zs[cg_ - a0 + 2]);
+                    if (MODE == 0) {
+                        const bool v0 = (cg_ >= c_lo), v1 = (cg_ + 1 >= c_lo) & (cg_ + 1 < c_hi);
+                        const bool v2 = (cg_ + 2 >= c_lo) & (cg_ + 2 < c_hi), v3 = (cg_ + 3 >= c_lo) & (cg_ + 3 < c_hi);
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            // entries outside the block belong to other nodes or are uninitialised: select them away
+                            double q0 = (v0 ? (double)w[rr][g].x : 0.0) * z0.x + (v1 ? (double)w[rr][g].y : 0.0) * z0.y;
+                            double q1 = (v2 ? (double)w[rr][g].z : 0.0) * z1.x + (v3 ? (double)w[rr][g].w : 0.0) * z1.y;
+                            acc[rr] += q0 + q1;
+                        }
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            double q0 = widen<MODE>(w[rr][g].x) * z0.x + widen<MODE>(w[rr][g].y) * z0.y;
+                            double q1 = widen<MODE>(w[rr][g].z) * z1.x + widen<MODE>(w[rr][g].w) * z1.y;
+                            acc[rr] += q0 + q1;
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            double t = warp_sum(acc[rr]);
+            int i = rb + rr;
+            if (lane == 0 && i < nr) S.ysl[i] = S.sv[i] * invb * (t + zs[r0 + i + pad]);   // (w + I) z
+        }
+    }
+}
+
 // grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot
-template <int C>
+template <int C, int MODE>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) {
     extern __shared__ __align__(16) double zs[];   // z = S v for the whole node on the 16-byte window of W's columns;
@@ -290,57 +384,24 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     int k = 0;
     int conv = 0;
     double th[2] = {0.0, 0.0};
+    // optional phase clock (debug): cycles of thread 0 between the block-wide syncs that end each phase
+    const bool prof = (e.dbg != nullptr) && tid == 0 && rank == 0;
+    long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = prof ? clock64() : 0;
+#define CL_PHASE(i) do { if (prof) { long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
+    const int pf = (e.xf >> 4) & 15;                   // passes of L2 prefetch distance (0 = off)
+    if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf);
     while (true) {
         const double invb = 1.0 / bprev;
         // basis row k+1 = current vector (slice)
         for (int i = tid; i < nr; i += CL_THREADS) B.row(k + 1)[i] = S.ysl[i] * invb;
         __syncthreads();
+        CL_PHASE(0);
         // ---- matvec of the slice: 2 rows per warp, 512 columns per iteration, 8 loads issued first ----
-        {
-            const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
-            for (int rb = warp * 2; rb < nr; rb += (CL_THREADS / 32) * 2) {
-                const float* rpt[2];
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-                    rpt[rr] = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld;
-                double acc[2] = {0.0, 0.0};
-                for (int c = a0 + lane * 4; c < c_hi; c += 512) {
-                    float4 w[2][4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int cg_ = c + 128 * g;
-                        const bool has = cg_ < c_hi;
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr)
-                            w[rr][g] = has ? ld_stream4(rpt[rr] + cg_) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int cg_ = c + 128 * g;
-                        if (cg_ < c_hi) {
-                            const double2 z0 = *reinterpret_cast<const double2*>(&zs[cg_ - a0]);
-                            const double2 z1 = *reinterpret_cast<const double2*>(&zs[cg_ - a0 + 2]);
-                            const bool v0 = (cg_ >= c_lo), v1 = (cg_ + 1 >= c_lo) & (cg_ + 1 < c_hi);
-                            const bool v2 = (cg_ + 2 >= c_lo) & (cg_ + 2 < c_hi), v3 = (cg_ + 3 >= c_lo) & (cg_ + 3 < c_hi);
-#pragma unroll
-                            for (int rr = 0; rr < 2; ++rr) {
-                                // entries outside the block belong to other nodes or are uninitialised: select them away
-                                double q0 = (v0 ? (double)w[rr][g].x : 0.0) * z0.x + (v1 ? (double)w[rr][g].y : 0.0) * z0.y;
-                                double q1 = (v2 ? (double)w[rr][g].z : 0.0) * z1.x + (v3 ? (double)w[rr][g].w : 0.0) * z1.y;
-                                acc[rr] += q0 + q1;
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-                    double t = warp_sum(acc[rr]);
-                    int i = rb + rr;
-                    if (lane == 0 && i < nr) S.ysl[i] = S.sv[i] * invb * (t + zs[r0 + i + pad]);   // (w + I) z
-                }
-            }
-        }
+        cl_matvec<MODE>(S, zs, v, r0, nr, pad, invb, pf);
+        if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf);      // first passes of the next step: in flight during Gram-Schmidt
         __syncthreads();
+        CL_PHASE(1);
         const int rows = k + 2;
         // ---- classical Gram-Schmidt against u1 and every Lanczos vector, always twice ("twice is enough").
         //      Measured: skipping the second pass under a DGKS-style test applied after the three-term part
@@ -351,14 +412,18 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         cl_reduce_h<C>(cl, S, rows, 0);
         const double a1 = S.hs[rows - 1];
         __syncthreads();
+        CL_PHASE(2);
         cl_update(S, B, rows, nr);
+        CL_PHASE(3);
         cl_partial_dots(S, B, rows, nr, 1);
         __syncthreads();
         cl_sync<C>(cl);
         cl_reduce_h<C>(cl, S, rows, 1);
         const double a2 = S.hs[rows - 1];
         __syncthreads();
+        CL_PHASE(4);
         cl_update(S, B, rows, nr);
+        CL_PHASE(5);
         // ---- norm, publication of z = S y for the next matvec ----
         double q = 0.0;
         for (int i = tid; i < nr; i += CL_THREADS) q += S.ysl[i] * S.ysl[i];
@@ -385,6 +450,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             for (int i = tid; i < nr; i += CL_THREADS) zs[i + pad] = S.sv[i] * S.ysl[i];
         }
         __syncthreads();
+        CL_PHASE(6);
         const bool breakdown = beta < 1e-13;
         if (breakdown || k >= kcap || (k % e.check_every) == 0) {
             double res = cluster_tridiag(S, k, th);
@@ -392,8 +458,15 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             bool c1 = (k >= n - 1) || breakdown || (res <= e.tol * gap);
             if (c1) { conv = 1; break; }
             if (k >= kcap) break;
+            CL_PHASE(7);
         }
     }
+    CL_PHASE(7);
+    if (prof) {
+        const int ci = (C == 1) ? 0 : (C == 2) ? 1 : (C == 4) ? 2 : 3;
+        for (int i = 0; i < 8; ++i) atomicAdd(&e.dbg[ci * 8 + i], (unsigned long long)tph[i]);
+    }
+#undef CL_PHASE
     // ---- Ritz vector of the slice, statistics for the cut kernels ----
     if (conv) {
         double xs = 0.0, xq = 0.0, xmn = 1e300, xmx = -1e300;

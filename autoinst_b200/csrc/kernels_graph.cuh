@@ -227,32 +227,42 @@ k_degree_dense(int n, const float* __restrict__ W, long long ld, double* __restr
     if (lane == 0) deg[row] = 1.0 + s;
 }
 
+// grid: (column tiles of 1024, row tiles of NRM_ROWS).  The row scales of the tile are computed once per
+// block into shared memory (one float64 rsqrt per row instead of one per row and thread: the first version
+// was bound by the FP64 pipe at 40 % of the HBM peak), the four column scales once per thread.
+constexpr int NRM_ROWS = 32;
 __global__ void __launch_bounds__(256)
 k_normalize_dense(int n, const float* __restrict__ W, long long ld, const double* __restrict__ deg,
                   float* __restrict__ M, long long ldm) {
+    __shared__ double srow[NRM_ROWS];
+    const int r0 = blockIdx.y * NRM_ROWS;
+    if (threadIdx.x < NRM_ROWS) srow[threadIdx.x] = (r0 + threadIdx.x < n) ? rsqrt(deg[r0 + threadIdx.x]) : 0.0;
+    __syncthreads();
     int c = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (c >= n) return;
     double sc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) sc[k] = (c + k < n) ? rsqrt(deg[c + k]) : 0.0;
-    int r0 = blockIdx.y * 16;
-    float4 w[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
-        if (r0 + r < n) w[r] = ld_stream4(W + (size_t)(r0 + r) * ld + c);
+    for (int rb = 0; rb < NRM_ROWS; rb += 8) {
+        float4 w[8];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        int row = r0 + r;
-        if (row >= n) break;
-        double si = rsqrt(deg[row]);
-        float in[4] = {w[r].x, w[r].y, w[r].z, w[r].w};
-        float out[4];
+        for (int r = 0; r < 8; ++r)
+            if (r0 + rb + r < n) w[r] = ld_stream4(W + (size_t)(r0 + rb + r) * ld + c);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            int cc = c + k;
-            out[k] = (cc < n) ? (float)(((double)in[k] + (cc == row ? 1.0 : 0.0)) * si * sc[k]) : 0.0f;
+        for (int r = 0; r < 8; ++r) {
+            int row = r0 + rb + r;
+            if (row >= n) break;
+            double si = srow[rb + r];
+            float in[4] = {w[r].x, w[r].y, w[r].z, w[r].w};
+            float out[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int cc = c + k;
+                out[k] = (cc < n) ? (float)(((double)in[k] + (cc == row ? 1.0 : 0.0)) * si * sc[k]) : 0.0f;
+            }
+            __stcs(reinterpret_cast<float4*>(M + (size_t)row * ldm + c), make_float4(out[0], out[1], out[2], out[3]));
         }
-        *reinterpret_cast<float4*>(M + (size_t)row * ldm + c) = make_float4(out[0], out[1], out[2], out[3]);
     }
 }
 
@@ -422,6 +432,16 @@ k_gather_blocks_cur(Eng e, int cur /* source buffer */) {
         for (int i = 0; i < rows; ++i) {
             int sr = e.val2[start + row0 + i] - base;
             dst[(size_t)(ro + row0 + i) * ld + ro + col] = __ldg(src + (size_t)sr * ld + sc);
+        }
+    }
+    // the matvec reads whole aligned float4 groups: up to 3 columns on either side of the block in the
+    // block's own rows.  Nobody else reads those entries; zero them so that the matvec needs no selects.
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        int j = threadIdx.x;
+        int fc = ro + ((j < 4) ? -1 - j : n + (j - 4));
+        if (fc >= 0 && fc < ld) {
+            int rows = min(16, n - row0);
+            for (int i = 0; i < rows; ++i) dst[(size_t)(ro + row0 + i) * ld + fc] = 0.f;
         }
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)

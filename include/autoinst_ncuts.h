@@ -162,6 +162,13 @@ int ancuts_last_accounting(ancuts_handle* h, double* bytes6, double* ms6, int64_
 /* CUDA-event timing of the library's own launches, summed per stage and read back with
  * ancuts_last_accounting: 0 = off, 1 = every launch, 2 = only the matvec launches (dominant kernel) */
 int ancuts_set_stage_timing(ancuts_handle* h, int on);
+/* Per-level trace of the last segment call in timing mode 2 (tools/level_profile.py): rows of 16 doubles
+ * [0] active nodes, [1] nodes above the cluster kernel's size limit, [2] ms of the concurrent cluster
+ * kernels of the level, [3..8] nodes per size bin, [9..14] cluster size used per bin.  Returns the row count. */
+int ancuts_last_levels(ancuts_handle* h, double* out, int cap_rows);
+/* Debug (handle created with ANCUTS_PHASES=1 in the environment): cycles spent by the persistent Lanczos kernel per
+ * phase, [cluster size 1,2,4,8][basis write, matvec, dots1, update1, dots2, update2, norm+publish, check]. */
+int ancuts_debug_phases(ancuts_handle* h, double* out32, int reset);
 
 #ifdef __cplusplus
 }
