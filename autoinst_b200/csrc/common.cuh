@@ -79,6 +79,36 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
     return r;
 }
 
+// ---- mbarrier / bulk-copy (TMA) helpers -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarrier_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarrier_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbarrier_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_addr_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a barrier that never completes traps instead of hanging the GPU
+__device__ __forceinline__ void mbarrier_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 24); ++it)
+        if (mbarrier_try_wait(bar, parity)) return;
+    __trap();
+}
+// 1-D bulk copy global -> shared memory of this CTA, completion counted in bytes on `bar`
+// (16-byte aligned addresses, size a multiple of 16)
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_addr_u32(bar)) : "memory");
+}
+
 // Every per-node / per-position array the kernels touch. Passed by value.
 struct Eng {
     // sizes

@@ -59,7 +59,8 @@ struct ancuts_handle {
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
     bool attrs_set = false;
-    int xflags = 0;                          // ANCUTS_X (experiments)
+    int xflags = 1 | 8 | (2 << 4) | 1024;    // matvec without selects, FMA chains, L2 prefetch 2 passes ahead, three-term + one
+                                             // Gram-Schmidt pass; ANCUTS_X in the environment overrides (A/B measurements)
     unsigned long long* dbg = nullptr;       // device, 32 entries: phase cycles of the cluster kernel (ANCUTS_PHASES=1)
 };
 
@@ -97,6 +98,8 @@ struct Plan {
     uint8_t* tarl_zero;
     void* cub_tmp;
     void* tc_scratch; size_t tc_scratch_bytes = 0;
+    PairQ* pairq = nullptr; int qcap = 0; int* qctr = nullptr;     // two-pass affinity: pair queue, [2c]=count [2c+1]=overflow
+    bool want_pairq = false;
     ancuts_node_stat* stats;
     Eng e;
 };
@@ -160,6 +163,14 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
         for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
         pl.tc_scratch_bytes = affinity_tc_scratch_bytes(nmax, tdim, ddim);
         pl.tc_scratch = ar.take<char>(pl.tc_scratch_bytes);
+    }
+    pl.pairq = nullptr; pl.qcap = 0; pl.qctr = nullptr;
+    if (pl.want_pairq) {
+        int nmax = 0;
+        for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
+        pl.qcap = (int)std::min<long long>(96ll * nmax, (long long)nmax * (nmax - 1) / 2 + 1);
+        pl.pairq = ar.take<PairQ>((size_t)pl.qcap);
+        pl.qctr = ar.take<int>(2 * (size_t)B);
     }
     pl.hW0.assign(B, nullptr); pl.hW1.assign(B, nullptr);
     for (int c = 0; c < B; ++c) {
@@ -265,6 +276,8 @@ static int set_attrs(ancuts_handle* h, int KS) {
     ANCUTS_CL_ATTR(1, 0); ANCUTS_CL_ATTR(2, 0); ANCUTS_CL_ATTR(4, 0); ANCUTS_CL_ATTR(8, 0);
     ANCUTS_CL_ATTR(1, 1); ANCUTS_CL_ATTR(2, 1); ANCUTS_CL_ATTR(4, 1); ANCUTS_CL_ATTR(8, 1);
     ANCUTS_CL_ATTR(1, 2); ANCUTS_CL_ATTR(2, 2); ANCUTS_CL_ATTR(4, 2); ANCUTS_CL_ATTR(8, 2);
+    ANCUTS_CL_ATTR(1, 3); ANCUTS_CL_ATTR(2, 3); ANCUTS_CL_ATTR(4, 3); ANCUTS_CL_ATTR(8, 3);
+    ANCUTS_CL_ATTR(1, 4); ANCUTS_CL_ATTR(2, 4); ANCUTS_CL_ATTR(4, 4); ANCUTS_CL_ATTR(8, 4);
 #undef ANCUTS_CL_ATTR
     h->attrs_set = true;
     return ANCUTS_OK;
@@ -339,8 +352,11 @@ static int resolve_kmax(const ancuts_params* p) {
     return std::min(std::max(k, 2), KMAX_LIMIT);
 }
 
+// qctr != NULL selects the two-pass form (feature terms only); parent != NULL additionally records the root-level
+// connected components (positions pos0 + i) while the pairs are at hand
 static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, const float* tarl, const float* dino,
-                        const ancuts_params* p, float* W, long long ld, uint8_t* tarl_zero, cudaStream_t st) {
+                        const ancuts_params* p, float* W, long long ld, uint8_t* tarl_zero, cudaStream_t st,
+                        int* qctr = nullptr, int* parent = nullptr, int pos0 = 0) {
     const bool use_tarl = p->theta != 0.0 && tarl != nullptr;
     const bool use_dino = p->gamma != 0.0 && dino != nullptr;
     if (p->theta != 0.0 && tarl == nullptr) { set_error("theta != 0 but no TARL features"); return ANCUTS_EINVAL; }
@@ -360,6 +376,14 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
                                     p->dino_dim, tarl_zero, p->alpha, p->theta, p->gamma, p->proximity, W, ld,
                                     pl.tc_scratch, pl.tc_scratch_bytes, st);
         if (rc != ANCUTS_OK) return rc;
+    } else if (qctr && (use_tarl || use_dino)) {
+        // two-pass form: distances + zero fill + pair queue, then the queued pairs spread over the whole grid
+        dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
+        LAUNCH(SG_AFFINITY, k_affinity_pairs<<<grid, 256, 0, st>>>(n, pts, p->alpha, p->proximity, W, ld, pl.pairq, pl.qcap, qctr,
+                                                                   parent, pos0));
+        LAUNCH(SG_AFFINITY, k_affinity_feats<<<148 * 4, 256, 0, st>>>(pl.pairq, qctr, pl.qcap, use_tarl ? tarl : nullptr, p->tarl_dim,
+                                                                        use_dino ? dino : nullptr, p->dino_dim, tarl_zero, p->theta,
+                                                                        p->gamma, W, ld));
     } else {
         dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
         LAUNCH(SG_AFFINITY, k_affinity_exact<<<grid, 256, 0, st>>>(n, pts, use_tarl ? tarl : nullptr, p->tarl_dim,
@@ -424,6 +448,8 @@ static cudaError_t launch_cluster_m(const Eng& e, int cur, const int* ids, int c
 // 1 = no selects (the gather zeroed the fringe), 2 = additionally the integer float->double widening
 static inline int cluster_mode(const Eng& e) {
     if (e.w_guard) return 0;
+    if (e.xf & 8192) return 4;
+    if (e.xf & 8) return 3;
     if ((e.xf & 2) && (e.xf & 1)) return 2;
     return (e.xf & 1) ? 1 : 0;
 }
@@ -431,6 +457,8 @@ static inline int cluster_mode(const Eng& e) {
 template <int C>
 static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
     switch (cluster_mode(e)) {
+        case 4: return launch_cluster_m<C, 4>(e, cur, ids, count, s);
+        case 3: return launch_cluster_m<C, 3>(e, cur, ids, count, s);
         case 2: return launch_cluster_m<C, 2>(e, cur, ids, count, s);
         case 1: return launch_cluster_m<C, 1>(e, cur, ids, count, s);
         default: return launch_cluster_m<C, 0>(e, cur, ids, count, s);
@@ -567,12 +595,13 @@ k_ev_stats(Eng e) {
 
 // split phase: components, sort, new table, gather.  Returns new counts through h->h_ctr.
 static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int max_split_n, bool components,
-                       cudaStream_t st, int* class_cnt = nullptr, int* big_cnt = nullptr) {
+                       cudaStream_t st, int* class_cnt = nullptr, int* big_cnt = nullptr, bool forest_ready = false) {
     Eng& e = pl.e;
     const int P = e.P;
     const int tb = 256, gP = (P + tb - 1) / tb;
-    LAUNCH(SG_PARTITION, k_cc_init<<<gP, tb, 0, st>>>(e));
-    if (components && num_split > 0) {
+    // forest_ready: the affinity pass already joined every in-mask pair of the (root) ranges in e.parent
+    if (!forest_ready) LAUNCH(SG_PARTITION, k_cc_init<<<gP, tb, 0, st>>>(e));
+    if (!forest_ready && components && num_split > 0) {
         dim3 g((max_split_n + 7) / 8, num_split);
         LAUNCH(SG_PARTITION, k_cc_union<<<g, 256, 0, st>>>(e, cur, e.split_ids));
     }
@@ -619,7 +648,7 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
 
 // the whole recursion for the chunks described by the plan; W of every chunk is in buffer `cur`
 static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cur, int32_t* d_labels,
-                      int32_t* h_num_segments, cudaStream_t st) {
+                      int32_t* h_num_segments, cudaStream_t st, bool root_forest_ready = false) {
     Eng& e = pl.e;
     const int P = e.P, B = e.B;
     ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 16 * sizeof(int), st));
@@ -637,7 +666,7 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
     int guard = 0;
     while (num_split > 0) {
         int class_cnt[CL_CLASSES] = {0}, big_cnt = 0;
-        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt);
+        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt, root_forest_ready && guard == 0);
         if (rc) return rc;
         int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
         if (num_active == 0) break;
@@ -805,15 +834,33 @@ int ancuts_affinity_f32(ancuts_handle* h, int n, const double* d_points, const f
     ANCUTS_CUDA(cudaSetDevice(h->device));
     Plan pl;
     size_t tcb = (p->affinity_impl == 1) ? affinity_tc_scratch_bytes(n, p->tarl_dim, p->dino_dim) : 0;
-    size_t need = align_up((size_t)n, 256) + 256 + tcb + 256;
+    const bool feats = (p->theta != 0.0 && d_tarl) || (p->gamma != 0.0 && d_dino);
+    const bool two_pass = p->affinity_impl == 0 && feats && !(h->xflags & 256);
+    const int qcap = two_pass ? (int)std::min<long long>(96ll * n, (long long)n * (n - 1) / 2 + 1) : 0;
+    const size_t o_tc = align_up((size_t)n, 256) + 256;
+    const size_t o_q = o_tc + align_up(tcb, 256) + 256;
+    const size_t o_ctr = o_q + align_up((size_t)qcap * sizeof(PairQ), 256);
+    size_t need = o_ctr + 256;
     rc = ensure_ws(h, need);
     if (rc) return rc;
     uint8_t* tz = (uint8_t*)h->ws;
-    pl.tc_scratch = h->ws + align_up((size_t)n, 256) + 256;
+    pl.tc_scratch = h->ws + o_tc;
     pl.tc_scratch_bytes = tcb;
+    pl.pairq = (PairQ*)(h->ws + o_q);
+    pl.qcap = qcap;
+    int* qctr = two_pass ? (int*)(h->ws + o_ctr) : nullptr;
     begin_accounting(h);
-    rc = run_affinity(h, pl, n, d_points, d_tarl, d_dino, p, d_W, ld, tz, st);
+    if (qctr) ANCUTS_CUDA(cudaMemsetAsync(qctr, 0, 2 * sizeof(int), st));
+    rc = run_affinity(h, pl, n, d_points, d_tarl, d_dino, p, d_W, ld, tz, st, qctr);
     if (rc) return rc;
+    if (qctr) {
+        // queue overflow (flag set by pass 1): the one-kernel form runs, otherwise its CTAs exit at once; no host sync
+        const bool use_tarl = p->theta != 0.0 && d_tarl != nullptr, use_dino = p->gamma != 0.0 && d_dino != nullptr;
+        dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
+        LAUNCH(SG_AFFINITY, k_affinity_exact<<<grid, 256, 0, st>>>(n, d_points, use_tarl ? d_tarl : nullptr, p->tarl_dim,
+                                                                   use_dino ? d_dino : nullptr, p->dino_dim, tz, p->alpha,
+                                                                   p->theta, p->gamma, p->proximity, d_W, ld, qctr + 1));
+    }
     if (d_rowsum) {
         LAUNCH(SG_DEGREE, k_degree_dense<<<(n + 7) / 8, 256, 0, st>>>(n, d_W, ld, d_rowsum));
         LAUNCH(SG_DEGREE, k_add_scalar<<<(n + 255) / 256, 256, 0, st>>>(n, d_rowsum, -1.0));
@@ -1123,6 +1170,9 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     make_plan(pl, num_chunks, n.data(), norig.data(), nullptr, kmax, 0);
     if (stats_cap < 0) stats_cap = 0;
     const bool need_tc = (p->affinity_impl == 1) && !d_W_dense;
+    const bool feats = (p->theta != 0.0 && d_tarl) || (p->gamma != 0.0 && d_dino);
+    pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && feats && !(h->xflags & 256);   // ANCUTS_X bit 8: one-kernel affinity
+    bool root_forest = pl.want_pairq;
     size_t bytes = layout(pl, nullptr, stats_cap, p->tarl_dim, p->dino_dim, need_tc);
     rc = ensure_ws(h, bytes);
     if (rc) return rc;
@@ -1145,19 +1195,45 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
                                       n[0], cudaMemcpyDeviceToDevice, st));
     } else {
         double aff_bytes = 0.0;
+        if (pl.qctr) {
+            ANCUTS_CUDA(cudaMemsetAsync(pl.qctr, 0, 2 * (size_t)num_chunks * sizeof(int), st));
+            const int gP = (pl.P + 255) / 256;
+            LAUNCH(SG_PARTITION, k_cc_init<<<gP, 256, 0, st>>>(pl.e));          // forest of the root-level components
+        }
         for (int c = 0; c < num_chunks; ++c) {
             int64_t o = h_chunk_off[c] - off0;
             const float* tz = d_tarl ? d_tarl + (size_t)(h_chunk_off[c]) * p->tarl_dim : nullptr;
             const float* dz = d_dino ? d_dino + (size_t)(h_chunk_off[c]) * p->dino_dim : nullptr;
             rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
-                              pl.tarl_zero + o, st);
+                              pl.tarl_zero + o, st, pl.qctr ? pl.qctr + 2 * c : nullptr, pl.qctr ? pl.e.parent : nullptr,
+                              pl.base[c]);
             if (rc) return rc;
             aff_bytes += 4.0 * n[c] * (double)n[c] +
                          4.0 * n[c] * (3 + (p->theta != 0 ? p->tarl_dim : 0) + (p->gamma != 0 ? p->dino_dim : 0));
         }
+        if (pl.qctr) {
+            // a pair queue that overflowed (more than 96 in-mask pairs per point on average) leaves W incomplete:
+            // redo the batch with the one-kernel form.  One small read-back per call.
+            std::vector<int> hq(2 * (size_t)num_chunks);
+            ANCUTS_CUDA(cudaMemcpyAsync(hq.data(), pl.qctr, hq.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+            ANCUTS_CUDA(cudaStreamSynchronize(st));
+            bool overflow = false;
+            for (int c = 0; c < num_chunks; ++c) overflow |= (hq[2 * c + 1] != 0);
+            if (overflow) {
+                root_forest = false;
+                for (int c = 0; c < num_chunks; ++c) {
+                    int64_t o = h_chunk_off[c] - off0;
+                    const float* tz = d_tarl ? d_tarl + (size_t)(h_chunk_off[c]) * p->tarl_dim : nullptr;
+                    const float* dz = d_dino ? d_dino + (size_t)(h_chunk_off[c]) * p->dino_dim : nullptr;
+                    rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
+                                      pl.tarl_zero + o, st);
+                    if (rc) return rc;
+                }
+            }
+        }
         h->stage_bytes[SG_AFFINITY] = aff_bytes;
     }
-    rc = run_levels(h, pl, p, 0, d_labels, h_num_segments, st);
+    rc = run_levels(h, pl, p, 0, d_labels, h_num_segments, st, root_forest);
     if (rc) return rc;
     rc = copy_stats(h, pl, h_stats, stats_cap, h_num_stats, st);
     if (rc) return rc;

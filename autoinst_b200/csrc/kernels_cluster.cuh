@@ -249,12 +249,28 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) 
 // Rows of the passes [pass0, pass0 + npass) of this warp (2 rows per pass, CL_WARPS * 2 rows apart): lane l asks for
 // row l of that list.  Issued `pf` passes ahead of their use, so the matvec loads below find W in L2 although the
 // node blocks of a large batch stream from HBM (ncu, batch 64: L2 hit rate 12 %, long-scoreboard stalls on the loads).
-__device__ __forceinline__ void cl_prefetch_rows(const NodeView& v, int r0, int nr, int pass0, int npass) {
+__device__ __forceinline__ void cl_prefetch_rows(const NodeView& v, int r0, int nr, int pass0, int npass, bool lanes = false) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a0 = v.ro & ~3;
+    if (lanes) {
+        // per-lane form: lane l asks for the 128-byte line l, l + 32, ... of each row (LSU path instead of the bulk engine)
+        const int lines = (((v.ro + v.n - a0) * 4) + 127) >> 7;
+        for (int p = pass0; p < pass0 + npass; ++p) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const int row = warp * 2 + p * (CL_WARPS * 2) + rr;
+                if (row < nr) {
+                    const char* rp = reinterpret_cast<const char*>(v.W + (size_t)(v.ro + r0 + row) * v.ld + a0);
+                    for (int l = lane; l < lines; l += 32)
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(rp + (size_t)l * 128));
+                }
+            }
+        }
+        return;
+    }
     if (lane < 2 * npass) {
         const int row = warp * 2 + (pass0 + (lane >> 1)) * (CL_WARPS * 2) + (lane & 1);
         if (row < nr) {
-            const int a0 = v.ro & ~3;
             const unsigned bytes = (unsigned)(((v.ro + v.n - a0) + 3) & ~3) * 4u;
             l2_prefetch_bulk(v.W + (size_t)(v.ro + r0 + row) * v.ld + a0, bytes);
         }
@@ -263,18 +279,18 @@ __device__ __forceinline__ void cl_prefetch_rows(const NodeView& v, int r0, int 
 
 template <int MODE>
 __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, const NodeView& v, int r0, int nr,
-                                          int pad, double invb, int pf) {
+                                          int pad, double invb, int pf, bool pfl) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = v.n;
     const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
     int pass = 0;
     for (int rb = warp * 2; rb < nr; rb += (CL_THREADS / 32) * 2, ++pass) {
-        if (pf > 0) cl_prefetch_rows(v, r0, nr, pass + pf, 1);
+        if (pf > 0) cl_prefetch_rows(v, r0, nr, pass + pf, 1, pfl);
         const float* rpt[2];
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr)
             rpt[rr] = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld;
-        double acc[2] = {0.0, 0.0};
+        double acc[2] = {0.0, 0.0}, acb[2] = {0.0, 0.0};
         for (int c = a0 + lane * 4; c < c_hi; c += 512) {
             float4 w[2][4];
 #pragma unroll
@@ -301,6 +317,15 @@ __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, co
                             double q1 = (v2 ? (double)w[rr][g].z : 0.0) * z1.x + (v3 ? (double)w[rr][g].w : 0.0) * z1.y;
                             acc[rr] += q0 + q1;
                         }
+                    } else if (MODE == 3) {
+                        // two FMA chains per row: one FP64 instruction per element instead of 1.5
+#pragma unroll
+                        for (int rr = 0; rr < 2; ++rr) {
+                            acc[rr] = fma((double)w[rr][g].x, z0.x, acc[rr]);
+                            acb[rr] = fma((double)w[rr][g].y, z0.y, acb[rr]);
+                            acc[rr] = fma((double)w[rr][g].z, z1.x, acc[rr]);
+                            acb[rr] = fma((double)w[rr][g].w, z1.y, acb[rr]);
+                        }
                     } else {
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
@@ -314,11 +339,112 @@ __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, co
         }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            double t = warp_sum(acc[rr]);
+            double t = warp_sum(MODE == 3 ? acc[rr] + acb[rr] : acc[rr]);
             int i = rb + rr;
             if (lane == 0 && i < nr) S.ysl[i] = S.sv[i] * invb * (t + zs[r0 + i + pad]);   // (w + I) z
         }
     }
+}
+
+// ---- TMA-fed matvec (MODE 4): every warp owns a ring of RING_ST stages in shared memory; a stage holds up to
+// RING_COLS columns of the warp's two current rows (4 KB).  Lane 0 issues one bulk copy per row and stage
+// (cp.async.bulk, completion counted on the stage's mbarrier); the warp waits for the stage, multiplies it with z
+// from shared memory and hands the slot back.  Registers limit the plain form to 4 KB per warp in flight and only
+// in bursts (issue 8 loads, wait, multiply: ncu puts 32 % of the kernel's stall samples on the first use of the
+// loaded registers); the ring keeps 4-8 KB per warp in flight all the time.  It takes the shared memory that held
+// basis rows: Gram-Schmidt then reads the basis from L2, which costs far less than the matvec gains.
+// W does not change between steps, so the first stages of the NEXT matvec are fetched during Gram-Schmidt.
+// (A first version with 1 KB stages, 4 per warp, was 20 % slower than the plain form: the per-stage wait / issue
+// overhead has to be spread over more data.)
+constexpr int RING_ST = 2;
+constexpr int RING_COLS = 512;                         // floats per row and stage
+constexpr int RING_STAGE_FLOATS = 2 * RING_COLS;
+constexpr int RING_WARP_FLOATS = RING_ST * RING_STAGE_FLOATS;
+constexpr int RING_BYTES = CL_WARPS * RING_WARP_FLOATS * 4;      // 128 KB
+
+struct RingGeom { int a0, width, nseg, npass, T; };
+__device__ __forceinline__ RingGeom ring_geom(const NodeView& v, int nr) {
+    RingGeom q;
+    const int warp = threadIdx.x >> 5;
+    q.a0 = v.ro & ~3;
+    q.width = (v.ro + v.n - q.a0 + 3) & ~3;            // columns fetched per row (multiple of 4)
+    q.nseg = (q.width + RING_COLS - 1) / RING_COLS;
+    q.npass = (warp * 2 < nr) ? (nr - warp * 2 + CL_WARPS * 2 - 1) / (CL_WARPS * 2) : 0;
+    q.T = q.npass * q.nseg;
+    return q;
+}
+// lane 0: fetch stage (p, sg) of the matvec into the slot of global stage index gi
+__device__ __forceinline__ void ring_issue(const NodeView& v, const RingGeom& q, int r0, int nr, int p, int sg,
+                                           float* ring_w, uint64_t* bars_w, uint32_t gi) {
+    const int warp = threadIdx.x >> 5;
+    const int rb = warp * 2 + p * (CL_WARPS * 2);
+    const int c = sg * RING_COLS;
+    const uint32_t bytes = (uint32_t)min(RING_COLS, q.width - c) * 4u;
+    const uint32_t slot = gi % RING_ST;
+    float* dst = ring_w + slot * RING_STAGE_FLOATS;
+    uint64_t* bar = bars_w + slot;
+    mbarrier_expect_tx(bar, 2u * bytes);
+    bulk_copy_g2s(dst, v.W + (size_t)(v.ro + r0 + min(rb, nr - 1)) * v.ld + q.a0 + c, bytes, bar);
+    bulk_copy_g2s(dst + RING_COLS, v.W + (size_t)(v.ro + r0 + min(rb + 1, nr - 1)) * v.ld + q.a0 + c, bytes, bar);
+}
+// the first min(RING_ST, T) stages of a matvec (before the first step and after every matvec)
+__device__ __forceinline__ void ring_prologue(const NodeView& v, const RingGeom& q, int r0, int nr, float* ring_w,
+                                              uint64_t* bars_w, uint32_t g) {
+    if ((threadIdx.x & 31) == 0) {
+        int p = 0, sg = 0;
+        for (int t = 0; t < min(RING_ST, q.T); ++t) {
+            ring_issue(v, q, r0, nr, p, sg, ring_w, bars_w, g + t);
+            if (++sg == q.nseg) { sg = 0; ++p; }
+        }
+    }
+}
+__device__ __forceinline__ void ring_drain(const RingGeom& q, uint64_t* bars_w, uint32_t g) {
+    for (int t = 0; t < min(RING_ST, q.T); ++t) mbarrier_wait(bars_w + ((g + t) % RING_ST), ((g + t) / RING_ST) & 1u);
+}
+
+__device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* zs, const NodeView& v, const RingGeom& q,
+                                               int r0, int nr, int pad, double invb, float* ring_w, uint64_t* bars_w,
+                                               uint32_t& g) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int ip = 0, isg = 0;                               // next stage to issue = stage t + RING_ST
+    for (int t = 0; t < min(RING_ST, q.T); ++t) if (++isg == q.nseg) { isg = 0; ++ip; }
+    int t = 0;
+    for (int p = 0; p < q.npass; ++p) {
+        double acc0 = 0.0, acb0 = 0.0, acc1 = 0.0, acb1 = 0.0;
+        for (int sg = 0; sg < q.nseg; ++sg, ++t) {
+            const uint32_t slot = g % RING_ST;
+            mbarrier_wait(bars_w + slot, (g / RING_ST) & 1u);
+            const float* buf = ring_w + slot * RING_STAGE_FLOATS;
+#pragma unroll
+            for (int gq = 0; gq < RING_COLS / 128; ++gq) {
+                const int cs = 128 * gq + 4 * lane;                // column inside the stage
+                const int cofs = sg * RING_COLS + cs;              // column - a0
+                if (cofs < q.width) {
+                    const float4 wa = *reinterpret_cast<const float4*>(buf + cs);
+                    const float4 wb = *reinterpret_cast<const float4*>(buf + RING_COLS + cs);
+                    const double2 z0 = *reinterpret_cast<const double2*>(&zs[cofs]);
+                    const double2 z1 = *reinterpret_cast<const double2*>(&zs[cofs + 2]);
+                    acc0 = fma((double)wa.x, z0.x, acc0); acb0 = fma((double)wa.y, z0.y, acb0);
+                    acc0 = fma((double)wa.z, z1.x, acc0); acb0 = fma((double)wa.w, z1.y, acb0);
+                    acc1 = fma((double)wb.x, z0.x, acc1); acb1 = fma((double)wb.y, z0.y, acb1);
+                    acc1 = fma((double)wb.z, z1.x, acc1); acb1 = fma((double)wb.w, z1.y, acb1);
+                }
+            }
+            __syncwarp();
+            ++g;
+            if (lane == 0 && t + RING_ST < q.T) {
+                ring_issue(v, q, r0, nr, ip, isg, ring_w, bars_w, g + RING_ST - 1);
+                if (++isg == q.nseg) { isg = 0; ++ip; }
+            }
+        }
+        const int rb = warp * 2 + p * (CL_WARPS * 2);
+        const double t0 = warp_sum(acc0 + acb0), t1 = warp_sum(acc1 + acb1);
+        if (lane == 0) {
+            S.ysl[rb] = S.sv[rb] * invb * (t0 + zs[r0 + rb + pad]);               // (w + I) z
+            if (rb + 1 < nr) S.ysl[rb + 1] = S.sv[rb + 1] * invb * (t1 + zs[r0 + rb + 1 + pad]);
+        }
+    }
+    ring_prologue(v, q, r0, nr, ring_w, bars_w, g);
 }
 
 // grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot
@@ -344,13 +470,26 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     {
         const int nz = (n + 8 + 3) & ~3;               // doubles used by zs
         B.nrp = (max(nr, 1) + 3) & ~3;
-        B.smem = zs + nz;
-        B.rows_s = max(0, (dyn_doubles - nz) / B.nrp);
+        const int nring = (MODE == 4) ? RING_BYTES / 8 : 0;       // the warps' W rings sit between z and the basis rows
+        B.smem = zs + nz + nring;
+        B.rows_s = (e.xf & 4096) ? 0 : max(0, (dyn_doubles - nz - nring) / B.nrp);     // bit 12: basis in global memory only
         B.glob = e.V + g0;
         B.P = P;
     }
     const int kcap = min(min(CL_KMAX, e.kmax), n - 1);
-
+    __shared__ uint64_t ring_bar[CL_WARPS * RING_ST];
+    float* ring_w = reinterpret_cast<float*>(zs + ((n + 8 + 3) & ~3)) + (size_t)warp * RING_WARP_FLOATS;
+    uint64_t* bars_w = ring_bar + warp * RING_ST;
+    const RingGeom rq = ring_geom(v, nr);
+    uint32_t ring_g = 0;                               // stages consumed by this warp so far
+    if (MODE == 4) {
+        if (lane == 0) {
+            for (int i = 0; i < RING_ST; ++i) mbarrier_init(bars_w + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        ring_prologue(v, rq, r0, nr, ring_w, bars_w, ring_g);     // W is ready: start streaming during the set-up
+    }
     // ---- init (every CTA redundantly: bit-identical scalars, no exchange needed) ----
     double s = 0.0;
     for (int i = tid; i < n; i += CL_THREADS) s += e.deg[v.start + i];
@@ -389,8 +528,10 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = prof ? clock64() : 0;
 #define CL_PHASE(i) do { if (prof) { long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
-    const int pf = (e.xf >> 4) & 15;                   // passes of L2 prefetch distance (0 = off)
-    if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf);
+    const bool gs1 = (e.xf & 1024) != 0;              // three-term recurrence + one Gram-Schmidt pass
+    const int pf = (e.xf >> 4) & 3;                   // passes of L2 prefetch distance (0 = off)
+    const bool pfl = (e.xf & 2048) != 0;               // per-lane prefetch.global.L2 instead of the bulk form
+    if (pf > 0 && MODE != 4) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);
     while (true) {
         const double invb = 1.0 / bprev;
         // basis row k+1 = current vector (slice)
@@ -398,19 +539,61 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         __syncthreads();
         CL_PHASE(0);
         // ---- matvec of the slice: 2 rows per warp, 512 columns per iteration, 8 loads issued first ----
-        cl_matvec<MODE>(S, zs, v, r0, nr, pad, invb, pf);
-        if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf);      // first passes of the next step: in flight during Gram-Schmidt
+        if (MODE == 4) {
+            cl_matvec_ring(S, zs, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g);
+        } else {
+            cl_matvec<MODE>(S, zs, v, r0, nr, pad, invb, pf, pfl);
+            if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);  // first passes of the next step: in flight during Gram-Schmidt
+        }
         __syncthreads();
         CL_PHASE(1);
         const int rows = k + 2;
+        double a1, a2;
+        if (gs1) {
+            // ---- three-term recurrence first, then ONE classical Gram-Schmidt pass against u1 and every Lanczos
+            //      vector.  In exact arithmetic w - alpha v_k - beta v_{k-1} is already orthogonal to the basis, so the
+            //      full pass only removes rounding-level components and plays the role of the SECOND pass of "twice is
+            //      enough": orthogonality stays at 2e-15 like CGS2 (numpy model, 151 nodes, identical steps and cuts),
+            //      with two sweeps over the basis instead of four.  A single CGS pass WITHOUT the three-term part
+            //      loses orthogonality within dozens of steps (measured in round 1 and again in the model). ----
+            const double* vk = B.row(k + 1);
+            double pa = 0.0;
+            for (int i = tid; i < nr; i += CL_THREADS) pa += vk[i] * S.ysl[i];
+            pa = block_sum_512(pa, S.red);
+            if (tid == 0) S.npart[1] = pa;
+            __syncthreads();
+            cl_sync<C>(cl);
+            a1 = 0.0;
+            if (C > 1) {
+#pragma unroll
+                for (int r = 0; r < C; ++r) a1 += cl.map_shared_rank(&S.npart[0], r)[1];      // rank order
+            } else {
+                a1 = S.npart[1];
+            }
+            {
+                const double bk = (k > 0) ? S.beta[k - 1] : 0.0;
+                const double* vp = B.row(k);                                                // v_{k-1} (u1 when k = 0: bk = 0)
+                for (int i = tid; i < nr; i += CL_THREADS) S.ysl[i] = (S.ysl[i] - a1 * vk[i]) - bk * vp[i];
+            }
+            __syncthreads();
+            CL_PHASE(2);
+            CL_PHASE(3);
+            cl_partial_dots(S, B, rows, nr, 1);
+            __syncthreads();
+            cl_sync<C>(cl);
+            cl_reduce_h<C>(cl, S, rows, 1);
+            a2 = S.hs[rows - 1];
+            __syncthreads();
+            CL_PHASE(4);
+            cl_update(S, B, rows, nr);
+            CL_PHASE(5);
+        } else {
         // ---- classical Gram-Schmidt against u1 and every Lanczos vector, always twice ("twice is enough").
-        //      Measured: skipping the second pass under a DGKS-style test applied after the three-term part
-        //      loses orthogonality within a few dozen steps (Ritz values outside [-1, 1]). ----
         cl_partial_dots(S, B, rows, nr, 0);
         __syncthreads();
         cl_sync<C>(cl);
         cl_reduce_h<C>(cl, S, rows, 0);
-        const double a1 = S.hs[rows - 1];
+        a1 = S.hs[rows - 1];
         __syncthreads();
         CL_PHASE(2);
         cl_update(S, B, rows, nr);
@@ -419,11 +602,12 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         __syncthreads();
         cl_sync<C>(cl);
         cl_reduce_h<C>(cl, S, rows, 1);
-        const double a2 = S.hs[rows - 1];
+        a2 = S.hs[rows - 1];
         __syncthreads();
         CL_PHASE(4);
         cl_update(S, B, rows, nr);
         CL_PHASE(5);
+        }
         // ---- norm, publication of z = S y for the next matvec ----
         double q = 0.0;
         for (int i = tid; i < nr; i += CL_THREADS) q += S.ysl[i] * S.ysl[i];
@@ -462,6 +646,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         }
     }
     CL_PHASE(7);
+    if (MODE == 4) ring_drain(rq, bars_w, ring_g);     // stages fetched ahead for a step that will not run
     if (prof) {
         const int ci = (C == 1) ? 0 : (C == 2) ? 1 : (C == 4) ? 2 : 3;
         for (int i = 0; i < 8; ++i) atomicAdd(&e.dbg[ci * 8 + i], (unsigned long long)tph[i]);

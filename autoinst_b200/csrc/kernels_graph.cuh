@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(256)
 k_affinity_exact(int n, const double* __restrict__ pts, const float* __restrict__ tarl, int tdim,
                  const float* __restrict__ dino, int ddim, const uint8_t* __restrict__ tarl_zero,
                  double alpha, double theta, double gamma, double prox,
-                 float* __restrict__ W, long long ld) {
+                 float* __restrict__ W, long long ld, const int* __restrict__ only_if = nullptr) {
+    if (only_if && !*only_if) return;       // conditional fallback after the two-pass form (pair queue overflow)
     __shared__ double pr[AT][3];
     __shared__ double pc[AT][3];
     __shared__ float pr32[AT][3];           // coordinates relative to the tile's first row point: float32 pre-filter
@@ -172,6 +173,138 @@ k_affinity_exact(int n, const double* __restrict__ pts, const float* __restrict_
         if (gr < n && gc < ld) {
             float4 v = *reinterpret_cast<const float4*>(&tile[r][cg]);
             *reinterpret_cast<float4*>(W + (size_t)gr * ld + gc) = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage 1, two-pass form used when feature terms are present (default).  The one-kernel form above evaluates the
+// feature distances of a tile inside the tile's CTA: tiles on the diagonal hold thousands of in-mask pairs, tiles
+// elsewhere none, and the dense tiles became the tail of the launch (0.18 ms at N = 8.6 k against a 0.05 ms store
+// floor).  Here pass 1 only tests distances on the upper triangle, zero-fills W and appends the in-mask pairs
+// (i < j) to a queue; pass 2 spreads the queue evenly over the grid, one 8-lane group per pair, and writes both
+// W_ij and W_ji (cdist is symmetric bit for bit).  Pass 1 also joins i and j in the union-find forest of the
+// root-level connected components, which saves the first k_cc_union pass over the dense matrix.
+// ---------------------------------------------------------------------------------------------
+struct PairQ { int i, j; double a; };      // a = alpha * spatial distance (float64)
+
+// forward declarations (defined with the component kernels below)
+__device__ __forceinline__ void uf_union(int* parent, int a, int b);
+
+__global__ void __launch_bounds__(256)
+k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double prox, float* __restrict__ W, long long ld,
+                 PairQ* __restrict__ q, int qcap, int* __restrict__ qctr, int* parent, int pos0) {
+    __shared__ double pr[AT][3];
+    __shared__ double pc[AT][3];
+    __shared__ float pr32[AT][3];
+    __shared__ float pc32[AT][3];
+    __shared__ unsigned short queue[AT * AT];
+    __shared__ int qn, qbase;
+
+    const int row0 = blockIdx.y * AT, col0 = blockIdx.x * AT;
+    const int tid = threadIdx.x;
+    const int cg = (tid & 15) * 4, rg = tid >> 4;
+    if (row0 > col0) {                               // mirror entries: written by pass 2
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int gr = row0 + rg + 16 * k, gc = col0 + cg;
+            if (gr < n && gc < ld) __stcs(reinterpret_cast<float4*>(W + (size_t)gr * ld + gc), make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+        return;
+    }
+    if (tid == 0) qn = 0;
+    for (int i = tid; i < AT * 3; i += 256) {
+        int p = i / 3, k = i % 3;
+        int gr = row0 + p, gc = col0 + p;
+        double org = pts[(size_t)min(row0, n - 1) * 3 + k];
+        double a = gr < n ? pts[(size_t)gr * 3 + k] : 0.0;
+        double b = gc < n ? pts[(size_t)gc * 3 + k] : 0.0;
+        pr[p][k] = a;
+        pc[p][k] = b;
+        pr32[p][k] = (float)(a - org);
+        pc32[p][k] = (float)(b - org);
+    }
+    __syncthreads();
+    const float lim32 = (float)((prox + 1e-2) * (prox + 1e-2) * 1.001);     // see k_affinity_exact
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = rg + 16 * k;
+        float out[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int c = cg + c4;
+            const int gi = row0 + r, gj = col0 + c;
+            if (gi == gj) { out[c4] = (gi < n) ? 1.0f : 0.0f; continue; }       // exp(-0)
+            float fx = pr32[r][0] - pc32[c][0], fy = pr32[r][1] - pc32[c][1], fz = pr32[r][2] - pc32[c][2];
+            if (gi < gj && gj < n && !(fx * fx + fy * fy + fz * fz > lim32)) {
+                double dx = pr[r][0] - pc[c][0], dy = pr[r][1] - pc[c][1], dz = pr[r][2] - pc[c][2];
+                double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (__dsqrt_rn(s) <= prox) {                                     // ncuts_utils.py:61, inclusive
+                    int qi = atomicAdd(&qn, 1);
+                    queue[qi] = (unsigned short)(r * AT + c);
+                }
+            }
+        }
+        const int gr = row0 + r, gc = col0 + cg;
+        if (gr < n && gc < ld) __stcs(reinterpret_cast<float4*>(W + (size_t)gr * ld + gc), make_float4(out[0], out[1], out[2], out[3]));
+    }
+    __syncthreads();
+    const int total = qn;
+    if (total == 0) return;
+    if (tid == 0) {
+        int b = atomicAdd(&qctr[0], total);
+        if (b + total > qcap) { atomicExch(&qctr[1], 1); b = -1; }      // the caller falls back to the one-kernel form
+        qbase = b;
+    }
+    __syncthreads();
+    const int base = qbase;
+    if (base < 0) return;
+    for (int t = tid; t < total; t += 256) {
+        int idx = queue[t];
+        int r = idx / AT, c = idx % AT;
+        double dx = pr[r][0] - pc[c][0], dy = pr[r][1] - pc[c][1], dz = pr[r][2] - pc[c][2];
+        double sd = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        PairQ e;
+        e.i = row0 + r; e.j = col0 + c;
+        e.a = alpha != 0.0 ? alpha * sd : 0.0;                           // ncuts_utils.py:63-66
+        q[base + t] = e;
+        // root-level connected components: 256 pairs per CTA at a time (in pass 2 only one lane in eight would work)
+        if (parent) uf_union(parent, pos0 + e.i, pos0 + e.j);
+    }
+}
+
+// pass 2: grid-stride over the queue, one 8-lane group per pair.
+__global__ void __launch_bounds__(256)
+k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int qcap,
+                 const float* __restrict__ tarl, int tdim, const float* __restrict__ dino, int ddim,
+                 const uint8_t* __restrict__ tarl_zero, double theta, double gamma,
+                 float* __restrict__ W, long long ld) {
+    const int total = min(qctr[0], qcap);
+    if (qctr[1]) return;                             // overflow: everything is redone by the one-kernel form
+    const int lane8 = threadIdx.x & 7;
+    const int groups = gridDim.x * 32;
+    const int grp = blockIdx.x * 32 + (threadIdx.x >> 3);
+    const int iters = (total + groups - 1) / groups;
+    for (int it = 0; it < iters; ++it) {
+        const int idx = it * groups + grp;
+        const bool live = idx < total;
+        int gi = 0, gj = 0;
+        double a = 0.0;
+        if (live) { PairQ e = q[idx]; gi = e.i; gj = e.j; a = e.a; }
+        double arg = 0.0;
+        if (theta != 0.0 && tarl != nullptr) {
+            double td = feat_dist8(tarl + (size_t)gi * tdim, tarl + (size_t)gj * tdim, tdim, lane8);
+            if (tarl_zero[gi] | tarl_zero[gj]) td = 0.0;                 // ncuts_utils.py:145-146
+            arg += theta * td;
+        }
+        if (gamma != 0.0 && dino != nullptr) {
+            double dd = feat_dist8(dino + (size_t)gi * ddim, dino + (size_t)gj * ddim, ddim, lane8);
+            arg += gamma * dd;                                           // :129-133
+        }
+        if (live && lane8 == 0) {
+            float w = (float)exp(-(a + arg));
+            W[(size_t)gi * ld + gj] = w;
+            W[(size_t)gj * ld + gi] = w;
         }
     }
 }

@@ -211,7 +211,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="chunks per GPU per step")
+    ap.add_argument("--batch", type=int, default=64, help="chunks per GPU per step")
     ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--cpu-chunks", type=int, default=1, help="chunks in the cpu_baseline sample (0 = skip)")
@@ -354,7 +354,7 @@ def main():
             "e2e": {"value": total_chunks / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": packed.h2d_bytes() * world, "d2h_bytes_per_step": packed.d2h_bytes() * world},
             "gpu_launches": int(launches) * world,
-            "roofline": {"bound": "hbm", "kernel": "k_matvec<4>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_lanczos_cluster<C> (matvec of the persistent Lanczos kernels, one timed launch = the concurrent kernels of one recursion level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "launches_timed": mv_launches, "avg_launch_us": 1e3 * mv_ms / max(mv_launches, 1),
                          "algorithmic_bytes_per_launch": mv_bytes / max(mv_launches, 1),
