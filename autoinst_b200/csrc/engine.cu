@@ -59,8 +59,12 @@ struct ancuts_handle {
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
     bool attrs_set = false;
-    int xflags = 1 | 8 | (2 << 4) | 1024;    // matvec without selects, FMA chains, L2 prefetch 2 passes ahead, three-term + one
-                                             // Gram-Schmidt pass; ANCUTS_X in the environment overrides (A/B measurements)
+    // Lanczos kernel variant (ANCUTS_X in the environment overrides, for A/B measurements; tools/gpu_s2_*.sh):
+    //   1 (always on) matvec without out-of-block selects   2 every second float->double widening on the integer pipe
+    //   bits 4-5 L2 bulk prefetch distance in passes (register-staged matvec only)   256 one-kernel affinity
+    //   1024 three-term recurrence + ONE Gram-Schmidt pass   4096 basis rows in global memory only
+    //   8192 TMA ring in shared memory instead of register-staged loads
+    int xflags = 1 | 2 | 1024 | 8192;
     unsigned long long* dbg = nullptr;       // device, 32 entries: phase cycles of the cluster kernel (ANCUTS_PHASES=1)
 };
 
@@ -100,6 +104,7 @@ struct Plan {
     void* tc_scratch; size_t tc_scratch_bytes = 0;
     PairQ* pairq = nullptr; int qcap = 0; int* qctr = nullptr;     // two-pass affinity: pair queue, [2c]=count [2c+1]=overflow
     bool want_pairq = false;
+    char* w0_begin = nullptr; size_t w0_bytes = 0;                 // the chunks' ping buffers (contiguous)
     ancuts_node_stat* stats;
     Eng e;
 };
@@ -173,11 +178,16 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
         pl.qctr = ar.take<int>(2 * (size_t)B);
     }
     pl.hW0.assign(B, nullptr); pl.hW1.assign(B, nullptr);
-    for (int c = 0; c < B; ++c) {
-        size_t elems = (size_t)pl.n[c] * pl.ld[c];
-        if (pl.own_w0) pl.hW0[c] = ar.take<float>(elems);
-        if (pl.own_w1) pl.hW1[c] = ar.take<float>(elems);
+    // all ping buffers first: one contiguous region, zero-filled by a single memset before the two-pass affinity
+    pl.w0_begin = nullptr; pl.w0_bytes = 0;
+    if (pl.own_w0) {
+        ar.off = align_up(ar.off, 256);
+        size_t start = ar.off;
+        for (int c = 0; c < B; ++c) pl.hW0[c] = ar.take<float>((size_t)pl.n[c] * pl.ld[c]);
+        pl.w0_begin = base ? base + start : nullptr;
+        pl.w0_bytes = ar.off - start;
     }
+    if (pl.own_w1) for (int c = 0; c < B; ++c) pl.hW1[c] = ar.take<float>((size_t)pl.n[c] * pl.ld[c]);
     return align_up(ar.off, 256);
 }
 
@@ -274,10 +284,10 @@ static int set_attrs(ancuts_handle* h, int KS) {
     const int cl_smem = CL_DYN_SMEM;
 #define ANCUTS_CL_ATTR(C, M) ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem))
     ANCUTS_CL_ATTR(1, 0); ANCUTS_CL_ATTR(2, 0); ANCUTS_CL_ATTR(4, 0); ANCUTS_CL_ATTR(8, 0);
-    ANCUTS_CL_ATTR(1, 1); ANCUTS_CL_ATTR(2, 1); ANCUTS_CL_ATTR(4, 1); ANCUTS_CL_ATTR(8, 1);
-    ANCUTS_CL_ATTR(1, 2); ANCUTS_CL_ATTR(2, 2); ANCUTS_CL_ATTR(4, 2); ANCUTS_CL_ATTR(8, 2);
     ANCUTS_CL_ATTR(1, 3); ANCUTS_CL_ATTR(2, 3); ANCUTS_CL_ATTR(4, 3); ANCUTS_CL_ATTR(8, 3);
     ANCUTS_CL_ATTR(1, 4); ANCUTS_CL_ATTR(2, 4); ANCUTS_CL_ATTR(4, 4); ANCUTS_CL_ATTR(8, 4);
+    ANCUTS_CL_ATTR(1, 5); ANCUTS_CL_ATTR(2, 5); ANCUTS_CL_ATTR(4, 5); ANCUTS_CL_ATTR(8, 5);
+    ANCUTS_CL_ATTR(1, 6); ANCUTS_CL_ATTR(2, 6); ANCUTS_CL_ATTR(4, 6); ANCUTS_CL_ATTR(8, 6);
 #undef ANCUTS_CL_ATTR
     h->attrs_set = true;
     return ANCUTS_OK;
@@ -356,7 +366,7 @@ static int resolve_kmax(const ancuts_params* p) {
 // connected components (positions pos0 + i) while the pairs are at hand
 static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, const float* tarl, const float* dino,
                         const ancuts_params* p, float* W, long long ld, uint8_t* tarl_zero, cudaStream_t st,
-                        int* qctr = nullptr, int* parent = nullptr, int pos0 = 0) {
+                        int* qctr = nullptr, int* parent = nullptr, int pos0 = 0, bool prezeroed = false) {
     const bool use_tarl = p->theta != 0.0 && tarl != nullptr;
     const bool use_dino = p->gamma != 0.0 && dino != nullptr;
     if (p->theta != 0.0 && tarl == nullptr) { set_error("theta != 0 but no TARL features"); return ANCUTS_EINVAL; }
@@ -379,6 +389,7 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
     } else if (qctr && (use_tarl || use_dino)) {
         // two-pass form: distances + zero fill + pair queue, then the queued pairs spread over the whole grid
         dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
+        (void)prezeroed;
         LAUNCH(SG_AFFINITY, k_affinity_pairs<<<grid, 256, 0, st>>>(n, pts, p->alpha, p->proximity, W, ld, pl.pairq, pl.qcap, qctr,
                                                                    parent, pos0));
         LAUNCH(SG_AFFINITY, k_affinity_feats<<<148 * 4, 256, 0, st>>>(pl.pairq, qctr, pl.qcap, use_tarl ? tarl : nullptr, p->tarl_dim,
@@ -447,20 +458,19 @@ static cudaError_t launch_cluster_m(const Eng& e, int cur, const int* ids, int c
 // matvec variant: 0 = out-of-block entries selected away (W may hold anything next to a block),
 // 1 = no selects (the gather zeroed the fringe), 2 = additionally the integer float->double widening
 static inline int cluster_mode(const Eng& e) {
-    if (e.w_guard) return 0;
-    if (e.xf & 8192) return 4;
-    if (e.xf & 8) return 3;
-    if ((e.xf & 2) && (e.xf & 1)) return 2;
-    return (e.xf & 1) ? 1 : 0;
+    if (e.w_guard) return 0;                           // 0: selects, W read in place (stage entry points)
+    const bool mix = (e.xf & 2) != 0;                  // every second element widened on the integer pipe
+    if (e.xf & 8192) return mix ? 6 : 4;               // 4/6: TMA ring in shared memory
+    return mix ? 5 : 3;                                // 3/5: register-staged loads + L2 prefetch
 }
 
 template <int C>
 static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
     switch (cluster_mode(e)) {
+        case 6: return launch_cluster_m<C, 6>(e, cur, ids, count, s);
+        case 5: return launch_cluster_m<C, 5>(e, cur, ids, count, s);
         case 4: return launch_cluster_m<C, 4>(e, cur, ids, count, s);
         case 3: return launch_cluster_m<C, 3>(e, cur, ids, count, s);
-        case 2: return launch_cluster_m<C, 2>(e, cur, ids, count, s);
-        case 1: return launch_cluster_m<C, 1>(e, cur, ids, count, s);
         default: return launch_cluster_m<C, 0>(e, cur, ids, count, s);
     }
 }
@@ -1206,7 +1216,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
             const float* dz = d_dino ? d_dino + (size_t)(h_chunk_off[c]) * p->dino_dim : nullptr;
             rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
                               pl.tarl_zero + o, st, pl.qctr ? pl.qctr + 2 * c : nullptr, pl.qctr ? pl.e.parent : nullptr,
-                              pl.base[c]);
+                              pl.base[c], pl.qctr != nullptr);
             if (rc) return rc;
             aff_bytes += 4.0 * n[c] * (double)n[c] +
                          4.0 * n[c] * (3 + (p->theta != 0 ? p->tarl_dim : 0) + (p->gamma != 0 ? p->dino_dim : 0));

@@ -227,16 +227,16 @@ __device__ __forceinline__ void cl_update(ClusterShared& S, const SliceBasis& B,
     __syncthreads();
 }
 
-// float -> double widening.  MODE 2: integer form for weights in {0} U [2^-126, 2): bits move 29 places, the
+// float -> double widening on the integer pipe, for weights in {0} U [2^-126, 2): the bits move 29 places and the
 // exponent is re-biased; +0 becomes 2^-127 (5.9e-39), which every later float64 sum absorbs exactly.
-template <int MODE>
-__device__ __forceinline__ double widen(float f) {
-    if (MODE == 2) {
-        const unsigned b = __float_as_uint(f);
-        return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
-    }
-    return (double)f;
+// cvt.f64.f32 runs on the XU pipe at 4 lanes per clock and scheduler: ncu shows it half busy during the matvec and
+// the warps waiting on it, so in the MIX variants every second element is widened with three integer instructions.
+__device__ __forceinline__ double widen_int(float f) {
+    const unsigned b = __float_as_uint(f);
+    return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
 }
+template <bool MIX>
+__device__ __forceinline__ double widen_alt(float f) { return MIX ? widen_int(f) : (double)f; }
 
 // y_slice = S (w + I) z * invb for the rows [r0, r0+nr) of the node.  MODE 0: entries outside the block are
 // selected away (they may be uninitialised).  MODE 1/2: the caller guarantees that the <= 3 columns on either
@@ -317,21 +317,15 @@ __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, co
                             double q1 = (v2 ? (double)w[rr][g].z : 0.0) * z1.x + (v3 ? (double)w[rr][g].w : 0.0) * z1.y;
                             acc[rr] += q0 + q1;
                         }
-                    } else if (MODE == 3) {
+                    } else {
                         // two FMA chains per row: one FP64 instruction per element instead of 1.5
+                        constexpr bool MIX = (MODE == 5);
 #pragma unroll
                         for (int rr = 0; rr < 2; ++rr) {
                             acc[rr] = fma((double)w[rr][g].x, z0.x, acc[rr]);
-                            acb[rr] = fma((double)w[rr][g].y, z0.y, acb[rr]);
+                            acb[rr] = fma(widen_alt<MIX>(w[rr][g].y), z0.y, acb[rr]);
                             acc[rr] = fma((double)w[rr][g].z, z1.x, acc[rr]);
-                            acb[rr] = fma((double)w[rr][g].w, z1.y, acb[rr]);
-                        }
-                    } else {
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            double q0 = widen<MODE>(w[rr][g].x) * z0.x + widen<MODE>(w[rr][g].y) * z0.y;
-                            double q1 = widen<MODE>(w[rr][g].z) * z1.x + widen<MODE>(w[rr][g].w) * z1.y;
-                            acc[rr] += q0 + q1;
+                            acb[rr] = fma(widen_alt<MIX>(w[rr][g].w), z1.y, acb[rr]);
                         }
                     }
                 }
@@ -339,7 +333,7 @@ __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, co
         }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            double t = warp_sum(MODE == 3 ? acc[rr] + acb[rr] : acc[rr]);
+            double t = warp_sum(MODE != 0 ? acc[rr] + acb[rr] : acc[rr]);
             int i = rb + rr;
             if (lane == 0 && i < nr) S.ysl[i] = S.sv[i] * invb * (t + zs[r0 + i + pad]);   // (w + I) z
         }
@@ -402,6 +396,7 @@ __device__ __forceinline__ void ring_drain(const RingGeom& q, uint64_t* bars_w, 
     for (int t = 0; t < min(RING_ST, q.T); ++t) mbarrier_wait(bars_w + ((g + t) % RING_ST), ((g + t) / RING_ST) & 1u);
 }
 
+template <bool MIX>
 __device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* zs, const NodeView& v, const RingGeom& q,
                                                int r0, int nr, int pad, double invb, float* ring_w, uint64_t* bars_w,
                                                uint32_t& g) {
@@ -424,10 +419,10 @@ __device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* z
                     const float4 wb = *reinterpret_cast<const float4*>(buf + RING_COLS + cs);
                     const double2 z0 = *reinterpret_cast<const double2*>(&zs[cofs]);
                     const double2 z1 = *reinterpret_cast<const double2*>(&zs[cofs + 2]);
-                    acc0 = fma((double)wa.x, z0.x, acc0); acb0 = fma((double)wa.y, z0.y, acb0);
-                    acc0 = fma((double)wa.z, z1.x, acc0); acb0 = fma((double)wa.w, z1.y, acb0);
-                    acc1 = fma((double)wb.x, z0.x, acc1); acb1 = fma((double)wb.y, z0.y, acb1);
-                    acc1 = fma((double)wb.z, z1.x, acc1); acb1 = fma((double)wb.w, z1.y, acb1);
+                    acc0 = fma((double)wa.x, z0.x, acc0); acb0 = fma(widen_alt<MIX>(wa.y), z0.y, acb0);
+                    acc0 = fma((double)wa.z, z1.x, acc0); acb0 = fma(widen_alt<MIX>(wa.w), z1.y, acb0);
+                    acc1 = fma((double)wb.x, z0.x, acc1); acb1 = fma(widen_alt<MIX>(wb.y), z0.y, acb1);
+                    acc1 = fma((double)wb.z, z1.x, acc1); acb1 = fma(widen_alt<MIX>(wb.w), z1.y, acb1);
                 }
             }
             __syncwarp();
@@ -470,7 +465,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     {
         const int nz = (n + 8 + 3) & ~3;               // doubles used by zs
         B.nrp = (max(nr, 1) + 3) & ~3;
-        const int nring = (MODE == 4) ? RING_BYTES / 8 : 0;       // the warps' W rings sit between z and the basis rows
+        const int nring = (MODE == 4 || MODE == 6) ? RING_BYTES / 8 : 0;       // the warps' W rings sit between z and the basis rows
         B.smem = zs + nz + nring;
         B.rows_s = (e.xf & 4096) ? 0 : max(0, (dyn_doubles - nz - nring) / B.nrp);     // bit 12: basis in global memory only
         B.glob = e.V + g0;
@@ -482,7 +477,8 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     uint64_t* bars_w = ring_bar + warp * RING_ST;
     const RingGeom rq = ring_geom(v, nr);
     uint32_t ring_g = 0;                               // stages consumed by this warp so far
-    if (MODE == 4) {
+    constexpr bool RING = (MODE == 4 || MODE == 6);
+    if (RING) {
         if (lane == 0) {
             for (int i = 0; i < RING_ST; ++i) mbarrier_init(bars_w + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -531,7 +527,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     const bool gs1 = (e.xf & 1024) != 0;              // three-term recurrence + one Gram-Schmidt pass
     const int pf = (e.xf >> 4) & 3;                   // passes of L2 prefetch distance (0 = off)
     const bool pfl = (e.xf & 2048) != 0;               // per-lane prefetch.global.L2 instead of the bulk form
-    if (pf > 0 && MODE != 4) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);
+    if (pf > 0 && !RING) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);
     while (true) {
         const double invb = 1.0 / bprev;
         // basis row k+1 = current vector (slice)
@@ -539,8 +535,8 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         __syncthreads();
         CL_PHASE(0);
         // ---- matvec of the slice: 2 rows per warp, 512 columns per iteration, 8 loads issued first ----
-        if (MODE == 4) {
-            cl_matvec_ring(S, zs, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g);
+        if (RING) {
+            cl_matvec_ring<MODE == 6>(S, zs, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g);
         } else {
             cl_matvec<MODE>(S, zs, v, r0, nr, pad, invb, pf, pfl);
             if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);  // first passes of the next step: in flight during Gram-Schmidt
@@ -646,7 +642,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         }
     }
     CL_PHASE(7);
-    if (MODE == 4) ring_drain(rq, bars_w, ring_g);     // stages fetched ahead for a step that will not run
+    if (RING) ring_drain(rq, bars_w, ring_g);     // stages fetched ahead for a step that will not run
     if (prof) {
         const int ci = (C == 1) ? 0 : (C == 2) ? 1 : (C == 4) ? 2 : 3;
         for (int i = 0; i < 8; ++i) atomicAdd(&e.dbg[ci * 8 + i], (unsigned long long)tph[i]);

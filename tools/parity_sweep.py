@@ -17,9 +17,17 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def cache_path(cache, name, seed, n_target):
+    return os.path.join(cache, f"{name}_{n_target}_{seed}.npz") if cache else None
+
+
 def oracle_job(a):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    seed, n_target, name = a
+    seed, n_target, name, cache = a
+    cp = cache_path(cache, name, seed, n_target)
+    if cp and os.path.exists(cp):
+        z = np.load(cp)
+        return seed, z["labels"], bool(z["stable"])
     import scipy.sparse as sp
     from autoinst_b200.synthetic import CONFIGS, make_chunk
     from oracle import ncut_ref as R
@@ -33,7 +41,11 @@ def oracle_job(a):
         with R.pinned_eigsh(kind, sd):
             g = R.normalized_cut_ref(w, ch.n, np.arange(ch.n), T=cfg["T"])
         out.append(R.labels_from_groups(g, ch.n))
-    return seed, out[0], R.same_partition(out[0], out[1])
+    stable = R.same_partition(out[0], out[1])
+    if cp:
+        os.makedirs(cache, exist_ok=True)
+        np.savez_compressed(cp, labels=out[0], stable=stable, n=ch.n)
+    return seed, out[0], stable
 
 
 def main():
@@ -44,7 +56,17 @@ def main():
     ap.add_argument("--seed", type=int, default=5000)
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--out", default="gpurun_out/parity.json")
+    ap.add_argument("--oracle-cache", default="", help="directory of cached oracle labels (filled when missing); the "
+                    "oracle is CPU-only, so it can be computed ahead of the GPU run")
+    ap.add_argument("--oracle-only", action="store_true", help="fill the cache and exit (no GPU needed)")
     args = ap.parse_args()
+    if args.oracle_only:
+        seeds = [args.seed + i for i in range(args.chunks)]
+        workers = args.workers or min(os.cpu_count() or 1, 32, args.chunks)
+        with mp.get_context("spawn").Pool(workers) as pool:
+            r = pool.map(oracle_job, [(s, args.n_target, args.config, args.oracle_cache) for s in seeds])
+        print("cached", len(r), "stable", sum(1 for x in r if x[2]))
+        return
     import torch
     from autoinst_b200 import api
     from autoinst_b200.synthetic import CONFIGS, make_chunk
@@ -55,7 +77,7 @@ def main():
     workers = args.workers or min(os.cpu_count() or 1, 32, args.chunks)
     t0 = time.time()
     with mp.get_context("spawn").Pool(workers) as pool:
-        async_res = pool.map_async(oracle_job, [(s, args.n_target, args.config) for s in seeds])
+        async_res = pool.map_async(oracle_job, [(s, args.n_target, args.config, args.oracle_cache) for s in seeds])
         chunks = [make_chunk(s, n_target=args.n_target, features=feats) for s in seeds]
         t1 = time.time()
         res = api.segment_chunks([c.points for c in chunks], [c.tarl for c in chunks],
