@@ -125,10 +125,10 @@ def alloc_matrix(n, device):
 # stage entry points
 # ------------------------------------------------------------------------------------------------
 def affinity(points, tarl=None, dino=None, *, alpha=1.0, theta=0.0, gamma=0.0, proximity=1.0, impl=0,
-             device=None, return_rowsum=False):
+             device=None, return_rowsum=False, lane: int = 0):
     """Stage 1: dense float32 affinity (ncuts_utils.py:60-156).  Returns the n x n view of an n x ld buffer."""
     device = _dev(device)
-    hd = Handle.get(device)
+    hd = Handle.get(device, lane)
     pts = _as_dev(points, torch.float64, device)
     n = pts.shape[0]
     t = _as_dev(tarl, torch.float32, device) if theta else None

@@ -154,6 +154,13 @@ class ClockSampler:
         return out
 
 
+def workload_string(n_target):
+    from autoinst_b200.synthetic import CONFIGS
+    cfg = CONFIGS[CONFIG_NAME]
+    return (f"config_{CONFIG_NAME} NCuts (alpha {cfg['alpha']}, theta {cfg['theta']}, T {cfg['T']}), "
+            f"synthetic SemanticKITTI-shaped chunks n_target={n_target}, 96-d TARL features")
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation (oracle port) on the host cores."""
     if rank != 0:
@@ -176,8 +183,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"config_{CONFIG_NAME} NCuts, synthetic SemanticKITTI-shaped chunks n_target={args.n_target}",
-                   "chunks_per_step": per_step, "points_per_sec": pts / (ms / 1e3)},
+        "config": {"workload": workload_string(args.n_target), "chunks_per_step": per_step, "points_per_sec": pts / (ms / 1e3)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -211,7 +217,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="chunks per GPU per step")
+    ap.add_argument("--batch", type=int, default=128, help="chunks per GPU per step")
     ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--cpu-chunks", type=int, default=1, help="chunks in the cpu_baseline sample (0 = skip)")
@@ -338,8 +344,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"config_{CONFIG_NAME} NCuts (alpha {cfg['alpha']}, theta {cfg['theta']}, T {cfg['T']}), "
-                                   f"synthetic SemanticKITTI-shaped chunks n_target={args.n_target}, 96-d TARL features",
+            "config": {"workload": workload_string(args.n_target),
                        "chunks_per_gpu_per_step": args.batch, "points_per_step": pts_total,
                        "points_per_sec": pts_total / (ms_step / 1e3),
                        "l2": "inputs larger than L2: every step rebuilds and streams %.1f GB of dense float32 affinities per GPU"

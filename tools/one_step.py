@@ -1,0 +1,26 @@
+#!/usr/bin/env python
+"""One warm-up pass and one pass of the bench workload with inputs resident in HBM (profiling target for ncu).
+
+    python tools/one_step.py --batch 128
+"""
+import argparse, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from autoinst_b200 import api
+from autoinst_b200.synthetic import CONFIGS, make_chunk
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=128)
+ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
+ap.add_argument("--seed", type=int, default=1000)
+ap.add_argument("--passes", type=int, default=2)
+args = ap.parse_args()
+dev = torch.device("cuda", 0)
+cfg = CONFIGS["tarl_spatial"]
+chunks = [make_chunk(args.seed + i, n_target=args.n_target, features="tarl") for i in range(args.batch)]
+packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"])
+devc = packed.to_device(dev)
+for _ in range(args.passes):
+    api.segment_packed(packed, dev_chunks=devc, alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"])
+torch.cuda.synchronize()
+print("ok", args.batch, int(packed.off[-1]))
