@@ -417,18 +417,15 @@ static int run_lanczos(ancuts_handle* h, Eng& e, int cur, int num_active, int ma
     while (true) {
         int burst = std::min(e.check_every, kcap_max - step);
         for (int s = 0; s < burst; ++s, ++step) {
-            // rows per warp: 4 keeps 8 loads per lane in flight, but a single 8 k node then has only 256 CTAs of 8 warps
-            // for 148 SMs (58 % of the HBM peak measured); smaller nodes get more, lighter warps instead
+            // rows per warp: with 4 a single 8-16 k node has only 256-512 CTAs of 8 warps for 148 SMs (58 / 62 % of the HBM peak
+            // measured at 8 / 16 k); 2 rows per warp gave 84 % at 16 k, 1 row per warp only 47 % at 8 k
             const long long rows_total = (long long)max_n * num_active;
-            if (rows_total >= 24576) {
+            if (rows_total >= 49152) {
                 dim3 gmv((max_n + 31) / 32, num_active);
                 LAUNCH(SG_MATVEC, k_matvec<4><<<gmv, 256, 0, st>>>(e, cur));
-            } else if (rows_total >= 12288) {
+            } else {
                 dim3 gmv((max_n + 15) / 16, num_active);
                 LAUNCH(SG_MATVEC, k_matvec<2><<<gmv, 256, 0, st>>>(e, cur));
-            } else {
-                dim3 gmv((max_n + 7) / 8, num_active);
-                LAUNCH(SG_MATVEC, k_matvec<1><<<gmv, 256, 0, st>>>(e, cur));
             }
             dim3 gd(nch_max, (step + 2 + 31) / 32, num_active);
             LAUNCH(SG_REORTH, k_dots<<<gd, 256, 0, st>>>(e));

@@ -410,19 +410,26 @@ __device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* z
             const uint32_t slot = g % RING_ST;
             mbarrier_wait(bars_w + slot, (g / RING_ST) & 1u);
             const float* buf = ring_w + slot * RING_STAGE_FLOATS;
+            auto fma8 = [&](const float4& wa, const float4& wb, const double2& z0, const double2& z1) {
+                acc0 = fma((double)wa.x, z0.x, acc0); acb0 = fma(widen_alt<MIX>(wa.y), z0.y, acb0);
+                acc0 = fma((double)wa.z, z1.x, acc0); acb0 = fma(widen_alt<MIX>(wa.w), z1.y, acb0);
+                acc1 = fma((double)wb.x, z0.x, acc1); acb1 = fma(widen_alt<MIX>(wb.y), z0.y, acb1);
+                acc1 = fma((double)wb.z, z1.x, acc1); acb1 = fma(widen_alt<MIX>(wb.w), z1.y, acb1);
+            };
+            {
+                // (hoisting all sixteen shared-memory loads of a full stage in front of the conversions, without the per-group
+                //  predicate, was measured 3 % slower: more live registers, no better overlap)
 #pragma unroll
-            for (int gq = 0; gq < RING_COLS / 128; ++gq) {
-                const int cs = 128 * gq + 4 * lane;                // column inside the stage
-                const int cofs = sg * RING_COLS + cs;              // column - a0
-                if (cofs < q.width) {
-                    const float4 wa = *reinterpret_cast<const float4*>(buf + cs);
-                    const float4 wb = *reinterpret_cast<const float4*>(buf + RING_COLS + cs);
-                    const double2 z0 = *reinterpret_cast<const double2*>(&zs[cofs]);
-                    const double2 z1 = *reinterpret_cast<const double2*>(&zs[cofs + 2]);
-                    acc0 = fma((double)wa.x, z0.x, acc0); acb0 = fma(widen_alt<MIX>(wa.y), z0.y, acb0);
-                    acc0 = fma((double)wa.z, z1.x, acc0); acb0 = fma(widen_alt<MIX>(wa.w), z1.y, acb0);
-                    acc1 = fma((double)wb.x, z0.x, acc1); acb1 = fma(widen_alt<MIX>(wb.y), z0.y, acb1);
-                    acc1 = fma((double)wb.z, z1.x, acc1); acb1 = fma(widen_alt<MIX>(wb.w), z1.y, acb1);
+                for (int gq = 0; gq < RING_COLS / 128; ++gq) {
+                    const int cs = 128 * gq + 4 * lane;                // column inside the stage
+                    const int cofs = sg * RING_COLS + cs;              // column - a0
+                    if (cofs < q.width) {
+                        const float4 wa = *reinterpret_cast<const float4*>(buf + cs);
+                        const float4 wb = *reinterpret_cast<const float4*>(buf + RING_COLS + cs);
+                        const double2 z0 = *reinterpret_cast<const double2*>(&zs[cofs]);
+                        const double2 z1 = *reinterpret_cast<const double2*>(&zs[cofs + 2]);
+                        fma8(wa, wb, z0, z1);
+                    }
                 }
             }
             __syncwarp();
