@@ -191,31 +191,11 @@ struct PairQ { int i, j; double a; };      // a = alpha * spatial distance (floa
 // forward declarations (defined with the component kernels below)
 __device__ __forceinline__ void uf_union(int* parent, int a, int b);
 
-// union-find on a small forest in SHARED memory (same hooking rule as uf_union below: larger root under smaller)
-__device__ __forceinline__ int uf_find_s(volatile int* lp, int x) {
-    int p = lp[x];
-    while (p != x) {
-        int gp = lp[p];
-        if (gp != p) lp[x] = gp;                     // path halving; only ever points to an ancestor
-        x = p;
-        p = gp;
-    }
-    return x;
-}
-__device__ __forceinline__ void uf_union_s(int* lp, int a, int b) {
-    while (true) {
-        a = uf_find_s(lp, a);
-        b = uf_find_s(lp, b);
-        if (a == b) return;
-        if (a < b) { int t = a; a = b; b = t; }
-        if (atomicCAS(lp + a, a, b) == a) return;
-    }
-}
-
 // Measured on B200 (N = 8.6 k): the zero stores of this kernel are free (replacing them by one cudaMemsetAsync at
-// 7.5 TB/s did not shorten it); what cost time were one shared-memory atomic per in-mask pair and one global
-// union per pair in the dense tiles on the diagonal.  Hits are therefore collected in a register bit mask and
-// appended with one atomic per warp, and the components are first merged inside the tile.
+// 7.5 TB/s did not shorten it); ncu showed it issue-bound at 47 instructions per pair, hence the register pre-filter
+// below.  Hits are collected in a register bit mask and appended with one atomic per warp.  Merging the components
+// inside the tile first (shared-memory union-find, then one global union per non-root) was measured SLOWER than one
+// global union per pair (24.3 vs 20.8 ms of affinity time per 128 chunks) and is not used.
 __global__ void __launch_bounds__(256)
 k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double prox, float* __restrict__ W, long long ld,
                  PairQ* __restrict__ q, int qcap, int* __restrict__ qctr, int* parent, int pos0) {
@@ -235,7 +215,6 @@ k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double pro
     __shared__ float pr32[AT][3];
     __shared__ float pc32[AT][3];
     __shared__ unsigned short queue[AT * AT];
-    __shared__ int lp[2 * AT];
     __shared__ int qn, qbase;
 
     if (tid == 0) qn = 0;
@@ -319,7 +298,6 @@ k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double pro
         if (b + total > qcap) { atomicExch(&qctr[1], 1); b = -1; }      // the caller falls back to the one-kernel form
         qbase = b;
     }
-    if (parent && tid < 2 * AT) lp[tid] = tid;
     __syncthreads();
     const int base = qbase;
     if (base < 0) return;
@@ -332,20 +310,8 @@ k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double pro
         e.i = row0 + r; e.j = col0 + c;
         e.a = alpha != 0.0 ? alpha * sd : 0.0;                           // ncuts_utils.py:63-66
         q[base + t] = e;
-        // root-level connected components, first inside the tile (shared memory) ...
-        if (parent) uf_union_s(lp, r, AT + c);
-    }
-    if (parent) {
-        __syncthreads();
-        // ... then one global union per tile point that is not its local root (instead of one per pair)
-        if (tid < 2 * AT) {
-            int root = uf_find_s(lp, tid);
-            if (root != tid) {
-                int ga = (tid < AT) ? row0 + tid : col0 + tid - AT;
-                int gb = (root < AT) ? row0 + root : col0 + root - AT;
-                uf_union(parent, pos0 + ga, pos0 + gb);
-            }
-        }
+        // root-level connected components (saves the first k_cc_union pass over the dense matrix)
+        if (parent) uf_union(parent, pos0 + e.i, pos0 + e.j);
     }
 }
 
@@ -625,6 +591,7 @@ __global__ void k_finish_ranges(Eng e, int num_ranges) {
 //   val2[new position] = old position.  grid: (col tiles of 256, row tiles of 16, active)
 __global__ void __launch_bounds__(256)
 k_gather_blocks_cur(Eng e, int cur /* source buffer */) {
+    // (one launch per size bin, so that no block exits at once, was measured: no gain)
     int a = blockIdx.z;
     int r = e.a_rid[a];
     int start = e.r_start[r], n = e.r_n[r], c = e.r_chunk[r];

@@ -38,26 +38,36 @@ def gather_labels(local_ids, local_labels, num_chunks: int, group=None, device=N
     world = dist.get_world_size(group)
     if device is None:
         device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    # table of (chunk id, length) per rank, padded to the largest local chunk count
+    # table of (chunk id, length) per rank, padded to the largest local chunk count (built on the host: one upload
+    # instead of two tiny fill kernels per chunk)
     cnt = torch.tensor([len(local_ids)], dtype=torch.int64, device=device)
     cnts = torch.empty(world, dtype=torch.int64, device=device)
     dist.all_gather_into_tensor(cnts, cnt, group=group)
     max_cnt = int(cnts.max().item())
-    meta = torch.full((max(max_cnt, 1), 2), -1, dtype=torch.int64, device=device)
+    meta_h = np.full((max(max_cnt, 1), 2), -1, dtype=np.int64)
     for j, (i, lab) in enumerate(zip(local_ids, local_labels)):
-        meta[j, 0] = i
-        meta[j, 1] = len(lab)
+        meta_h[j, 0] = i
+        meta_h[j, 1] = len(lab)
+    meta = torch.from_numpy(meta_h).to(device)
     metas = torch.empty((world * meta.shape[0], 2), dtype=torch.int64, device=device)      # concatenated form
     dist.all_gather_into_tensor(metas, meta, group=group)
     metas_h = metas.cpu().numpy().reshape(world, meta.shape[0], 2)
     totals = [int(m[m[:, 0] >= 0, 1].sum()) for m in metas_h]
     pad = max(max(totals), 1)
     flat = torch.zeros(pad, dtype=torch.int32, device=device)
-    o = 0
-    for lab in local_labels:
-        t = lab if isinstance(lab, torch.Tensor) else torch.as_tensor(np.asarray(lab, dtype=np.int32))
-        flat[o:o + len(t)] = t.to(device=device, dtype=torch.int32)
-        o += len(t)
+    mine = int(meta_h[meta_h[:, 0] >= 0, 1].sum())
+    if mine:
+        tens = [lab if isinstance(lab, torch.Tensor) else torch.as_tensor(np.asarray(lab, dtype=np.int32)) for lab in local_labels]
+        same_dev = all(t.device == flat.device and t.dtype == torch.int32 for t in tens)
+        adjacent = same_dev and all(t.is_contiguous() for t in tens) and all(
+            a.data_ptr() + 4 * a.numel() == b.data_ptr() for a, b in zip(tens[:-1], tens[1:]))
+        if adjacent:
+            # the usual case: consecutive slices of one label buffer (DeviceChunks.labels): one copy, no per-chunk kernels
+            base = tens[0]
+            whole = torch.as_strided(base, (mine,), (1,)) if len(tens) > 1 else base
+            flat[:mine] = whole
+        else:
+            flat[:mine] = torch.cat([t.reshape(-1).to(dtype=torch.int32) for t in tens]).to(device)
     allflat = torch.empty(world * pad, dtype=torch.int32, device=device)
     dist.all_gather_into_tensor(allflat, flat, group=group)
     allflat_h = allflat.cpu().numpy().reshape(world, pad)
