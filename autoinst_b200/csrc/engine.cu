@@ -795,6 +795,7 @@ int64_t ancuts_segment_workspace_bytes(int num_chunks, const int32_t* h_chunk_n,
     Plan pl;
     int kmax = lanczos_max_steps > 0 ? lanczos_max_steps : KMAX_DEFAULT;
     make_plan(pl, num_chunks, h_chunk_n, nullptr, nullptr, kmax, 0);
+    pl.want_pairq = true;                              // upper bound: tensor-core scratch and pair queue both counted
     return (int64_t)layout(pl, nullptr, 1 << 16, 96, 384, true);
 }
 
