@@ -65,6 +65,9 @@ struct ancuts_handle {
     //   1024 three-term recurrence + ONE Gram-Schmidt pass   4096 basis rows in global memory only
     //   8192 TMA ring in shared memory instead of register-staged loads
     int xflags = 1 | 2 | 1024 | 8192;
+    cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
+    std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
+    const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
     unsigned long long* dbg = nullptr;       // device, 32 entries: phase cycles of the cluster kernel (ANCUTS_PHASES=1)
 };
 
@@ -770,6 +773,7 @@ int ancuts_create(int device, ancuts_handle** out) {
         ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
     }
     ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    ANCUTS_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     ANCUTS_CUDA(cudaMallocHost((void**)&h->h_acct, SG_COUNT * sizeof(unsigned long long)));
     *out = h;
     return ANCUTS_OK;
@@ -781,6 +785,8 @@ int ancuts_destroy(ancuts_handle* h) {
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
     if (h->dbg) cudaFree(h->dbg);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto ev : h->copy_ev) cudaEventDestroy(ev);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_acct) cudaFreeHost(h->h_acct);
     for (auto ev : h->pool) cudaEventDestroy(ev);
@@ -1172,6 +1178,8 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
                           const float* d_tarl, const float* d_dino, const float* d_W_dense, int64_t ld_dense,
                           int num_points_orig, const ancuts_params* p, int32_t* d_labels, int32_t* h_num_segments,
                           ancuts_node_stat* h_stats, int32_t stats_cap, int32_t* h_num_stats, cudaStream_t st) {
+    const cudaEvent_t* wait_ev = h ? h->wait_ev : nullptr;      // per-chunk "inputs have arrived" events of the host entry point
+    if (h) h->wait_ev = nullptr;                                 // consumed by this call
     int rc = check_params(p);
     if (rc) return rc;
     if (!h || num_chunks <= 0 || !h_chunk_off || !d_labels) { set_error("bad argument to segment"); return ANCUTS_EINVAL; }
@@ -1223,6 +1231,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
             int64_t o = h_chunk_off[c] - off0;
             const float* tz = d_tarl ? d_tarl + (size_t)(h_chunk_off[c]) * p->tarl_dim : nullptr;
             const float* dz = d_dino ? d_dino + (size_t)(h_chunk_off[c]) * p->dino_dim : nullptr;
+            if (wait_ev) ANCUTS_CUDA(cudaStreamWaitEvent(st, wait_ev[c], 0));       // this chunk's inputs have arrived
             rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
                               pl.tarl_zero + o, st, pl.qctr ? pl.qctr + 2 * c : nullptr, pl.qctr ? pl.e.parent : nullptr,
                               pl.base[c], pl.qctr != nullptr);
@@ -1305,13 +1314,30 @@ int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* 
     float* d_dino = use_d ? (float*)(stage + align_up(bp, 256) + align_up(bt, 256)) : nullptr;
     int32_t* d_labels = (int32_t*)(stage + align_up(bp, 256) + align_up(bt, 256) + align_up(bd, 256));
     int rc = ANCUTS_OK;
-    cudaError_t ce = cudaMemcpyAsync(d_points, h_points, bp, cudaMemcpyHostToDevice, st);
-    if (ce == cudaSuccess && use_t) ce = cudaMemcpyAsync(d_tarl, h_tarl, bt, cudaMemcpyHostToDevice, st);
-    if (ce == cudaSuccess && use_d) ce = cudaMemcpyAsync(d_dino, h_dino, bd, cudaMemcpyHostToDevice, st);
-    if (ce != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(ce)); rc = ANCUTS_ECUDA; }
+    // per-chunk copies on their own stream, one event per chunk: the affinity kernels of chunk c start as soon as its
+    // inputs are there, the copies of the later chunks overlap with them (pinned host memory)
+    while ((int)h->copy_ev.size() < num_chunks + 1) {
+        cudaEvent_t ev;
+        ANCUTS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->copy_ev.push_back(ev);
+    }
+    cudaError_t ce = cudaEventRecord(h->copy_ev[num_chunks], st);           // earlier work on st may still read the staging area
+    if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->copy_stream, h->copy_ev[num_chunks], 0);
+    for (int c = 0; c < num_chunks && ce == cudaSuccess; ++c) {
+        const size_t o = (size_t)h_chunk_off[c], m = (size_t)(h_chunk_off[c + 1] - h_chunk_off[c]);
+        ce = cudaMemcpyAsync(d_points + o * 3, h_points + o * 3, m * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream);
+        if (ce == cudaSuccess && use_t)
+            ce = cudaMemcpyAsync(d_tarl + o * p->tarl_dim, h_tarl + o * p->tarl_dim, m * p->tarl_dim * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream);
+        if (ce == cudaSuccess && use_d)
+            ce = cudaMemcpyAsync(d_dino + o * p->dino_dim, h_dino + o * p->dino_dim, m * p->dino_dim * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(h->copy_ev[c], h->copy_stream);
+    }
+    if (ce != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(ce)); rc = ANCUTS_ECUDA; cudaStreamSynchronize(h->copy_stream); }
+    if (rc == ANCUTS_OK) h->wait_ev = h->copy_ev.data();
     if (rc == ANCUTS_OK)
         rc = segment_common(h, num_chunks, h_chunk_off, d_points, d_tarl, d_dino, nullptr, 0, 0, p, d_labels,
                             h_num_segments, h_stats, stats_cap, h_num_stats, st);
+    if (rc != ANCUTS_OK) cudaStreamSynchronize(h->copy_stream);        // the caller may release its buffers after an error
     if (rc == ANCUTS_OK) {
         ce = cudaMemcpyAsync(h_labels, d_labels, bl, cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
