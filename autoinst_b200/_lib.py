@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libautoinst_ncuts.so")
+LIB_PATH = os.environ.get("ANCUTS_LIB_PATH") or os.path.join(_HERE, "lib", "libautoinst_ncuts.so")   # override: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 
 NUM_CUTS = 10

@@ -23,7 +23,10 @@ constexpr int CL_KMAX = 256;             // steps the cluster kernel can take; n
 constexpr int CL_KS = CL_KMAX + 4;
 constexpr int CL_RPMAX = 512;            // rows per CTA (two per thread)
 constexpr int CL_NMAX = 4096;            // largest node handled here (8 CTAs x 512 rows)
-constexpr int CL_THREADS = 512;
+#ifndef ANCUTS_CL_THREADS
+#define ANCUTS_CL_THREADS 512
+#endif
+constexpr int CL_THREADS = ANCUTS_CL_THREADS;    // 512 (default) or 1024 (-DANCUTS_CL_THREADS=1024: 64 registers per thread)
 constexpr int CL_WARPS = CL_THREADS / 32;
 constexpr int CL_HALF = CL_THREADS / 2;     // shifts per eigenvalue and bisection round
 constexpr int CL_CLASSES = 6;            // node size bins (kernels_graph.cuh::cluster_class); cluster sizes 1, 2, 4, 8
@@ -39,7 +42,7 @@ struct ClusterShared {
     double be2[CL_KS], dd[CL_KS], du[CL_KS], du2[CL_KS], dl[CL_KS], yv[CL_KS];
     double ysl[CL_RPMAX];        // this CTA's slice of the current vector
     double sv[CL_RPMAX];         // D^-1/2 of the slice
-    double red[16];
+    double red[32];
     double bounds[4];
     double gb[3];
     int swp[CL_KS];
@@ -178,17 +181,20 @@ struct SliceBasis {
 __device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const SliceBasis& B, int rows, int nr, int buf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int M = (CL_RPMAX + 31) / 32;
-    double yr[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) { int i = lane + 32 * m; yr[m] = (i < nr) ? S.ysl[i] : 0.0; }
+    constexpr int MH = (CL_THREADS > 512) ? M / 2 : M;          // 1024 threads: 64 registers, two halves of 8
     for (int j = warp; j < rows; j += CL_THREADS / 32) {
         const double* vr = B.row(j);
-        double t[M];
-#pragma unroll
-        for (int m = 0; m < M; ++m) { int i = lane + 32 * m; t[m] = (i < nr) ? vr[i] : 0.0; }
         double s = 0.0;
 #pragma unroll
-        for (int m = 0; m < M; ++m) s += t[m] * yr[m];
+        for (int h = 0; h < M; h += MH) {
+            double t[MH], yr[MH];
+#pragma unroll
+            for (int m = 0; m < MH; ++m) { int i = lane + 32 * (h + m); t[m] = (i < nr) ? vr[i] : 0.0; }
+#pragma unroll
+            for (int m = 0; m < MH; ++m) { int i = lane + 32 * (h + m); yr[m] = (i < nr) ? S.ysl[i] : 0.0; }
+#pragma unroll
+            for (int m = 0; m < MH; ++m) s += t[m] * yr[m];
+        }
         s = warp_sum(s);
         if (lane == 0) S.hpart[buf][j] = s;
     }
@@ -351,7 +357,7 @@ __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, co
 // (A first version with 1 KB stages, 4 per warp, was 20 % slower than the plain form: the per-stage wait / issue
 // overhead has to be spread over more data.)
 constexpr int RING_ST = 2;
-constexpr int RING_COLS = 512;                         // floats per row and stage
+constexpr int RING_COLS = (CL_THREADS > 512) ? 256 : 512;   // floats per row and stage
 constexpr int RING_STAGE_FLOATS = 2 * RING_COLS;
 constexpr int RING_WARP_FLOATS = RING_ST * RING_STAGE_FLOATS;
 constexpr int RING_BYTES = CL_WARPS * RING_WARP_FLOATS * 4;      // 128 KB
@@ -527,7 +533,8 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     int conv = 0;
     double th[2] = {0.0, 0.0};
     // optional phase clock (debug): cycles of thread 0 between the block-wide syncs that end each phase
-    const bool prof = (e.dbg != nullptr) && tid == 0 && rank == 0;
+    constexpr bool CL_PROF = (CL_THREADS <= 512);      // the 1024-thread build has no registers to spare for the clocks
+    const bool prof = CL_PROF && (e.dbg != nullptr) && tid == 0 && rank == 0;
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = prof ? clock64() : 0;
 #define CL_PHASE(i) do { if (prof) { long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)

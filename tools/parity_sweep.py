@@ -17,14 +17,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def cache_path(cache, name, seed, n_target):
-    return os.path.join(cache, f"{name}_{n_target}_{seed}.npz") if cache else None
+def cache_path(cache, name, seed, n_target, clutter=0):
+    tag = f"_c{clutter}" if clutter else ""
+    return os.path.join(cache, f"{name}_{n_target}_{seed}{tag}.npz") if cache else None
 
 
 def oracle_job(a):
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    seed, n_target, name, cache = a
-    cp = cache_path(cache, name, seed, n_target)
+    seed, n_target, name, cache, clutter = a
+    cp = cache_path(cache, name, seed, n_target, clutter)
     if cp and os.path.exists(cp):
         z = np.load(cp)
         return seed, z["labels"], bool(z["stable"])
@@ -33,7 +34,7 @@ def oracle_job(a):
     from oracle import ncut_ref as R
     from oracle.affinity_ref import affinity_ref
     cfg = CONFIGS[name]
-    ch = make_chunk(seed, n_target=n_target, features="tarl_dino" if cfg["gamma"] else "tarl")
+    ch = make_chunk(seed, n_target=n_target, features="tarl_dino" if cfg["gamma"] else "tarl", clutter=clutter)
     A = affinity_ref(ch.points, ch.tarl, ch.dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
     w = sp.csr_matrix(A)
     out = []
@@ -58,13 +59,15 @@ def main():
     ap.add_argument("--out", default="gpurun_out/parity.json")
     ap.add_argument("--oracle-cache", default="", help="directory of cached oracle labels (filled when missing); the "
                     "oracle is CPU-only, so it can be computed ahead of the GPU run")
+    ap.add_argument("--clutter", type=int, default=0, help="2-12 voxel fragments per chunk (robustness set: the unpinned "
+                    "reference disagrees with itself on such chunks; they are reported as oracle-unstable)")
     ap.add_argument("--oracle-only", action="store_true", help="fill the cache and exit (no GPU needed)")
     args = ap.parse_args()
     if args.oracle_only:
         seeds = [args.seed + i for i in range(args.chunks)]
         workers = args.workers or min(os.cpu_count() or 1, 32, args.chunks)
         with mp.get_context("spawn").Pool(workers) as pool:
-            r = pool.map(oracle_job, [(s, args.n_target, args.config, args.oracle_cache) for s in seeds])
+            r = pool.map(oracle_job, [(s, args.n_target, args.config, args.oracle_cache, args.clutter) for s in seeds])
         print("cached", len(r), "stable", sum(1 for x in r if x[2]))
         return
     import torch
@@ -77,8 +80,8 @@ def main():
     workers = args.workers or min(os.cpu_count() or 1, 32, args.chunks)
     t0 = time.time()
     with mp.get_context("spawn").Pool(workers) as pool:
-        async_res = pool.map_async(oracle_job, [(s, args.n_target, args.config, args.oracle_cache) for s in seeds])
-        chunks = [make_chunk(s, n_target=args.n_target, features=feats) for s in seeds]
+        async_res = pool.map_async(oracle_job, [(s, args.n_target, args.config, args.oracle_cache, args.clutter) for s in seeds])
+        chunks = [make_chunk(s, n_target=args.n_target, features=feats, clutter=args.clutter) for s in seeds]
         t1 = time.time()
         res = api.segment_chunks([c.points for c in chunks], [c.tarl for c in chunks],
                                  [c.dino for c in chunks] if cfg["gamma"] else None, alpha=cfg["alpha"],
@@ -100,7 +103,7 @@ def main():
             bad.append(dict(seed=s, n=ch.n, segs_gpu=int(lab.max() + 1), segs_ref=int(ref.max() + 1),
                             moved=int((lab != ref).sum())))
     st = res.stats
-    summary = dict(config=args.config, chunks=args.chunks, n_target=args.n_target, oracle_stable=stable, matched=matched,
+    summary = dict(config=args.config, chunks=args.chunks, n_target=args.n_target, clutter=args.clutter, oracle_stable=stable, matched=matched,
                    match_rate=matched / max(stable, 1), oracle_unstable=args.chunks - stable, mismatches=bad,
                    gpu_seconds_incl_h2d=t_gpu, wall_seconds=t_all, oracle_workers=workers,
                    eig_nodes=int(len(st)), unconverged=int((st["converged"] == 0).sum()),
