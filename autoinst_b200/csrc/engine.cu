@@ -59,12 +59,15 @@ struct ancuts_handle {
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
     bool attrs_set = false;
-    // Lanczos kernel variant (ANCUTS_X in the environment overrides, for A/B measurements; tools/gpu_s2_*.sh):
-    //   1 (always on) matvec without out-of-block selects   2 every second float->double widening on the integer pipe
-    //   bits 4-5 L2 bulk prefetch distance in passes (register-staged matvec only)   256 one-kernel affinity
-    //   1024 three-term recurrence + ONE Gram-Schmidt pass   4096 basis rows in global memory only
-    //   8192 TMA ring in shared memory instead of register-staged loads
-    int xflags = 1 | 2 | 1024 | 8192;
+    // Kernel variants (ANCUTS_X in the environment overrides the default, for A/B measurements; tools/gpu_s2_*.sh):
+    //   2     every second float->double widening of the matvec on the integer pipe
+    //   16,32 L2 bulk prefetch distance in passes (bits 4-5; register-staged matvec only); 2048: per-lane prefetch instead
+    //   256   one-kernel affinity (k_affinity_exact) instead of the two-pass form
+    //   1024  three-term recurrence + ONE Gram-Schmidt pass (otherwise classical Gram-Schmidt twice)
+    //   4096  basis rows in global memory only
+    //   8192  TMA ring in shared memory (otherwise register-staged loads)
+    // The matvec reads out-of-block columns without selects whenever the blocks come from k_gather_blocks_cur.
+    int xflags = 2 | 1024 | 8192;
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
@@ -107,7 +110,6 @@ struct Plan {
     void* tc_scratch; size_t tc_scratch_bytes = 0;
     PairQ* pairq = nullptr; int qcap = 0; int* qctr = nullptr;     // two-pass affinity: pair queue, [2c]=count [2c+1]=overflow
     bool want_pairq = false;
-    char* w0_begin = nullptr; size_t w0_bytes = 0;                 // the chunks' ping buffers (contiguous)
     ancuts_node_stat* stats;
     Eng e;
 };
@@ -181,15 +183,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
         pl.qctr = ar.take<int>(2 * (size_t)B);
     }
     pl.hW0.assign(B, nullptr); pl.hW1.assign(B, nullptr);
-    // all ping buffers first: one contiguous region, zero-filled by a single memset before the two-pass affinity
-    pl.w0_begin = nullptr; pl.w0_bytes = 0;
-    if (pl.own_w0) {
-        ar.off = align_up(ar.off, 256);
-        size_t start = ar.off;
-        for (int c = 0; c < B; ++c) pl.hW0[c] = ar.take<float>((size_t)pl.n[c] * pl.ld[c]);
-        pl.w0_begin = base ? base + start : nullptr;
-        pl.w0_bytes = ar.off - start;
-    }
+    if (pl.own_w0) for (int c = 0; c < B; ++c) pl.hW0[c] = ar.take<float>((size_t)pl.n[c] * pl.ld[c]);
     if (pl.own_w1) for (int c = 0; c < B; ++c) pl.hW1[c] = ar.take<float>((size_t)pl.n[c] * pl.ld[c]);
     return align_up(ar.off, 256);
 }
@@ -369,7 +363,7 @@ static int resolve_kmax(const ancuts_params* p) {
 // connected components (positions pos0 + i) while the pairs are at hand
 static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, const float* tarl, const float* dino,
                         const ancuts_params* p, float* W, long long ld, uint8_t* tarl_zero, cudaStream_t st,
-                        int* qctr = nullptr, int* parent = nullptr, int pos0 = 0, bool prezeroed = false) {
+                        int* qctr = nullptr, int* parent = nullptr, int pos0 = 0) {
     const bool use_tarl = p->theta != 0.0 && tarl != nullptr;
     const bool use_dino = p->gamma != 0.0 && dino != nullptr;
     if (p->theta != 0.0 && tarl == nullptr) { set_error("theta != 0 but no TARL features"); return ANCUTS_EINVAL; }
@@ -392,7 +386,6 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
     } else if (qctr && (use_tarl || use_dino)) {
         // two-pass form: distances + zero fill + pair queue, then the queued pairs spread over the whole grid
         dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
-        (void)prezeroed;
         LAUNCH(SG_AFFINITY, k_affinity_pairs<<<grid, 256, 0, st>>>(n, pts, p->alpha, p->proximity, W, ld, pl.pairq, pl.qcap, qctr,
                                                                    parent, pos0));
         LAUNCH(SG_AFFINITY, k_affinity_feats<<<148 * 4, 256, 0, st>>>(pl.pairq, qctr, pl.qcap, use_tarl ? tarl : nullptr, p->tarl_dim,
@@ -1234,7 +1227,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
             if (wait_ev) ANCUTS_CUDA(cudaStreamWaitEvent(st, wait_ev[c], 0));       // this chunk's inputs have arrived
             rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
                               pl.tarl_zero + o, st, pl.qctr ? pl.qctr + 2 * c : nullptr, pl.qctr ? pl.e.parent : nullptr,
-                              pl.base[c], pl.qctr != nullptr);
+                              pl.base[c]);
             if (rc) return rc;
             aff_bytes += 4.0 * n[c] * (double)n[c] +
                          4.0 * n[c] * (3 + (p->theta != 0 ? p->tarl_dim : 0) + (p->gamma != 0 ? p->dino_dim : 0));

@@ -43,10 +43,10 @@ def check_affinity(W, A):
     assert np.array_equal(W, W.T)
 
 
-# 1 | 2 | 1024 | 8192 is the default; 256 = one-kernel affinity; 1|8|32|1024 = register-staged matvec with L2 prefetch;
-# 0 = matvec with selects, two Gram-Schmidt passes (round-1 form); 4096 = basis rows in global memory only
-VARIANTS = {"default": 1 | 2 | 1024 | 8192, "one_kernel_affinity": 1 | 2 | 1024 | 8192 | 256, "register_matvec": 1 | 2 | 32 | 1024,
-            "round1": 0, "ring_cgs2": 1 | 8192, "basis_in_global": 1 | 2 | 1024 | 8192 | 4096}
+# ANCUTS_X bits (engine.cu): 2 = integer widening of every second element, 32 = L2 prefetch two passes ahead, 256 = one-kernel
+# affinity, 1024 = three-term + one Gram-Schmidt pass, 4096 = basis rows in global memory only, 8192 = TMA ring.
+VARIANTS = {"default": 2 | 1024 | 8192, "one_kernel_affinity": 2 | 1024 | 8192 | 256, "register_matvec_prefetch": 2 | 32 | 1024,
+            "register_matvec_cgs2": 0, "ring_cgs2": 8192, "basis_in_global": 2 | 1024 | 8192 | 4096}
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))

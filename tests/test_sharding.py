@@ -34,13 +34,18 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, sizes, q):
+def _worker(rank, world, port, sizes, q, adjacent=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         mine = sharding.shard_chunks(sizes, world)[rank]
         labels = [np.full(sizes[i], i, dtype=np.int32) + np.arange(sizes[i], dtype=np.int32) % 3 for i in mine]
+        if adjacent:
+            # consecutive slices of ONE label buffer, as bench.py and DeviceChunks.labels hand them over (single-copy path)
+            flat = torch.from_numpy(np.concatenate(labels)) if labels else torch.zeros(0, dtype=torch.int32)
+            offs = np.cumsum([0] + [sizes[i] for i in mine])
+            labels = [flat[a:b] for a, b in zip(offs[:-1], offs[1:])]
         out = sharding.gather_labels(mine, labels, len(sizes))
         ok = all(np.array_equal(out[i], np.full(sizes[i], i, dtype=np.int32) + np.arange(sizes[i], dtype=np.int32) % 3)
                  for i in range(len(sizes)))
@@ -49,13 +54,13 @@ def _worker(rank, world, port, sizes, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_gather_labels_gloo(world):
+@pytest.mark.parametrize("world,adjacent", [(2, False), (3, False), (2, True)])
+def test_gather_labels_gloo(world, adjacent):
     sizes = [7, 120, 33, 64, 5, 90, 1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, sizes, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, sizes, q, adjacent)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
