@@ -8,13 +8,17 @@ for cfg in spatial tarl_spatial tarl_spatial_dino; do
   timeout 900 python tools/parity_sweep.py --config $cfg --chunks 32 --n-target 8192 --seed 7000 --oracle-cache parity_cache --out gpurun_out/parity_$cfg.json > gpurun_out/parity_$cfg.log 2>&1; echo "parity $cfg exit $?" >> gpurun_out/summary.txt
   tail -1 gpurun_out/parity_$cfg.log | cut -c1-300
 done
+timeout 900 python tools/parity_sweep.py --config tarl_spatial --chunks 6 --n-target 16384 --seed 7200 --oracle-cache parity_cache --out gpurun_out/parity_tarl_spatial_16k.json > gpurun_out/parity_16k.log 2>&1; echo "parity 16k exit $?" >> gpurun_out/summary.txt
+tail -1 gpurun_out/parity_16k.log | cut -c1-300
+timeout 900 python tools/parity_sweep.py --config tarl_spatial --chunks 16 --n-target 8192 --seed 7400 --clutter 40 --oracle-cache parity_cache --out gpurun_out/parity_tarl_spatial_clutter40.json > gpurun_out/parity_clutter.log 2>&1; echo "parity clutter exit $?" >> gpurun_out/summary.txt
+tail -1 gpurun_out/parity_clutter.log | cut -c1-400
 timeout 900 python tools/map_eval.py --chunks 24 --n-per-chunk 6000 --out gpurun_out/map_eval.json > gpurun_out/map_eval.log 2>&1; echo "map exit $?" >> gpurun_out/summary.txt
 tail -1 gpurun_out/map_eval.log | cut -c1-600
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?" >> gpurun_out/summary.txt
 head -c 600 gpurun_out/bench.json; echo
 timeout 900 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; echo "reference arm exit $?" >> gpurun_out/summary.txt
 head -c 500 gpurun_out/bench_reference.json; echo
-timeout 600 python tools/nsweep.py --sizes 4096 8192 16384 32768 --out gpurun_out/nsweep.json > gpurun_out/nsweep.log 2>&1; echo "nsweep exit $?" >> gpurun_out/summary.txt
+timeout 900 python tools/nsweep.py --sizes 1024 2048 4096 8192 16384 32768 --cpu --out gpurun_out/nsweep.json > gpurun_out/nsweep.log 2>&1; echo "nsweep exit $?" >> gpurun_out/summary.txt
 python - <<'PY'
 import json
 for r in json.load(open('gpurun_out/nsweep.json')):
@@ -27,8 +31,4 @@ python tools/ncu_summarise.py gpurun_out/launches.csv gpurun_out/launch_list.csv
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:k_lanczos_cluster -c 200 --csv --log-file gpurun_out/cluster_dram.csv $CMD > gpurun_out/ncu_dram.log 2>&1
 echo "dram list exit $?" >> gpurun_out/summary.txt
 python tools/ncu_summarise.py gpurun_out/cluster_dram.csv gpurun_out/cluster_dram_summary.csv
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_lanczos_cluster -s 1 -c 2 -o /tmp/prof_cluster "python" tools/one_step.py --batch 128 --passes 1 > gpurun_out/ncu_full.log 2>&1
-echo "full capture exit $?" >> gpurun_out/summary.txt
-ncu -i /tmp/prof_cluster.ncu-rep --page raw --csv > gpurun_out/ncu_cluster_raw.csv 2>/dev/null
-ncu -i /tmp/prof_cluster.ncu-rep --page source --csv > gpurun_out/ncu_cluster_source.csv 2>/dev/null
 cat gpurun_out/summary.txt
