@@ -146,3 +146,34 @@ def same_partition(a, b):
         return False
     pairs = len(set(zip(a.tolist(), b.tolist())))
     return pairs == len(set(a.tolist())) == len(set(b.tolist()))
+
+
+def residual_group_report(lab, ref, n_orig, split_lim=0.01):
+    """How a labeling `lab` relates to the reference labeling `ref` on a chunk with tiny fragments.
+
+    On a disconnected node the normalised Laplacian is block diagonal and its null vectors are
+    localised on single connected components; the two eigenvalues `eigsh(..., sigma=1e-10)` returns
+    (`normalized_cut.py:49-53`) are the two largest ROUNDING residues of those null vectors, so every
+    degenerate split peels exactly one component (threshold k = 1) and the chain stops when what is
+    left is at most `split_lim`·N points (`:39-40`): one residual leaf made of whole tiny components,
+    chosen by rounding noise of the float64 matrix.  A labeling that gives every component its own
+    segment therefore equals the reference up to that residual grouping.
+    Returns dict(refines, groups=[(ref_label, parts, points)], residual_only): `refines` — every
+    segment of `lab` lies inside one segment of `ref`; `groups` — the reference segments that hold
+    more than one segment of `lab`; `residual_only` — refines and every such group is a leaf by the
+    size rule (points <= split_lim·N)."""
+    lab = np.asarray(lab).ravel()
+    ref = np.asarray(ref).ravel()
+    owner = {}
+    refines = True
+    for g, r in set(zip(lab.tolist(), ref.tolist())):
+        if g in owner:
+            refines = False
+        owner[g] = r
+    parts = {}
+    for g, r in owner.items():
+        parts[r] = parts.get(r, 0) + 1
+    groups = [(int(r), int(c), int((ref == r).sum())) for r, c in sorted(parts.items()) if c > 1]
+    lim = split_lim * (n_orig + 1e-8)
+    return dict(refines=refines, groups=groups,
+                residual_only=bool(refines and all(p <= lim for _, _, p in groups)))

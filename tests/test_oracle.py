@@ -141,3 +141,34 @@ def test_merge_ref_unites_instances_across_overlapping_chunks():
     assert pred.min() == 0 and (pred == 0).sum() == (glab == 0).sum()
     cleaned = M.remove_semantics(M.compact_labels(glab), pred)
     assert np.array_equal(cleaned, pred)                                   # nothing sits on GT background here
+
+
+@pytest.mark.parametrize("seed,expect_groups", [(42, 0), (43, 1)])
+def test_disconnected_nodes_peel_one_component_and_leave_a_residual_group(seed, expect_groups):
+    """What the reference does with tiny fragments: every split of a disconnected node peels ONE
+    connected component (the null vectors of the block-diagonal Laplacian are localised on components and
+    `eigsh` returns the two with the largest rounding residue, `normalized_cut.py:49-53`), and the chain ends in
+    one leaf of whole components once it is at most 1 % of N (`:39-40`).  The device algorithm gives every
+    component its own segment, so it equals the reference up to that residual leaf."""
+    from scipy.sparse.csgraph import connected_components
+    cfg = CONFIGS["tarl_spatial"]
+    ch = make_chunk(seed, n_target=1500, features="tarl", clutter=10)
+    A = affinity_ref(ch.points, ch.tarl, alpha=cfg["alpha"], theta=cfg["theta"])
+    w = sp.csr_matrix(A)
+    ncomp, cc = connected_components(w, directed=False)
+    sizes = set(np.bincount(cc).tolist())
+    trace = []
+    with R.pinned_eigsh():
+        g = R.normalized_cut_ref(w, ch.n, np.arange(ch.n), T=cfg["T"], trace=trace)
+    ref = R.labels_from_groups(g, ch.n)
+    degenerate = [t for t in trace if "vals" in t and abs(t["vals"][1]) < 1e-12]
+    assert len(degenerate) >= ncomp - 3
+    for t in degenerate:
+        assert t["split"] and abs(t["mcut"]) < 1e-9
+        assert t["n_side"] in sizes or (t["n"] - t["n_side"]) in sizes     # one whole component leaves the node
+    lab = segment_model(A.astype(np.float32), cfg["T"])
+    rep = R.residual_group_report(lab, ref, ch.n)
+    assert rep["refines"] and rep["residual_only"]
+    assert len(rep["groups"]) == expect_groups
+    for _, _, pts in rep["groups"]:
+        assert pts <= 0.01 * ch.n
