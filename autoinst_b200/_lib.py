@@ -22,7 +22,7 @@ EXPORTS = [
     "ancuts_lanczos_fiedler_batched", "ancuts_ncut_scan_batched", "ancuts_partition_batched",
     "ancuts_segment_chunks", "ancuts_segment_chunks_host", "ancuts_segment_dense_f32",
     "ancuts_launch_count", "ancuts_last_accounting", "ancuts_set_stage_timing", "ancuts_nn_reproject",
-    "ancuts_last_levels", "ancuts_debug_phases",
+    "ancuts_last_levels", "ancuts_debug_phases", "ancuts_feature_pool_workspace_bytes", "ancuts_feature_pool",
 ]
 
 
@@ -98,6 +98,10 @@ def load():
     lib.ancuts_segment_dense_f32.argtypes = [vp, C.c_int, vp, C.c_int64, C.c_int, pp, vp, i32p, sp,
                                              C.c_int32, i32p, vp]
     lib.ancuts_nn_reproject.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, C.c_double, C.c_int32, vp, vp, vp]
+    lib.ancuts_feature_pool_workspace_bytes.argtypes = [C.c_int]
+    lib.ancuts_feature_pool_workspace_bytes.restype = C.c_int64
+    lib.ancuts_feature_pool.argtypes = [vp, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_double, dp, dp, C.c_int, vp, vp, vp,
+                                        C.c_int64, vp]
     lib.ancuts_launch_count.argtypes = [vp, C.c_int]
     lib.ancuts_launch_count.restype = C.c_int64
     lib.ancuts_last_accounting.argtypes = [vp, dp, dp, i64p]

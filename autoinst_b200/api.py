@@ -262,6 +262,33 @@ def nn_reproject(query_points, source_points, source_labels=None, max_radius=Non
     return out, idx
 
 
+def feature_pool(major_points, scan_points, scan_features, radius, box_min, box_max, *, normalise=False,
+                 return_count=False, device=None):
+    """Mean of the feature rows of the scan points strictly closer than `radius` to every major point
+    (`tarl_features_per_patch`, chunk_generation.py:205-258; C ABI `ancuts_feature_pool`).  Scan points outside
+    the open box (box_min, box_max) are ignored (:233-236).  Returns float64 [n_major, F] on the device
+    (zero rows where nothing is in range) and, with return_count, the int32 neighbour counts."""
+    device = _dev(device)
+    hd = Handle.get(device)
+    q = _as_dev(major_points, torch.float64, device).reshape(-1, 3)
+    sp = _as_dev(scan_points, torch.float64, device).reshape(-1, 3)
+    ft = _as_dev(scan_features, torch.float32, device)
+    m = int(sp.shape[0])
+    ft = ft.reshape(m, -1) if m else ft.reshape(0, ft.shape[-1] if ft.dim() > 1 else 1)
+    fdim = int(ft.shape[1])
+    out = torch.empty((q.shape[0], fdim), dtype=torch.float64, device=device)
+    cnt = torch.empty(q.shape[0], dtype=torch.int32, device=device)
+    wsb = int(hd.lib.ancuts_feature_pool_workspace_bytes(m))
+    ws = torch.empty(max(wsb, 256), dtype=torch.uint8, device=device)
+    lo = (C.c_double * 3)(*[float(v) for v in np.asarray(box_min, dtype=np.float64).ravel()[:3]])
+    hi = (C.c_double * 3)(*[float(v) for v in np.asarray(box_max, dtype=np.float64).ravel()[:3]])
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_feature_pool(hd.h, q.shape[0], _ptr(q), m, _ptr(sp) if m else None, _ptr(ft) if m else None,
+                                         fdim, float(radius), lo, hi, 1 if normalise else 0, _ptr(out), _ptr(cnt),
+                                         _ptr(ws), wsb, _stream(device)))
+    return (out, cnt) if return_count else out
+
+
 # ------------------------------------------------------------------------------------------------
 # whole path
 # ------------------------------------------------------------------------------------------------

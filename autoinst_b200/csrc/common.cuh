@@ -117,6 +117,7 @@ struct Eng {
     int KS;           // stride of per-node Krylov arrays = kmax + 4
     int kmax;
     int check_every;
+    int check_adapt;  // 1: caller left lanczos_check_every at 0, the cluster kernel places its checks adaptively
     double tol;
     double T;
     // chunk table

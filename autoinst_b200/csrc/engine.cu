@@ -11,6 +11,7 @@
 #include "kernels_lanczos.cuh"
 #include "kernels_ncut.cuh"
 #include "kernels_cluster.cuh"
+#include "kernels_pool.cuh"
 
 namespace ancuts {
 
@@ -66,8 +67,11 @@ struct ancuts_handle {
     //   1024  three-term recurrence + ONE Gram-Schmidt pass (otherwise classical Gram-Schmidt twice)
     //   4096  basis rows in global memory only
     //   8192  TMA ring in shared memory (otherwise register-staged loads)
+    //   65536 128 instead of 256 multisection shifts per eigenvalue and round in those checks
+    //   32768 division-free Sturm counts in the cluster kernel's convergence checks
+    //   16384 adaptive placement of the convergence checks in the cluster kernel (otherwise every check_every steps)
     // The matvec reads out-of-block columns without selects whenever the blocks come from k_gather_blocks_cur.
-    int xflags = 2 | 1024 | 8192;
+    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536;
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
@@ -350,6 +354,7 @@ static void fill_params(Eng& e, const ancuts_params* p, int kmax) {
     e.kmax = kmax;
     e.KS = kmax + 4;
     e.check_every = p->lanczos_check_every > 0 ? p->lanczos_check_every : CHECK_DEFAULT;
+    e.check_adapt = p->lanczos_check_every <= 0;
     e.tol = p->lanczos_tol > 0 ? p->lanczos_tol : TOL_DEFAULT;
     e.T = p->T;
 }
@@ -1163,6 +1168,74 @@ int ancuts_nn_reproject(ancuts_handle* h, int num_query, const double* d_query, 
     ANCUTS_CUDA(cudaSetDevice(h->device));
     LAUNCH(SG_PARTITION, k_nn_reproject<<<(num_query + 255) / 256, 256, 0, st>>>(
         num_query, d_query, num_source, d_source, d_source_label, max_radius, no_label, d_out_label, d_out_index));
+    ANCUTS_CUDA(cudaGetLastError());
+    return ANCUTS_OK;
+}
+
+// ---- next row N3 (TARL half): radius-mean pooling of scan-point features onto the major points ----
+static size_t pool_sort_tmp_bytes(int m) {
+    size_t a = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, a, (unsigned*)nullptr, (unsigned*)nullptr, (int*)nullptr, (int*)nullptr, m, 0, 32);
+    return align_up(a, 256);
+}
+
+int64_t ancuts_feature_pool_workspace_bytes(int num_scan) {
+    if (num_scan < 0) return -1;
+    const size_t m = (size_t)std::max(num_scan, 1);
+    return (int64_t)(4 * align_up(m * 4, 256) + pool_sort_tmp_bytes((int)m) + 256);
+}
+
+int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, int num_scan, const double* d_scan_points,
+                        const float* d_scan_feat, int feat_dim, double radius, const double* h_box_min,
+                        const double* h_box_max, int normalise, double* d_out, int32_t* d_out_count, void* d_workspace,
+                        int64_t workspace_bytes, void* stream) {
+    if (!h || num_major <= 0 || num_scan < 0 || !d_major || !d_out || feat_dim <= 0 || feat_dim > 384 || !(radius > 0.0) ||
+        !h_box_min || !h_box_max || (num_scan > 0 && (!d_scan_points || !d_scan_feat))) {
+        set_error("bad argument to ancuts_feature_pool");
+        return ANCUTS_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    if (num_scan == 0) {                         // no scan point at all: every row stays zero (chunk_generation.py:247,255-256)
+        ANCUTS_CUDA(cudaMemsetAsync(d_out, 0, (size_t)num_major * feat_dim * sizeof(double), st));
+        if (d_out_count) ANCUTS_CUDA(cudaMemsetAsync(d_out_count, 0, (size_t)num_major * sizeof(int32_t), st));
+        return ANCUTS_OK;
+    }
+    if (!d_workspace || workspace_bytes < ancuts_feature_pool_workspace_bytes(num_scan)) {
+        set_error("ancuts_feature_pool: workspace of %lld bytes needed", (long long)ancuts_feature_pool_workspace_bytes(num_scan));
+        return ANCUTS_EINVAL;
+    }
+    PoolGrid g;
+    double ext = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        g.lo[a] = h_box_min[a]; g.hi[a] = h_box_max[a];
+        if (!(g.hi[a] > g.lo[a])) { set_error("ancuts_feature_pool: empty box"); return ANCUTS_EINVAL; }
+        ext = std::max(ext, g.hi[a] - g.lo[a]);
+    }
+    const double pitch = std::max(radius, ext / 1024.0);       // <= 1024 cells per axis: keys fit 30 bits
+    g.inv_h = 1.0 / pitch;
+    for (int a = 0; a < 3; ++a) g.n[a] = std::min(1025, (int)std::floor((g.hi[a] - g.lo[a]) * g.inv_h) + 1);
+    char* w = (char*)d_workspace;
+    const size_t seg = align_up((size_t)num_scan * 4, 256);
+    unsigned* keys = (unsigned*)w;  unsigned* keys2 = (unsigned*)(w + seg);
+    int* idx = (int*)(w + 2 * seg); int* idx2 = (int*)(w + 3 * seg);
+    int* inside = (int*)(w + 4 * seg);
+    void* tmp = w + 4 * seg + 256;
+    size_t tmp_bytes = pool_sort_tmp_bytes(num_scan);
+    ANCUTS_CUDA(cudaMemsetAsync(inside, 0, sizeof(int), st));
+    LAUNCH(SG_PARTITION, k_pool_keys<<<(num_scan + 255) / 256, 256, 0, st>>>(num_scan, d_scan_points, g, keys, idx, inside));
+    int bits = 1;
+    while (bits < 32 && (1ull << bits) < (unsigned long long)g.n[0] * g.n[1] * g.n[2]) ++bits;
+    h->launches_total += 1;
+    ANCUTS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, num_scan, 0, 32, st));
+    (void)bits;                                  // all 32 bits: the UINT_MAX keys of the cropped points must end up last
+    const int blocks = (num_major + 7) / 8;
+    const double r2 = radius * radius;
+    const int fpl = (feat_dim + 31) / 32;
+#define POOL_CASE(F) LAUNCH(SG_PARTITION, k_pool_gather<F><<<blocks, 256, 0, st>>>(num_major, d_major, num_scan, d_scan_points, \
+        d_scan_feat, feat_dim, g, r2, normalise, keys2, idx2, inside, d_out, d_out_count))
+    if (fpl <= 1) POOL_CASE(1); else if (fpl <= 3) POOL_CASE(3); else if (fpl <= 4) POOL_CASE(4); else POOL_CASE(12);
+#undef POOL_CASE
     ANCUTS_CUDA(cudaGetLastError());
     return ANCUTS_OK;
 }

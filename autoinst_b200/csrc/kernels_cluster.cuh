@@ -47,7 +47,21 @@ struct ClusterShared {
     double gb[3];
     int swp[CL_KS];
     int cnts[CL_THREADS];
+    long long tmark;             // debug phase clock: end of the multisection rounds inside cluster_tridiag
+    double prev_res;             // adaptive check schedule: residual estimate and step of the last check
+    int prev_k;
+    int next_check;
 };
+
+// Adaptive convergence checks.  The fixed schedule (every 16 steps) runs 8 steps past convergence on average
+// (14 % of the steps of the benchmark workload; no node converges before step 38).  Here the residual estimates
+// of the last two checks give a geometric rate, the next check is placed at CL_CHECK_SAFETY x the predicted
+// number of steps (Lanczos converges faster than geometrically at the end), clamped to [LO, HI].  numpy model
+// over 87 nodes: 1.009 x the minimum number of steps (fixed 16: 1.14) with the same number of checks.
+constexpr int CL_CHECK_FIRST = 28;
+constexpr int CL_CHECK_LO = 2;
+constexpr int CL_CHECK_HI = 12;
+constexpr double CL_CHECK_SAFETY = 0.7;
 
 __device__ __forceinline__ double block_sum_512(double v, double* red) {
     v = warp_sum(v);
@@ -72,86 +86,140 @@ __device__ __forceinline__ double block_min_512(double v, double* red) {
     return t;
 }
 
+// Sturm count without divisions: the characteristic polynomials of the leading blocks,
+// p_i = (a_i - x) p_{i-1} - b_{i-1}^2 p_{i-2}, change sign between consecutive i exactly where the pivots
+// q_i = p_i / p_{i-1} of sturm_count() are negative.  One dependent FMA per element instead of one division
+// (a float64 division is a ~12-instruction dependent sequence; the convergence checks were 8-13 % of the CTA time).
+// |a_i - x| <= 2.3 and b^2 <= 1 bound the growth to 3.3x per step, so the pair is rescaled every 4 elements;
+// an exact zero takes the sign opposite to its predecessor (the q = -pivmin rule).
+__device__ __forceinline__ int sturm_count_poly(const double* al, const double* be2, int k, double x) {
+    double pm = 1.0, p = al[0] - x;
+    bool neg = !(p > 0.0);                       // sign of p_0 (zero counts as negative), p_{-1} = 1 > 0
+    int cnt = neg ? 1 : 0;
+#define STURM_STEP(c, e) do {                                              \
+        const double pn_ = fma((c), p, -((e) * pm));                       \
+        pm = p; p = pn_;                                                   \
+        const bool ng_ = (p < 0.0) || (p == 0.0 && !neg);                  \
+        cnt += (ng_ != neg) ? 1 : 0; neg = ng_;                            \
+    } while (0)
+    int i = 1;
+    // groups of four; the (broadcast) shared-memory loads of the NEXT group are issued before the dependent
+    // FMA chain of the current one, so the chain is one FMA per element
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    if (i + 3 < k) { a0 = al[i]; a1 = al[i + 1]; a2 = al[i + 2]; a3 = al[i + 3]; b0 = be2[i - 1]; b1 = be2[i]; b2 = be2[i + 1]; b3 = be2[i + 2]; }
+    while (i + 3 < k) {
+        const double c0 = a0 - x, c1 = a1 - x, c2 = a2 - x, c3 = a3 - x;
+        const double e0 = b0, e1 = b1, e2 = b2, e3 = b3;
+        i += 4;
+        if (i + 3 < k) { a0 = al[i]; a1 = al[i + 1]; a2 = al[i + 2]; a3 = al[i + 3]; b0 = be2[i - 1]; b1 = be2[i]; b2 = be2[i + 1]; b3 = be2[i + 2]; }
+        STURM_STEP(c0, e0); STURM_STEP(c1, e1); STURM_STEP(c2, e2); STURM_STEP(c3, e3);
+        const int ex = (__double2hiint(p) >> 20) & 0x7ff;          // biased exponent
+        if (ex > 1023 + 256) { p *= 0x1p-256; pm *= 0x1p-256; }
+        else if (ex < 1023 - 256 && p != 0.0) { p *= 0x1p256; pm *= 0x1p256; }
+    }
+    for (; i < k; ++i) STURM_STEP(al[i] - x, be2[i - 1]);          // at most three elements: no rescaling needed
+#undef STURM_STEP
+    return cnt;     // number of eigenvalues < x
+}
+
 // tridiagonal analysis by the whole CTA (512 threads): top two eigenvalues by multisection with 256
 // shifts each (257^8 > 2^64), eigenvector of the largest by a twisted factorisation (thread 0).
 // Returns the residual estimate beta_{k-1} |y_{k-1}|; th[0], th[1] = eigenvalues; S.yv = eigenvector.
-__device__ double cluster_tridiag(ClusterShared& S, int k, double* th) {
+__device__ double cluster_tridiag(ClusterShared& S, int k, double* th, bool poly, int sh) {
     const int tid = threadIdx.x;
-    for (int i = tid; i < k; i += CL_THREADS) S.be2[i] = S.beta[i] * S.beta[i];
-    __syncthreads();
+    // Gershgorin bracket of the spectrum and the pivot floor, by the whole CTA
+    double lo_t = 1e300, hi_t = -1e300, bm_t = 0.0;
+    for (int i = tid; i < k; i += CL_THREADS) {
+        const double b = S.beta[i];
+        S.be2[i] = b * b;
+        const double rad = (i > 0 ? fabs(S.beta[i - 1]) : 0.0) + (i < k - 1 ? fabs(b) : 0.0);
+        lo_t = fmin(lo_t, S.alpha[i] - rad);
+        hi_t = fmax(hi_t, S.alpha[i] + rad);
+        if (i < k - 1) bm_t = fmax(bm_t, b * b);
+    }
+    lo_t = block_min_512(lo_t, S.red);
+    hi_t = -block_min_512(-hi_t, S.red);
+    bm_t = -block_min_512(-bm_t, S.red);
     if (tid == 0) {
-        double lo = 1e300, hi = -1e300, bmax = 0.0;
-        for (int i = 0; i < k; ++i) {
-            double rad = (i > 0 ? fabs(S.beta[i - 1]) : 0.0) + (i < k - 1 ? fabs(S.beta[i]) : 0.0);
-            lo = fmin(lo, S.alpha[i] - rad);
-            hi = fmax(hi, S.alpha[i] + rad);
-            if (i < k - 1) bmax = fmax(bmax, S.be2[i]);
-        }
-        double w = fmax(fmax(fabs(lo), fabs(hi)), 1e-300);
-        S.gb[0] = lo - 1e-10 * w;
-        S.gb[1] = hi + 1e-10 * w;
-        S.gb[2] = fmax(bmax, 1.0) * 1.0020841800044864e-292;
+        double w = fmax(fmax(fabs(lo_t), fabs(hi_t)), 1e-300);
+        S.gb[0] = lo_t - 1e-10 * w;
+        S.gb[1] = hi_t + 1e-10 * w;
+        S.gb[2] = fmax(bm_t, 1.0) * 1.0020841800044864e-292;
     }
     __syncthreads();
     const double glo = S.gb[0], ghi = S.gb[1], pivmin = S.gb[2];
     {
-        const int which = tid / CL_HALF, t256 = tid % CL_HALF;
+        // sh shifts per eigenvalue and round.  256 (all 512 threads) resolves 8 bits per round, 128 resolves 7:
+        // 129^8 > 2^56 still brackets a float64 in 8 rounds, with half as many warps competing for the FP64 pipe.
+        const int which = tid / sh, t256 = tid % sh;
+        const bool act = which < 2;
         const int m = k - 1 - which;
         double lo = glo, hi = ghi;
-        const int rounds = 8;                       // 257^8 > 2^64: full float64 resolution (the residual
-                                                    // estimate below is only as good as the eigenvalue)
+        const int rounds = 8;                       // full float64 resolution (the residual estimate below is only
+                                                    // as good as the eigenvalue)
+        const double den = 1.0 / (double)(sh + 1);
         for (int round = 0; round < rounds; ++round) {
-            double x = lo + (hi - lo) * ((double)(t256 + 1) / (double)(CL_HALF + 1));
-            S.cnts[tid] = (m >= 0) ? sturm_count(S.alpha, S.be2, k, x, pivmin) : 0;
+            if (act) {
+                double x = lo + (hi - lo) * ((double)(t256 + 1) * den);
+                S.cnts[tid] = (m < 0) ? 0 : poly ? sturm_count_poly(S.alpha, S.be2, k, x) : sturm_count(S.alpha, S.be2, k, x, pivmin);
+            }
             __syncthreads();
-            if (t256 < 32) {                 // one warp per eigenvalue finds the last shift with count <= m
+            if (act && t256 < 32) {          // one warp per eigenvalue finds the last shift with count <= m
                 int best = -1;
-                for (int i = t256; i < CL_HALF; i += 32) if (S.cnts[which * CL_HALF + i] <= m) best = max(best, i);
+                for (int i = t256; i < sh; i += 32) if (S.cnts[which * sh + i] <= m) best = max(best, i);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
                 if (t256 == 0) {
-                    S.bounds[2 * which] = (best >= 0) ? lo + (hi - lo) * ((double)(best + 1) / (double)(CL_HALF + 1)) : lo;
-                    S.bounds[2 * which + 1] = (best < CL_HALF - 1) ? lo + (hi - lo) * ((double)(best + 2) / (double)(CL_HALF + 1)) : hi;
+                    S.bounds[2 * which] = (best >= 0) ? lo + (hi - lo) * ((double)(best + 1) * den) : lo;
+                    S.bounds[2 * which + 1] = (best < sh - 1) ? lo + (hi - lo) * ((double)(best + 2) * den) : hi;
                 }
             }
             __syncthreads();
-            lo = S.bounds[2 * which];
-            hi = S.bounds[2 * which + 1];
+            if (act) { lo = S.bounds[2 * which]; hi = S.bounds[2 * which + 1]; }
             __syncthreads();
         }
     }
     const double th1 = 0.5 * (S.bounds[0] + S.bounds[1]);
     const double th2 = (k > 1) ? 0.5 * (S.bounds[2] + S.bounds[3]) : -1e300;
     if (tid == 0) {
+        S.tmark = clock64();
         // Eigenvector of th1 from the factorisation of T - th1 I twisted at the FIRST index: bottom-up
         // pivots p_k = a_k - th, p_i = a_i - th - b_i^2 / p_{i+1}.  The trailing blocks of T do not contain
         // the converged part of the Krylov space, their eigenvalues stay below th1 (interlacing), so every
         // pivot is safely negative and the recurrence z_1 = 1, z_{i+1} = -b_i z_i / p_{i+1} is stable; it
         // replaces a pivoted LU plus inverse iteration (2k divisions, agreement with LAPACK to 1e-14).
+        // S.dd holds the RECIPROCAL pivots, so the vector recurrence below has no division of its own.
         double d = S.alpha[k - 1] - th1;
         if (fabs(d) < pivmin) d = -pivmin;
-        S.dd[k - 1] = d;
+        double r = 1.0 / d;
+        S.dd[k - 1] = r;
         for (int i = k - 2; i >= 0; --i) {
-            d = S.alpha[i] - th1 - S.be2[i] / d;
+            d = fma(-S.be2[i], r, S.alpha[i] - th1);
             if (fabs(d) < pivmin) d = -pivmin;
-            S.dd[i] = d;
+            r = 1.0 / d;
+            S.dd[i] = r;
         }
         double z = 1.0, ss = 1.0;
         S.yv[0] = 1.0;
         for (int i = 0; i < k - 1; ++i) {
-            z = -S.beta[i] * z / S.dd[i + 1];
+            z = -(S.beta[i] * S.dd[i + 1]) * z;
             if (fabs(z) > 1e150) {                       // start vector almost orthogonal to the Ritz vector
                 for (int j = 0; j <= i; ++j) S.yv[j] *= 1e-150;
                 z *= 1e-150;
                 ss *= 1e-300;
             }
             S.yv[i + 1] = z;
-            ss += z * z;
+            ss = fma(z, z, ss);
         }
-        double inv = 1.0 / sqrt(ss);
-        for (int i = 0; i < k; ++i) S.yv[i] *= inv;
-        S.gb[0] = fabs(S.beta[k - 1] * S.yv[k - 1]);
+        S.gb[1] = 1.0 / sqrt(ss);
     }
+    __syncthreads();
+    {
+        const double inv = S.gb[1];
+        for (int i = tid; i < k; i += CL_THREADS) S.yv[i] *= inv;
+    }
+    __syncthreads();
+    if (tid == 0) S.gb[0] = fabs(S.beta[k - 1] * S.yv[k - 1]);
     __syncthreads();
     th[0] = th1;
     th[1] = th2;
@@ -532,6 +600,8 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     int k = 0;
     int conv = 0;
     double th[2] = {0.0, 0.0};
+    const bool adapt = e.check_adapt && (e.xf & 16384);
+    if (tid == 0) { S.prev_res = 1.0; S.prev_k = 0; S.next_check = adapt ? CL_CHECK_FIRST : e.check_every; }
     // optional phase clock (debug): cycles of thread 0 between the block-wide syncs that end each phase
     constexpr bool CL_PROF = (CL_THREADS <= 512);      // the 1024-thread build has no registers to spare for the clocks
     const bool prof = CL_PROF && (e.dbg != nullptr) && tid == 0 && rank == 0;
@@ -646,12 +716,29 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         __syncthreads();
         CL_PHASE(6);
         const bool breakdown = beta < 1e-13;
-        if (breakdown || k >= kcap || (k % e.check_every) == 0) {
-            double res = cluster_tridiag(S, k, th);
+        if (breakdown || k >= kcap || k == S.next_check) {
+            double res = cluster_tridiag(S, k, th, (e.xf & 32768) != 0, (e.xf & 65536) ? CL_HALF / 2 : CL_HALF);
+            if (prof && gs1) { tph[3] += S.tmark - tlast; tlast = S.tmark; }     // slot 3 (unused with gs1): multisection part of the check
             double gap = fmax(th[0] - th[1], 1e-300);
             bool c1 = (k >= n - 1) || breakdown || (res <= e.tol * gap);
             if (c1) { conv = 1; break; }
             if (k >= kcap) break;
+            if (tid == 0) {                  // every CTA of the cluster holds the same alpha/beta: identical schedules
+                int adv = e.check_every;
+                if (adapt) {
+                    adv = CL_CHECK_HI;
+                    const double pr = S.prev_res;
+                    if (res < pr && res > 0.0) {
+                        const double rate = log(res / pr) / (double)(k - S.prev_k);          // < 0
+                        const double need = CL_CHECK_SAFETY * log(e.tol * gap / res) / rate;   // > 0: not converged yet
+                        adv = (int)fmin((double)CL_CHECK_HI, fmax((double)CL_CHECK_LO, ceil(need)));
+                    }
+                    S.prev_res = res;
+                    S.prev_k = k;
+                }
+                S.next_check = k + adv;
+            }
+            __syncthreads();
             CL_PHASE(7);
         }
     }

@@ -332,3 +332,32 @@ def small_chunk(seed: int, n_obj: int = 4, pts_per_obj: int = 400, features: str
         g[rng.random(n) < 0.30] = 0.0
         ch.dino = g.astype(np.float64)
     return ch
+
+
+def make_scans(chunk: Chunk, n_scans: int = 21, pts_per_major: float = 3.0, seed: int = 0, fdim: int = 96,
+               outside_frac: float = 0.15, empty_frac: float = 0.05):
+    """Synthetic per-scan TARL inputs of one chunk for the feature-pooling row (SURVEY.md §8f N3;
+    `chunk_generation.py:205-258`): `n_scans` scans (ADJACENT_FRAMES_TARL = (10, 10) -> 21, config.py:69), each a list
+    entry (coords (m,3) float64 already in the chunk frame, feats (m,fdim) float32).  Scan points are the
+    major points jittered by up to 0.3 m (so some fall outside the 0.175 m radius), `empty_frac` of the major
+    points get no scan point at all (zero TARL rows, `:255-256`), and `outside_frac` extra points lie outside
+    the 25 m cube (cropped away, `:233-236`).  Features = instance prototype + noise, float32."""
+    rng = np.random.default_rng(9000 + 131 * chunk.chunk_id + seed)
+    n = chunk.n
+    n_inst = int(chunk.instance.max()) + 1
+    proto = rng.normal(0, 1, size=(n_inst, fdim))
+    covered = rng.random(n) >= empty_frac
+    src = np.flatnonzero(covered)
+    half = CHUNK_EDGE / 2
+    scans = []
+    per_scan = max(1, int(round(n * pts_per_major)))
+    for s in range(n_scans):
+        pick = src[rng.integers(0, src.shape[0], size=per_scan)]
+        p = chunk.points[pick] + rng.uniform(-0.3, 0.3, size=(per_scan, 3)) * rng.random((per_scan, 1))
+        f = (proto[chunk.instance[pick]] + 0.3 * rng.normal(0, 1, size=(per_scan, fdim))).astype(np.float32)
+        n_out = int(per_scan * outside_frac)
+        po = chunk.center + rng.uniform(half, half + 5.0, size=(n_out, 3)) * rng.choice([-1.0, 1.0], size=(n_out, 3))
+        fo = rng.normal(0, 1, size=(n_out, fdim)).astype(np.float32)
+        order = rng.permutation(per_scan + n_out)
+        scans.append((np.concatenate((p, po))[order], np.concatenate((f, fo))[order]))
+    return scans

@@ -153,6 +153,23 @@ int ancuts_nn_reproject(ancuts_handle* h, int num_query, const double* d_query, 
                         const double* d_source, const int32_t* d_source_label, double max_radius,
                         int32_t no_label, int32_t* d_out_label, int32_t* d_out_index, void* stream);
 
+/* "Next" row N3 (TARL half) — replaces the per-point KD-tree loop of tarl_features_per_patch
+ * (pipeline/utils/point_cloud/chunk_generation.py:205-258, called at ncuts_utils.py:135-141): every major point
+ * takes the float64 mean of the feature rows of the scan points strictly closer than `radius`
+ * (MAJOR_VOXEL_SIZE / 2, :212,249-252; Open3D's radius search keeps squared distance < radius^2); major points
+ * without such a neighbour keep a zero row (:247,255-256).  Scan points take part only if strictly inside the
+ * box (h_box_min, h_box_max) = center_position -/+ CHUNK_SIZE / 2 (:220-221,233-236); the two bounds are HOST
+ * arrays of 3 doubles.  d_scan_points: num_scan x 3 float64 (already in the chunk frame, :228-231),
+ * d_scan_feat: num_scan x feat_dim float32 (feat_dim <= 384), d_out: num_major x feat_dim float64,
+ * d_out_count: neighbours per major point (may be NULL).  normalise != 0 divides each non-empty row by its
+ * L2 norm (TARL_NORM, :253-254).  The workspace is the caller's (ancuts_feature_pool_workspace_bytes).
+ * Asynchronous on `stream`; deterministic (fixed summation order). */
+int64_t ancuts_feature_pool_workspace_bytes(int num_scan);
+int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, int num_scan,
+                        const double* d_scan_points, const float* d_scan_feat, int feat_dim, double radius,
+                        const double* h_box_min, const double* h_box_max, int normalise, double* d_out,
+                        int32_t* d_out_count, void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* Counters for bench.py: kernels launched by this handle since the last reset, and the per-kernel
  * CUDA-event time of the kernels named by ancuts_timing_select(). */
 int64_t ancuts_launch_count(ancuts_handle* h, int reset);

@@ -3,7 +3,8 @@
 The affinity build and the recursive cut (`ncuts_utils.py:56-174`) run on the GPU through
 `autoinst_b200.api` (C ABI: `ancuts_segment_chunks_host`).  Everything around them — feature
 fetching from the dataset, colour coding, ground handling — stays the reference's own helper code under
-`utils/` (the 1-NN re-projection to the 5 cm cloud also runs on the GPU, `ancuts_nn_reproject`), imported lazily so that this module also
+`utils/` (the TARL radius-mean pooling and the 1-NN re-projection to the 5 cm cloud also run on the GPU,
+`ancuts_feature_pool` / `ancuts_nn_reproject`), imported lazily so that this module also
 loads where Open3D is absent (the array-level entry `segment_major_points` needs none of it).
 
 Configuration is read the way the reference reads it: module globals star-imported from `config`
@@ -63,7 +64,8 @@ def ncuts_chunk(dataset, chunk_downsample_dict, pcd_nonground_minor, T_pcd, samp
     from autoinst_b200 import api
     from utils.visualization_utils import generate_random_colors
     from utils.image.image_utils import dinov2_mean, image_based_features_per_patch
-    from utils.point_cloud.chunk_generation import tarl_features_per_patch, get_indices_feature_reprojection
+    from utils.point_cloud.chunk_generation import get_indices_feature_reprojection
+    from autoinst_b200.pooling import tarl_features_per_patch      # radius-mean pooling on the GPU (ancuts_feature_pool)
 
     d = chunk_downsample_dict
     print("Start of sequence", sequence)

@@ -38,11 +38,18 @@ def tridiag_top2(alpha, beta):
     return th1, th2, vecs[:, -1]
 
 
-def lanczos_fiedler(Wb32: np.ndarray, d: np.ndarray, *, tol=1e-10, check_every=16, kmax=1024,
+# placement of the convergence checks in the cluster kernel (csrc/kernels_cluster.cuh, CL_CHECK_*)
+CHECK_FIRST, CHECK_LO, CHECK_HI, CHECK_SAFETY = 28, 2, 12, 0.7
+
+
+def lanczos_fiedler(Wb32: np.ndarray, d: np.ndarray, *, tol=1e-10, check_every=0, kmax=1024,
                     stats=None):
     """Fiedler vector of L = I - S (w+I) S, S = D^-1/2, for one connected block.
 
     Wb32: (n,n) float32 block of w (unit diagonal); d: float64 degrees of W = w + I.
+    check_every = 0: adaptive placement of the checks as in the cluster kernel (first at step 28, then at
+    0.7 x the number of steps predicted from the geometric rate between the last two residual estimates,
+    clamped to [2, 12]); > 0: fixed period (the grid-wide path uses 16).
     Returns unit-norm ev with sum(ev) >= 0 and lambda_2.
     """
     n = Wb32.shape[0]
@@ -67,6 +74,8 @@ def lanczos_fiedler(Wb32: np.ndarray, d: np.ndarray, *, tol=1e-10, check_every=1
     converged = False
     th1 = th2 = 0.0
     y = None
+    next_check = CHECK_FIRST if check_every <= 0 else check_every
+    prev_k, prev_res = 0, 1.0
     while k < kcap:
         w = matvec(V[k])
         # full re-orthogonalisation, classical Gram-Schmidt twice, against u1 and V[0..k]
@@ -83,13 +92,22 @@ def lanczos_fiedler(Wb32: np.ndarray, d: np.ndarray, *, tol=1e-10, check_every=1
         breakdown = b < 1e-14
         if not breakdown:
             V[k] = w / b
-        if breakdown or k == kcap or k % check_every == 0:
+        if breakdown or k == kcap or k == next_check:
             th1, th2, y = tridiag_top2(alpha[:k], beta[:k])
             res = abs(b * y[-1])
             gap = max(th1 - th2, 1e-300)
             if breakdown or k == kcap or res <= tol * gap:
                 converged = breakdown or (k == n - 1) or res <= tol * gap
                 break
+            adv = check_every
+            if check_every <= 0:
+                adv = CHECK_HI
+                if 0.0 < res < prev_res:
+                    rate = np.log(res / prev_res) / (k - prev_k)
+                    need = CHECK_SAFETY * np.log(tol * gap / res) / rate
+                    adv = int(min(CHECK_HI, max(CHECK_LO, np.ceil(need))))
+                prev_k, prev_res = k, res
+            next_check = k + adv
     ev = V[:k].T @ y
     ev /= np.linalg.norm(ev)
     if ev.sum() < 0:
