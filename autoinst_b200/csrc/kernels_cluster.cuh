@@ -92,32 +92,34 @@ __device__ __forceinline__ double block_min_512(double v, double* red) {
 // (a float64 division is a ~12-instruction dependent sequence; the convergence checks were 8-13 % of the CTA time).
 // |a_i - x| <= 2.3 and b^2 <= 1 bound the growth to 3.3x per step, so the pair is rescaled every 4 elements;
 // an exact zero takes the sign opposite to its predecessor (the q = -pivmin rule).
+// Signs are compared on the high words (integer pipe): an exact +-0 then takes the sign of its zero, and the total
+// over the two steps around it is the same as with the q = -pivmin rule (p_{i+1} = -b^2 p_{i-1} there).
+// al and be2 must be readable up to index k + 3 (CL_KS = CL_KMAX + 4 entries): the loads of the next group of four
+// are unconditional so that they sit in front of the dependent FMA chain of the current one.
 __device__ __forceinline__ int sturm_count_poly(const double* al, const double* be2, int k, double x) {
     double pm = 1.0, p = al[0] - x;
-    bool neg = !(p > 0.0);                       // sign of p_0 (zero counts as negative), p_{-1} = 1 > 0
-    int cnt = neg ? 1 : 0;
-#define STURM_STEP(c, e) do {                                              \
-        const double pn_ = fma((c), p, -((e) * pm));                       \
-        pm = p; p = pn_;                                                   \
-        const bool ng_ = (p < 0.0) || (p == 0.0 && !neg);                  \
-        cnt += (ng_ != neg) ? 1 : 0; neg = ng_;                            \
+    int cnt = (int)((unsigned)__double2hiint(p) >> 31);       // p_{-1} = 1 > 0
+#define STURM_STEP(c, e) do {                                                             \
+        const double pn_ = fma((c), p, -((e) * pm));                                      \
+        cnt += (int)((unsigned)(__double2hiint(pn_) ^ __double2hiint(p)) >> 31);          \
+        pm = p; p = pn_;                                                                  \
     } while (0)
     int i = 1;
-    // groups of four; the (broadcast) shared-memory loads of the NEXT group are issued before the dependent
-    // FMA chain of the current one, so the chain is one FMA per element
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-    if (i + 3 < k) { a0 = al[i]; a1 = al[i + 1]; a2 = al[i + 2]; a3 = al[i + 3]; b0 = be2[i - 1]; b1 = be2[i]; b2 = be2[i + 1]; b3 = be2[i + 2]; }
+    double a0 = al[1], a1 = al[2], a2 = al[3], a3 = al[4], b0 = be2[0], b1 = be2[1], b2 = be2[2], b3 = be2[3];
     while (i + 3 < k) {
         const double c0 = a0 - x, c1 = a1 - x, c2 = a2 - x, c3 = a3 - x;
         const double e0 = b0, e1 = b1, e2 = b2, e3 = b3;
         i += 4;
-        if (i + 3 < k) { a0 = al[i]; a1 = al[i + 1]; a2 = al[i + 2]; a3 = al[i + 3]; b0 = be2[i - 1]; b1 = be2[i]; b2 = be2[i + 1]; b3 = be2[i + 2]; }
+        a0 = al[i]; a1 = al[i + 1]; a2 = al[i + 2]; a3 = al[i + 3];
+        b0 = be2[i - 1]; b1 = be2[i]; b2 = be2[i + 1]; b3 = be2[i + 2];
         STURM_STEP(c0, e0); STURM_STEP(c1, e1); STURM_STEP(c2, e2); STURM_STEP(c3, e3);
         const int ex = (__double2hiint(p) >> 20) & 0x7ff;          // biased exponent
         if (ex > 1023 + 256) { p *= 0x1p-256; pm *= 0x1p-256; }
-        else if (ex < 1023 - 256 && p != 0.0) { p *= 0x1p256; pm *= 0x1p256; }
+        else if (ex < 1023 - 256 && ex != 0) { p *= 0x1p256; pm *= 0x1p256; }
     }
-    for (; i < k; ++i) STURM_STEP(al[i] - x, be2[i - 1]);          // at most three elements: no rescaling needed
+    if (i < k) STURM_STEP(a0 - x, b0);                             // at most three elements left: no rescaling needed
+    if (i + 1 < k) STURM_STEP(a1 - x, b1);
+    if (i + 2 < k) STURM_STEP(a2 - x, b2);
 #undef STURM_STEP
     return cnt;     // number of eigenvalues < x
 }
@@ -473,7 +475,7 @@ __device__ __forceinline__ void ring_drain(const RingGeom& q, uint64_t* bars_w, 
 template <bool MIX>
 __device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* zs, const NodeView& v, const RingGeom& q,
                                                int r0, int nr, int pad, double invb, float* ring_w, uint64_t* bars_w,
-                                               uint32_t& g) {
+                                               uint32_t& g, int npf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ip = 0, isg = 0;                               // next stage to issue = stage t + RING_ST
     for (int t = 0; t < min(RING_ST, q.T); ++t) if (++isg == q.nseg) { isg = 0; ++ip; }
@@ -521,6 +523,19 @@ __device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* z
         }
     }
     ring_prologue(v, q, r0, nr, ring_w, bars_w, g);
+    // The stages right behind the prologue of the NEXT matvec are asked into L2 now (lane l: stage RING_ST + l), so
+    // HBM keeps streaming for this SM while it is busy with Gram-Schmidt, norms and checks (40 % of a step).
+    {
+        const int tn = RING_ST + lane;
+        if (lane < npf && tn < q.T) {
+            const int p = tn / q.nseg, sg = tn - p * q.nseg;
+            const int rb = warp * 2 + p * (CL_WARPS * 2);
+            const int c = sg * RING_COLS;
+            const unsigned bytes = (unsigned)min(RING_COLS, q.width - c) * 4u;
+            l2_prefetch_bulk(v.W + (size_t)(v.ro + r0 + min(rb, nr - 1)) * v.ld + q.a0 + c, bytes);
+            if (rb + 1 < nr) l2_prefetch_bulk(v.W + (size_t)(v.ro + r0 + rb + 1) * v.ld + q.a0 + c, bytes);
+        }
+    }
 }
 
 // grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot
@@ -620,7 +635,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         CL_PHASE(0);
         // ---- matvec of the slice: 2 rows per warp, 512 columns per iteration, 8 loads issued first ----
         if (RING) {
-            cl_matvec_ring<MODE == 6>(S, zs, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g);
+            cl_matvec_ring<MODE == 6>(S, zs, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g, 4 * pf);
         } else {
             cl_matvec<MODE>(S, zs, v, r0, nr, pad, invb, pf, pfl);
             if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);  // first passes of the next step: in flight during Gram-Schmidt

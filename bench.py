@@ -154,10 +154,13 @@ class ClockSampler:
         return out
 
 
+TRAFFIC_FILE = "r1c_cluster_dram_b128.csv"        # written by tools/gpu_final_s3.sh (ncu, same build)
+
+
 def measured_traffic(batch, n_target, launches_per_step):
-    """DRAM bytes per timed launch of the dominant kernel from the committed ncu list (profiles/r1b_cluster_dram_b128.csv:
+    """DRAM bytes per timed launch of the dominant kernel from the committed ncu list (profiles/r1c_cluster_dram_b128.csv:
     two passes over 128 chunks of n_target 8192), or None when the workload differs."""
-    path = os.path.join(ROOT, "profiles", "r1b_cluster_dram_b128.csv")
+    path = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
     if batch != 128 or n_target != 8192 or not os.path.exists(path) or launches_per_step <= 0:
         return None
     total = 0.0
@@ -377,7 +380,7 @@ def main():
                          "frac": achieved / peak,
                          "traffic": measured_traffic(args.batch, args.n_target, mv_launches / max(args.steps, 1)),
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the cluster kernels, "
-                                           "profiles/r1b_cluster_dram_b128.csv, per level like achieved",
+                                           "profiles/" + TRAFFIC_FILE + ", per level like achieved",
                          "peak_source": peak_src,
                          "launches_timed": mv_launches, "avg_launch_us": 1e3 * mv_ms / max(mv_launches, 1),
                          "algorithmic_bytes_per_launch": mv_bytes / max(mv_launches, 1),

@@ -8,9 +8,10 @@ import pytest
 import scipy.sparse as sp
 
 from conftest import CONFIG_NAMES, GOLDEN_SEEDS, load_golden
-from autoinst_b200.synthetic import CONFIGS, make_chunk
+from autoinst_b200.synthetic import CONFIGS, make_chunk, make_scans
 from oracle import ncut_ref as R
 from oracle.affinity_ref import affinity_ref
+from oracle.pool_ref import pool_features_ref
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -74,8 +75,7 @@ def install_fake_reference_modules(monkeypatch, chunk):
                 out[i] = f.mean(axis=0)
         return out
     img.dinov2_mean = dinov2_mean
-    cg = types.ModuleType("utils.point_cloud.chunk_generation")
-    cg.tarl_features_per_patch = lambda *a, **k: chunk.tarl
+    cg = types.ModuleType("utils.point_cloud.chunk_generation")      # tarl_features_per_patch is autoinst_b200.pooling's now
 
     def get_indices_feature_reprojection(global_indices, first_id, adjacent_frames=(8, 5)):
         i = global_indices.index(first_id)
@@ -103,13 +103,24 @@ def test_ncuts_chunk_drop_in(cuda_device, monkeypatch, name):
          "pcd_nonground_chunks": [FakeCloud(minor)], "pcd_ground_chunks": [FakeCloud(ground)],
          "pcd_nonground_chunks_major_downsampling": [FakeCloud(ch.points)],
          "kitti_labels": {"ground": {"instance": [np.zeros(500, int)], "semantic": [np.full(500, 40)]}}}
-    merged, pcd_chunk, cut_hight, inst_g, seg_g = nu.ncuts_chunk(None, d, None, np.eye(4), list(range(40)),
+    # TARL inputs come per scan from the dataset and are pooled onto the major points on the GPU
+    # (chunk_generation.py:205-258 -> autoinst_b200.pooling); scans 4, 5, 6 carry points, the others are empty
+    scans = dict(zip((4, 5, 6), make_scans(ch, n_scans=3, pts_per_major=2.0)))
+    none = (np.zeros((0, 3)), np.zeros((0, 96), dtype=np.float32))
+
+    class FakeDataset:
+        def get_pose(self, i): return np.eye(4)
+        def get_point_cloud(self, i): return scans.get(i, none)[0]
+        def get_tarl_features(self, i): return scans.get(i, none)[1]
+    merged, pcd_chunk, cut_hight, inst_g, seg_g = nu.ncuts_chunk(FakeDataset(), d, None, np.eye(4), list(range(40)),
                                                                  sequence=0, patchwise_indices=[[5]])
     # the five return values of the reference (ncuts_utils.py:204)
     assert len(merged.points) == len(minor) + len(cut_hight.points) and len(inst_g) == len(seg_g) == len(cut_hight.points)
     assert np.all(np.asarray(cut_hight.colors) == 0)                     # ground painted black
     # colours encode the segments: decode and compare with the oracle labels re-projected by nearest neighbour
-    A = affinity_ref(ch.points, ch.tarl, ch.dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
+    tarl_ref = pool_features_ref(ch.points, [scans[i] for i in (4, 5, 6)], np.zeros(3))
+    assert (~tarl_ref.any(axis=1)).any()                                 # some rows have no scan point (no_tarl_mask)
+    A = affinity_ref(ch.points, tarl_ref, ch.dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
     with R.pinned_eigsh():
         g = R.normalized_cut_ref(sp.csr_matrix(A), ch.n, np.arange(ch.n), T=cfg["T"])
     ref_major = R.labels_from_groups(g, ch.n)
@@ -120,4 +131,4 @@ def test_ncuts_chunk_drop_in(cuda_device, monkeypatch, name):
     with pytest.raises(ValueError):
         monkeypatch.setattr(nu, "CONFIG", dict(cfg, gamma=0.1))
         sys.modules["utils.image.image_utils"].image_based_features_per_patch = lambda *a, **k: ([], None)
-        nu.ncuts_chunk(None, d, None, np.eye(4), list(range(40)), sequence=0, patchwise_indices=[[5]])
+        nu.ncuts_chunk(FakeDataset(), d, None, np.eye(4), list(range(40)), sequence=0, patchwise_indices=[[5]])
