@@ -168,6 +168,7 @@ struct Eng {
     int xf;               // experiment flags (ANCUTS_X): 1 = matvec without out-of-block selects, 2 = integer float->double widening
     unsigned long long* dbg;   // optional [4 cluster sizes][8] phase cycle sums of the cluster kernel (thread 0 of rank 0), or NULL
     int w_guard;          // 1 = entries next to a block may be non-finite (caller-provided W without a gather)
+    const double* pts;    // [P][3] input coordinates (chunk c at c_base[c], input order) for the Lanczos start vector, or NULL
 };
 
 }  // namespace ancuts

@@ -67,11 +67,12 @@ struct ancuts_handle {
     //   1024  three-term recurrence + ONE Gram-Schmidt pass (otherwise classical Gram-Schmidt twice)
     //   4096  basis rows in global memory only
     //   8192  TMA ring in shared memory (otherwise register-staged loads)
+    //   131072 Lanczos start vector from the point coordinates (segment calls) instead of the hash
     //   65536 128 instead of 256 multisection shifts per eigenvalue and round in those checks
     //   32768 division-free Sturm counts in the cluster kernel's convergence checks
     //   16384 adaptive placement of the convergence checks in the cluster kernel (otherwise every check_every steps)
     // The matvec reads out-of-block columns without selects whenever the blocks come from k_gather_blocks_cur.
-    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536;
+    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072;
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
@@ -944,7 +945,7 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
     rc = upload_tables(pl, st);
     if (rc) return rc;
     fill_params(pl.e, p, kmax);
-    pl.e.xf = 0; pl.e.w_guard = 1; pl.e.dbg = nullptr;           // caller's W is read in place: anything may sit next to a block
+    pl.e.xf = 0; pl.e.w_guard = 1; pl.e.dbg = nullptr; pl.e.pts = nullptr;           // caller's W is read in place: anything may sit next to a block
     pl.e.stats = nullptr; pl.e.stats_cap = 0;
     rc = set_attrs(h, pl.KS);
     if (rc) return rc;
@@ -1274,6 +1275,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     if (rc) return rc;
     fill_params(pl.e, p, kmax);
     pl.e.dbg = h->dbg;
+    pl.e.pts = d_W_dense ? nullptr : d_points;
     pl.e.w_guard = 0;                         // every node block is written by k_gather_blocks_cur (fringe zeroed)
     pl.e.xf = d_W_dense ? (h->xflags & ~2) : h->xflags;    // caller-provided weights may be negative or denormal
     pl.e.stats = (h_stats && stats_cap > 0) ? pl.stats : nullptr;

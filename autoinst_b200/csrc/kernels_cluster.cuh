@@ -588,7 +588,8 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     const double vol = block_sum_512(s, S.red);
     const double ivol = 1.0 / sqrt(vol);
     s = 0.0;
-    for (int i = tid; i < n; i += CL_THREADS) s += sqrt(e.deg[v.start + i]) * ivol * start_value(i);
+    const StartVec sv0(e, v.chunk, v.start);
+    for (int i = tid; i < n; i += CL_THREADS) s += sqrt(e.deg[v.start + i]) * ivol * sv0.at(v.start + i, i);
     const double dot = block_sum_512(s, S.red);
     s = 0.0;
     for (int i = tid; i < n + 8; i += CL_THREADS) {
@@ -596,7 +597,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         double z = 0.0;
         if (j >= 0 && j < n) {
             double u = sqrt(e.deg[v.start + j]) * ivol;
-            double x = start_value(j) - dot * u;
+            double x = sv0.at(v.start + j, j) - dot * u;
             z = e.sinv[v.start + j] * x;
             s += x * x;
         }
@@ -607,7 +608,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         int j = r0 + i;
         double u = sqrt(e.deg[v.start + j]) * ivol;
         B.row(0)[i] = u;                                 // basis row 0 = u1
-        S.ysl[i] = start_value(j) - dot * u;
+        S.ysl[i] = sv0.at(v.start + j, j) - dot * u;
         S.sv[i] = e.sinv[v.start + j];
     }
     __syncthreads();

@@ -42,8 +42,18 @@ def tridiag_top2(alpha, beta):
 CHECK_FIRST, CHECK_LO, CHECK_HI, CHECK_SAFETY = 28, 2, 12, 0.7
 
 
+START_DIR = np.array([1.0, 0.7, 0.4])      # csrc/kernels_lanczos.cuh::StartVec
+
+
+def smooth_start(points: np.ndarray, d: np.ndarray) -> np.ndarray:
+    """Start vector of a node when coordinates are at hand: D^1/2 (q - q_0) with q the projection on START_DIR,
+    plus 1 % of the hash (csrc StartVec).  The device indexes the hash by position, the model by node order."""
+    q = (points - points[0]) @ START_DIR
+    return np.sqrt(d) * q + 0.01 * start_vector(points.shape[0])
+
+
 def lanczos_fiedler(Wb32: np.ndarray, d: np.ndarray, *, tol=1e-10, check_every=0, kmax=1024,
-                    stats=None):
+                    stats=None, v0=None):
     """Fiedler vector of L = I - S (w+I) S, S = D^-1/2, for one connected block.
 
     Wb32: (n,n) float32 block of w (unit diagonal); d: float64 degrees of W = w + I.
@@ -66,7 +76,7 @@ def lanczos_fiedler(Wb32: np.ndarray, d: np.ndarray, *, tol=1e-10, check_every=0
     V = np.zeros((kcap + 1, n))
     alpha = np.zeros(kcap)
     beta = np.zeros(kcap)
-    v = start_vector(n)
+    v = start_vector(n) if v0 is None else np.array(v0, dtype=np.float64)
     v -= u1 * (u1 @ v)
     v /= np.linalg.norm(v)
     V[0] = v
@@ -155,8 +165,9 @@ def components_of(Wb32):
 
 
 def segment_model(W32: np.ndarray, T: float, split_lim: float = 0.01, *, tol=1e-10, kmax=1024,
-                  stats=None):
-    """Labels (int32, one segment id per point) the device algorithm assigns for dense float32 W."""
+                  stats=None, points=None):
+    """Labels (int32, one segment id per point) the device algorithm assigns for dense float32 W.
+    points: (N,3) coordinates -> smooth Lanczos start vectors as in the segment calls of the library."""
     N = W32.shape[0]
     labels = np.full(N, -1, dtype=np.int32)
     next_label = 0
@@ -185,7 +196,8 @@ def segment_model(W32: np.ndarray, T: float, split_lim: float = 0.01, *, tol=1e-
                 continue
             Wb = W32[np.ix_(idx, idx)]
             d = 1.0 + Wb.astype(np.float64).sum(axis=1)
-            ev, lam2 = lanczos_fiedler(Wb, d, tol=tol, kmax=kmax, stats=stats)
+            ev, lam2 = lanczos_fiedler(Wb, d, tol=tol, kmax=kmax, stats=stats,
+                                       v0=None if points is None else smooth_start(points[idx], d))
             k, cost, bucket = scan_cuts(Wb, d, ev)
             if stats is not None:
                 stats[-1].update(mcut=float(cost), best_k=int(k))
