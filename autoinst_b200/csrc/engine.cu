@@ -67,12 +67,13 @@ struct ancuts_handle {
     //   1024  three-term recurrence + ONE Gram-Schmidt pass (otherwise classical Gram-Schmidt twice)
     //   4096  basis rows in global memory only
     //   8192  TMA ring in shared memory (otherwise register-staged loads)
+    //   262144 deferred affinity: pass 1 only queues pairs; W is written block by block after the root split
     //   131072 Lanczos start vector from the point coordinates (segment calls) instead of the hash
     //   65536 128 instead of 256 multisection shifts per eigenvalue and round in those checks
     //   32768 division-free Sturm counts in the cluster kernel's convergence checks
     //   16384 adaptive placement of the convergence checks in the cluster kernel (otherwise every check_every steps)
     // The matvec reads out-of-block columns without selects whenever the blocks come from k_gather_blocks_cur.
-    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072;
+    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072 | 262144;
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
@@ -115,6 +116,9 @@ struct Plan {
     void* tc_scratch; size_t tc_scratch_bytes = 0;
     PairQ* pairq = nullptr; int qcap = 0; int* qctr = nullptr;     // two-pass affinity: pair queue, [2c]=count [2c+1]=overflow
     bool want_pairq = false;
+    bool deferred = false;                 // per-chunk pair queues kept until the root split (deferred affinity)
+    std::vector<size_t> qoff;              // deferred: first queue entry of chunk c
+    std::vector<int> qcap_c;               // deferred: queue capacity of chunk c
     ancuts_node_stat* stats;
     Eng e;
 };
@@ -184,7 +188,18 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
         int nmax = 0;
         for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
         pl.qcap = (int)std::min<long long>(96ll * nmax, (long long)nmax * (nmax - 1) / 2 + 1);
-        pl.pairq = ar.take<PairQ>((size_t)pl.qcap);
+        size_t total = (size_t)pl.qcap;
+        pl.qoff.assign(B, 0); pl.qcap_c.assign(B, pl.qcap);
+        if (pl.deferred) {
+            total = 0;
+            for (int c = 0; c < B; ++c) {
+                const long long nc = pl.n[c];
+                pl.qoff[c] = total;
+                pl.qcap_c[c] = (int)std::min<long long>(96ll * nc, nc * (nc - 1) / 2 + 1);
+                total += (size_t)pl.qcap_c[c];
+            }
+        }
+        pl.pairq = ar.take<PairQ>(total);
         pl.qctr = ar.take<int>(2 * (size_t)B);
     }
     pl.hW0.assign(B, nullptr); pl.hW1.assign(B, nullptr);
@@ -369,7 +384,7 @@ static int resolve_kmax(const ancuts_params* p) {
 // connected components (positions pos0 + i) while the pairs are at hand
 static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, const float* tarl, const float* dino,
                         const ancuts_params* p, float* W, long long ld, uint8_t* tarl_zero, cudaStream_t st,
-                        int* qctr = nullptr, int* parent = nullptr, int pos0 = 0) {
+                        int* qctr = nullptr, int* parent = nullptr, int pos0 = 0, int defer_chunk = -1) {
     const bool use_tarl = p->theta != 0.0 && tarl != nullptr;
     const bool use_dino = p->gamma != 0.0 && dino != nullptr;
     if (p->theta != 0.0 && tarl == nullptr) { set_error("theta != 0 but no TARL features"); return ANCUTS_EINVAL; }
@@ -392,6 +407,14 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
     } else if (qctr && (use_tarl || use_dino)) {
         // two-pass form: distances + zero fill + pair queue, then the queued pairs spread over the whole grid
         dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
+        if (defer_chunk >= 0) {
+            // deferred: pairs and root-level components only; W is written after the root split (run_rebuild)
+            LAUNCH(SG_AFFINITY, k_affinity_pairs<<<grid, 256, 0, st>>>(n, pts, p->alpha, p->proximity, nullptr, ld,
+                                                                       pl.pairq + pl.qoff[defer_chunk], pl.qcap_c[defer_chunk],
+                                                                       qctr, parent, pos0));
+            ANCUTS_CUDA(cudaGetLastError());
+            return ANCUTS_OK;
+        }
         LAUNCH(SG_AFFINITY, k_affinity_pairs<<<grid, 256, 0, st>>>(n, pts, p->alpha, p->proximity, W, ld, pl.pairq, pl.qcap, qctr,
                                                                    parent, pos0));
         LAUNCH(SG_AFFINITY, k_affinity_feats<<<148 * 4, 256, 0, st>>>(pl.pairq, qctr, pl.qcap, use_tarl ? tarl : nullptr, p->tarl_dim,
@@ -614,8 +637,17 @@ k_ev_stats(Eng e) {
 }
 
 // split phase: components, sort, new table, gather.  Returns new counts through h->h_ctr.
+// inputs of the deferred second affinity pass (run_rebuild of the root split)
+struct DeferredAffinity {
+    const ancuts_params* p;
+    const float* tarl;      // all chunks, input order
+    const float* dino;
+    const int64_t* chunk_off;
+};
+
 static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int max_split_n, bool components,
-                       cudaStream_t st, int* class_cnt = nullptr, int* big_cnt = nullptr, bool forest_ready = false) {
+                       cudaStream_t st, int* class_cnt = nullptr, int* big_cnt = nullptr, bool forest_ready = false,
+                       const DeferredAffinity* df = nullptr) {
     Eng& e = pl.e;
     const int P = e.P;
     const int tb = 256, gP = (P + tb - 1) / tb;
@@ -657,7 +689,25 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
     std::swap(e.r_start, e.q_start); std::swap(e.r_n, e.q_n); std::swap(e.r_chunk, e.q_chunk);
     std::swap(e.r_status, e.q_status); std::swap(e.r_level, e.q_level);
     std::swap(e.rid, e.rid2); std::swap(e.perm, e.perm2);
-    if (num_active > 0) {
+    if (num_active > 0 && df) {
+        // deferred affinity: there is no matrix to gather from.  Zero the blocks of the active ranges (unit diagonal)
+        // and scatter the queued pairs of every chunk to the positions their points have now.
+        dim3 g((max_n + 255) / 256, (max_n + 15) / 16, num_active);
+        LAUNCH(SG_AFFINITY, k_zero_blocks<<<g, 256, 0, st>>>(e, cur));
+        LAUNCH(SG_PARTITION, k_inverse_positions<<<gP, tb, 0, st>>>(e, e.val));
+        const ancuts_params* p = df->p;
+        const bool use_tarl = p->theta != 0.0 && df->tarl, use_dino = p->gamma != 0.0 && df->dino;
+        for (int c = 0; c < e.B; ++c) {
+            const size_t o = (size_t)df->chunk_off[c];
+            float* dst = cur ? pl.hW0[c] : pl.hW1[c];
+            LAUNCH(SG_AFFINITY, k_affinity_feats<<<148 * 4, 256, 0, st>>>(
+                pl.pairq + pl.qoff[c], pl.qctr + 2 * c, pl.qcap_c[c], use_tarl ? df->tarl + o * p->tarl_dim : nullptr, p->tarl_dim,
+                use_dino ? df->dino + o * p->dino_dim : nullptr, p->dino_dim, pl.tarl_zero + (o - (size_t)df->chunk_off[0]),
+                p->theta, p->gamma, dst, pl.ld[c], e.val, pl.base[c], e.rid, e.r_status));
+        }
+        ANCUTS_CUDA(cudaGetLastError());
+        cur ^= 1;
+    } else if (num_active > 0) {
         dim3 g((max_n + 255) / 256, (max_n + 15) / 16, num_active);
         LAUNCH(SG_PARTITION, k_gather_blocks_cur<<<g, 256, 0, st>>>(e, cur));
         ANCUTS_CUDA(cudaGetLastError());
@@ -668,7 +718,8 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
 
 // the whole recursion for the chunks described by the plan; W of every chunk is in buffer `cur`
 static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cur, int32_t* d_labels,
-                      int32_t* h_num_segments, cudaStream_t st, bool root_forest_ready = false) {
+                      int32_t* h_num_segments, cudaStream_t st, bool root_forest_ready = false,
+                      const DeferredAffinity* df = nullptr) {
     Eng& e = pl.e;
     const int P = e.P, B = e.B;
     ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 16 * sizeof(int), st));
@@ -686,7 +737,8 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
     int guard = 0;
     while (num_split > 0) {
         int class_cnt[CL_CLASSES] = {0}, big_cnt = 0;
-        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt, root_forest_ready && guard == 0);
+        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt, root_forest_ready && guard == 0,
+                         guard == 0 ? df : nullptr);
         if (rc) return rc;
         int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
         if (num_active == 0) break;
@@ -801,6 +853,7 @@ int64_t ancuts_segment_workspace_bytes(int num_chunks, const int32_t* h_chunk_n,
     int kmax = lanczos_max_steps > 0 ? lanczos_max_steps : KMAX_DEFAULT;
     make_plan(pl, num_chunks, h_chunk_n, nullptr, nullptr, kmax, 0);
     pl.want_pairq = true;                              // upper bound: tensor-core scratch and pair queue both counted
+    pl.deferred = true;
     return (int64_t)layout(pl, nullptr, 1 << 16, 96, 384, true);
 }
 
@@ -1266,7 +1319,9 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     const bool need_tc = (p->affinity_impl == 1) && !d_W_dense;
     const bool feats = (p->theta != 0.0 && d_tarl) || (p->gamma != 0.0 && d_dino);
     pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && feats && !(h->xflags & 256);   // ANCUTS_X bit 8: one-kernel affinity
+    pl.deferred = pl.want_pairq && (h->xflags & 262144);       // bit 18: W written block by block after the root split
     bool root_forest = pl.want_pairq;
+    bool deferred = pl.deferred;
     size_t bytes = layout(pl, nullptr, stats_cap, p->tarl_dim, p->dino_dim, need_tc);
     rc = ensure_ws(h, bytes);
     if (rc) return rc;
@@ -1302,7 +1357,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
             if (wait_ev) ANCUTS_CUDA(cudaStreamWaitEvent(st, wait_ev[c], 0));       // this chunk's inputs have arrived
             rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
                               pl.tarl_zero + o, st, pl.qctr ? pl.qctr + 2 * c : nullptr, pl.qctr ? pl.e.parent : nullptr,
-                              pl.base[c]);
+                              pl.base[c], deferred ? c : -1);
             if (rc) return rc;
             aff_bytes += 4.0 * n[c] * (double)n[c] +
                          4.0 * n[c] * (3 + (p->theta != 0 ? p->tarl_dim : 0) + (p->gamma != 0 ? p->dino_dim : 0));
@@ -1317,6 +1372,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
             for (int c = 0; c < num_chunks; ++c) overflow |= (hq[2 * c + 1] != 0);
             if (overflow) {
                 root_forest = false;
+                deferred = false;
                 for (int c = 0; c < num_chunks; ++c) {
                     int64_t o = h_chunk_off[c] - off0;
                     const float* tz = d_tarl ? d_tarl + (size_t)(h_chunk_off[c]) * p->tarl_dim : nullptr;
@@ -1329,7 +1385,8 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
         }
         h->stage_bytes[SG_AFFINITY] = aff_bytes;
     }
-    rc = run_levels(h, pl, p, 0, d_labels, h_num_segments, st, root_forest);
+    DeferredAffinity df{p, d_tarl, d_dino, h_chunk_off};
+    rc = run_levels(h, pl, p, 0, d_labels, h_num_segments, st, root_forest, deferred ? &df : nullptr);
     if (rc) return rc;
     rc = copy_stats(h, pl, h_stats, stats_cap, h_num_stats, st);
     if (rc) return rc;

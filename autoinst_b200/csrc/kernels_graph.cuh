@@ -203,6 +203,7 @@ k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double pro
     const int tid = threadIdx.x;
     const int cg = (tid & 15) * 4, rg = tid >> 4;
     if (row0 > col0) {                               // mirror entries: written by pass 2
+        if (!W) return;                              // deferred mode: W is written block by block after the root split
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             int gr = row0 + rg + 16 * k, gc = col0 + cg;
@@ -262,6 +263,7 @@ k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double pro
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        if (!W) break;
         const int gi = row0 + rg + 16 * k, gc = col0 + cg;
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         if (diag_tile && gi < n) {                                       // unit diagonal: exp(-0)
@@ -320,7 +322,11 @@ __global__ void __launch_bounds__(256)
 k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int qcap,
                  const float* __restrict__ tarl, int tdim, const float* __restrict__ dino, int ddim,
                  const uint8_t* __restrict__ tarl_zero, double theta, double gamma,
-                 float* __restrict__ W, long long ld) {
+                 float* __restrict__ W, long long ld,
+                 const int* __restrict__ inv = nullptr, int base = 0, const int* __restrict__ rid = nullptr,
+                 const int* __restrict__ r_status = nullptr) {
+    // inv != NULL (deferred mode): the pair is written at the positions its points have AFTER the root split
+    // (inv[old global position] = new global position), and only if their range goes on to the eigensolver.
     const int total = min(qctr[0], qcap);
     if (qctr[1]) return;                             // overflow: everything is redone by the one-kernel form
     const int lane8 = threadIdx.x & 7;
@@ -345,8 +351,17 @@ k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int 
         }
         if (live && lane8 == 0) {
             float w = (float)exp(-(a + arg));
-            W[(size_t)gi * ld + gj] = w;
-            W[(size_t)gj * ld + gi] = w;
+            int wi = gi, wj = gj;
+            bool keep = true;
+            if (inv) {
+                const int pi = inv[base + gi], pj = inv[base + gj];
+                keep = r_status[rid[pi]] == ST_ACTIVE;
+                wi = pi - base; wj = pj - base;
+            }
+            if (keep) {
+                W[(size_t)wi * ld + wj] = w;
+                W[(size_t)wj * ld + wi] = w;
+            }
         }
     }
 }
@@ -622,6 +637,42 @@ k_gather_blocks_cur(Eng e, int cur /* source buffer */) {
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
         atomicAdd(&e.acct[SG_PARTITION], 8ull * n * n);
+}
+
+// Deferred affinity (segment calls with feature terms): pass 1 only queues the in-mask pairs and joins the root-level
+// components; W is never written in input order.  After the root split the blocks of the ACTIVE ranges are zeroed
+// with a unit diagonal here (sum n_c^2 floats instead of N^2: the zero fill was the store-bound part of the affinity
+// stage, and k_gather_blocks_cur then read the whole N x N matrix once more to pick the blocks out of it) and
+// k_affinity_feats scatters the queued pairs to their new positions.
+// grid: (col tiles of 256, row tiles of 16, active)
+__global__ void __launch_bounds__(256)
+k_zero_blocks(Eng e, int cur /* buffer the gather would read; the blocks go to the other one */) {
+    int a = blockIdx.z;
+    int r = e.a_rid[a];
+    int start = e.r_start[r], n = e.r_n[r], c = e.r_chunk[r];
+    int col = blockIdx.x * 256 + threadIdx.x;
+    int row0 = blockIdx.y * 16;
+    if (row0 >= n) return;
+    int base = e.c_base[c], ld = e.c_ld[c];
+    float* dst = cur ? e.c_W0[c] : e.c_W1[c];
+    int ro = start - base;
+    const int rows = min(16, n - row0);
+    if (col < n) {
+        for (int i = 0; i < rows; ++i) dst[(size_t)(ro + row0 + i) * ld + ro + col] = (col == row0 + i) ? 1.0f : 0.0f;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8) {               // fringe of the block, as in k_gather_blocks_cur
+        int j = threadIdx.x;
+        int fc = ro + ((j < 4) ? -1 - j : n + (j - 4));
+        if (fc >= 0 && fc < ld) for (int i = 0; i < rows; ++i) dst[(size_t)(ro + row0 + i) * ld + fc] = 0.f;
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0)
+        atomicAdd(&e.acct[SG_PARTITION], 4ull * n * n);
+}
+
+// inv[old global position] = new global position, from val2[new] = old (after the sort of a rebuild)
+__global__ void k_inverse_positions(Eng e, int* __restrict__ inv) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < e.P) inv[e.val2[p]] = p;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -44,8 +44,13 @@ def check_affinity(W, A):
 
 
 # ANCUTS_X bits (engine.cu): 2 = integer widening of every second element, 32 = L2 prefetch two passes ahead, 256 = one-kernel
-# affinity, 1024 = three-term + one Gram-Schmidt pass, 4096 = basis rows in global memory only, 8192 = TMA ring.
-VARIANTS = {"default": 2 | 1024 | 8192, "one_kernel_affinity": 2 | 1024 | 8192 | 256, "register_matvec_prefetch": 2 | 32 | 1024,
+# affinity, 1024 = three-term + one Gram-Schmidt pass, 4096 = basis rows in global memory only, 8192 = TMA ring,
+# 16384 = adaptive convergence checks, 32768 = division-free Sturm counts, 65536 = 128 shifts per round,
+# 131072 = start vector from the coordinates, 262144 = deferred affinity (W written block by block after the root split).
+S3 = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072
+VARIANTS = {"session3_default": S3 | 262144, "session3_dense_affinity": S3, "session3_prefetch_next_matvec": S3 | 262144 | 16,
+            "session3_hash_start_256_shifts": 2 | 1024 | 8192 | 16384 | 32768 | 262144,
+            "default": 2 | 1024 | 8192, "one_kernel_affinity": 2 | 1024 | 8192 | 256, "register_matvec_prefetch": 2 | 32 | 1024,
             "register_matvec_cgs2": 0, "ring_cgs2": 8192, "basis_in_global": 2 | 1024 | 8192 | 4096}
 
 
@@ -72,7 +77,7 @@ def test_two_pass_and_one_kernel_affinity_agree_with_the_oracle(cuda_device, nam
     cfg = CONFIGS[name]
     ch = make_chunk(41, n_target=2500, features="tarl_dino" if cfg["gamma"] else "tarl")
     A = affinity_ref(ch.points, ch.tarl, ch.dino if cfg["gamma"] else None, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
-    lane1 = variant_lane(cuda_device, VARIANTS["one_kernel_affinity"], 11)
+    lane1 = variant_lane(cuda_device, VARIANTS["one_kernel_affinity"], 10 + list(VARIANTS).index("one_kernel_affinity"))
     for lane in (0, lane1):
         W = api.affinity(ch.points, ch.tarl, ch.dino if cfg["gamma"] else None, alpha=cfg["alpha"], theta=cfg["theta"],
                          gamma=cfg["gamma"], device=cuda_device, lane=lane)
