@@ -67,13 +67,14 @@ struct ancuts_handle {
     //   1024  three-term recurrence + ONE Gram-Schmidt pass (otherwise classical Gram-Schmidt twice)
     //   4096  basis rows in global memory only
     //   8192  TMA ring in shared memory (otherwise register-staged loads)
+    //   524288 deferred affinity: pairs from a cell grid (counting sort + 27-cell search) instead of the N^2 tile sweep
     //   262144 deferred affinity: pass 1 only queues pairs; W is written block by block after the root split
     //   131072 Lanczos start vector from the point coordinates (segment calls) instead of the hash
     //   65536 128 instead of 256 multisection shifts per eigenvalue and round in those checks
     //   32768 division-free Sturm counts in the cluster kernel's convergence checks
     //   16384 adaptive placement of the convergence checks in the cluster kernel (otherwise every check_every steps)
     // The matvec reads out-of-block columns without selects whenever the blocks come from k_gather_blocks_cur.
-    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072 | 262144;
+    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072 | 262144;      // 524288 stays off: correct but 10 x slower in its first form
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
@@ -119,6 +120,8 @@ struct Plan {
     bool deferred = false;                 // per-chunk pair queues kept until the root split (deferred affinity)
     std::vector<size_t> qoff;              // deferred: first queue entry of chunk c
     std::vector<int> qcap_c;               // deferred: queue capacity of chunk c
+    int* pg_cells = nullptr; int* pg_sorted = nullptr; PairGrid* pg_grid = nullptr;   // deferred: cell grids of the pair search
+    bool grid_pairs = false;
     ancuts_node_stat* stats;
     Eng e;
 };
@@ -201,6 +204,11 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
         }
         pl.pairq = ar.take<PairQ>(total);
         pl.qctr = ar.take<int>(2 * (size_t)B);
+        if (pl.deferred) {
+            pl.pg_cells = ar.take<int>((size_t)B * PG_STRIDE);
+            pl.pg_sorted = ar.take<int>((size_t)P);
+            pl.pg_grid = ar.take<PairGrid>((size_t)B);
+        }
     }
     pl.hW0.assign(B, nullptr); pl.hW1.assign(B, nullptr);
     if (pl.own_w0) for (int c = 0; c < B; ++c) pl.hW0[c] = ar.take<float>((size_t)pl.n[c] * pl.ld[c]);
@@ -409,6 +417,18 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
         dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
         if (defer_chunk >= 0) {
             // deferred: pairs and root-level components only; W is written after the root split (run_rebuild)
+            if (pl.grid_pairs) {
+                const int c = defer_chunk;
+                int* cells = pl.pg_cells + (size_t)c * PG_STRIDE;
+                int* sorted = pl.pg_sorted + pos0;
+                LAUNCH(SG_AFFINITY, k_pair_grid<<<1, 1024, PG_CELLS * sizeof(int), st>>>(n, pts, p->proximity, cells, sorted,
+                                                                                      pl.pg_grid + c));
+                LAUNCH(SG_AFFINITY, k_pair_search<<<(n + 255) / 256, 256, 0, st>>>(n, pts, p->alpha, p->proximity, pl.pg_grid + c,
+                                                                                 cells, sorted, pl.pairq + pl.qoff[c],
+                                                                                 pl.qcap_c[c], qctr, parent, pos0));
+                ANCUTS_CUDA(cudaGetLastError());
+                return ANCUTS_OK;
+            }
             LAUNCH(SG_AFFINITY, k_affinity_pairs<<<grid, 256, 0, st>>>(n, pts, p->alpha, p->proximity, nullptr, ld,
                                                                        pl.pairq + pl.qoff[defer_chunk], pl.qcap_c[defer_chunk],
                                                                        qctr, parent, pos0));
@@ -1320,6 +1340,8 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     const bool feats = (p->theta != 0.0 && d_tarl) || (p->gamma != 0.0 && d_dino);
     pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && feats && !(h->xflags & 256);   // ANCUTS_X bit 8: one-kernel affinity
     pl.deferred = pl.want_pairq && (h->xflags & 262144);       // bit 18: W written block by block after the root split
+    pl.grid_pairs = pl.deferred && (h->xflags & 524288);       // bit 19: pairs from a cell grid instead of the tile sweep
+    if (pl.grid_pairs) ANCUTS_CUDA(cudaFuncSetAttribute(k_pair_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PG_CELLS * sizeof(int))));
     bool root_forest = pl.want_pairq;
     bool deferred = pl.deferred;
     size_t bytes = layout(pl, nullptr, stats_cap, p->tarl_dim, p->dino_dim, need_tc);

@@ -317,6 +317,170 @@ k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double pro
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pass 1 of the deferred affinity without the N^2 tile sweep: the in-mask pairs are the pairs closer than `prox`,
+// so they are found with a cell grid of pitch >= prox (at most PG_DIM cells per axis): one CTA bins the points of a
+// chunk by counting sort in shared memory (k_pair_grid), then one thread per point walks the 3 x 3 runs of three
+// x-adjacent cells around it (k_pair_search).  About 150 float64 distance tests per point instead of N / 2 float32
+// pre-filter tests: the tile sweep was issue-bound at ~95 us per 8.4 k-point chunk even without its stores.
+// Same inclusive float64 test and operation order as k_affinity_pairs (ncuts_utils.py:60-61); every pair i < j is
+// queued exactly once; queue order is arbitrary (as before), W and the union-find forest do not depend on it.
+// ---------------------------------------------------------------------------------------------
+constexpr int PG_DIM = 25;
+constexpr int PG_CELLS = PG_DIM * PG_DIM * PG_DIM;       // 15625 counters = 61 KB of shared memory
+constexpr int PG_STRIDE = PG_CELLS + 7;                  // ints per chunk in the global cell table (start offsets + end)
+struct PairGrid { double lo[3]; double inv_h; int n[3]; int pad; };
+
+__device__ __forceinline__ int pg_cell1(const PairGrid& g, double x, int a) {
+    int c = (int)floor((x - g.lo[a]) * g.inv_h);
+    return max(0, min(g.n[a] - 1, c));
+}
+
+// one CTA of 1024 threads per launch (one chunk); dynamic shared memory: PG_CELLS ints
+__global__ void __launch_bounds__(1024)
+k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict__ cell_start, int* __restrict__ sorted,
+            PairGrid* __restrict__ gout) {
+    extern __shared__ int hist[];
+    __shared__ double red[6][32];
+    __shared__ PairGrid g;
+    __shared__ int wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (int i = tid; i < n; i += 1024) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { double x = pts[(size_t)i * 3 + a]; mn[a] = fmin(mn[a], x); mx[a] = fmax(mx[a], x); }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double lo = warp_min(mn[a]), hi = -warp_min(-mx[a]);
+        if (lane == 0) { red[a][warp] = lo; red[3 + a][warp] = hi; }
+    }
+    for (int c = tid; c < PG_CELLS; c += 1024) hist[c] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        double ext = 0.0;
+        for (int a = 0; a < 3; ++a) {
+            double lo = red[a][0], hi = red[3 + a][0];
+            for (int w = 1; w < 32; ++w) { lo = fmin(lo, red[a][w]); hi = fmax(hi, red[3 + a][w]); }
+            g.lo[a] = lo; red[3 + a][0] = hi;
+            ext = fmax(ext, hi - lo);
+        }
+        const double pitch = fmax(fmax(prox, ext / (double)(PG_DIM - 1)), 1e-300);
+        g.inv_h = 1.0 / pitch;
+        for (int a = 0; a < 3; ++a) g.n[a] = min(PG_DIM, (int)floor((red[3 + a][0] - g.lo[a]) * g.inv_h) + 1);
+        g.pad = 0;
+        *gout = g;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = (pg_cell1(g, pts[(size_t)i * 3 + 2], 2) * g.n[1] + pg_cell1(g, pts[(size_t)i * 3 + 1], 1)) * g.n[0]
+                      + pg_cell1(g, pts[(size_t)i * 3], 0);
+        atomicAdd(&hist[c], 1);
+    }
+    __syncthreads();
+    // exclusive scan over the cells: 16 consecutive cells per thread, then a scan of the 1024 partial sums
+    constexpr int PER = (PG_CELLS + 1023) / 1024;          // 16
+    const int c0 = tid * PER;
+    int loc[PER];
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) { int c = c0 + k; int v = (c < PG_CELLS) ? hist[c] : 0; loc[k] = s; s += v; }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = wsum[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        wsum[lane] = wi - w;                               // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const int base = wsum[warp] + incl - s;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+        int c = c0 + k;
+        if (c < PG_CELLS) { hist[c] = base + loc[k]; cell_start[c] = base + loc[k]; }
+    }
+    if (tid == 0) cell_start[PG_CELLS] = n;
+    __syncthreads();
+    for (int i = tid; i < n; i += 1024) {
+        const int c = (pg_cell1(g, pts[(size_t)i * 3 + 2], 2) * g.n[1] + pg_cell1(g, pts[(size_t)i * 3 + 1], 1)) * g.n[0]
+                      + pg_cell1(g, pts[(size_t)i * 3], 0);
+        sorted[atomicAdd(&hist[c], 1)] = i;
+    }
+}
+
+// one thread per point (in cell order, so that the threads of a CTA walk the same runs); count, reserve, write
+__global__ void __launch_bounds__(256)
+k_pair_search(int n, const double* __restrict__ pts, double alpha, double prox, const PairGrid* __restrict__ gp,
+              const int* __restrict__ cell_start, const int* __restrict__ sorted, PairQ* __restrict__ q, int qcap,
+              int* __restrict__ qctr, int* parent, int pos0) {
+    __shared__ int wtot[8];
+    __shared__ int qbase;
+    const PairGrid g = *gp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = blockIdx.x * 256 + tid;
+    const bool live = t < n;
+    const int i = live ? sorted[t] : 0;
+    const double px = pts[(size_t)i * 3], py = pts[(size_t)i * 3 + 1], pz = pts[(size_t)i * 3 + 2];
+    const int cx = pg_cell1(g, px, 0), cy = pg_cell1(g, py, 1), cz = pg_cell1(g, pz, 2);
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.n[0] - 1);
+    int off = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int cnt = 0;
+        if (live) {
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int z = cz + dz;
+                if (z < 0 || z >= g.n[2]) continue;
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int y = cy + dy;
+                    if (y < 0 || y >= g.n[1]) continue;
+                    const int rowc = (z * g.n[1] + y) * g.n[0];
+                    const int lo = cell_start[rowc + x0], hi = cell_start[rowc + x1 + 1];
+                    for (int s = lo; s < hi; ++s) {
+                        const int j = sorted[s];
+                        if (j <= i) continue;                                       // every pair once, i < j
+                        double dx = px - pts[(size_t)j * 3], dy2 = py - pts[(size_t)j * 3 + 1], dz2 = pz - pts[(size_t)j * 3 + 2];
+                        double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy2, dy2)), __dmul_rn(dz2, dz2));
+                        double sd = __dsqrt_rn(s2);
+                        if (sd <= prox) {                                           // ncuts_utils.py:61, inclusive
+                            if (pass == 1) {
+                                PairQ e;
+                                e.i = i; e.j = j;
+                                e.a = alpha != 0.0 ? alpha * sd : 0.0;              // ncuts_utils.py:63-66
+                                q[off + cnt] = e;
+                                if (parent) uf_union(parent, pos0 + i, pos0 + j);
+                            }
+                            ++cnt;
+                        }
+                    }
+                }
+            }
+        }
+        if (pass == 1) break;
+        // exclusive prefix of the counts over the CTA, one global atomic per CTA
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+        if (lane == 31) wtot[warp] = incl;
+        __syncthreads();
+        int wbase = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { if (w < warp) wbase += wtot[w]; total += wtot[w]; }
+        if (tid == 0) {
+            int b = total > 0 ? atomicAdd(&qctr[0], total) : 0;
+            if (b + total > qcap) { atomicExch(&qctr[1], 1); b = -1; }              // the caller falls back to the dense form
+            qbase = b;
+        }
+        __syncthreads();
+        if (qbase < 0 || total == 0) return;
+        off = qbase + wbase + incl - cnt;
+    }
+}
+
 // pass 2: grid-stride over the queue, one 8-lane group per pair.
 __global__ void __launch_bounds__(256)
 k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int qcap,

@@ -364,8 +364,9 @@ def main():
             "config": {"workload": workload_string(args.n_target),
                        "chunks_per_gpu_per_step": args.batch, "points_per_step": pts_total,
                        "points_per_sec": pts_total / (ms_step / 1e3),
-                       "l2": "inputs larger than L2: every step rebuilds and streams %.1f GB of dense float32 affinities per GPU"
-                             % (sum(4.0 * c.n * c.n for c in chunks) / 1e9),
+                       "l2": "inputs larger than L2: every step rebuilds the float32 affinity blocks of all recursion nodes "
+                             "(%.1f GB per GPU, 126 MB of L2) and streams them from HBM once per Lanczos step"
+                             % (acc_all["degree"]["bytes"] / max(args.steps, 1) / 1e9),
                        "arithmetic": "W float32 in HBM; vectors, degrees, dots and cut sums float64",
                        "segments_per_chunk": float(np.mean(res.num_segments)),
                        "eig_nodes_per_chunk": (len(stats) / args.batch) if stats is not None else None,

@@ -46,9 +46,10 @@ def check_affinity(W, A):
 # ANCUTS_X bits (engine.cu): 2 = integer widening of every second element, 32 = L2 prefetch two passes ahead, 256 = one-kernel
 # affinity, 1024 = three-term + one Gram-Schmidt pass, 4096 = basis rows in global memory only, 8192 = TMA ring,
 # 16384 = adaptive convergence checks, 32768 = division-free Sturm counts, 65536 = 128 shifts per round,
-# 131072 = start vector from the coordinates, 262144 = deferred affinity (W written block by block after the root split).
+# 131072 = start vector from the coordinates, 262144 = deferred affinity (W written block by block after the root split),
+# 524288 = pairs of the deferred affinity from a cell grid instead of the tile sweep.
 S3 = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072
-VARIANTS = {"session3_default": S3 | 262144, "session3_dense_affinity": S3, "session3_prefetch_next_matvec": S3 | 262144 | 16,
+VARIANTS = {"session3_default": S3 | 262144, "session3_grid_pairs": S3 | 262144 | 524288, "session3_dense_affinity": S3, "session3_prefetch_next_matvec": S3 | 262144 | 16,
             "session3_hash_start_256_shifts": 2 | 1024 | 8192 | 16384 | 32768 | 262144,
             "default": 2 | 1024 | 8192, "one_kernel_affinity": 2 | 1024 | 8192 | 256, "register_matvec_prefetch": 2 | 32 | 1024,
             "register_matvec_cgs2": 0, "ring_cgs2": 8192, "basis_in_global": 2 | 1024 | 8192 | 4096}
