@@ -74,7 +74,7 @@ struct ancuts_handle {
     //   32768 division-free Sturm counts in the cluster kernel's convergence checks
     //   16384 adaptive placement of the convergence checks in the cluster kernel (otherwise every check_every steps)
     // The matvec reads out-of-block columns without selects whenever the blocks come from k_gather_blocks_cur.
-    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072 | 262144;      // 524288 stays off: correct but 10 x slower in its first form
+    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072 | 262144;      // 524288 stays off: measured slower than the tile sweep
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
@@ -120,7 +120,7 @@ struct Plan {
     bool deferred = false;                 // per-chunk pair queues kept until the root split (deferred affinity)
     std::vector<size_t> qoff;              // deferred: first queue entry of chunk c
     std::vector<int> qcap_c;               // deferred: queue capacity of chunk c
-    int* pg_cells = nullptr; int* pg_sorted = nullptr; PairGrid* pg_grid = nullptr;   // deferred: cell grids of the pair search
+    int* pg_cells = nullptr; int* pg_sorted = nullptr; double* pg_spts = nullptr; PairGrid* pg_grid = nullptr;   // deferred: cell grids of the pair search
     bool grid_pairs = false;
     ancuts_node_stat* stats;
     Eng e;
@@ -207,6 +207,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
         if (pl.deferred) {
             pl.pg_cells = ar.take<int>((size_t)B * PG_STRIDE);
             pl.pg_sorted = ar.take<int>((size_t)P);
+            pl.pg_spts = ar.take<double>((size_t)P * 3);
             pl.pg_grid = ar.take<PairGrid>((size_t)B);
         }
     }
@@ -421,9 +422,10 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
                 const int c = defer_chunk;
                 int* cells = pl.pg_cells + (size_t)c * PG_STRIDE;
                 int* sorted = pl.pg_sorted + pos0;
-                LAUNCH(SG_AFFINITY, k_pair_grid<<<1, 1024, PG_CELLS * sizeof(int), st>>>(n, pts, p->proximity, cells, sorted,
+                double* spts = pl.pg_spts + (size_t)pos0 * 3;
+                LAUNCH(SG_AFFINITY, k_pair_grid<<<1, 1024, PG_CELLS * sizeof(int), st>>>(n, pts, p->proximity, cells, sorted, spts,
                                                                                       pl.pg_grid + c));
-                LAUNCH(SG_AFFINITY, k_pair_search<<<(n + 255) / 256, 256, 0, st>>>(n, pts, p->alpha, p->proximity, pl.pg_grid + c,
+                LAUNCH(SG_AFFINITY, k_pair_search<<<(n + 7) / 8, 256, 0, st>>>(n, spts, p->alpha, p->proximity, pl.pg_grid + c,
                                                                                  cells, sorted, pl.pairq + pl.qoff[c],
                                                                                  pl.qcap_c[c], qctr, parent, pos0));
                 ANCUTS_CUDA(cudaGetLastError());

@@ -339,7 +339,7 @@ __device__ __forceinline__ int pg_cell1(const PairGrid& g, double x, int a) {
 // one CTA of 1024 threads per launch (one chunk); dynamic shared memory: PG_CELLS ints
 __global__ void __launch_bounds__(1024)
 k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict__ cell_start, int* __restrict__ sorted,
-            PairGrid* __restrict__ gout) {
+            double* __restrict__ spts, PairGrid* __restrict__ gout) {
     extern __shared__ int hist[];
     __shared__ double red[6][32];
     __shared__ PairGrid g;
@@ -409,63 +409,75 @@ k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict_
     for (int i = tid; i < n; i += 1024) {
         const int c = (pg_cell1(g, pts[(size_t)i * 3 + 2], 2) * g.n[1] + pg_cell1(g, pts[(size_t)i * 3 + 1], 1)) * g.n[0]
                       + pg_cell1(g, pts[(size_t)i * 3], 0);
-        sorted[atomicAdd(&hist[c], 1)] = i;
+        const int pos = atomicAdd(&hist[c], 1);
+        sorted[pos] = i;
+        spts[(size_t)pos * 3] = pts[(size_t)i * 3];
+        spts[(size_t)pos * 3 + 1] = pts[(size_t)i * 3 + 1];
+        spts[(size_t)pos * 3 + 2] = pts[(size_t)i * 3 + 2];
     }
 }
 
-// one thread per point (in cell order, so that the threads of a CTA walk the same runs); count, reserve, write
+// one WARP per point (in cell order), lanes over the candidates of a run: coordinates and indices of the candidates are
+// read in cell order (coalesced: k_pair_grid also stores the points sorted by cell).  Count, reserve with one atomic per
+// CTA, write.  (A first version with one thread per point and scattered candidate loads ran 1.5 ms per chunk: a chain of
+// dependent L2 round trips on 8 warps per SM.)
 __global__ void __launch_bounds__(256)
-k_pair_search(int n, const double* __restrict__ pts, double alpha, double prox, const PairGrid* __restrict__ gp,
+k_pair_search(int n, const double* __restrict__ spts, double alpha, double prox, const PairGrid* __restrict__ gp,
               const int* __restrict__ cell_start, const int* __restrict__ sorted, PairQ* __restrict__ q, int qcap,
               int* __restrict__ qctr, int* parent, int pos0) {
     __shared__ int wtot[8];
     __shared__ int qbase;
     const PairGrid g = *gp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = blockIdx.x * 256 + tid;
+    const int t = blockIdx.x * 8 + warp;                 // sorted position of this warp's point
     const bool live = t < n;
-    const int i = live ? sorted[t] : 0;
-    const double px = pts[(size_t)i * 3], py = pts[(size_t)i * 3 + 1], pz = pts[(size_t)i * 3 + 2];
+    const int tt = live ? t : 0;
+    const int i = sorted[tt];
+    const double px = spts[(size_t)tt * 3], py = spts[(size_t)tt * 3 + 1], pz = spts[(size_t)tt * 3 + 2];
     const int cx = pg_cell1(g, px, 0), cy = pg_cell1(g, py, 1), cz = pg_cell1(g, pz, 2);
     const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.n[0] - 1);
+    // run bounds: lane r < 9 looks up the run (dy, dz) = (r % 3 - 1, r / 3 - 1)
+    int rlo = 0, rhi = 0;
+    {
+        const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
+        if (live && lane < 9 && y >= 0 && y < g.n[1] && z >= 0 && z < g.n[2]) {
+            const int rowc = (z * g.n[1] + y) * g.n[0];
+            rlo = cell_start[rowc + x0];
+            rhi = cell_start[rowc + x1 + 1];
+        }
+    }
     int off = 0;
     for (int pass = 0; pass < 2; ++pass) {
-        int cnt = 0;
-        if (live) {
-            for (int dz = -1; dz <= 1; ++dz) {
-                const int z = cz + dz;
-                if (z < 0 || z >= g.n[2]) continue;
-                for (int dy = -1; dy <= 1; ++dy) {
-                    const int y = cy + dy;
-                    if (y < 0 || y >= g.n[1]) continue;
-                    const int rowc = (z * g.n[1] + y) * g.n[0];
-                    const int lo = cell_start[rowc + x0], hi = cell_start[rowc + x1 + 1];
-                    for (int s = lo; s < hi; ++s) {
-                        const int j = sorted[s];
-                        if (j <= i) continue;                                       // every pair once, i < j
-                        double dx = px - pts[(size_t)j * 3], dy2 = py - pts[(size_t)j * 3 + 1], dz2 = pz - pts[(size_t)j * 3 + 2];
+        int cnt = 0;                                     // warp-uniform
+        for (int r = 0; r < 9; ++r) {
+            const int lo = __shfl_sync(0xffffffffu, rlo, r), hi = __shfl_sync(0xffffffffu, rhi, r);
+            for (int s0 = lo; s0 < hi; s0 += 32) {
+                const int sidx = s0 + lane;
+                bool hit = false;
+                int j = 0;
+                double sd = 0.0;
+                if (sidx < hi) {
+                    j = sorted[sidx];
+                    if (j > i) {                                                    // every pair once, i < j
+                        double dx = px - spts[(size_t)sidx * 3], dy2 = py - spts[(size_t)sidx * 3 + 1], dz2 = pz - spts[(size_t)sidx * 3 + 2];
                         double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy2, dy2)), __dmul_rn(dz2, dz2));
-                        double sd = __dsqrt_rn(s2);
-                        if (sd <= prox) {                                           // ncuts_utils.py:61, inclusive
-                            if (pass == 1) {
-                                PairQ e;
-                                e.i = i; e.j = j;
-                                e.a = alpha != 0.0 ? alpha * sd : 0.0;              // ncuts_utils.py:63-66
-                                q[off + cnt] = e;
-                                if (parent) uf_union(parent, pos0 + i, pos0 + j);
-                            }
-                            ++cnt;
-                        }
+                        sd = __dsqrt_rn(s2);
+                        hit = sd <= prox;                                           // ncuts_utils.py:61, inclusive
                     }
                 }
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (pass == 1 && hit) {
+                    PairQ e;
+                    e.i = i; e.j = j;
+                    e.a = alpha != 0.0 ? alpha * sd : 0.0;                          // ncuts_utils.py:63-66
+                    q[off + cnt + __popc(mask & ((1u << lane) - 1u))] = e;
+                    if (parent) uf_union(parent, pos0 + i, pos0 + j);
+                }
+                cnt += __popc(mask);
             }
         }
         if (pass == 1) break;
-        // exclusive prefix of the counts over the CTA, one global atomic per CTA
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-        if (lane == 31) wtot[warp] = incl;
+        if (lane == 0) wtot[warp] = cnt;
         __syncthreads();
         int wbase = 0, total = 0;
 #pragma unroll
@@ -477,7 +489,7 @@ k_pair_search(int n, const double* __restrict__ pts, double alpha, double prox, 
         }
         __syncthreads();
         if (qbase < 0 || total == 0) return;
-        off = qbase + wbase + incl - cnt;
+        off = qbase + wbase;
     }
 }
 
