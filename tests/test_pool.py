@@ -45,6 +45,30 @@ def test_oracle_scans_are_concatenated_in_order():
     assert not pool_features_ref(major, [], np.zeros(3)).any()
 
 
+def test_host_side_transform_and_fail_loudly_without_gpu():
+    """Host logic of autoinst_b200.pooling: the rigid transform of `transform_pcd` (point_cloud_utils.py:24-35) and no CPU
+    fallback for the pooling itself."""
+    import torch
+    from autoinst_b200.pooling import transform_points, tarl_features_per_patch
+    rng = np.random.default_rng(0)
+    a = 0.7
+    T = np.eye(4)
+    T[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+    T[:3, 3] = [1.0, -2.0, 0.5]
+    pts = rng.normal(size=(50, 3))
+    hom = (T @ np.concatenate([pts, np.ones((50, 1))], axis=1).T).T
+    assert np.allclose(transform_points(pts, T), hom[:, :3], rtol=0, atol=1e-14)
+    if torch.cuda.is_available():
+        return
+
+    class Dataset:
+        def get_pose(self, i): return np.eye(4)
+        def get_point_cloud(self, i): return pts
+        def get_tarl_features(self, i): return np.ones((50, 96), dtype=np.float32)
+    with pytest.raises(Exception):                      # the CUDA library cannot create a handle: nothing is computed on the CPU
+        tarl_features_per_patch(Dataset(), pts, np.eye(4), np.zeros(3), [0])
+
+
 @pytest.mark.gpu
 def test_pool_hand_case_gpu(cuda_device):
     from autoinst_b200 import api
