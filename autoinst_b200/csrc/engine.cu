@@ -1300,11 +1300,9 @@ int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, 
     size_t tmp_bytes = pool_sort_tmp_bytes(num_scan);
     ANCUTS_CUDA(cudaMemsetAsync(inside, 0, sizeof(int), st));
     LAUNCH(SG_PARTITION, k_pool_keys<<<(num_scan + 255) / 256, 256, 0, st>>>(num_scan, d_scan_points, g, keys, idx, inside));
-    int bits = 1;
-    while (bits < 32 && (1ull << bits) < (unsigned long long)g.n[0] * g.n[1] * g.n[2]) ++bits;
     h->launches_total += 1;
+    // all 32 key bits: the UINT_MAX keys of the cropped points must end up behind every cell
     ANCUTS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys2, idx, idx2, num_scan, 0, 32, st));
-    (void)bits;                                  // all 32 bits: the UINT_MAX keys of the cropped points must end up last
     const int blocks = (num_major + 7) / 8;
     const double r2 = radius * radius;
     const int fpl = (feat_dim + 31) / 32;

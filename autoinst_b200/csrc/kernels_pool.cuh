@@ -115,11 +115,9 @@ k_pool_gather(int nmajor, const double* __restrict__ major, int m, const double*
         }
     }
     if (cnt > 0) {
-        const double inv = 1.0 / (double)cnt;
         double nn = 0.0;
 #pragma unroll
-        for (int t = 0; t < FPL; ++t) { acc[t] = acc[t] / (double)cnt; nn += acc[t] * acc[t]; }
-        (void)inv;
+        for (int t = 0; t < FPL; ++t) { acc[t] = acc[t] / (double)cnt; nn += acc[t] * acc[t]; }      // np.mean: sum / count
         if (normalise) {                                       // TARL_NORM (chunk_generation.py:253-254; False in config.py:64)
             nn = sqrt(warp_sum(nn));
 #pragma unroll
