@@ -14,6 +14,13 @@ What it pins (SURVEY.md §8c — the reference has no tests of its own for this 
    that matrix with the eigsh pin of `oracle.ncut_ref.pinned_eigsh`; `oracle.ncut_ref` must return
    the same groups in the same order, else this script fails.
 3. the captured matrices and groups are written as fixtures for the CPU and GPU test suites.
+4. feature pooling (row N3): the reference's own `tarl_features_per_patch`
+   (`pipeline/utils/point_cloud/chunk_generation.py:205-258`) is run unmodified on synthetic scans with a
+   stand-in for the three Open3D pieces it touches (`PointCloud.transform`, `Vector3dVector`, `KDTreeFlann.
+   search_radius_vector_3d`; the KD-tree stand-in is scipy's cKDTree with nanoflann's published rule: squared
+   distance strictly below radius^2, results sorted by distance).  `oracle.pool_ref` must reproduce its output bit
+   for bit, else this script fails; inputs and output go to tests/golden/pooling.npz.  What stays unpinned is only
+   Open3D's own behaviour at the sphere boundary and its result order (which moves a mean by rounding).
 """
 from __future__ import annotations
 
@@ -202,6 +209,107 @@ def main():
             print(f"KAT {name} T={T}: {[list(map(int, g)) for g in g_ref]}")
     np.savez_compressed(os.path.join(OUT, "known_answers.npz"), **kat)
     golden_metrics()
+    golden_pooling()
+
+
+class _O3dCloud:
+    """Stand-in for open3d.geometry.PointCloud as used by get_pcd / transform_pcd (point_cloud_utils.py:11-35)."""
+    def __init__(self):
+        self.points = np.zeros((0, 3))
+
+    def transform(self, T):                       # Open3D: homogeneous transform of every point, in place, returns self
+        P = np.asarray(self.points, dtype=np.float64)
+        hom = np.concatenate([P, np.ones((P.shape[0], 1))], axis=1) @ np.asarray(T, dtype=np.float64).T
+        self.points = hom[:, :3] / hom[:, 3:4]
+        return self
+
+
+class _O3dKDTree:
+    """Stand-in for open3d.geometry.KDTreeFlann (nanoflann radiusSearch: dist^2 < radius^2, sorted by distance)."""
+    def __init__(self, pcd):
+        from scipy.spatial import cKDTree
+        self.P = np.asarray(pcd.points, dtype=np.float64)
+        self.tree = cKDTree(self.P) if self.P.shape[0] else None
+
+    def search_radius_vector_3d(self, query, radius):
+        if self.tree is None:
+            return 0, np.zeros(0, dtype=np.int64), np.zeros(0)
+        q = np.asarray(query, dtype=np.float64)
+        cand = np.asarray(self.tree.query_ball_point(q, radius * (1.0 + 1e-9)), dtype=np.int64)
+        d2 = ((self.P[cand] - q) ** 2).sum(axis=1) if cand.size else np.zeros(0)
+        keep = d2 < radius * radius
+        order = np.argsort(d2[keep], kind="stable")
+        idx = cand[keep][order]
+        return int(idx.size), idx, d2[keep][order]
+
+
+def golden_pooling():
+    """Run the reference's tarl_features_per_patch on synthetic scans and pin oracle.pool_ref against it."""
+    from autoinst_b200.synthetic import small_chunk, make_scans
+    from oracle.pool_ref import pool_features_ref
+    for name in ["open3d", "open3d.geometry", "open3d.utility", "open3d.io", "open3d.pipelines",
+                 "open3d.pipelines.registration"]:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    o3d = sys.modules["open3d"]
+    o3d.geometry = sys.modules["open3d.geometry"]
+    o3d.utility = sys.modules["open3d.utility"]
+    o3d.pipelines = sys.modules["open3d.pipelines"]
+    o3d.pipelines.registration = sys.modules["open3d.pipelines.registration"]
+    o3d.geometry.PointCloud = _O3dCloud
+    o3d.geometry.KDTreeFlann = _O3dKDTree
+    o3d.utility.Vector3dVector = lambda a: np.asarray(a, dtype=np.float64)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    stash = {m: sys.modules.pop(m) for m in [k for k in sys.modules if k == "config" or k == "utils" or k.startswith("utils.")]}
+    try:
+        import utils.point_cloud.chunk_generation as cg
+        assert cg.__file__.startswith(REF)
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+    ch = small_chunk(21, n_obj=2, pts_per_obj=160, features="tarl")
+    scans = make_scans(ch, n_scans=3, pts_per_major=1.5, seed=3)
+
+    def pose(k):
+        a = 0.2 * k
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+        T[:3, 3] = [1.5 * k, -0.5 * k, 0.05 * k]
+        return T
+    T_pcd = pose(2)
+    lidar = []                                   # every scan in its own lidar frame; the reference brings it back (:228-231)
+    for k, (pts, _) in enumerate(scans):
+        Tinv = np.linalg.inv(np.linalg.inv(T_pcd) @ pose(k))
+        lidar.append(pts @ Tinv[:3, :3].T + Tinv[:3, 3])
+
+    class Dataset:
+        def get_pose(self, i): return pose(i)
+        def get_point_cloud(self, i): return lidar[i]
+        def get_tarl_features(self, i): return scans[i][1]
+    pcd = _O3dCloud()
+    pcd.points = ch.points
+    ref_out = cg.tarl_features_per_patch(Dataset(), pcd, T_pcd, ch.center, list(range(len(scans))))
+    # the oracle gets the scans as the reference sees them after its own transform (:231)
+    seen = []
+    for k in range(len(scans)):
+        c = _O3dCloud()
+        c.points = lidar[k]
+        seen.append((c.transform(np.linalg.inv(T_pcd) @ pose(k)).points, scans[k][1]))
+    mine, cnt = pool_features_ref(ch.points, seen, ch.center, radius=cg.MAJOR_VOXEL_SIZE / 2., chunk_size=cg.CHUNK_SIZE,
+                                  normalise=cg.TARL_NORM, return_count=True)
+    if not np.array_equal(ref_out, mine):
+        raise SystemExit(f"oracle pooling differs from the reference: max abs diff {np.abs(ref_out - mine).max()}")
+    assert (cnt == 0).any() and (cnt > 3).any()
+    np.savez_compressed(os.path.join(OUT, "pooling.npz"), major=ch.points, center=ch.center,
+                        scan_points=np.concatenate([s[0] for s in seen]), scan_features=np.concatenate([s[1] for s in seen]),
+                        scan_sizes=np.array([s[0].shape[0] for s in seen]), radius=cg.MAJOR_VOXEL_SIZE / 2.,
+                        chunk_size=np.asarray(cg.CHUNK_SIZE, dtype=np.float64), out=ref_out, count=cnt)
+    print(f"pooling.npz: {ch.n} major points, {sum(s[0].shape[0] for s in seen)} scan points, zero rows {(cnt == 0).sum()}")
+    for m_ in [k for k in sys.modules if k == "config" or k == "utils" or k.startswith("utils.")]:
+        sys.modules.pop(m_)
+    sys.modules.update(stash)
 
 
 def golden_metrics():

@@ -11,8 +11,12 @@ Third-party arithmetic: the radius search is Open3D 0.17 `KDTreeFlann.search_rad
 `setup.sh:9`, not vendored, not installable here).  Its published algorithm: nanoflann `radiusSearch` with
 `radius * radius`, whose `RadiusResultSet::addPoint` keeps a point iff `dist < radius` on SQUARED distances, results
 sorted by distance.  Restated with scipy's cKDTree (candidates within the radius, then the strict float64 test and
-the distance sort).  **Parity unpinned for this row**: no fixture of the reference exists and Open3D cannot be run
-here; the CUDA path is compared with this restatement (means agree to rounding: the summation orders differ).
+the distance sort).
+Pinned: `oracle/make_golden.py::golden_pooling` runs the reference's own, unmodified `tarl_features_per_patch` on
+synthetic scans (with that cKDTree restatement standing in for Open3D's KD-tree and a numpy `PointCloud.transform`)
+and this module reproduces its output bit for bit; inputs and output are committed as `tests/golden/pooling.npz`.
+What no fixture here can pin is Open3D's own behaviour exactly on the sphere and its result order (the latter moves
+a mean by rounding only).
 """
 from __future__ import annotations
 

@@ -37,6 +37,26 @@ def test_oracle_hand_case():
     assert abs(np.linalg.norm(outn[0]) - 1.0) < 1e-15 and not outn[2].any()
 
 
+def load_pooling_golden():
+    import os
+    from conftest import GOLDEN
+    g = np.load(os.path.join(GOLDEN, "pooling.npz"))
+    sizes = g["scan_sizes"]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    scans = [(g["scan_points"][a:b], g["scan_features"][a:b]) for a, b in zip(offs[:-1], offs[1:])]
+    return g, scans
+
+
+def test_oracle_matches_the_reference_function_golden():
+    """tests/golden/pooling.npz holds the output of the reference's own `tarl_features_per_patch`
+    (`chunk_generation.py:205-258`, run unmodified by oracle/make_golden.py with a cKDTree stand-in for Open3D's KD-tree)."""
+    g, scans = load_pooling_golden()
+    out, cnt = pool_features_ref(g["major"], scans, g["center"], radius=float(g["radius"]), chunk_size=g["chunk_size"],
+                                 return_count=True)
+    assert np.array_equal(out, g["out"]) and np.array_equal(cnt, g["count"])
+    assert (cnt == 0).any() and not out[cnt == 0].any()
+
+
 def test_oracle_scans_are_concatenated_in_order():
     major, pts, feats = hand_case()
     a = pool_features_ref(major, [(pts, feats)], np.zeros(3), radius=R)
@@ -78,6 +98,19 @@ def test_pool_hand_case_gpu(cuda_device):
     ref, rc = pool_features_ref(major, [(pts, feats)], np.zeros(3), radius=R, return_count=True)
     assert cnt.cpu().numpy().tolist() == rc.tolist() == [2, 1, 0]
     assert np.array_equal(out.cpu().numpy(), ref)              # two terms: no rounding freedom
+
+
+@pytest.mark.gpu
+def test_pool_matches_the_reference_golden(cuda_device):
+    from autoinst_b200 import api
+    g, scans = load_pooling_golden()
+    half = 0.5 * g["chunk_size"]
+    out, cnt = api.feature_pool(g["major"], g["scan_points"], g["scan_features"], float(g["radius"]), g["center"] - half,
+                                g["center"] + half, return_count=True, device=cuda_device)
+    assert np.array_equal(cnt.cpu().numpy(), g["count"])       # the reference's neighbour sets, point for point
+    out = out.cpu().numpy()
+    assert np.array_equal(out[g["count"] == 0], g["out"][g["count"] == 0])
+    assert np.allclose(out, g["out"], rtol=1e-13, atol=1e-14)  # float64 means, different summation order
 
 
 @pytest.mark.gpu
