@@ -210,6 +210,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "known_answers.npz"), **kat)
     golden_metrics()
     golden_pooling()
+    golden_merge()
 
 
 class _O3dCloud:
@@ -307,6 +308,113 @@ def golden_pooling():
                         scan_sizes=np.array([s[0].shape[0] for s in seen]), radius=cg.MAJOR_VOXEL_SIZE / 2.,
                         chunk_size=np.asarray(cg.CHUNK_SIZE, dtype=np.float64), out=ref_out, count=cnt)
     print(f"pooling.npz: {ch.n} major points, {sum(s[0].shape[0] for s in seen)} scan points, zero rows {(cnt == 0).sum()}")
+    for m_ in [k for k in sys.modules if k == "config" or k == "utils" or k.startswith("utils.")]:
+        sys.modules.pop(m_)
+    sys.modules.update(stash)
+
+
+class _O3dColourCloud(_O3dCloud):
+    """PointCloud stand-in with colours for the merge (`point_cloud_utils.py:320-329,387-491`): `+=`, `crop` with an
+    inclusive axis-aligned box (Open3D `GetPointIndicesWithinBoundingBox`), `remove_duplicated_points` keeping the first
+    occurrence of every exact coordinate in point order."""
+    def __init__(self, points=None, colors=None):
+        self.points = np.zeros((0, 3)) if points is None else np.asarray(points, dtype=np.float64)
+        self.colors = np.zeros((len(self.points), 3)) if colors is None else np.asarray(colors, dtype=np.float64)
+
+    def __iadd__(self, other):
+        self.points = np.concatenate([np.asarray(self.points), np.asarray(other.points)])
+        self.colors = np.concatenate([np.asarray(self.colors), np.asarray(other.colors)])
+        return self
+
+    def crop(self, box):
+        P = np.asarray(self.points)
+        m = np.all((P >= box.min_bound) & (P <= box.max_bound), axis=1)
+        return _O3dColourCloud(P[m], np.asarray(self.colors)[m])
+
+    def remove_duplicated_points(self):
+        _, first = np.unique(np.asarray(self.points), axis=0, return_index=True)
+        keep = np.sort(first)
+        self.points = np.asarray(self.points)[keep]
+        self.colors = np.asarray(self.colors)[keep]
+        return self
+
+
+class _O3dBox:
+    def __init__(self, min_bound=None, max_bound=None):
+        self.min_bound = np.asarray(min_bound, dtype=np.float64)
+        self.max_bound = np.asarray(max_bound, dtype=np.float64)
+
+
+def golden_merge():
+    """Run the reference's merge_chunks_unite_instances2 / merge_unite_gt / remove_semantics on a synthetic map and pin
+    oracle.merge_ref against them (labels <-> colours: label l is the colour (l / 4096, 0, 0), black = background, so the
+    reference's np.unique order of colours is the order of the labels)."""
+    from autoinst_b200.synthetic import make_map
+    from oracle import merge_ref as M
+    for name in ["open3d", "open3d.geometry", "open3d.utility", "open3d.io", "open3d.pipelines",
+                 "open3d.pipelines.registration"]:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    o3d = sys.modules["open3d"]
+    o3d.geometry = sys.modules["open3d.geometry"]
+    o3d.utility = sys.modules["open3d.utility"]
+    o3d.pipelines = sys.modules["open3d.pipelines"]
+    o3d.pipelines.registration = sys.modules["open3d.pipelines.registration"]
+    o3d.geometry.PointCloud = _O3dColourCloud
+    o3d.geometry.AxisAlignedBoundingBox = _O3dBox
+    o3d.utility.Vector3dVector = lambda a: np.asarray(a, dtype=np.float64)
+    cwd = os.getcwd()
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    stash = {m: sys.modules.pop(m) for m in [k for k in sys.modules if k == "config" or k == "utils" or k.startswith("utils.")]}
+    try:
+        import utils.point_cloud.point_cloud_utils as pcu
+        assert pcu.__file__.startswith(REF)
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+    chunks = [c for c in make_map(4, 1500, seed=5) if c.n > 0]
+    rng = np.random.default_rng(1)
+    parts = []
+    for c in chunks:
+        # imperfect "predictions": GT instances with one of them split in two and some points on background
+        lab = c.instance.astype(np.int64).copy()
+        if (lab > 0).any():
+            big = np.bincount(lab[lab > 0]).argmax()
+            half = (lab == big) & (c.points[:, 0] > np.median(c.points[lab == big, 0]))
+            lab[half] = lab.max() + 1
+        lab[rng.random(c.n) < 0.03] = 0
+        lab = np.where(lab > 0, (np.int64(c.chunk_id + 1) << 6) + lab, 0)            # unique across chunks, < 4096
+        parts.append((c.points, lab))
+    assert max(int(l.max()) for _, l in parts) < 4096
+
+    def cloud(p, l):
+        col = np.zeros((len(l), 3))
+        col[:, 0] = l / 4096.0
+        return _O3dColourCloud(p, col)
+    merged = pcu.merge_chunks_unite_instances2([cloud(p, l) for p, l in parts])
+    ref_pts = np.asarray(merged.points)
+    ref_lab = np.rint(np.asarray(merged.colors)[:, 0] * 4096.0).astype(np.int64)
+    pts, lab = M.merge_chunks_unite_instances(parts)
+    if not (np.array_equal(pts, ref_pts) and np.array_equal(lab, ref_lab)):
+        raise SystemExit("oracle merge differs from the reference's merge_chunks_unite_instances2")
+    gt = pcu.merge_unite_gt([cloud(c.points, c.instance.astype(np.int64)) for c in chunks])
+    gpts, glab = M.merge_unite_gt([(c.points, c.instance) for c in chunks])
+    if not (np.array_equal(gpts, np.asarray(gt.points)) and
+            np.array_equal(glab, np.rint(np.asarray(gt.colors)[:, 0] * 4096.0).astype(np.int64))):
+        raise SystemExit("oracle merge_unite_gt differs from the reference")
+    assert np.array_equal(gpts, pts)
+    pred = M.compact_labels(lab)
+    ref_clean = pcu.remove_semantics(M.compact_labels(glab), pred.copy())
+    mine_clean = M.remove_semantics(M.compact_labels(glab), pred)
+    if not np.array_equal(ref_clean, mine_clean):
+        raise SystemExit("oracle remove_semantics differs from the reference")
+    np.savez_compressed(os.path.join(OUT, "merge.npz"), n_chunks=len(parts),
+                        **{f"p{i}": p for i, (p, _) in enumerate(parts)}, **{f"l{i}": l for i, (_, l) in enumerate(parts)},
+                        **{f"g{i}": c.instance.astype(np.int64) for i, c in enumerate(chunks)},
+                        merged_points=ref_pts, merged_labels=ref_lab, gt_labels=glab, cleaned=ref_clean)
+    print(f"merge.npz: {len(parts)} chunks, {sum(len(l) for _, l in parts)} points -> {len(ref_lab)} merged, "
+          f"{len(np.unique(ref_lab)) - 1} instances (from {sum(len(np.unique(l)) - 1 for _, l in parts)} per-chunk segments)")
     for m_ in [k for k in sys.modules if k == "config" or k == "utils" or k.startswith("utils.")]:
         sys.modules.pop(m_)
     sys.modules.update(stash)

@@ -6,9 +6,11 @@ Restates, on plain arrays with integer labels instead of RGB colours:
   merge_unite_gt                  `:320-329`
   remove_semantics                `:253-287`
   colour -> integer label glue    `pipeline/run_pipeline.py:203-223`
-Open3D is not available here, so this part is NOT pinned against the reference (its `crop` and
-`remove_duplicated_points` are Open3D calls); both sides of the level-3 comparison go through this same
-restatement, so it only has to be the same function for both.
+Pinned: `oracle/make_golden.py::golden_merge` runs the reference's own, unmodified functions on a synthetic 4-chunk map
+with a numpy stand-in for the Open3D `PointCloud` (inclusive `crop`, `+=`, `remove_duplicated_points` keeping the first
+occurrence in point order) and labels encoded as colours; this module reproduces their outputs exactly
+(`tests/golden/merge.npz`, `tests/test_oracle.py`).  Not pinnable here: Open3D's own duplicate-removal order (it cannot
+be installed); both sides of the level-3 comparison go through this same restatement.
 Label 0 is the background ("black" in the reference).
 """
 from __future__ import annotations

@@ -172,3 +172,20 @@ def test_disconnected_nodes_peel_one_component_and_leave_a_residual_group(seed, 
     assert len(rep["groups"]) == expect_groups
     for _, _, pts in rep["groups"]:
         assert pts <= 0.01 * ch.n
+
+
+def test_merge_ref_matches_the_reference_golden():
+    """tests/golden/merge.npz: outputs of the reference's own merge_chunks_unite_instances2 / merge_unite_gt /
+    remove_semantics (`point_cloud_utils.py:253-287,320-329,387-491`), run unmodified by oracle/make_golden.py with a
+    numpy stand-in for the Open3D PointCloud (crop, +=, remove_duplicated_points)."""
+    from oracle import merge_ref as M
+    g = np.load(f"{GOLDEN}/merge.npz")
+    n = int(g["n_chunks"])
+    parts = [(g[f"p{i}"], g[f"l{i}"]) for i in range(n)]
+    pts, lab = M.merge_chunks_unite_instances(parts)
+    assert np.array_equal(pts, g["merged_points"]) and np.array_equal(lab, g["merged_labels"])
+    assert len(np.unique(lab)) < sum(len(np.unique(l)) for _, l in parts) - n          # instances were united across chunks
+    gpts, glab = M.merge_unite_gt([(g[f"p{i}"], g[f"g{i}"]) for i in range(n)])
+    assert np.array_equal(gpts, pts) and np.array_equal(glab, g["gt_labels"])
+    cleaned = M.remove_semantics(M.compact_labels(glab), M.compact_labels(lab))
+    assert np.array_equal(cleaned, g["cleaned"])
