@@ -23,7 +23,11 @@ EXPORTS = [
     "ancuts_segment_chunks", "ancuts_segment_chunks_host", "ancuts_segment_dense_f32",
     "ancuts_launch_count", "ancuts_last_accounting", "ancuts_set_stage_timing", "ancuts_nn_reproject",
     "ancuts_last_levels", "ancuts_debug_phases", "ancuts_feature_pool_workspace_bytes", "ancuts_feature_pool",
+    "ancuts_last_unconverged", "ancuts_set_option",
 ]
+
+# ancuts_set_option (include/autoinst_ncuts.h)
+OPT_AFFINITY_FORM, OPT_PAIR_SEARCH, OPT_MATVEC = 0, 1, 2
 
 
 class Params(C.Structure):
@@ -48,6 +52,14 @@ class AncutsError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libautoinst_ncuts error {code}: {msg}")
         self.code = code
+
+
+class AncutsNoConvergence(RuntimeError):
+    """The Lanczos eigensolver stopped at its step limit on `count` recursion nodes (the reference's eigsh raises
+    ArpackNoConvergence there, normalized_cut.py:49)."""
+    def __init__(self, count):
+        super().__init__(f"Lanczos eigensolver: {count} node(s) stopped at lanczos_max_steps without converging")
+        self.count = int(count)
 
 
 _lib = None
@@ -108,6 +120,8 @@ def load():
     lib.ancuts_set_stage_timing.argtypes = [vp, C.c_int]
     lib.ancuts_last_levels.argtypes = [vp, dp, C.c_int]
     lib.ancuts_debug_phases.argtypes = [vp, dp, C.c_int]
+    lib.ancuts_last_unconverged.argtypes = [vp]
+    lib.ancuts_set_option.argtypes = [vp, C.c_int, C.c_int]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("ancuts_version",):

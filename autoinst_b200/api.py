@@ -12,8 +12,10 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
+import warnings
+
 from . import _lib
-from ._lib import NodeStat, Params, check
+from ._lib import AncutsNoConvergence, NodeStat, Params, check
 
 STAGES = ("affinity", "degree", "matvec", "reorth", "scan", "partition")
 
@@ -52,6 +54,15 @@ class Handle:
             cls._cache[key] = Handle(int(device))
         return cls._cache[key]
 
+    def set_option(self, option: int, value: int):
+        """Alternative implementations behind the same results (`ancuts_set_option`): _lib.OPT_AFFINITY_FORM
+        (0 deferred, 1 dense two-pass, 2 dense one-kernel), OPT_PAIR_SEARCH (0 tile sweep, 1 cell grid),
+        OPT_MATVEC (0 dense blocks from HBM, 1 slices compressed into shared memory)."""
+        check(self.lib.ancuts_set_option(self.h, int(option), int(value)))
+
+    def last_unconverged(self) -> int:
+        return int(self.lib.ancuts_last_unconverged(self.h))
+
     def launch_count(self, reset=False) -> int:
         return int(self.lib.ancuts_launch_count(self.h, 1 if reset else 0))
 
@@ -70,7 +81,7 @@ class Handle:
         """Cycles per phase of the persistent Lanczos kernel (needs ANCUTS_PHASES=1 before the handle is created)."""
         buf = (C.c_double * 32)()
         check(self.lib.ancuts_debug_phases(self.h, buf, 1 if reset else 0))
-        names = ["basis", "matvec", "dots1", "update1", "dots2", "update2", "norm", "check"]
+        names = ["basis", "matvec", "alpha_3term", "check_multisection", "dots", "update_norm", "z_exchange", "check_rest"]
         return {c: {nm: buf[8 * i + j] for j, nm in enumerate(names)} for i, c in enumerate((1, 2, 4, 8))}
 
     def levels(self, cap: int = 256) -> list:
@@ -297,6 +308,19 @@ class SegmentResult:
     labels: list            # one int32 numpy array per chunk
     num_segments: np.ndarray
     stats: np.ndarray | None   # structured array of ancuts_node_stat rows (all chunks of the call)
+    unconverged: int = 0       # eigensolver nodes that stopped at max_steps (their cut used an unconverged vector)
+
+
+def _report_unconverged(hd, strict: bool) -> int:
+    """Non-convergence is never silent: the drop-in callers raise (as the reference's eigsh would), the array
+    level warns unless `strict`."""
+    cnt = hd.last_unconverged()
+    if cnt > 0:
+        if strict:
+            raise AncutsNoConvergence(cnt)
+        warnings.warn(f"Lanczos eigensolver: {cnt} recursion node(s) stopped at the step limit without converging; "
+                      "their cuts used the unconverged Ritz vector (raise max_steps)", RuntimeWarning, stacklevel=3)
+    return cnt
 
 
 _STAT_DTYPE = np.dtype([("chunk", "<i4"), ("n", "<i4"), ("steps", "<i4"), ("converged", "<i4"), ("best_k", "<i4"),
@@ -413,7 +437,8 @@ def _run_segment(hd, fn_host, packed, dev_chunks, p, want_stats, device):
 
 def segment_packed(packed: PackedChunks, *, alpha=1.0, theta=0.0, gamma=0.0, T=0.01, proximity=1.0, split_lim=0.01,
                    device=None, dev_chunks: DeviceChunks | None = None, want_stats=False, max_steps=0,
-                   check_every=0, tol=0.0, affinity_impl=0, lanczos_impl=0, lane: int = 0) -> SegmentResult:
+                   check_every=0, tol=0.0, affinity_impl=0, lanczos_impl=0, lane: int = 0,
+                   strict: bool = False) -> SegmentResult:
     """Segment a packed batch.  With `dev_chunks` the inputs are already resident in HBM (labels stay on
     the device in dev_chunks.labels); otherwise host buffers go through ancuts_segment_chunks_host."""
     device = _dev(device if dev_chunks is None else dev_chunks.device)
@@ -422,12 +447,13 @@ def segment_packed(packed: PackedChunks, *, alpha=1.0, theta=0.0, gamma=0.0, T=0
                     tarl_dim=packed.tarl_dim, dino_dim=packed.dino_dim, max_steps=max_steps, check_every=check_every,
                     tol=tol, affinity_impl=affinity_impl, lanczos_impl=lanczos_impl)
     nseg, stats = _run_segment(hd, dev_chunks is None, packed, dev_chunks, p, want_stats, device)
+    unconv = _report_unconverged(hd, strict)
     src = packed.labels if dev_chunks is None else dev_chunks.labels
     labels = None
     if dev_chunks is None:
         arr = src.numpy()
         labels = [arr[a:b].copy() for a, b in zip(packed.off[:-1], packed.off[1:])]
-    return SegmentResult(labels=labels, num_segments=nseg, stats=stats)
+    return SegmentResult(labels=labels, num_segments=nseg, stats=stats, unconverged=unconv)
 
 
 def segment_packed_lanes(packed_lanes, dev_lanes=None, **kw):
@@ -476,6 +502,7 @@ def segment_chunks(points_list, tarl_list=None, dino_list=None, *, alpha=1.0, th
     labels = [None] * len(sizes)
     nseg = np.zeros(len(sizes), dtype=np.int32)
     stats_all = []
+    unconv = 0
     for batch in batches:
         pk = PackedChunks([points_list[i] for i in batch],
                           [tarl_list[i] for i in batch] if tarl_list is not None else None,
@@ -483,6 +510,7 @@ def segment_chunks(points_list, tarl_list=None, dino_list=None, *, alpha=1.0, th
                           theta=theta, gamma=gamma, pin=False)
         res = segment_packed(pk, alpha=alpha, theta=theta, gamma=gamma, T=T, proximity=proximity,
                              split_lim=split_lim, device=device, want_stats=want_stats, **kw)
+        unconv += res.unconverged
         for j, i in enumerate(batch):
             labels[i] = res.labels[j]
             nseg[i] = res.num_segments[j]
@@ -491,7 +519,7 @@ def segment_chunks(points_list, tarl_list=None, dino_list=None, *, alpha=1.0, th
             st["chunk"] = np.asarray(batch, dtype=np.int32)[st["chunk"]]
             stats_all.append(st)
     stats = np.concatenate(stats_all) if stats_all else None
-    return SegmentResult(labels=labels, num_segments=nseg, stats=stats)
+    return SegmentResult(labels=labels, num_segments=nseg, stats=stats, unconverged=unconv)
 
 
 def segment_chunk(points, tarl=None, dino=None, **kw):
@@ -500,7 +528,8 @@ def segment_chunk(points, tarl=None, dino=None, **kw):
     return res.labels[0]
 
 
-def segment_dense(W, num_points_orig=None, *, T=0.01, split_lim=0.01, want_stats=False, max_steps=0, tol=0.0):
+def segment_dense(W, num_points_orig=None, *, T=0.01, split_lim=0.01, want_stats=False, max_steps=0, tol=0.0,
+                  strict: bool = False):
     """normalized_cut(w, num_points_orig, labels, T, split_lim) (normalized_cut.py:37) for a dense float32
     copy of w on the device.  Returns int32 labels (numpy), and stats if requested."""
     W, ld = _matrix_args(W)
@@ -518,5 +547,6 @@ def segment_dense(W, num_points_orig=None, *, T=0.01, split_lim=0.01, want_stats
             hd.h, n, _ptr(W), ld, int(num_points_orig if num_points_orig is not None else n), C.byref(p), _ptr(labels),
             nseg.ctypes.data_as(C.POINTER(C.c_int32)), stats.ctypes.data_as(C.POINTER(NodeStat)) if want_stats else None,
             cap, C.byref(nstats), _stream(device)))
+    _report_unconverged(hd, strict)
     out = labels.cpu().numpy()
     return (out, stats[:nstats.value].copy()) if want_stats else out

@@ -23,7 +23,8 @@ constexpr int KMAX_LIMIT = 2048;            // the check kernel keeps 8.5 arrays
 constexpr int CHECK_DEFAULT = 16;
 constexpr double TOL_DEFAULT = 1e-10;
 constexpr double CHILD_SPLIT_LIM = 0.01;   // normalized_cut.py:37 default, not forwarded at :57-58
-constexpr double FIX_SCALE = 1099511627776.0;   // 2^40 fixed point for order-independent cut sums
+constexpr int FIX_SHIFT = 40;              // 2^-40 fixed point for order-independent cut sums (fewer bits for huge volumes)
+constexpr int CTR_COUNT = 32;              // device counters, see Eng::ctr
 
 enum : int { ST_LEAF = 0, ST_ACTIVE = 1, ST_SPLIT = 2 };
 enum : int { DONE_NO = 0, DONE_YES = 1, DONE_HOLD = 2 };
@@ -162,10 +163,12 @@ struct Eng {
     double* p_stat;       // [cslot][4]  sum, min, max, sum of squares
     double* p_vol;        // [cslot][NB]
     // counters (device)
-    int* ctr;             // 16 ints: [8..12]=nodes per cluster class [13]=nodes for the multi-launch path; [0]=numRanges [1]=numActive [2]=maxActiveN [3]=cslots [4]=notDone [5]=numSplit [6]=statCount [7]=maxSplitN
+    int* ctr;             // CTR_COUNT ints: [0]=numRanges [1]=numActive [2]=maxActiveN [3]=cslots [4]=notDone [5]=numSplit [6]=statCount
+                          // [7]=maxSplitN [8..13]=nodes per cluster class [14]=nodes for the multi-launch path
+                          // [16]=eigensolver nodes that stopped unconverged (whole call, never reset between levels)
     unsigned long long* acct;   // [SG_COUNT] algorithmic bytes
     ancuts_node_stat* stats; int stats_cap;
-    int xf;               // experiment flags (ANCUTS_X): 1 = matvec without out-of-block selects, 2 = integer float->double widening
+    int w_own;            // 1 = W holds the library's own affinities (0 or [2^-126, 2)): the matvec may widen on the integer pipe
     unsigned long long* dbg;   // optional [4 cluster sizes][8] phase cycle sums of the cluster kernel (thread 0 of rank 0), or NULL
     int w_guard;          // 1 = entries next to a block may be non-finite (caller-provided W without a gather)
     const double* pts;    // [P][3] input coordinates (chunk c at c_base[c], input order) for the Lanczos start vector, or NULL

@@ -44,7 +44,7 @@ struct ancuts_handle {
     size_t ws_bytes = 0;
     char* stage = nullptr;                   // device staging of host inputs / labels (host entry point)
     size_t stage_cap = 0;
-    int* h_ctr = nullptr;                    // pinned, 16 ints
+    int* h_ctr = nullptr;                    // pinned, CTR_COUNT ints
     cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per node size bin
     cudaEvent_t ev_fork = nullptr;
     cudaEvent_t ev_join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -60,21 +60,9 @@ struct ancuts_handle {
     std::vector<cudaEvent_t> pool;
     size_t pool_used = 0;
     bool attrs_set = false;
-    // Kernel variants (ANCUTS_X in the environment overrides the default, for A/B measurements; tools/gpu_s2_*.sh):
-    //   2     every second float->double widening of the matvec on the integer pipe
-    //   16,32 L2 bulk prefetch distance in passes (bits 4-5; register-staged matvec only); 2048: per-lane prefetch instead
-    //   256   one-kernel affinity (k_affinity_exact) instead of the two-pass form
-    //   1024  three-term recurrence + ONE Gram-Schmidt pass (otherwise classical Gram-Schmidt twice)
-    //   4096  basis rows in global memory only
-    //   8192  TMA ring in shared memory (otherwise register-staged loads)
-    //   524288 deferred affinity: pairs from a cell grid (counting sort + 27-cell search) instead of the N^2 tile sweep
-    //   262144 deferred affinity: pass 1 only queues pairs; W is written block by block after the root split
-    //   131072 Lanczos start vector from the point coordinates (segment calls) instead of the hash
-    //   65536 128 instead of 256 multisection shifts per eigenvalue and round in those checks
-    //   32768 division-free Sturm counts in the cluster kernel's convergence checks
-    //   16384 adaptive placement of the convergence checks in the cluster kernel (otherwise every check_every steps)
-    // The matvec reads out-of-block columns without selects whenever the blocks come from k_gather_blocks_cur.
-    int xflags = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072 | 262144;      // 524288 stays off: measured slower than the tile sweep
+    // Code paths with more than one implementation behind the same results (ancuts_set_option; every one is parity-tested):
+    int opt[ANCUTS_OPT_COUNT] = {0, 0, 0};
+    int last_unconverged = 0;                // eigensolver nodes of the last segment call that stopped at lanczos_max_steps
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
@@ -168,7 +156,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     const int C = pl.cslot_cap;
     e.p_dot = ar.take<double>((size_t)C * KS); e.p_dot2 = ar.take<double>((size_t)C * KS);
     e.p_norm = ar.take<double>(C); e.p_stat = ar.take<double>((size_t)C * 4); e.p_vol = ar.take<double>((size_t)C * NB);
-    e.ctr = ar.take<int>(16);
+    e.ctr = ar.take<int>(CTR_COUNT);
     e.a_path = ar.take<int>(A);
     e.cl_ids = ar.take<int>((size_t)CL_CLASSES * A);
     e.active_cap = A;
@@ -310,9 +298,7 @@ static int set_attrs(ancuts_handle* h, int KS) {
     const int cl_smem = CL_DYN_SMEM;
 #define ANCUTS_CL_ATTR(C, M) ANCUTS_CUDA(cudaFuncSetAttribute(k_lanczos_cluster<C, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, cl_smem))
     ANCUTS_CL_ATTR(1, 0); ANCUTS_CL_ATTR(2, 0); ANCUTS_CL_ATTR(4, 0); ANCUTS_CL_ATTR(8, 0);
-    ANCUTS_CL_ATTR(1, 3); ANCUTS_CL_ATTR(2, 3); ANCUTS_CL_ATTR(4, 3); ANCUTS_CL_ATTR(8, 3);
     ANCUTS_CL_ATTR(1, 4); ANCUTS_CL_ATTR(2, 4); ANCUTS_CL_ATTR(4, 4); ANCUTS_CL_ATTR(8, 4);
-    ANCUTS_CL_ATTR(1, 5); ANCUTS_CL_ATTR(2, 5); ANCUTS_CL_ATTR(4, 5); ANCUTS_CL_ATTR(8, 5);
     ANCUTS_CL_ATTR(1, 6); ANCUTS_CL_ATTR(2, 6); ANCUTS_CL_ATTR(4, 6); ANCUTS_CL_ATTR(8, 6);
 #undef ANCUTS_CL_ATTR
     h->attrs_set = true;
@@ -320,7 +306,7 @@ static int set_attrs(ancuts_handle* h, int KS) {
 }
 
 static int read_ctr(ancuts_handle* h, const Eng& e, cudaStream_t st) {
-    ANCUTS_CUDA(cudaMemcpyAsync(h->h_ctr, e.ctr, 16 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(h->h_ctr, e.ctr, CTR_COUNT * sizeof(int), cudaMemcpyDeviceToHost, st));
     ANCUTS_CUDA(cudaStreamSynchronize(st));
     return ANCUTS_OK;
 }
@@ -510,22 +496,19 @@ static cudaError_t launch_cluster_m(const Eng& e, int cur, const int* ids, int c
     return cudaLaunchKernelEx(&cfg, k_lanczos_cluster<C, MODE>, e, cur, ids, (int)(CL_DYN_SMEM / 8));
 }
 
-// matvec variant: 0 = out-of-block entries selected away (W may hold anything next to a block),
-// 1 = no selects (the gather zeroed the fringe), 2 = additionally the integer float->double widening
+// matvec variant: 0 = guarded (out-of-block entries selected away: the caller's W is read in place and may hold anything next
+// to a block), 4 = TMA ring (blocks written by k_gather_blocks_cur / k_zero_blocks: fringe zeroed, no selects),
+// 6 = TMA ring + integer widening of every second element (the library's own affinities: 0 or [2^-126, 2))
 static inline int cluster_mode(const Eng& e) {
-    if (e.w_guard) return 0;                           // 0: selects, W read in place (stage entry points)
-    const bool mix = (e.xf & 2) != 0;                  // every second element widened on the integer pipe
-    if (e.xf & 8192) return mix ? 6 : 4;               // 4/6: TMA ring in shared memory
-    return mix ? 5 : 3;                                // 3/5: register-staged loads + L2 prefetch
+    if (e.w_guard) return 0;
+    return e.w_own ? 6 : 4;
 }
 
 template <int C>
 static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
     switch (cluster_mode(e)) {
         case 6: return launch_cluster_m<C, 6>(e, cur, ids, count, s);
-        case 5: return launch_cluster_m<C, 5>(e, cur, ids, count, s);
         case 4: return launch_cluster_m<C, 4>(e, cur, ids, count, s);
-        case 3: return launch_cluster_m<C, 3>(e, cur, ids, count, s);
         default: return launch_cluster_m<C, 0>(e, cur, ids, count, s);
     }
 }
@@ -744,7 +727,7 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
                       const DeferredAffinity* df = nullptr) {
     Eng& e = pl.e;
     const int P = e.P, B = e.B;
-    ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 16 * sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, CTR_COUNT * sizeof(int), st));
     {
         int nmax = 0;
         for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
@@ -836,11 +819,10 @@ int ancuts_create(int device, ancuts_handle** out) {
     }
     ancuts_handle* h = new ancuts_handle();
     h->device = device;
-    if (const char* x = getenv("ANCUTS_X")) h->xflags = atoi(x);
     if (const char* x = getenv("ANCUTS_PHASES")) {
         if (atoi(x)) { ANCUTS_CUDA(cudaMalloc((void**)&h->dbg, 32 * sizeof(unsigned long long))); ANCUTS_CUDA(cudaMemset(h->dbg, 0, 32 * sizeof(unsigned long long))); }
     }
-    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_ctr, 16 * sizeof(int)));
+    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_ctr, CTR_COUNT * sizeof(int)));
     for (int i = 0; i < 6; ++i) {
         ANCUTS_CUDA(cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking));
         ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
@@ -908,6 +890,14 @@ int ancuts_debug_phases(ancuts_handle* h, double* out32, int reset) {
     return ANCUTS_OK;
 }
 
+int ancuts_set_option(ancuts_handle* h, int option, int value) {
+    if (!h || option < 0 || option >= ANCUTS_OPT_COUNT) { set_error("unknown option %d", option); return ANCUTS_EINVAL; }
+    h->opt[option] = value;
+    return ANCUTS_OK;
+}
+
+int ancuts_last_unconverged(ancuts_handle* h) { return h ? h->last_unconverged : ANCUTS_EINVAL; }
+
 int ancuts_set_stage_timing(ancuts_handle* h, int on) {
     if (!h) return ANCUTS_EINVAL;
     h->stage_timing = on;
@@ -934,7 +924,7 @@ int ancuts_affinity_f32(ancuts_handle* h, int n, const double* d_points, const f
     Plan pl;
     size_t tcb = (p->affinity_impl == 1) ? affinity_tc_scratch_bytes(n, p->tarl_dim, p->dino_dim) : 0;
     const bool feats = (p->theta != 0.0 && d_tarl) || (p->gamma != 0.0 && d_dino);
-    const bool two_pass = p->affinity_impl == 0 && feats && !(h->xflags & 256);
+    const bool two_pass = p->affinity_impl == 0 && feats && h->opt[ANCUTS_OPT_AFFINITY_FORM] != 2;
     const int qcap = two_pass ? (int)std::min<long long>(96ll * n, (long long)n * (n - 1) / 2 + 1) : 0;
     const size_t o_tc = align_up((size_t)n, 256) + 256;
     const size_t o_q = o_tc + align_up(tcb, 256) + 256;
@@ -1020,7 +1010,7 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
     rc = upload_tables(pl, st);
     if (rc) return rc;
     fill_params(pl.e, p, kmax);
-    pl.e.xf = 0; pl.e.w_guard = 1; pl.e.dbg = nullptr; pl.e.pts = nullptr;           // caller's W is read in place: anything may sit next to a block
+    pl.e.w_own = 0; pl.e.w_guard = 1; pl.e.dbg = nullptr; pl.e.pts = nullptr;           // caller's W is read in place: anything may sit next to a block
     pl.e.stats = nullptr; pl.e.stats_cap = 0;
     rc = set_attrs(h, pl.KS);
     if (rc) return rc;
@@ -1083,6 +1073,7 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
     ANCUTS_CUDA(cudaMemcpyAsync(e.a_nch, anch.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
     ANCUTS_CUDA(cudaMemcpyAsync(e.a_slot0, aslot.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
     ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 8 * sizeof(int), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 16, 0, (CTR_COUNT - 16) * sizeof(int), st));
     ANCUTS_CUDA(cudaMemsetAsync(e.acct, 0, SG_COUNT * sizeof(unsigned long long), st));
     ANCUTS_CUDA(cudaStreamSynchronize(st));
     *max_n_out = maxn;
@@ -1338,9 +1329,10 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     if (stats_cap < 0) stats_cap = 0;
     const bool need_tc = (p->affinity_impl == 1) && !d_W_dense;
     const bool feats = (p->theta != 0.0 && d_tarl) || (p->gamma != 0.0 && d_dino);
-    pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && feats && !(h->xflags & 256);   // ANCUTS_X bit 8: one-kernel affinity
-    pl.deferred = pl.want_pairq && (h->xflags & 262144);       // bit 18: W written block by block after the root split
-    pl.grid_pairs = pl.deferred && (h->xflags & 524288);       // bit 19: pairs from a cell grid instead of the tile sweep
+    const int aform = h->opt[ANCUTS_OPT_AFFINITY_FORM];        // 0 deferred (default), 1 dense two-pass, 2 dense one-kernel
+    pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && feats && aform != 2;
+    pl.deferred = pl.want_pairq && aform == 0;                 // W written block by block after the root split
+    pl.grid_pairs = pl.deferred && h->opt[ANCUTS_OPT_PAIR_SEARCH] == 1;     // pairs from a cell grid instead of the tile sweep
     if (pl.grid_pairs) ANCUTS_CUDA(cudaFuncSetAttribute(k_pair_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PG_CELLS * sizeof(int))));
     bool root_forest = pl.want_pairq;
     bool deferred = pl.deferred;
@@ -1354,7 +1346,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     pl.e.dbg = h->dbg;
     pl.e.pts = d_W_dense ? nullptr : d_points;
     pl.e.w_guard = 0;                         // every node block is written by k_gather_blocks_cur (fringe zeroed)
-    pl.e.xf = d_W_dense ? (h->xflags & ~2) : h->xflags;    // caller-provided weights may be negative or denormal
+    pl.e.w_own = d_W_dense ? 0 : 1;           // caller-provided weights may be negative or denormal: plain widening
     pl.e.stats = (h_stats && stats_cap > 0) ? pl.stats : nullptr;
     pl.e.stats_cap = stats_cap;
     rc = set_attrs(h, pl.KS);
@@ -1412,6 +1404,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     if (rc) return rc;
     rc = copy_stats(h, pl, h_stats, stats_cap, h_num_stats, st);
     if (rc) return rc;
+    h->last_unconverged = h->h_ctr[16];        // counted by k_decide, read back by copy_stats
     return end_accounting(h, pl.e, st);
 }
 

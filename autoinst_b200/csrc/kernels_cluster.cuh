@@ -5,10 +5,11 @@
 //
 // The C CTAs of a cluster own C row slices of the node's block.  Per step:
 //   matvec of the slice (W streamed from L2/HBM, z = S v for the whole node in shared memory),
-//   classical Gram-Schmidt twice against u1 = D^1/2 1 and every Lanczos vector: each CTA forms the
-//   partial dots over its slice, the partials are exchanged through distributed shared memory
-//   (cluster barrier, then every CTA sums the C partials in rank order, so all CTAs hold bit-identical
-//   alpha/beta and take identical decisions), three cluster barriers per step.
+//   the three-term recurrence (alpha comes out of the matvec epilogue), then ONE classical Gram-Schmidt pass
+//   against u1 = D^1/2 1 and every Lanczos vector: each CTA forms the partial dots over its slice, the
+//   partials are exchanged through distributed shared memory (cluster barrier, then every CTA sums the C
+//   partials in rank order, so all CTAs hold bit-identical alpha/beta and take identical decisions); the
+//   squared norm is accumulated by the update pass.  Three cluster barriers and four block barriers per step.
 // Every sum is float64 and evaluated in a fixed order: results do not depend on scheduling.
 #pragma once
 #include <cooperative_groups.h>
@@ -23,14 +24,11 @@ constexpr int CL_KMAX = 256;             // steps the cluster kernel can take; n
 constexpr int CL_KS = CL_KMAX + 4;
 constexpr int CL_RPMAX = 512;            // rows per CTA (two per thread)
 constexpr int CL_NMAX = 4096;            // largest node handled here (8 CTAs x 512 rows)
-#ifndef ANCUTS_CL_THREADS
-#define ANCUTS_CL_THREADS 512
-#endif
-constexpr int CL_THREADS = ANCUTS_CL_THREADS;    // 512 (default) or 1024 (-DANCUTS_CL_THREADS=1024: 64 registers per thread)
+constexpr int CL_THREADS = 512;          // 1024 threads (64 registers, 2 KB ring stages) measured 9 % slower
 constexpr int CL_WARPS = CL_THREADS / 32;
 constexpr int CL_HALF = CL_THREADS / 2;     // shifts per eigenvalue and bisection round
 constexpr int CL_CLASSES = 6;            // node size bins (kernels_graph.cuh::cluster_class); cluster sizes 1, 2, 4, 8
-constexpr int CL_DYN_SMEM = 190 * 1024;  // z for the whole node + as many basis rows of the slice as fit
+constexpr int CL_DYN_SMEM = 195 * 1024;  // z for the whole node + as many basis rows of the slice as fit
                                          // (one CTA per SM; 256 threads x 2 CTAs per SM measured 25 % slower)
 
 struct ClusterShared {
@@ -39,13 +37,13 @@ struct ClusterShared {
     double spart[4];             // at the end: partial (sum, min, max, sum of squares) of the Ritz vector
     double hs[CL_KS];            // reduced projection coefficients
     double alpha[CL_KS], beta[CL_KS];
-    double be2[CL_KS], dd[CL_KS], du[CL_KS], du2[CL_KS], dl[CL_KS], yv[CL_KS];
-    double ysl[CL_RPMAX];        // this CTA's slice of the current vector
+    double be2[CL_KS], dd[CL_KS], yv[CL_KS];
+    double ysl[2][CL_RPMAX];     // this CTA's slice of the current vector (ping) and of the matvec result (pong)
+    double wred[CL_WARPS];       // per-warp partials of the fused reductions (alpha in the matvec, norm in the update)
     double sv[CL_RPMAX];         // D^-1/2 of the slice
     double red[32];
     double bounds[4];
     double gb[3];
-    int swp[CL_KS];
     int cnts[CL_THREADS];
     long long tmark;             // debug phase clock: end of the multisection rounds inside cluster_tridiag
     double prev_res;             // adaptive check schedule: residual estimate and step of the last check
@@ -246,25 +244,23 @@ struct SliceBasis {
     }
 };
 
-// partial dots of the slice vector with basis rows [0, rows): S.hpart[buf][j].  One warp per row,
-// up to 10 loads per lane in flight (nr <= CL_RPMAX = 10 * 32 + ...).
-__device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const SliceBasis& B, int rows, int nr, int buf) {
+// partial dots of the slice vector y with basis rows [0, rows): S.hpart[buf][j].  One warp per row,
+// all loads of a row in flight at once (nr <= CL_RPMAX = 16 * 32).
+__device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const double* __restrict__ y, const SliceBasis& B,
+                                                int rows, int nr, int buf) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int M = (CL_RPMAX + 31) / 32;
-    constexpr int MH = (CL_THREADS > 512) ? M / 2 : M;          // 1024 threads: 64 registers, two halves of 8
-    for (int j = warp; j < rows; j += CL_THREADS / 32) {
+    double yr[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { int i = lane + 32 * m; yr[m] = (i < nr) ? y[i] : 0.0; }
+    for (int j = warp; j < rows; j += CL_WARPS) {
         const double* vr = B.row(j);
+        double t[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) { int i = lane + 32 * m; t[m] = (i < nr) ? vr[i] : 0.0; }
         double s = 0.0;
 #pragma unroll
-        for (int h = 0; h < M; h += MH) {
-            double t[MH], yr[MH];
-#pragma unroll
-            for (int m = 0; m < MH; ++m) { int i = lane + 32 * (h + m); t[m] = (i < nr) ? vr[i] : 0.0; }
-#pragma unroll
-            for (int m = 0; m < MH; ++m) { int i = lane + 32 * (h + m); yr[m] = (i < nr) ? S.ysl[i] : 0.0; }
-#pragma unroll
-            for (int m = 0; m < MH; ++m) s += t[m] * yr[m];
-        }
+        for (int m = 0; m < M; ++m) s += t[m] * yr[m];
         s = warp_sum(s);
         if (lane == 0) S.hpart[buf][j] = s;
     }
@@ -285,28 +281,41 @@ __device__ __forceinline__ void cl_reduce_h(cg::cluster_group& cl, ClusterShared
     __syncthreads();
 }
 
-// slice -= sum_j hs[j] V[j][slice]
-__device__ __forceinline__ void cl_update(ClusterShared& S, const SliceBasis& B, int rows, int nr) {
+// y_i -= sum_j hs[j] V[j][i] for the slice; returns this thread's share of |y|^2 (the norm rides on the update pass)
+__device__ __forceinline__ double cl_update_norm(ClusterShared& S, double* __restrict__ y, const SliceBasis& B, int rows, int nr) {
+    double q = 0.0;
     for (int i = threadIdx.x; i < nr; i += CL_THREADS) {
-        double y = S.ysl[i];
+        double v = y[i];
         int j = 0;
         for (; j + 8 <= rows; j += 8) {
             double t[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) t[u] = B.row(j + u)[i];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) y -= S.hs[j + u] * t[u];
+            for (int u = 0; u < 8; ++u) v -= S.hs[j + u] * t[u];
         }
-        for (; j < rows; ++j) y -= S.hs[j] * B.row(j)[i];
-        S.ysl[i] = y;
+        for (; j < rows; ++j) v -= S.hs[j] * B.row(j)[i];
+        y[i] = v;
+        q = fma(v, v, q);
     }
+    return q;
+}
+
+// sum over the CTA of one value per thread: warp partials in S.wred, ONE block barrier, fixed order
+__device__ __forceinline__ double cl_block_sum1(ClusterShared& S, double v) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) S.wred[threadIdx.x >> 5] = v;
     __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < CL_WARPS; ++i) t += S.wred[i];
+    return t;
 }
 
 // float -> double widening on the integer pipe, for weights in {0} U [2^-126, 2): the bits move 29 places and the
 // exponent is re-biased; +0 becomes 2^-127 (5.9e-39), which every later float64 sum absorbs exactly.
 // cvt.f64.f32 runs on the XU pipe at 4 lanes per clock and scheduler: ncu shows it half busy during the matvec and
-// the warps waiting on it, so in the MIX variants every second element is widened with three integer instructions.
+// the warps waiting on it, so in the MIX variant every second element is widened with three integer instructions.
 __device__ __forceinline__ double widen_int(float f) {
     const unsigned b = __float_as_uint(f);
     return __hiloint2double((int)((b >> 3) + 0x38000000u), (int)(b << 29));
@@ -314,59 +323,21 @@ __device__ __forceinline__ double widen_int(float f) {
 template <bool MIX>
 __device__ __forceinline__ double widen_alt(float f) { return MIX ? widen_int(f) : (double)f; }
 
-// y_slice = S (w + I) z * invb for the rows [r0, r0+nr) of the node.  MODE 0: entries outside the block are
-// selected away (they may be uninitialised).  MODE 1/2: the caller guarantees that the <= 3 columns on either
-// side of the block hold finite values (k_gather_blocks_cur zeroes them) and zs is zero there.
-// L2 prefetch of one row segment (16-byte aligned, size a multiple of 16): one instruction, no registers, no barrier.
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
-}
-
-// Rows of the passes [pass0, pass0 + npass) of this warp (2 rows per pass, CL_WARPS * 2 rows apart): lane l asks for
-// row l of that list.  Issued `pf` passes ahead of their use, so the matvec loads below find W in L2 although the
-// node blocks of a large batch stream from HBM (ncu, batch 64: L2 hit rate 12 %, long-scoreboard stalls on the loads).
-__device__ __forceinline__ void cl_prefetch_rows(const NodeView& v, int r0, int nr, int pass0, int npass, bool lanes = false) {
+// ---- guarded matvec (MODE 0, stage entry points on the caller's W): register-staged loads, entries outside the block
+// are selected away (they may be uninitialised or belong to other nodes).
+// yout_i = s_i * invb * (sum_j w_ij z_j + z_i) for the rows [r0, r0+nr); returns (lane 0) the warp's share of
+// alpha = v . (M v), v_i = yin_i * invb.
+__device__ __forceinline__ double cl_matvec_guard(ClusterShared& S, const double* zs, const double* __restrict__ yin,
+                                                  double* __restrict__ yout, const NodeView& v, int r0, int nr, int pad,
+                                                  double invb) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int a0 = v.ro & ~3;
-    if (lanes) {
-        // per-lane form: lane l asks for the 128-byte line l, l + 32, ... of each row (LSU path instead of the bulk engine)
-        const int lines = (((v.ro + v.n - a0) * 4) + 127) >> 7;
-        for (int p = pass0; p < pass0 + npass; ++p) {
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                const int row = warp * 2 + p * (CL_WARPS * 2) + rr;
-                if (row < nr) {
-                    const char* rp = reinterpret_cast<const char*>(v.W + (size_t)(v.ro + r0 + row) * v.ld + a0);
-                    for (int l = lane; l < lines; l += 32)
-                        asm volatile("prefetch.global.L2 [%0];" :: "l"(rp + (size_t)l * 128));
-                }
-            }
-        }
-        return;
-    }
-    if (lane < 2 * npass) {
-        const int row = warp * 2 + (pass0 + (lane >> 1)) * (CL_WARPS * 2) + (lane & 1);
-        if (row < nr) {
-            const unsigned bytes = (unsigned)(((v.ro + v.n - a0) + 3) & ~3) * 4u;
-            l2_prefetch_bulk(v.W + (size_t)(v.ro + r0 + row) * v.ld + a0, bytes);
-        }
-    }
-}
-
-template <int MODE>
-__device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, const NodeView& v, int r0, int nr,
-                                          int pad, double invb, int pf, bool pfl) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = v.n;
-    const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
-    int pass = 0;
-    for (int rb = warp * 2; rb < nr; rb += (CL_THREADS / 32) * 2, ++pass) {
-        if (pf > 0) cl_prefetch_rows(v, r0, nr, pass + pf, 1, pfl);
+    const int c_lo = v.ro, c_hi = v.ro + v.n, a0 = c_lo & ~3;
+    double pa = 0.0;
+    for (int rb = warp * 2; rb < nr; rb += CL_WARPS * 2) {
         const float* rpt[2];
 #pragma unroll
-        for (int rr = 0; rr < 2; ++rr)
-            rpt[rr] = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld;
-        double acc[2] = {0.0, 0.0}, acb[2] = {0.0, 0.0};
+        for (int rr = 0; rr < 2; ++rr) rpt[rr] = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld;
+        double acc[2] = {0.0, 0.0};
         for (int c = a0 + lane * 4; c < c_hi; c += 512) {
             float4 w[2][4];
 #pragma unroll
@@ -374,8 +345,7 @@ __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, co
                 const int cg_ = c + 128 * g;
                 const bool has = cg_ < c_hi;
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-                    w[rr][g] = has ? ld_stream4(rpt[rr] + cg_) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int rr = 0; rr < 2; ++rr) w[rr][g] = has ? ld_stream4(rpt[rr] + cg_) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -383,51 +353,44 @@ __device__ __forceinline__ void cl_matvec(ClusterShared& S, const double* zs, co
                 if (cg_ < c_hi) {
                     const double2 z0 = *reinterpret_cast<const double2*>(&zs[cg_ - a0]);
                     const double2 z1 = *reinterpret_cast<const double2*>(&zs[cg_ - a0 + 2]);
-                    if (MODE == 0) {
-                        const bool v0 = (cg_ >= c_lo), v1 = (cg_ + 1 >= c_lo) & (cg_ + 1 < c_hi);
-                        const bool v2 = (cg_ + 2 >= c_lo) & (cg_ + 2 < c_hi), v3 = (cg_ + 3 >= c_lo) & (cg_ + 3 < c_hi);
+                    const bool v0 = (cg_ >= c_lo), v1 = (cg_ + 1 >= c_lo) & (cg_ + 1 < c_hi);
+                    const bool v2 = (cg_ + 2 >= c_lo) & (cg_ + 2 < c_hi), v3 = (cg_ + 3 >= c_lo) & (cg_ + 3 < c_hi);
 #pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            // entries outside the block belong to other nodes or are uninitialised: select them away
-                            double q0 = (v0 ? (double)w[rr][g].x : 0.0) * z0.x + (v1 ? (double)w[rr][g].y : 0.0) * z0.y;
-                            double q1 = (v2 ? (double)w[rr][g].z : 0.0) * z1.x + (v3 ? (double)w[rr][g].w : 0.0) * z1.y;
-                            acc[rr] += q0 + q1;
-                        }
-                    } else {
-                        // two FMA chains per row: one FP64 instruction per element instead of 1.5
-                        constexpr bool MIX = (MODE == 5);
-#pragma unroll
-                        for (int rr = 0; rr < 2; ++rr) {
-                            acc[rr] = fma((double)w[rr][g].x, z0.x, acc[rr]);
-                            acb[rr] = fma(widen_alt<MIX>(w[rr][g].y), z0.y, acb[rr]);
-                            acc[rr] = fma((double)w[rr][g].z, z1.x, acc[rr]);
-                            acb[rr] = fma(widen_alt<MIX>(w[rr][g].w), z1.y, acb[rr]);
-                        }
+                    for (int rr = 0; rr < 2; ++rr) {
+                        double q0 = (v0 ? (double)w[rr][g].x : 0.0) * z0.x + (v1 ? (double)w[rr][g].y : 0.0) * z0.y;
+                        double q1 = (v2 ? (double)w[rr][g].z : 0.0) * z1.x + (v3 ? (double)w[rr][g].w : 0.0) * z1.y;
+                        acc[rr] += q0 + q1;
                     }
                 }
             }
         }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            double t = warp_sum(MODE != 0 ? acc[rr] + acb[rr] : acc[rr]);
-            int i = rb + rr;
-            if (lane == 0 && i < nr) S.ysl[i] = S.sv[i] * invb * (t + zs[r0 + i + pad]);   // (w + I) z
+            const double t = warp_sum(acc[rr]);
+            const int i = rb + rr;
+            if (lane == 0 && i < nr) {
+                const double yn = S.sv[i] * invb * (t + zs[r0 + i + pad]);      // (w + I) z
+                yout[i] = yn;
+                pa = fma(yin[i] * invb, yn, pa);
+            }
         }
     }
+    return pa;
 }
 
-// ---- TMA-fed matvec (MODE 4): every warp owns a ring of RING_ST stages in shared memory; a stage holds up to
+// ---- TMA-fed matvec (MODE 4 / 6): every warp owns a ring of RING_ST stages in shared memory; a stage holds up to
 // RING_COLS columns of the warp's two current rows (4 KB).  Lane 0 issues one bulk copy per row and stage
 // (cp.async.bulk, completion counted on the stage's mbarrier); the warp waits for the stage, multiplies it with z
-// from shared memory and hands the slot back.  Registers limit the plain form to 4 KB per warp in flight and only
-// in bursts (issue 8 loads, wait, multiply: ncu puts 32 % of the kernel's stall samples on the first use of the
+// from shared memory and hands the slot back.  Registers limit a register-staged form to 4 KB per warp in flight and
+// only in bursts (issue 8 loads, wait, multiply: ncu put 32 % of that kernel's stall samples on the first use of the
 // loaded registers); the ring keeps 4-8 KB per warp in flight all the time.  It takes the shared memory that held
-// basis rows: Gram-Schmidt then reads the basis from L2, which costs far less than the matvec gains.
+// basis rows: Gram-Schmidt then reads the basis from L2, which costs less than the matvec gains.
 // W does not change between steps, so the first stages of the NEXT matvec are fetched during Gram-Schmidt.
-// (A first version with 1 KB stages, 4 per warp, was 20 % slower than the plain form: the per-stage wait / issue
-// overhead has to be spread over more data.)
+// The blocks come from k_gather_blocks_cur / k_zero_blocks, which zero the <= 3-column fringe of every block, and
+// zs is zero there: no selects.  (Measured and dropped, DESIGN.md 5a: 1 KB stages x 4, register-staged loads with L2
+// bulk prefetch, per-lane prefetch, L2 prefetch of the next matvec's stages, all loads of a stage hoisted.)
 constexpr int RING_ST = 2;
-constexpr int RING_COLS = (CL_THREADS > 512) ? 256 : 512;   // floats per row and stage
+constexpr int RING_COLS = 512;                               // floats per row and stage
 constexpr int RING_STAGE_FLOATS = 2 * RING_COLS;
 constexpr int RING_WARP_FLOATS = RING_ST * RING_STAGE_FLOATS;
 constexpr int RING_BYTES = CL_WARPS * RING_WARP_FLOATS * 4;      // 128 KB
@@ -472,14 +435,17 @@ __device__ __forceinline__ void ring_drain(const RingGeom& q, uint64_t* bars_w, 
     for (int t = 0; t < min(RING_ST, q.T); ++t) mbarrier_wait(bars_w + ((g + t) % RING_ST), ((g + t) / RING_ST) & 1u);
 }
 
+// returns (lane 0) the warp's share of alpha = v . (M v), v_i = yin_i * invb
 template <bool MIX>
-__device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* zs, const NodeView& v, const RingGeom& q,
-                                               int r0, int nr, int pad, double invb, float* ring_w, uint64_t* bars_w,
-                                               uint32_t& g, int npf) {
+__device__ __forceinline__ double cl_matvec_ring(ClusterShared& S, const double* zs, const double* __restrict__ yin,
+                                                 double* __restrict__ yout, const NodeView& v, const RingGeom& q,
+                                                 int r0, int nr, int pad, double invb, float* ring_w, uint64_t* bars_w,
+                                                 uint32_t& g) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int ip = 0, isg = 0;                               // next stage to issue = stage t + RING_ST
     for (int t = 0; t < min(RING_ST, q.T); ++t) if (++isg == q.nseg) { isg = 0; ++ip; }
     int t = 0;
+    double pa = 0.0;
     for (int p = 0; p < q.npass; ++p) {
         double acc0 = 0.0, acb0 = 0.0, acc1 = 0.0, acb1 = 0.0;
         for (int sg = 0; sg < q.nseg; ++sg, ++t) {
@@ -492,20 +458,16 @@ __device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* z
                 acc1 = fma((double)wb.x, z0.x, acc1); acb1 = fma(widen_alt<MIX>(wb.y), z0.y, acb1);
                 acc1 = fma((double)wb.z, z1.x, acc1); acb1 = fma(widen_alt<MIX>(wb.w), z1.y, acb1);
             };
-            {
-                // (hoisting all sixteen shared-memory loads of a full stage in front of the conversions, without the per-group
-                //  predicate, was measured 3 % slower: more live registers, no better overlap)
 #pragma unroll
-                for (int gq = 0; gq < RING_COLS / 128; ++gq) {
-                    const int cs = 128 * gq + 4 * lane;                // column inside the stage
-                    const int cofs = sg * RING_COLS + cs;              // column - a0
-                    if (cofs < q.width) {
-                        const float4 wa = *reinterpret_cast<const float4*>(buf + cs);
-                        const float4 wb = *reinterpret_cast<const float4*>(buf + RING_COLS + cs);
-                        const double2 z0 = *reinterpret_cast<const double2*>(&zs[cofs]);
-                        const double2 z1 = *reinterpret_cast<const double2*>(&zs[cofs + 2]);
-                        fma8(wa, wb, z0, z1);
-                    }
+            for (int gq = 0; gq < RING_COLS / 128; ++gq) {
+                const int cs = 128 * gq + 4 * lane;                // column inside the stage
+                const int cofs = sg * RING_COLS + cs;              // column - a0
+                if (cofs < q.width) {
+                    const float4 wa = *reinterpret_cast<const float4*>(buf + cs);
+                    const float4 wb = *reinterpret_cast<const float4*>(buf + RING_COLS + cs);
+                    const double2 z0 = *reinterpret_cast<const double2*>(&zs[cofs]);
+                    const double2 z1 = *reinterpret_cast<const double2*>(&zs[cofs + 2]);
+                    fma8(wa, wb, z0, z1);
                 }
             }
             __syncwarp();
@@ -518,32 +480,29 @@ __device__ __forceinline__ void cl_matvec_ring(ClusterShared& S, const double* z
         const int rb = warp * 2 + p * (CL_WARPS * 2);
         const double t0 = warp_sum(acc0 + acb0), t1 = warp_sum(acc1 + acb1);
         if (lane == 0) {
-            S.ysl[rb] = S.sv[rb] * invb * (t0 + zs[r0 + rb + pad]);               // (w + I) z
-            if (rb + 1 < nr) S.ysl[rb + 1] = S.sv[rb + 1] * invb * (t1 + zs[r0 + rb + 1 + pad]);
+            const double y0 = S.sv[rb] * invb * (t0 + zs[r0 + rb + pad]);               // (w + I) z
+            yout[rb] = y0;
+            pa = fma(yin[rb] * invb, y0, pa);
+            if (rb + 1 < nr) {
+                const double y1 = S.sv[rb + 1] * invb * (t1 + zs[r0 + rb + 1 + pad]);
+                yout[rb + 1] = y1;
+                pa = fma(yin[rb + 1] * invb, y1, pa);
+            }
         }
     }
     ring_prologue(v, q, r0, nr, ring_w, bars_w, g);
-    // The stages right behind the prologue of the NEXT matvec are asked into L2 now (lane l: stage RING_ST + l), so
-    // HBM keeps streaming for this SM while it is busy with Gram-Schmidt, norms and checks (40 % of a step).
-    {
-        const int tn = RING_ST + lane;
-        if (lane < npf && tn < q.T) {
-            const int p = tn / q.nseg, sg = tn - p * q.nseg;
-            const int rb = warp * 2 + p * (CL_WARPS * 2);
-            const int c = sg * RING_COLS;
-            const unsigned bytes = (unsigned)min(RING_COLS, q.width - c) * 4u;
-            l2_prefetch_bulk(v.W + (size_t)(v.ro + r0 + min(rb, nr - 1)) * v.ld + q.a0 + c, bytes);
-            if (rb + 1 < nr) l2_prefetch_bulk(v.W + (size_t)(v.ro + r0 + rb + 1) * v.ld + q.a0 + c, bytes);
-        }
-    }
+    return pa;
 }
 
-// grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot
+// grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot.
+// MODE 0: guarded register-staged matvec (caller's W read in place); 4: TMA ring; 6: TMA ring + integer widening of
+// every second element (weights in {0} U [2^-126, 2): the library's own affinities).
 template <int C, int MODE>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) {
     extern __shared__ __align__(16) double zs[];   // z = S v for the whole node on the 16-byte window of W's columns;
-                                                   // behind it: the first rows of the basis, restricted to this CTA's slice
+                                                   // behind it: the warps' W rings, then the first rows of the basis,
+                                                   // restricted to this CTA's slice
     __shared__ ClusterShared S;
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (C > 1) ? (int)cl.block_rank() : 0;
@@ -557,23 +516,23 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     const size_t P = (size_t)e.P;
     const int g0 = v.start + r0;                       // global position of the slice
     const int pad = v.ro & 3;                          // zs[j + pad] <-> column v.ro + j
+    constexpr bool RING = (MODE == 4 || MODE == 6);
+    const int nz = (n + 8 + 3) & ~3;                   // doubles used by zs
     SliceBasis B;
     {
-        const int nz = (n + 8 + 3) & ~3;               // doubles used by zs
         B.nrp = (max(nr, 1) + 3) & ~3;
-        const int nring = (MODE == 4 || MODE == 6) ? RING_BYTES / 8 : 0;       // the warps' W rings sit between z and the basis rows
+        const int nring = RING ? RING_BYTES / 8 : 0;
         B.smem = zs + nz + nring;
-        B.rows_s = (e.xf & 4096) ? 0 : max(0, (dyn_doubles - nz - nring) / B.nrp);     // bit 12: basis in global memory only
+        B.rows_s = max(0, (dyn_doubles - nz - nring) / B.nrp);
         B.glob = e.V + g0;
         B.P = P;
     }
     const int kcap = min(min(CL_KMAX, e.kmax), n - 1);
     __shared__ uint64_t ring_bar[CL_WARPS * RING_ST];
-    float* ring_w = reinterpret_cast<float*>(zs + ((n + 8 + 3) & ~3)) + (size_t)warp * RING_WARP_FLOATS;
+    float* ring_w = reinterpret_cast<float*>(zs + nz) + (size_t)warp * RING_WARP_FLOATS;
     uint64_t* bars_w = ring_bar + warp * RING_ST;
     const RingGeom rq = ring_geom(v, nr);
     uint32_t ring_g = 0;                               // stages consumed by this warp so far
-    constexpr bool RING = (MODE == 4 || MODE == 6);
     if (RING) {
         if (lane == 0) {
             for (int i = 0; i < RING_ST; ++i) mbarrier_init(bars_w + i, 1);
@@ -604,11 +563,13 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         zs[i] = z;
     }
     double bprev = sqrt(block_sum_512(s, S.red));
+    double* yc = S.ysl[0];                               // current (unnormalised) Lanczos vector of the slice
+    double* yn = S.ysl[1];                               // matvec result, orthogonalised in place
     for (int i = tid; i < nr; i += CL_THREADS) {
         int j = r0 + i;
         double u = sqrt(e.deg[v.start + j]) * ivol;
         B.row(0)[i] = u;                                 // basis row 0 = u1
-        S.ysl[i] = sv0.at(v.start + j, j) - dot * u;
+        yc[i] = sv0.at(v.start + j, j) - dot * u;
         S.sv[i] = e.sinv[v.start + j];
     }
     __syncthreads();
@@ -616,125 +577,84 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     int k = 0;
     int conv = 0;
     double th[2] = {0.0, 0.0};
-    const bool adapt = e.check_adapt && (e.xf & 16384);
+    const bool adapt = e.check_adapt != 0;
     if (tid == 0) { S.prev_res = 1.0; S.prev_k = 0; S.next_check = adapt ? CL_CHECK_FIRST : e.check_every; }
-    // optional phase clock (debug): cycles of thread 0 between the block-wide syncs that end each phase
-    constexpr bool CL_PROF = (CL_THREADS <= 512);      // the 1024-thread build has no registers to spare for the clocks
-    const bool prof = CL_PROF && (e.dbg != nullptr) && tid == 0 && rank == 0;
+    // optional phase clock (debug): cycles of thread 0 of rank 0 between the block-wide syncs that end each phase
+    // (a barrier's wait is charged to the phase AFTER it: BAR.SYNC does not block at issue)
+    const bool prof = (e.dbg != nullptr) && tid == 0 && rank == 0;
     long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = prof ? clock64() : 0;
 #define CL_PHASE(i) do { if (prof) { long long t_ = clock64(); tph[i] += t_ - tlast; tlast = t_; } } while (0)
-    const bool gs1 = (e.xf & 1024) != 0;              // three-term recurrence + one Gram-Schmidt pass
-    const int pf = (e.xf >> 4) & 3;                   // passes of L2 prefetch distance (0 = off)
-    const bool pfl = (e.xf & 2048) != 0;               // per-lane prefetch.global.L2 instead of the bulk form
-    if (pf > 0 && !RING) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);
     while (true) {
         const double invb = 1.0 / bprev;
-        // basis row k+1 = current vector (slice)
-        for (int i = tid; i < nr; i += CL_THREADS) B.row(k + 1)[i] = S.ysl[i] * invb;
-        __syncthreads();
+        // basis row k+1 = current vector (slice).  The matvec below only reads yc and writes yn: no barrier in between.
+        double* vk = B.row(k + 1);
+        for (int i = tid; i < nr; i += CL_THREADS) vk[i] = yc[i] * invb;
         CL_PHASE(0);
-        // ---- matvec of the slice: 2 rows per warp, 512 columns per iteration, 8 loads issued first ----
-        if (RING) {
-            cl_matvec_ring<MODE == 6>(S, zs, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g, 4 * pf);
-        } else {
-            cl_matvec<MODE>(S, zs, v, r0, nr, pad, invb, pf, pfl);
-            if (pf > 0) cl_prefetch_rows(v, r0, nr, 0, pf, pfl);  // first passes of the next step: in flight during Gram-Schmidt
-        }
+        // ---- matvec of the slice; alpha = v_k . (M v_k) rides on its epilogue ----
+        double pa;
+        if (RING) pa = cl_matvec_ring<MODE == 6>(S, zs, yc, yn, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g);
+        else pa = cl_matvec_guard(S, zs, yc, yn, v, r0, nr, pad, invb);
+        if (lane == 0) S.wred[warp] = pa;
         __syncthreads();
         CL_PHASE(1);
-        const int rows = k + 2;
-        double a1, a2;
-        if (gs1) {
-            // ---- three-term recurrence first, then ONE classical Gram-Schmidt pass against u1 and every Lanczos
-            //      vector.  In exact arithmetic w - alpha v_k - beta v_{k-1} is already orthogonal to the basis, so the
-            //      full pass only removes rounding-level components and plays the role of the SECOND pass of "twice is
-            //      enough": orthogonality stays at 2e-15 like CGS2 (numpy model, 151 nodes, identical steps and cuts),
-            //      with two sweeps over the basis instead of four.  A single CGS pass WITHOUT the three-term part
-            //      loses orthogonality within dozens of steps (measured in round 1 and again in the model). ----
-            const double* vk = B.row(k + 1);
-            double pa = 0.0;
-            for (int i = tid; i < nr; i += CL_THREADS) pa += vk[i] * S.ysl[i];
-            pa = block_sum_512(pa, S.red);
-            if (tid == 0) S.npart[1] = pa;
-            __syncthreads();
-            cl_sync<C>(cl);
-            a1 = 0.0;
-            if (C > 1) {
+        double a1 = 0.0;
 #pragma unroll
-                for (int r = 0; r < C; ++r) a1 += cl.map_shared_rank(&S.npart[0], r)[1];      // rank order
-            } else {
-                a1 = S.npart[1];
-            }
-            {
-                const double bk = (k > 0) ? S.beta[k - 1] : 0.0;
-                const double* vp = B.row(k);                                                // v_{k-1} (u1 when k = 0: bk = 0)
-                for (int i = tid; i < nr; i += CL_THREADS) S.ysl[i] = (S.ysl[i] - a1 * vk[i]) - bk * vp[i];
-            }
-            __syncthreads();
-            CL_PHASE(2);
-            CL_PHASE(3);
-            cl_partial_dots(S, B, rows, nr, 1);
-            __syncthreads();
-            cl_sync<C>(cl);
-            cl_reduce_h<C>(cl, S, rows, 1);
-            a2 = S.hs[rows - 1];
-            __syncthreads();
-            CL_PHASE(4);
-            cl_update(S, B, rows, nr);
-            CL_PHASE(5);
-        } else {
-        // ---- classical Gram-Schmidt against u1 and every Lanczos vector, always twice ("twice is enough").
-        cl_partial_dots(S, B, rows, nr, 0);
-        __syncthreads();
-        cl_sync<C>(cl);
-        cl_reduce_h<C>(cl, S, rows, 0);
-        a1 = S.hs[rows - 1];
+        for (int i = 0; i < CL_WARPS; ++i) a1 += S.wred[i];
+        if (C > 1) {
+            if (tid == 0) S.npart[1] = a1;
+            cl.sync();
+            a1 = 0.0;
+#pragma unroll
+            for (int r = 0; r < C; ++r) a1 += cl.map_shared_rank(&S.npart[0], r)[1];      // rank order
+        }
+        const int rows = k + 2;
+        // ---- three-term recurrence first, then ONE classical Gram-Schmidt pass against u1 and every Lanczos
+        //      vector.  In exact arithmetic w - alpha v_k - beta v_{k-1} is already orthogonal to the basis, so the
+        //      full pass only removes rounding-level components and plays the role of the SECOND pass of "twice is
+        //      enough": orthogonality stays at 2e-15 like CGS2 (numpy model, 151 nodes, identical steps and cuts),
+        //      with two sweeps over the basis instead of four.  A single CGS pass WITHOUT the three-term part
+        //      loses orthogonality within dozens of steps (measured in round 1 and again in the model). ----
+        {
+            const double bk = (k > 0) ? S.beta[k - 1] : 0.0;
+            const double* vp = B.row(k);                                                // v_{k-1} (u1 when k = 0: bk = 0)
+            for (int i = tid; i < nr; i += CL_THREADS) yn[i] = (yn[i] - a1 * vk[i]) - bk * vp[i];   // own elements of vk, vp
+        }
         __syncthreads();
         CL_PHASE(2);
-        cl_update(S, B, rows, nr);
-        CL_PHASE(3);
-        cl_partial_dots(S, B, rows, nr, 1);
-        __syncthreads();
+        cl_partial_dots(S, yn, B, rows, nr, 1);
         cl_sync<C>(cl);
         cl_reduce_h<C>(cl, S, rows, 1);
-        a2 = S.hs[rows - 1];
-        __syncthreads();
+        const double a2 = S.hs[rows - 1];
         CL_PHASE(4);
-        cl_update(S, B, rows, nr);
+        // ---- update, squared norm, z = S y for the next matvec ----
+        double q = cl_update_norm(S, yn, B, rows, nr);
+        if (C > 1) { for (int i = tid; i < nr; i += CL_THREADS) e.zbuf[g0 + i] = S.sv[i] * yn[i]; }
+        else { for (int i = tid; i < nr; i += CL_THREADS) zs[i + pad] = S.sv[i] * yn[i]; }
+        q = cl_block_sum1(S, q);
         CL_PHASE(5);
-        }
-        // ---- norm, publication of z = S y for the next matvec ----
-        double q = 0.0;
-        for (int i = tid; i < nr; i += CL_THREADS) q += S.ysl[i] * S.ysl[i];
-        q = block_sum_512(q, S.red);
-        if (tid == 0) S.npart[0] = q;
-        if (C > 1) for (int i = tid; i < nr; i += CL_THREADS) e.zbuf[g0 + i] = S.sv[i] * S.ysl[i];
-        __syncthreads();
-        cl_sync<C>(cl);
-        double nn = 0.0;
+        double nn = q;
         if (C > 1) {
+            if (tid == 0) S.npart[0] = q;
+            cl.sync();
+            nn = 0.0;
 #pragma unroll
             for (int r = 0; r < C; ++r) nn += cl.map_shared_rank(&S.npart[0], r)[0];
-        } else {
-            nn = S.npart[0];
+            // z of the whole node.  (Through global memory: a CTA reads its peers' slices from L2 at ~64 B/clk, distributed
+            // shared memory moves 17-21 B/clk per SM, B300_MICROARCH.md; the cluster barrier above orders the two sides.)
+            for (int i = tid; i < n; i += CL_THREADS) zs[i + pad] = __ldcg(e.zbuf + v.start + i);
         }
         const double beta = sqrt(nn);
         if (tid == 0) { S.alpha[k] = a1 + a2; S.beta[k] = beta; }
         bprev = beta;
         k += 1;
-        // refill z for the whole node
-        if (C > 1) {
-            for (int i = tid; i < n; i += CL_THREADS) zs[i + pad] = __ldcg(e.zbuf + v.start + i);
-        } else {
-            for (int i = tid; i < nr; i += CL_THREADS) zs[i + pad] = S.sv[i] * S.ysl[i];
-        }
+        { double* t_ = yc; yc = yn; yn = t_; }
         __syncthreads();
         CL_PHASE(6);
         const bool breakdown = beta < 1e-13;
         if (breakdown || k >= kcap || k == S.next_check) {
-            double res = cluster_tridiag(S, k, th, (e.xf & 32768) != 0, (e.xf & 65536) ? CL_HALF / 2 : CL_HALF);
-            if (prof && gs1) { tph[3] += S.tmark - tlast; tlast = S.tmark; }     // slot 3 (unused with gs1): multisection part of the check
+            double res = cluster_tridiag(S, k, th, true, CL_HALF / 2);
+            if (prof) { tph[3] += S.tmark - tlast; tlast = S.tmark; }     // slot 3: multisection part of the check
             double gap = fmax(th[0] - th[1], 1e-300);
             bool c1 = (k >= n - 1) || breakdown || (res <= e.tol * gap);
             if (c1) { conv = 1; break; }
@@ -779,7 +699,6 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         double mn = block_min_512(xmn, S.red);
         double mx = -block_min_512(-xmx, S.red);
         if (tid == 0) { S.spart[0] = sm_; S.spart[1] = mn; S.spart[2] = mx; S.spart[3] = sq; }
-        __syncthreads();
         cl_sync<C>(cl);
         if (rank == 0 && tid == 0) {
             double ts = 0.0, tmn = 1e300, tmx = -1e300, tq = 0.0;

@@ -30,7 +30,7 @@ struct StartVec {
     const double* deg;
     double o0, o1, o2;
     __device__ __forceinline__ StartVec(const Eng& e, int chunk, int start) {
-        base = ((e.xf & 131072) && e.pts) ? e.pts + (size_t)e.c_base[chunk] * 3 : nullptr;
+        base = e.pts ? e.pts + (size_t)e.c_base[chunk] * 3 : nullptr;
         perm = e.perm;
         deg = e.deg;
         o0 = o1 = o2 = 0.0;

@@ -12,6 +12,14 @@
 
 namespace ancuts {
 
+// Fixed-point exponent of a node's cut sums from its volume (sum of degrees >= twice the total weight): 2^-40 steps
+// unless the running sums could leave 62 bits (caller-provided w with weights far above 1, or a huge
+// PROXIMITY_THRESHOLD); then fewer fraction bits.  Every CTA of k_scan and k_decide derive the same value.
+__device__ __forceinline__ int fix_shift(double vol) {
+    const int e = ilogb(fmax(vol, 1.0));                 // vol < 2^(e+1)
+    return min(FIX_SHIFT, 61 - e);
+}
+
 // one thread per active node: sign (sum(ev) >= 0, the oracle's canonical sign), min/max,
 // np.allclose(mn, mx) (normalized_cut.py:22-23), thresholds exactly as np.linspace(endpoint=False)
 // computes them (k*step + mn with separate roundings), and accumulator reset.
@@ -91,13 +99,28 @@ k_bucket(Eng e) {
 __global__ void __launch_bounds__(256)
 k_scan(Eng e, int cur) {
     __shared__ unsigned long long sdiff[NB + 1];
+    __shared__ double svol[NB];
+    __shared__ double sscale;
     int a = blockIdx.y;
     if (e.a_nocut[a]) return;
     NodeView v = node_view(e, e.a_rid[a], cur);
     int row0 = blockIdx.x * 8;
     if (row0 >= v.n) return;
     if (threadIdx.x <= NB) sdiff[threadIdx.x] = 0ull;
+    if (threadIdx.x < NB) {                        // volume per bucket, chunk slots in order (as k_decide)
+        const int s0 = e.a_slot0[a], nch = e.a_nch[a];
+        double t = 0.0;
+        for (int ch = 0; ch < nch; ++ch) t += e.p_vol[(size_t)(s0 + ch) * NB + threadIdx.x];
+        svol[threadIdx.x] = t;
+    }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int b = 0; b < NB; ++b) t += svol[b];
+        sscale = ldexp(1.0, fix_shift(t));
+    }
+    __syncthreads();
+    const double fscale = sscale;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int row = row0 + warp;
     if (row < v.n) {
@@ -116,7 +139,7 @@ k_scan(Eng e, int cur) {
                     int bj = bkt[cc];
                     if (bj != bi) {
                         int lo = min(bi, bj), hi = max(bi, bj);
-                        long long q = __double2ll_rn((double)in[k] * FIX_SCALE);
+                        long long q = __double2ll_rn((double)in[k] * fscale);
                         atomicAdd(&sdiff[lo], (unsigned long long)q);
                         atomicAdd(&sdiff[hi], (unsigned long long)(-q));
                     }
@@ -148,10 +171,13 @@ __global__ void k_decide(Eng e, int num_active) {
         for (int b = 0; b < NB; ++b) vol[b] = 0.0;
         for (int ch = 0; ch < nch; ++ch)
             for (int b = 0; b < NB; ++b) vol[b] += e.p_vol[(size_t)(s0 + ch) * NB + b];
+        double vtot = 0.0;
+        for (int b = 0; b < NB; ++b) vtot += vol[b];
+        const double unfix = ldexp(1.0, -fix_shift(vtot));
         long long run = 0;
         for (int k = 0; k < NCUT; ++k) {
             run += (long long)e.a_diff[a * (NB + 1) + k];
-            double cut = (double)run * (1.0 / FIX_SCALE);
+            double cut = (double)run * unfix;
             double assoc_b = 0.0, assoc_a = 0.0;
             for (int b = 0; b <= k; ++b) assoc_b += vol[b];          // mask false: ev <= t_k
             for (int b = k + 1; b < NB; ++b) assoc_a += vol[b];       // mask true
@@ -179,6 +205,7 @@ __global__ void k_decide(Eng e, int num_active) {
     } else {
         e.r_status[r] = ST_LEAF;
     }
+    if (!e.a_conv[a]) atomicAdd(&e.ctr[16], 1);      // stopped at lanczos_max_steps: reported by every segment call
     if (e.stats != nullptr) {
         int s = atomicAdd(&e.ctr[6], 1);
         if (s < e.stats_cap) {

@@ -9,9 +9,15 @@ the C ABI `ancuts_feature_pool`.  There is no CPU fallback.
 """
 import numpy as np
 
+import warnings
+
 try:                                            # cwd = pipeline/ in the reference layout
     from config import MAJOR_VOXEL_SIZE, CHUNK_SIZE, TARL_NORM      # config.py:56,57,64
-except Exception:                               # stand-alone use: the shipped values
+except ModuleNotFoundError as _e:               # stand-alone use ONLY: the shipped values; any other failure of config.py
+    if _e.name != "config":                     # propagates (a wrong cwd must not silently change the parameters)
+        raise
+    warnings.warn("autoinst_b200.pooling: no `config` module on sys.path; using MAJOR_VOXEL_SIZE 0.35, CHUNK_SIZE 25, "
+                  "TARL_NORM False", RuntimeWarning)
     MAJOR_VOXEL_SIZE = 0.35
     CHUNK_SIZE = np.array([25, 25, 25])
     TARL_NORM = False
@@ -19,7 +25,7 @@ except Exception:                               # stand-alone use: the shipped v
 
 def transform_points(coords, T):
     """`transform_pcd` (point_cloud_utils.py:24-35, Open3D `transform`): rigid 4 x 4 transform of n x 3 points."""
-    coords = np.asarray(coords, dtype=np.float64)
+    coords = np.asarray(coords, dtype=np.float64)[:, :3]        # raw KITTI scans are n x 4 (get_pcd(points[:, :3]), :24-35)
     T = np.asarray(T, dtype=np.float64)
     return coords @ T[:3, :3].T + T[:3, 3]
 

@@ -30,7 +30,7 @@ extern "C" {
 #define ANCUTS_EINVAL       -1   /* bad argument */
 #define ANCUTS_ECUDA        -2   /* CUDA runtime error (message holds cudaGetErrorString) */
 #define ANCUTS_ENOMEM       -3   /* workspace allocation failed */
-#define ANCUTS_ENOTCONV     -4   /* reserved: non-convergence is reported per node, not as an error */
+#define ANCUTS_ENOTCONV     -4   /* reserved; non-convergence is counted per call: ancuts_last_unconverged() */
 #define ANCUTS_EUNSUPPORTED -5   /* e.g. beta != 0 (SAM term, ncuts_utils.py:115-123) */
 
 #define ANCUTS_NUM_CUTS 10       /* normalized_cut.py:54 calls get_min_ncut(ev, D, w, 10) */
@@ -169,6 +169,24 @@ int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, 
                         const double* d_scan_points, const float* d_scan_feat, int feat_dim, double radius,
                         const double* h_box_min, const double* h_box_max, int normalise, double* d_out,
                         int32_t* d_out_count, void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* Eigensolver nodes of the handle's last segment call (ancuts_segment_chunks / _host / _dense_f32) that stopped at
+ * lanczos_max_steps without meeting the residual test.  Their cut used the unconverged Ritz vector; the reference's
+ * eigsh (normalized_cut.py:49) raises ArpackNoConvergence in that situation, so callers must look at this count
+ * (the Python drop-in raises, the array-level API warns). */
+int ancuts_last_unconverged(ancuts_handle* h);
+
+/* Alternative implementations behind the same results (each one parity-tested; defaults = 0):
+ *   ANCUTS_OPT_AFFINITY_FORM  0 deferred (pairs queued, W written block by block after the root split),
+ *                             1 dense two-pass (pairs + feature pass on the full N x N matrix), 2 dense one-kernel
+ *   ANCUTS_OPT_PAIR_SEARCH    0 upper-triangle tile sweep, 1 cell grid (deferred form only)
+ *   ANCUTS_OPT_MATVEC         0 dense blocks streamed from HBM every Lanczos step (north-star form),
+ *                             1 the cluster's row slices compressed into shared memory once per node */
+#define ANCUTS_OPT_AFFINITY_FORM 0
+#define ANCUTS_OPT_PAIR_SEARCH   1
+#define ANCUTS_OPT_MATVEC        2
+#define ANCUTS_OPT_COUNT         3
+int ancuts_set_option(ancuts_handle* h, int option, int value);
 
 /* Counters for bench.py: kernels launched by this handle since the last reset, and the per-kernel
  * CUDA-event time of the kernels named by ancuts_timing_select(). */

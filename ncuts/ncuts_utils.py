@@ -14,9 +14,15 @@ import os
 
 import numpy as np
 
+import warnings
+
 try:                                            # cwd = pipeline/ in the reference layout (config.py:79)
     from config import *                        # noqa: F401,F403  CONFIG, PROXIMITY_THRESHOLD, SPLIT_LIM, ...
-except Exception:                               # stand-alone use: the shipped defaults (config.py:17-26,55-73)
+except ModuleNotFoundError as _e:               # stand-alone use ONLY (no `config` module at all): the shipped defaults
+    if _e.name != "config":                     # (config.py:17-26,55-73); a config.py that fails for any other reason
+        raise                                   # (e.g. wrong cwd for its yaml, config.py:79) must not be papered over
+    warnings.warn("ncuts.ncuts_utils: no `config` module on sys.path; using the shipped config_tarl_spatial defaults",
+                  RuntimeWarning)
     CONFIG = {"name": "spatial_1.0_tarl_0.5_t_0.03", "out_folder": "ncuts_data_tarl_spatial/", "gamma": 0.0,
               "alpha": 1.0, "theta": 0.5, "beta": 0.0, "T": 0.03, "gt": True}
     PROXIMITY_THRESHOLD = 1.0
@@ -48,7 +54,8 @@ def segment_major_points(points_major, tarl_features=None, dino_features=None, c
     seg = api.segment_chunk(points_major, tarl_features if cfg["theta"] else None, dino,
                             alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"], T=cfg["T"],
                             proximity=PROXIMITY_THRESHOLD if proximity is None else proximity,
-                            split_lim=SPLIT_LIM if split_lim is None else split_lim)
+                            split_lim=SPLIT_LIM if split_lim is None else split_lim,
+                            strict=True)        # non-convergence raises, as the reference's eigsh would
     if return_labels:
         return seg
     order = np.argsort(seg, kind="stable")

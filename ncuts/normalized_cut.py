@@ -39,7 +39,7 @@ def normalized_cut(w, num_points_orig, labels, T=0.01, split_lim=0.01):
     if n == 0:
         return [labels]
     seg = api.segment_dense(_to_device_matrix(w), num_points_orig=int(num_points_orig), T=float(T),
-                            split_lim=float(split_lim))
+                            split_lim=float(split_lim), strict=True)      # raises AncutsNoConvergence like eigsh
     order = np.argsort(seg, kind="stable")
     bounds = np.flatnonzero(np.diff(seg[order])) + 1
     return [labels[idx] for idx in np.split(order, bounds)]

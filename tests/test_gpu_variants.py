@@ -1,7 +1,5 @@
-"""GPU tests of the kernel variants behind the same C ABI: two-pass affinity and its overflow fallback, the
-Lanczos matvec / Gram-Schmidt variants (ANCUTS_X, read when a handle is created), the per-level trace."""
-import os
-
+"""GPU tests of the alternative implementations behind the same C ABI (ancuts_set_option): affinity forms and the
+pair-queue overflow fallback, pair search, matvec forms; non-convergence reporting; the per-level trace."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -20,18 +18,12 @@ def _api():
     return api
 
 
-def variant_lane(dev, flags, lane):
-    """A library handle created with ANCUTS_X=flags (its own workspace), addressed by `lane`."""
+def variant_lane(dev, options, lane):
+    """A library handle of its own (`lane`) with the given ancuts_set_option values."""
     api = _api()
-    old = os.environ.get("ANCUTS_X")
-    os.environ["ANCUTS_X"] = str(flags)
-    try:
-        api.Handle.get(dev, lane)
-    finally:
-        if old is None:
-            del os.environ["ANCUTS_X"]
-        else:
-            os.environ["ANCUTS_X"] = old
+    hd = api.Handle.get(dev, lane)
+    for opt, val in options.items():
+        hd.set_option(opt, val)
     return lane
 
 
@@ -43,16 +35,11 @@ def check_affinity(W, A):
     assert np.array_equal(W, W.T)
 
 
-# ANCUTS_X bits (engine.cu): 2 = integer widening of every second element, 32 = L2 prefetch two passes ahead, 256 = one-kernel
-# affinity, 1024 = three-term + one Gram-Schmidt pass, 4096 = basis rows in global memory only, 8192 = TMA ring,
-# 16384 = adaptive convergence checks, 32768 = division-free Sturm counts, 65536 = 128 shifts per round,
-# 131072 = start vector from the coordinates, 262144 = deferred affinity (W written block by block after the root split),
-# 524288 = pairs of the deferred affinity from a cell grid instead of the tile sweep.
-S3 = 2 | 1024 | 8192 | 16384 | 32768 | 65536 | 131072
-VARIANTS = {"session3_default": S3 | 262144, "session3_grid_pairs": S3 | 262144 | 524288, "session3_dense_affinity": S3, "session3_prefetch_next_matvec": S3 | 262144 | 16,
-            "session3_hash_start_256_shifts": 2 | 1024 | 8192 | 16384 | 32768 | 262144,
-            "default": 2 | 1024 | 8192, "one_kernel_affinity": 2 | 1024 | 8192 | 256, "register_matvec_prefetch": 2 | 32 | 1024,
-            "register_matvec_cgs2": 0, "ring_cgs2": 8192, "basis_in_global": 2 | 1024 | 8192 | 4096}
+# include/autoinst_ncuts.h: ANCUTS_OPT_AFFINITY_FORM 0 (0 deferred, 1 dense two-pass, 2 dense one-kernel),
+# ANCUTS_OPT_PAIR_SEARCH 1 (0 tile sweep, 1 cell grid), ANCUTS_OPT_MATVEC 2 (0 dense from HBM, 1 shared-memory slices)
+AFF, PAIRS, MATVEC = 0, 1, 2
+VARIANTS = {"default": {}, "grid_pairs": {PAIRS: 1}, "dense_two_pass_affinity": {AFF: 1}, "one_kernel_affinity": {AFF: 2},
+            "smem_sparse_matvec": {MATVEC: 1}, "smem_sparse_matvec_grid_pairs": {MATVEC: 1, PAIRS: 1}}
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
@@ -64,12 +51,62 @@ def test_variants_give_oracle_labels(cuda_device, variant):
     packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"])
     res = api.segment_packed(packed, device=cuda_device, lane=lane, alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"],
                              want_stats=True)
-    assert int((res.stats["converged"] == 0).sum()) == 0
+    assert int((res.stats["converged"] == 0).sum()) == 0 and res.unconverged == 0
     for ch, lab in zip(chunks, res.labels):
         A = affinity_ref(ch.points, ch.tarl, None, alpha=cfg["alpha"], theta=cfg["theta"])
         with R.pinned_eigsh():
             g = R.normalized_cut_ref(sp.csr_matrix(A), ch.n, np.arange(ch.n), T=cfg["T"])
         assert R.same_partition(lab, R.labels_from_groups(g, ch.n)), variant
+
+
+def test_non_convergence_is_never_silent(cuda_device):
+    """Nodes that stop at lanczos_max_steps are counted by every segment call: the array level warns, `strict`
+    (what the drop-in `ncuts` package passes) raises, as the reference's eigsh would."""
+    api = _api()
+    from autoinst_b200._lib import AncutsNoConvergence
+    cfg = CONFIGS["tarl_spatial"]
+    ch = make_chunk(310, n_target=1500, features="tarl")
+    kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"], device=cuda_device, max_steps=4)
+    with pytest.warns(RuntimeWarning, match="without converging"):
+        res = api.segment_chunks([ch.points], [ch.tarl], want_stats=True, **kw)
+    assert res.unconverged > 0 and res.unconverged == int((res.stats["converged"] == 0).sum())
+    with pytest.raises(AncutsNoConvergence):
+        api.segment_chunk(ch.points, ch.tarl, strict=True, **kw)
+    A = affinity_ref(ch.points, ch.tarl, None, alpha=cfg["alpha"], theta=cfg["theta"])
+    import ncuts.normalized_cut as NC
+    with pytest.raises(AncutsNoConvergence):
+        api.segment_dense(torch.as_tensor(A, dtype=torch.float32, device=cuda_device), T=cfg["T"], max_steps=4, strict=True)
+    assert len(NC.normalized_cut(sp.csr_matrix(A), ch.n, np.arange(ch.n), T=cfg["T"])) > 1      # default limit: converges
+    res = api.segment_chunks([ch.points], [ch.tarl], alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"], device=cuda_device)
+    assert res.unconverged == 0
+
+
+def test_cut_sums_do_not_overflow_on_heavy_weights(cuda_device):
+    """Caller-provided w with weights far above 1: the fixed-point cut sums scale with the node's volume
+    (2^-40 steps would overflow int64 beyond a cut weight of 2^23)."""
+    api = _api()
+    rng = np.random.default_rng(3)
+    n = 600
+    w = np.zeros((n, n))
+    half = n // 2
+    for lo, hi in ((0, half), (half, n)):
+        blk = rng.uniform(2e4, 6e4, size=(hi - lo, hi - lo))
+        w[lo:hi, lo:hi] = (blk + blk.T) / 2
+    link = rng.uniform(1.0, 2.0, size=(half, n - half)) * (rng.random((half, n - half)) < 0.02)
+    w[:half, half:] = link
+    w[half:, :half] = link.T
+    np.fill_diagonal(w, 1.0)
+    w = w.astype(np.float32).astype(np.float64)
+    with R.pinned_eigsh():
+        g = R.normalized_cut_ref(sp.csr_matrix(w), n, np.arange(n), T=0.01)
+    ref = R.labels_from_groups(g, n)
+    assert len(set(ref.tolist())) == 2
+    got, stats = api.segment_dense(torch.as_tensor(w, dtype=torch.float32, device=cuda_device), T=0.01, want_stats=True)
+    assert R.same_partition(got, ref)
+    top = stats[stats["n"] == n][0]
+    cut = w[:half, half:].sum()
+    volA, volB = w[:half].sum() + half, w[half:].sum() + (n - half)
+    assert abs(top["mcut"] - (cut / volA + cut / volB)) <= 1e-6 * top["mcut"]
 
 
 @pytest.mark.parametrize("name", ["tarl_spatial", "tarl_spatial_dino"])

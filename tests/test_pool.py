@@ -78,6 +78,9 @@ def test_host_side_transform_and_fail_loudly_without_gpu():
     pts = rng.normal(size=(50, 3))
     hom = (T @ np.concatenate([pts, np.ones((50, 1))], axis=1).T).T
     assert np.allclose(transform_points(pts, T), hom[:, :3], rtol=0, atol=1e-14)
+    # raw KITTI scans are n x 4 (x, y, z, remission): the reference slices points[:, :3] (point_cloud_utils.py:24-35)
+    pts4 = np.concatenate([pts, rng.random((50, 1))], axis=1)
+    assert np.array_equal(transform_points(pts4, T), transform_points(pts, T))
     if torch.cuda.is_available():
         return
 
