@@ -24,6 +24,8 @@ EXPORTS = [
     "ancuts_launch_count", "ancuts_last_accounting", "ancuts_set_stage_timing", "ancuts_nn_reproject",
     "ancuts_last_levels", "ancuts_debug_phases", "ancuts_feature_pool_workspace_bytes", "ancuts_feature_pool",
     "ancuts_last_unconverged", "ancuts_set_option",
+    "ancuts_merge_chunks", "ancuts_remove_semantics", "ancuts_instance_metrics", "ancuts_map_labels",
+    "ancuts_last_sparse_accounting",
 ]
 
 # ancuts_set_option (include/autoinst_ncuts.h)
@@ -67,7 +69,7 @@ _lib = None
 
 def build(verbose: bool = False) -> str:
     """Compile the CUDA sources for sm_100a into autoinst_b200/lib (nvcc cross-compiles without a GPU)."""
-    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j", "4", "-C", CSRC], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout)
         print(r.stderr)
@@ -122,6 +124,11 @@ def load():
     lib.ancuts_debug_phases.argtypes = [vp, dp, C.c_int]
     lib.ancuts_last_unconverged.argtypes = [vp]
     lib.ancuts_set_option.argtypes = [vp, C.c_int, C.c_int]
+    lib.ancuts_merge_chunks.argtypes = [vp, C.c_int, i64p, vp, vp, dp, C.c_double, C.c_double, vp, vp, i64p, vp]
+    lib.ancuts_last_sparse_accounting.argtypes = [vp, dp]
+    lib.ancuts_map_labels.argtypes = [vp, C.c_int, i64p, vp, C.c_int, vp, vp]
+    lib.ancuts_remove_semantics.argtypes = [vp, C.c_int64, vp, vp, C.c_double, vp, vp]
+    lib.ancuts_instance_metrics.argtypes = [vp, C.c_int64, vp, vp, vp, C.c_int, dp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("ancuts_version",):

@@ -60,6 +60,12 @@ class Handle:
         OPT_MATVEC (0 dense blocks from HBM, 1 slices compressed into shared memory)."""
         check(self.lib.ancuts_set_option(self.h, int(option), int(value)))
 
+    def sparse_accounting(self) -> dict:
+        """Shared-memory sparse matvec form, last segment call: sum of steps x stored entries, stored entries."""
+        b = (C.c_double * 2)()
+        check(self.lib.ancuts_last_sparse_accounting(self.h, b))
+        return {"entry_steps": b[0], "entries": b[1]}
+
     def last_unconverged(self) -> int:
         return int(self.lib.ancuts_last_unconverged(self.h))
 
@@ -301,6 +307,139 @@ def feature_pool(major_points, scan_points, scan_features, radius, box_min, box_
 
 
 # ------------------------------------------------------------------------------------------------
+# map level: merge (N2), remove_semantics, instance metrics (N4)
+# ------------------------------------------------------------------------------------------------
+METRIC_KEYS = ("p", "r", "f1", "ap", "ap0.25", "ap0.5", "S_assoc")     # sequence_stats, metrics_class.py:262-269
+
+
+def _as_i32_labels(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32).contiguous()
+    a = np.asarray(x)
+    if a.size and (a.min() < -2 ** 31 or a.max() >= 2 ** 31):
+        raise ValueError("labels must fit int32")
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+
+
+def merge_chunks(chunks, *, crop_side=40.0, min_iou=0.01, device=None, return_device=False):
+    """merge_chunks_unite_instances2 (point_cloud_utils.py:387-491) on the device (C ABI `ancuts_merge_chunks`).
+    chunks: list of (points (n,3) float64, labels (n,) int, 0 = background) in file-name order.
+    Returns (merged points, merged labels) as numpy arrays (or device tensors with return_device)."""
+    device = _dev(device)
+    hd = Handle.get(device)
+    sizes = [int(np.asarray(p).shape[0]) if not isinstance(p, torch.Tensor) else int(p.shape[0]) for p, _ in chunks]
+    off = np.zeros(len(sizes) + 1, dtype=np.int64)
+    off[1:] = np.cumsum(sizes)
+    # chunk centres with the reference's own expression (column means of the chunk's points, :397-403)
+    centers = np.stack([np.array([np.asarray(p)[:, 0].mean(), np.asarray(p)[:, 1].mean(), np.asarray(p)[:, 2].mean()])
+                        if not isinstance(p, torch.Tensor) else p.double().cpu().numpy().mean(axis=0) for p, _ in chunks])
+    pts = torch.cat([_as_dev(p, torch.float64, device).reshape(-1, 3) for p, _ in chunks])
+    lab = torch.cat([_as_i32_labels(l, device).reshape(-1) for _, l in chunks])
+    out_lab, idx, kept = _merge_device(hd, off, pts, lab, centers, crop_side / 2.0, min_iou, device)
+    mp, ml = pts[idx[:kept]], out_lab[idx[:kept]]
+    if return_device:
+        return mp, ml
+    return mp.cpu().numpy(), ml.cpu().numpy().astype(np.int64)
+
+
+def _merge_device(hd, off, pts, lab, centers, half_side, min_iou, device):
+    P = int(off[-1])
+    out_lab = torch.empty(P, dtype=torch.int32, device=device)
+    idx = torch.empty(P, dtype=torch.int64, device=device)
+    kept = C.c_int64(0)
+    off = np.ascontiguousarray(off, dtype=np.int64)
+    centers = np.ascontiguousarray(centers, dtype=np.float64)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_merge_chunks(hd.h, len(off) - 1, off.ctypes.data_as(C.POINTER(C.c_int64)), _ptr(pts), _ptr(lab),
+                                         centers.ctypes.data_as(C.POINTER(C.c_double)), float(half_side), float(min_iou),
+                                         _ptr(out_lab), _ptr(idx), C.byref(kept), _stream(device)))
+    return out_lab, idx, int(kept.value)
+
+
+def remove_semantics(gt_labels, pred_labels, threshold=0.8, device=None, return_device=False):
+    """remove_semantics (point_cloud_utils.py:253-287): predicted labels with more than `threshold` of their points on
+    GT background become 0 (C ABI `ancuts_remove_semantics`)."""
+    device = _dev(device)
+    hd = Handle.get(device)
+    gt = _as_i32_labels(gt_labels, device)
+    pr = _as_i32_labels(pred_labels, device)
+    out = torch.empty_like(pr)
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_remove_semantics(hd.h, int(pr.numel()), _ptr(gt), _ptr(pr), float(threshold), _ptr(out),
+                                             _stream(device)))
+    return out if return_device else out.cpu().numpy().astype(np.int64)
+
+
+def instance_metrics(all_labels, pred_labels, gt_labels, min_points=200, device=None, full=False):
+    """Metrics(...).update_stats(all_labels, pred_labels, gt_labels) for a fresh Metrics object
+    (metrics_class.py:137-179; C ABI `ancuts_instance_metrics`).  Returns the dict of sequence_stats' keys."""
+    device = _dev(device)
+    hd = Handle.get(device)
+    a = _as_i32_labels(all_labels, device)
+    p = _as_i32_labels(pred_labels, device)
+    g = _as_i32_labels(gt_labels, device)
+    out = (C.c_double * 21)()
+    with torch.cuda.device(device):
+        check(hd.lib.ancuts_instance_metrics(hd.h, int(p.numel()), _ptr(a), _ptr(p), _ptr(g), int(min_points), out,
+                                             _stream(device)))
+    if out[8] == 0 or out[9] == 0:
+        raise ZeroDivisionError("no predicted or no ground-truth instances (metrics_class.py:325-326)")
+    res = {k: float(out[i]) for i, k in enumerate(METRIC_KEYS)}
+    if full:
+        res.update(tp=int(out[7]), n_pred=int(out[8]), n_gt=int(out[9]), ap_per_overlap=[float(out[10 + t]) for t in range(11)])
+    return res
+
+
+class MapPost:
+    """Everything after the per-chunk cuts of one map, on the device (run_pipeline.py:197-238): labels of all chunks ->
+    globally unique instance ids -> merge (N2) -> remove_semantics -> metrics (N4).  Set up once per map (points, GT
+    and the chunk table go to the device, the GT map is the de-duplicated concatenation, `merge_unite_gt`,
+    point_cloud_utils.py:320-329), then `merge_and_score` per labeling."""
+
+    def __init__(self, chunks, device=None, min_points=200, crop_side=40.0, min_iou=0.01, threshold=0.8):
+        self.device = _dev(device)
+        self.hd = Handle.get(self.device)
+        self.sizes = [int(c.n) for c in chunks]
+        self.off = np.zeros(len(chunks) + 1, dtype=np.int64)
+        self.off[1:] = np.cumsum(self.sizes)
+        self.centers = np.stack([np.array([c.points[:, 0].mean(), c.points[:, 1].mean(), c.points[:, 2].mean()]) for c in chunks])
+        self.pts = torch.as_tensor(np.concatenate([c.points for c in chunks]), dtype=torch.float64).to(self.device)
+        self.gt_all = _as_i32_labels(np.concatenate([c.instance for c in chunks]), self.device)
+        self.min_points, self.half, self.min_iou, self.threshold = int(min_points), crop_side / 2.0, float(min_iou), float(threshold)
+        self.keep = None
+
+    def global_labels(self, seg_flat):
+        """Per-chunk segment ids (concatenated, chunk order) -> ids unique across the map; segments are numbered by first
+        occurrence in point order inside every chunk, like oracle.merge_ref.canonical_labels + globally_unique (the
+        reference draws a random colour per segment; the greedy rules downstream depend on the order of the values).
+        C ABI `ancuts_map_labels`."""
+        seg = _as_i32_labels(seg_flat, self.device)
+        out = torch.empty_like(seg)
+        with torch.cuda.device(self.device):
+            check(self.hd.lib.ancuts_map_labels(self.hd.h, len(self.sizes), self.off.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                _ptr(seg), 20, _ptr(out), _stream(self.device)))
+        return out
+
+    def merge(self, seg_flat):
+        lab = self.global_labels(seg_flat)
+        out_lab, idx, kept = _merge_device(self.hd, self.off, self.pts, lab, self.centers, self.half, self.min_iou, self.device)
+        keep = idx[:kept]
+        if self.keep is None:
+            self.keep = keep
+            self.gt = self.gt_all[keep].contiguous()
+        return out_lab[keep].contiguous()
+
+    def merge_and_score(self, seg_flat):
+        """seg_flat: int32 segment ids of all chunks concatenated in chunk order (device or host).  Returns the metrics."""
+        merged = self.merge(seg_flat)
+        with torch.cuda.device(self.device):
+            inst = torch.empty_like(merged)
+            check(self.hd.lib.ancuts_remove_semantics(self.hd.h, int(merged.numel()), _ptr(self.gt), _ptr(merged),
+                                                      self.threshold, _ptr(inst), _stream(self.device)))
+        return instance_metrics(merged, inst, self.gt, min_points=self.min_points, device=self.device)
+
+
+# ------------------------------------------------------------------------------------------------
 # whole path
 # ------------------------------------------------------------------------------------------------
 @dataclass
@@ -398,19 +537,26 @@ class PackedChunks:
     def d2h_bytes(self):
         return self.labels.numel() * 4
 
-    def to_device(self, device):
+    def to_device(self, device, labels=None):
+        """Inputs resident in HBM.  `labels`: optional int32 device tensor the segment call writes into (e.g. the send
+        buffer of sharding.LabelGather, so that the gather needs no copy)."""
         device = _dev(device)
-        return DeviceChunks(self, device)
+        return DeviceChunks(self, device, labels)
 
 
 class DeviceChunks:
-    def __init__(self, packed: PackedChunks, device):
+    def __init__(self, packed: PackedChunks, device, labels=None):
         self.packed = packed
         self.device = device
         self.points = packed.points.to(device, non_blocking=True)
         self.tarl = packed.tarl.to(device, non_blocking=True) if packed.use_t else None
         self.dino = packed.dino.to(device, non_blocking=True) if packed.use_d else None
-        self.labels = torch.empty(int(packed.off[-1]), dtype=torch.int32, device=device)
+        total = int(packed.off[-1])
+        if labels is not None:
+            assert labels.dtype == torch.int32 and labels.is_contiguous() and labels.numel() >= total
+            self.labels = labels
+        else:
+            self.labels = torch.empty(total, dtype=torch.int32, device=device)
 
 
 def _run_segment(hd, fn_host, packed, dev_chunks, p, want_stats, device):

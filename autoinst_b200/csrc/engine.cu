@@ -30,44 +30,11 @@ int launch_affinity_tc(int n, const double* pts, const float* tarl, int tdim, co
                        float* W, long long ld, void* scratch, size_t scratch_bytes, cudaStream_t st);
 size_t affinity_tc_scratch_bytes(int n, int tdim, int ddim);
 
-struct TimedLaunch { int stage; cudaEvent_t a, b; int level = -1; };
-// one record per recursion level (timing mode 2): node counts per size bin and the time of the cluster phase
-struct LevelRec { int num_active, big; int cls[6]; int cmap[6]; double ms; };
-
 }  // namespace ancuts
 
-using namespace ancuts;
+#include "handle.cuh"
 
-struct ancuts_handle {
-    int device = 0;
-    char* ws = nullptr;
-    size_t ws_bytes = 0;
-    char* stage = nullptr;                   // device staging of host inputs / labels (host entry point)
-    size_t stage_cap = 0;
-    int* h_ctr = nullptr;                    // pinned, CTR_COUNT ints
-    cudaStream_t side[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // one per node size bin
-    cudaEvent_t ev_fork = nullptr;
-    cudaEvent_t ev_join[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    bool cluster16_ok = true;
-    unsigned long long* h_acct = nullptr;    // pinned, SG_COUNT
-    int64_t launches_total = 0;
-    int64_t stage_launches[SG_COUNT] = {0};
-    double stage_bytes[SG_COUNT] = {0};
-    double stage_ms[SG_COUNT] = {0};
-    int stage_timing = 0;                    // 0 off, 1 every launch, 2 matvec launches only
-    std::vector<TimedLaunch> timed;
-    std::vector<LevelRec> levels;
-    std::vector<cudaEvent_t> pool;
-    size_t pool_used = 0;
-    bool attrs_set = false;
-    // Code paths with more than one implementation behind the same results (ancuts_set_option; every one is parity-tested):
-    int opt[ANCUTS_OPT_COUNT] = {0, 0, 0};
-    int last_unconverged = 0;                // eigensolver nodes of the last segment call that stopped at lanczos_max_steps
-    cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
-    std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
-    const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
-    unsigned long long* dbg = nullptr;       // device, 32 entries: phase cycles of the cluster kernel (ANCUTS_PHASES=1)
-};
+using namespace ancuts;
 
 namespace ancuts {
 
@@ -160,7 +127,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     e.a_path = ar.take<int>(A);
     e.cl_ids = ar.take<int>((size_t)CL_CLASSES * A);
     e.active_cap = A;
-    e.acct = ar.take<unsigned long long>(SG_COUNT);
+    e.acct = ar.take<unsigned long long>(SG_ACCT);
     pl.stats = ar.take<ancuts_node_stat>(std::max(stats_cap, 1));
     pl.labels_scratch = ar.take<int>(P);
     pl.nseg = ar.take<int>(B);
@@ -276,9 +243,11 @@ static void begin_accounting(ancuts_handle* h) {
 }
 
 static int end_accounting(ancuts_handle* h, const Eng& e, cudaStream_t st) {
-    ANCUTS_CUDA(cudaMemcpyAsync(h->h_acct, e.acct, SG_COUNT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(h->h_acct, e.acct, SG_ACCT * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     ANCUTS_CUDA(cudaStreamSynchronize(st));
     for (int i = 0; i < SG_COUNT; ++i) h->stage_bytes[i] += (double)h->h_acct[i];
+    h->sparse_entry_steps = (double)h->h_acct[SG_SPARSE_STEPS];
+    h->sparse_nnz = (double)h->h_acct[SG_SPARSE_NNZ];
     for (auto& t : h->timed) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
@@ -300,6 +269,7 @@ static int set_attrs(ancuts_handle* h, int KS) {
     ANCUTS_CL_ATTR(1, 0); ANCUTS_CL_ATTR(2, 0); ANCUTS_CL_ATTR(4, 0); ANCUTS_CL_ATTR(8, 0);
     ANCUTS_CL_ATTR(1, 4); ANCUTS_CL_ATTR(2, 4); ANCUTS_CL_ATTR(4, 4); ANCUTS_CL_ATTR(8, 4);
     ANCUTS_CL_ATTR(1, 6); ANCUTS_CL_ATTR(2, 6); ANCUTS_CL_ATTR(4, 6); ANCUTS_CL_ATTR(8, 6);
+    ANCUTS_CL_ATTR(1, 7); ANCUTS_CL_ATTR(2, 7); ANCUTS_CL_ATTR(4, 7); ANCUTS_CL_ATTR(8, 7);
 #undef ANCUTS_CL_ATTR
     h->attrs_set = true;
     return ANCUTS_OK;
@@ -505,7 +475,8 @@ static inline int cluster_mode(const Eng& e) {
 }
 
 template <int C>
-static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s) {
+static cudaError_t launch_cluster(const Eng& e, int cur, const int* ids, int count, cudaStream_t s, bool sparse = false) {
+    if (sparse && cluster_mode(e) == 6) return launch_cluster_m<C, 7>(e, cur, ids, count, s);
     switch (cluster_mode(e)) {
         case 6: return launch_cluster_m<C, 6>(e, cur, ids, count, s);
         case 4: return launch_cluster_m<C, 4>(e, cur, ids, count, s);
@@ -529,9 +500,13 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
     // node do the same work with fewer cluster barriers.
     static const int c_latency[CL_CLASSES] = {1, 2, 2, 4, 8, 8};
     static const int c_throughput[CL_CLASSES] = {1, 1, 2, 2, 4, 8};
+    // shared-memory sparse form (ANCUTS_OPT_MATVEC = 1): slices of at most 256-320 rows, so that the CSR slice AND most of the
+    // basis fit the CTA's shared memory; nodes above 2048 points keep the dense form (their slices do not fit)
+    static const int c_sparse[CL_CLASSES] = {1, 2, 2, 4, 8, 8};
+    const bool sparse_on = h->opt[ANCUTS_OPT_MATVEC] == 1 && cluster_mode(e) == 6;
     int ctas = 0;
     for (int b = 0; b < CL_CLASSES; ++b) ctas += class_cnt[b] * c_latency[b];
-    const int* cmap = (ctas <= 148) ? c_latency : c_throughput;
+    const int* cmap = sparse_on ? c_sparse : (ctas <= 148) ? c_latency : c_throughput;
     for (int cls = CL_CLASSES - 1; cls >= 0; --cls) {          // largest nodes first
         int cnt = class_cnt[cls];
         if (cnt <= 0) continue;
@@ -541,11 +516,12 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
         cudaError_t err = cudaSuccess;
         {
             h->launches_total++;
+            const bool sp = sparse_on && cls < CL_CLASSES - 1;
             switch (cmap[cls]) {
-                case 1: err = launch_cluster<1>(e, cur, ids, cnt, s); break;
-                case 2: err = launch_cluster<2>(e, cur, ids, cnt, s); break;
-                case 4: err = launch_cluster<4>(e, cur, ids, cnt, s); break;
-                default: err = launch_cluster<8>(e, cur, ids, cnt, s); break;
+                case 1: err = launch_cluster<1>(e, cur, ids, cnt, s, sp); break;
+                case 2: err = launch_cluster<2>(e, cur, ids, cnt, s, sp); break;
+                case 4: err = launch_cluster<4>(e, cur, ids, cnt, s, sp); break;
+                default: err = launch_cluster<8>(e, cur, ids, cnt, s, sp); break;
             }
         }
         if (err != cudaSuccess) {                               // e.g. cluster size not schedulable: multi-launch path
@@ -829,7 +805,7 @@ int ancuts_create(int device, ancuts_handle** out) {
     }
     ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     ANCUTS_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_acct, SG_COUNT * sizeof(unsigned long long)));
+    ANCUTS_CUDA(cudaMallocHost((void**)&h->h_acct, SG_ACCT * sizeof(unsigned long long)));
     *out = h;
     return ANCUTS_OK;
 }
@@ -840,6 +816,8 @@ int ancuts_destroy(ancuts_handle* h) {
     if (h->ws) cudaFree(h->ws);
     if (h->stage) cudaFree(h->stage);
     if (h->dbg) cudaFree(h->dbg);
+    if (h->post_ws) cudaFree(h->post_ws);
+    if (h->h_post) cudaFreeHost(h->h_post);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto ev : h->copy_ev) cudaEventDestroy(ev);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -897,6 +875,13 @@ int ancuts_set_option(ancuts_handle* h, int option, int value) {
 }
 
 int ancuts_last_unconverged(ancuts_handle* h) { return h ? h->last_unconverged : ANCUTS_EINVAL; }
+
+int ancuts_last_sparse_accounting(ancuts_handle* h, double* out2) {
+    if (!h || !out2) return ANCUTS_EINVAL;
+    out2[0] = h->sparse_entry_steps;
+    out2[1] = h->sparse_nnz;
+    return ANCUTS_OK;
+}
 
 int ancuts_set_stage_timing(ancuts_handle* h, int on) {
     if (!h) return ANCUTS_EINVAL;
@@ -1074,7 +1059,7 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
     ANCUTS_CUDA(cudaMemcpyAsync(e.a_slot0, aslot.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
     ANCUTS_CUDA(cudaMemsetAsync(e.ctr, 0, 8 * sizeof(int), st));
     ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 16, 0, (CTR_COUNT - 16) * sizeof(int), st));
-    ANCUTS_CUDA(cudaMemsetAsync(e.acct, 0, SG_COUNT * sizeof(unsigned long long), st));
+    ANCUTS_CUDA(cudaMemsetAsync(e.acct, 0, SG_ACCT * sizeof(unsigned long long), st));
     ANCUTS_CUDA(cudaStreamSynchronize(st));
     *max_n_out = maxn;
     return ANCUTS_OK;
@@ -1352,7 +1337,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     rc = set_attrs(h, pl.KS);
     if (rc) return rc;
     begin_accounting(h);
-    ANCUTS_CUDA(cudaMemsetAsync(pl.e.acct, 0, SG_COUNT * sizeof(unsigned long long), st));
+    ANCUTS_CUDA(cudaMemsetAsync(pl.e.acct, 0, SG_ACCT * sizeof(unsigned long long), st));
     const int64_t off0 = h_chunk_off[0];
     if (d_W_dense) {
         ANCUTS_CUDA(cudaMemcpy2DAsync(pl.hW0[0], (size_t)pl.ld[0] * 4, d_W_dense, (size_t)ld_dense * 4, (size_t)n[0] * 4,

@@ -494,9 +494,72 @@ __device__ __forceinline__ double cl_matvec_ring(ClusterShared& S, const double*
     return pa;
 }
 
+// ---- shared-memory sparse matvec (MODE 7, ANCUTS_OPT_MATVEC = 1): W is 99.5 % zeros (27-66 stored entries per row
+// against n <= 4096 columns), yet the dense form streams every block from HBM once per Lanczos step.  Here the CTA reads
+// its row slice of the dense block TWICE at the start of the node (count, then fill) and keeps it as CSR in shared memory
+// (float32 value + uint16 column, rows in slice order, columns ascending) for all the steps: 8 n^2 bytes per node instead
+// of k (4 n^2 + 8 n).  No ring, so the basis rows get the shared memory the ring took.  Same float64 products; the sum of a
+// row is taken by four lanes over its entries round-robin and combined (l0 + l1) + (l2 + l3): a fixed order, but not
+// the dense kernels' order, so alpha/beta differ from the dense form in the last bits (parity is against the oracle).
+// A slice that does not fit (dense little nodes far above 100 entries per row) sends the node to the grid-wide path.
+struct SparseSlice {
+    const float* val; const unsigned short* col; const int* ptr; int nnz;
+};
+constexpr int SP_LANES = 4;
+
+// entries of row `rowp` inside the block's aligned window, counted (FILL = false) or written (FILL = true) by one warp
+template <bool FILL>
+__device__ __forceinline__ int sp_scan_row(const float* __restrict__ rowp, int a0, int c_lo, int c_hi, int lane,
+                                           float* val, unsigned short* col, int base) {
+    int total = 0;
+    for (int c = a0 + lane * 4; c - lane * 4 < c_hi; c += 128) {          // warp-uniform trip count
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < c_hi) w = ld_stream4(rowp + c);
+        const float in[4] = {w.x, w.y, w.z, w.w};
+        unsigned m = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) m |= (in[q] != 0.0f && c + q >= c_lo && c + q < c_hi) ? (1u << q) : 0u;
+        const int cnt = __popc(m);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (FILL) {
+            int pos = base + total + incl - cnt;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (m & (1u << q)) { val[pos] = in[q]; col[pos] = (unsigned short)(c + q - c_lo); ++pos; }
+        }
+        total += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    return total;
+}
+
+// returns (every lane) the thread's share of alpha = v . (M v), v_i = yin_i * invb; the caller reduces it over the warp
+__device__ __forceinline__ double cl_matvec_sparse(ClusterShared& S, const double* zs, const double* __restrict__ yin,
+                                                   double* __restrict__ yout, const SparseSlice& sp, int r0, int nr, int pad,
+                                                   double invb) {
+    const int tid = threadIdx.x, sub = tid & (SP_LANES - 1);
+    double pa = 0.0;
+    for (int base = 0; base < nr; base += CL_THREADS / SP_LANES) {         // warp-uniform loop: the shuffles need all lanes
+        const int i = base + tid / SP_LANES;
+        double acc = 0.0;
+        if (i < nr) {
+            const int b = sp.ptr[i], e = sp.ptr[i + 1];
+            for (int q = b + sub; q < e; q += SP_LANES) acc = fma((double)sp.val[q], zs[sp.col[q] + pad], acc);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (sub == 0 && i < nr) {
+            const double y = S.sv[i] * invb * (acc + zs[r0 + i + pad]);      // (w + I) z
+            yout[i] = y;
+            pa = fma(yin[i] * invb, y, pa);
+        }
+    }
+    return pa;
+}
+
 // grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot.
 // MODE 0: guarded register-staged matvec (caller's W read in place); 4: TMA ring; 6: TMA ring + integer widening of
-// every second element (weights in {0} U [2^-126, 2): the library's own affinities).
+// every second element (weights in {0} U [2^-126, 2): the library's own affinities); 7: row slice as CSR in shared memory.
 template <int C, int MODE>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) {
@@ -517,13 +580,67 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     const int g0 = v.start + r0;                       // global position of the slice
     const int pad = v.ro & 3;                          // zs[j + pad] <-> column v.ro + j
     constexpr bool RING = (MODE == 4 || MODE == 6);
+    constexpr bool SP = (MODE == 7);
     const int nz = (n + 8 + 3) & ~3;                   // doubles used by zs
+    SparseSlice sp;
+    sp.val = nullptr; sp.col = nullptr; sp.ptr = nullptr; sp.nnz = 0;
+    int sp_doubles = 0;
+    if (SP) {
+        // ---- build the CSR slice: count the entries per row, scan, fill (two passes over the slice) ----
+        const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
+        int* rowcnt = S.cnts;                          // free until the first convergence check
+        __shared__ int sp_wtot[CL_WARPS + 1];
+        for (int i = warp; i < nr; i += CL_WARPS) {
+            const int t = sp_scan_row<false>(v.W + (size_t)(v.ro + r0 + i) * v.ld, a0, c_lo, c_hi, lane, nullptr, nullptr, 0);
+            if (lane == 0) rowcnt[i] = t;
+        }
+        __syncthreads();
+        const int mine = (tid < nr) ? rowcnt[tid] : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) sp_wtot[warp] = incl;
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int w = 0; w < CL_WARPS; ++w) { int t = sp_wtot[w]; sp_wtot[w] = run; run += t; }
+            sp_wtot[CL_WARPS] = run;
+        }
+        __syncthreads();
+        const int total = sp_wtot[CL_WARPS];
+        int* ptr = reinterpret_cast<int*>(zs + nz);
+        const int ptr_d = (nr + 1 + 1) / 2;                                  // doubles
+        const int val_d = (total + 1) / 2, col_d = (total + 3) / 4;
+        sp_doubles = ptr_d + val_d + col_d;
+        double misfit = (nz + sp_doubles > dyn_doubles) ? 1.0 : 0.0;
+        if (C > 1) {                                                         // the whole cluster takes the same decision
+            if (tid == 0) S.npart[1] = misfit;
+            cl.sync();
+            misfit = 0.0;
+#pragma unroll
+            for (int r = 0; r < C; ++r) misfit += cl.map_shared_rank(&S.npart[0], r)[1];
+            cl.sync();                                                       // peers have read the flag: the slot is free again
+        }
+        if (misfit != 0.0) {
+            if (rank == 0 && tid == 0) { e.a_done[a] = DONE_NO; e.a_path[a] = 1; atomicAdd(&e.ctr[4], 1); }
+            return;                                                          // grid-wide path (kernels_lanczos.cuh)
+        }
+        float* val = reinterpret_cast<float*>(zs + nz + ptr_d);
+        unsigned short* col = reinterpret_cast<unsigned short*>(zs + nz + ptr_d + val_d);
+        if (tid < nr) ptr[tid] = sp_wtot[warp] + incl - mine;
+        if (tid == 0) ptr[nr] = total;
+        __syncthreads();
+        for (int i = warp; i < nr; i += CL_WARPS)
+            sp_scan_row<true>(v.W + (size_t)(v.ro + r0 + i) * v.ld, a0, c_lo, c_hi, lane, val, col, ptr[i]);
+        sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total;
+        __syncthreads();
+    }
     SliceBasis B;
     {
         B.nrp = (max(nr, 1) + 3) & ~3;
-        const int nring = RING ? RING_BYTES / 8 : 0;
-        B.smem = zs + nz + nring;
-        B.rows_s = max(0, (dyn_doubles - nz - nring) / B.nrp);
+        const int nfront = RING ? RING_BYTES / 8 : sp_doubles;              // the warps' W rings or the CSR slice sit in front
+        B.smem = zs + nz + nfront;
+        B.rows_s = max(0, (dyn_doubles - nz - nfront) / B.nrp);
         B.glob = e.V + g0;
         B.P = P;
     }
@@ -594,6 +711,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         // ---- matvec of the slice; alpha = v_k . (M v_k) rides on its epilogue ----
         double pa;
         if (RING) pa = cl_matvec_ring<MODE == 6>(S, zs, yc, yn, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g);
+        else if (SP) pa = warp_sum(cl_matvec_sparse(S, zs, yc, yn, sp, r0, nr, pad, invb));
         else pa = cl_matvec_guard(S, zs, yc, yn, v, r0, nr, pad, invb);
         if (lane == 0) S.wred[warp] = pa;
         __syncthreads();
@@ -717,7 +835,12 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             e.a_theta[2 * a + 1] = th[1];
             e.a_done[a] = DONE_YES;
             e.a_path[a] = 0;                    // Ritz vector and statistics are already in place
-            atomicAdd(&e.acct[SG_MATVEC], (unsigned long long)k * (4ull * n * n + 8ull * n));
+            if (!SP) atomicAdd(&e.acct[SG_MATVEC], (unsigned long long)k * (4ull * n * n + 8ull * n));
+        }
+        if (SP && tid == 0) {      // what this form really moves: the slice twice from HBM, then k sweeps over its entries
+            atomicAdd(&e.acct[SG_MATVEC], 8ull * (unsigned long long)nr * n);
+            atomicAdd(&e.acct[SG_SPARSE_STEPS], (unsigned long long)k * (unsigned long long)sp.nnz);
+            atomicAdd(&e.acct[SG_SPARSE_NNZ], (unsigned long long)sp.nnz);
         }
     } else if (rank == 0 && tid == 0) {
         e.a_done[a] = DONE_NO;                  // left for the multi-launch path (more steps)

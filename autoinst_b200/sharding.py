@@ -23,60 +23,104 @@ def shard_chunks(sizes, world_size: int):
     return [sorted(x) for x in out]
 
 
+class LabelGather:
+    """The label exchange of one map (or one benchmark batch), set up once and reused every pass.
+
+    The (chunk id, length) table of every rank is exchanged ONCE here (chunk sizes are known when the inputs are
+    packed, before anything is segmented).  A pass is then one `all_gather_into_tensor` from a persistent send
+    buffer into a persistent receive buffer and, on the destination rank(s) only, one asynchronous copy into a
+    pinned host buffer; the per-chunk results are VIEWS into that buffer (no per-chunk copies, no `.item()` syncs).
+    `send` (int32, device) is where the segment call should write its labels: `segment_packed(..., dev_chunks=...)`
+    takes it through `DeviceChunks.labels = gather.send_view()`.
+    """
+
+    def __init__(self, local_ids, local_sizes, num_chunks: int, *, group=None, device=None, dst=0):
+        self.group = group
+        self.num_chunks = int(num_chunks)
+        self.local_ids = [int(i) for i in local_ids]
+        self.local_sizes = [int(n) for n in local_sizes]
+        self.mine = int(sum(self.local_sizes))
+        self.dist = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if self.dist else 1
+        self.rank = dist.get_rank(group) if self.dist else 0
+        self.dst = dst                                   # rank that needs the labels on the host; None = every rank
+        if device is None:
+            nccl = self.dist and dist.get_backend(group) == "nccl"
+            device = torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu")
+        self.device = torch.device(device)
+        table = (self.local_ids, self.local_sizes)
+        if self.dist:
+            tables = [None] * self.world
+            dist.all_gather_object(tables, table, group=group)          # once per map, not per pass
+        else:
+            tables = [table]
+        self.tables = tables
+        self.pad = max(max((sum(t[1]) for t in tables), default=0), 1)
+        seen = sorted(i for t in tables for i in t[0])
+        if seen != list(range(self.num_chunks)):
+            raise ValueError("the ranks' chunk lists do not tile range(num_chunks)")
+        self.send = torch.zeros(self.pad, dtype=torch.int32, device=self.device)
+        self.recv = torch.empty(self.world * self.pad, dtype=torch.int32, device=self.device) if self.dist else self.send
+        self.is_dst = self.dst is None or self.rank == self.dst
+        self.host = None
+        if self.is_dst:
+            self.host = torch.empty(self.world * self.pad, dtype=torch.int32)
+            if self.device.type == "cuda":
+                self.host = self.host.pin_memory()
+        self._event = torch.cuda.Event() if self.device.type == "cuda" else None
+
+    def send_view(self):
+        """The first `mine` entries of the send buffer: hand this to the segment call as its label output."""
+        return self.send[:self.mine]
+
+    def load(self, local_labels):
+        """Copy label arrays (numpy / torch, host or device) into the send buffer, in local_ids order."""
+        o = 0
+        for n, lab in zip(self.local_sizes, local_labels):
+            t = lab if isinstance(lab, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(lab, dtype=np.int32))
+            self.send[o:o + n].copy_(t.reshape(-1).to(torch.int32), non_blocking=True)
+            o += n
+
+    def load_flat(self, flat):
+        """Same for labels that are already one concatenated int32 tensor (e.g. PackedChunks.labels, pinned)."""
+        self.send[:self.mine].copy_(flat[:self.mine], non_blocking=True)
+
+    def start(self):
+        """Issue the collective and (on the destination) the device-to-host copy; does not block the host."""
+        if self.dist:
+            dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
+        if self.is_dst:
+            self.host.copy_(self.recv, non_blocking=True)
+            if self._event is not None:
+                self._event.record()
+
+    def finish(self):
+        """Wait for the copy; returns a list of `num_chunks` numpy int32 views (None on ranks that are not dst)."""
+        if not self.is_dst:
+            return None
+        if self._event is not None:
+            self._event.synchronize()
+        arr = self.host.numpy()
+        out = [None] * self.num_chunks
+        for r, (ids, sizes) in enumerate(self.tables):
+            o = r * self.pad
+            for cid, n in zip(ids, sizes):
+                out[cid] = arr[o:o + n]
+                o += n
+        return out
+
+    def gather(self, local_labels=None):
+        if local_labels is not None:
+            self.load(local_labels)
+        self.start()
+        return self.finish()
+
+
 def gather_labels(local_ids, local_labels, num_chunks: int, group=None, device=None):
-    """All-gather the label arrays of the chunks each rank segmented.
+    """One-shot form: all-gather the label arrays of the chunks each rank segmented.
 
     local_ids: chunk indices owned by this rank; local_labels: matching list of int32 arrays
     (numpy or torch).  Returns a list of `num_chunks` numpy int32 arrays, identical on every rank.
-    Two collectives: sizes, then one padded all_gather_into_tensor of the concatenated labels.
     """
-    if not (dist.is_available() and dist.is_initialized()):
-        out = [None] * num_chunks
-        for i, lab in zip(local_ids, local_labels):
-            out[i] = np.asarray(lab.cpu() if isinstance(lab, torch.Tensor) else lab, dtype=np.int32)
-        return out
-    world = dist.get_world_size(group)
-    if device is None:
-        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    # table of (chunk id, length) per rank, padded to the largest local chunk count (built on the host: one upload
-    # instead of two tiny fill kernels per chunk)
-    cnt = torch.tensor([len(local_ids)], dtype=torch.int64, device=device)
-    cnts = torch.empty(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(cnts, cnt, group=group)
-    max_cnt = int(cnts.max().item())
-    meta_h = np.full((max(max_cnt, 1), 2), -1, dtype=np.int64)
-    for j, (i, lab) in enumerate(zip(local_ids, local_labels)):
-        meta_h[j, 0] = i
-        meta_h[j, 1] = len(lab)
-    meta = torch.from_numpy(meta_h).to(device)
-    metas = torch.empty((world * meta.shape[0], 2), dtype=torch.int64, device=device)      # concatenated form
-    dist.all_gather_into_tensor(metas, meta, group=group)
-    metas_h = metas.cpu().numpy().reshape(world, meta.shape[0], 2)
-    totals = [int(m[m[:, 0] >= 0, 1].sum()) for m in metas_h]
-    pad = max(max(totals), 1)
-    flat = torch.zeros(pad, dtype=torch.int32, device=device)
-    mine = int(meta_h[meta_h[:, 0] >= 0, 1].sum())
-    if mine:
-        tens = [lab if isinstance(lab, torch.Tensor) else torch.as_tensor(np.asarray(lab, dtype=np.int32)) for lab in local_labels]
-        same_dev = all(t.device == flat.device and t.dtype == torch.int32 for t in tens)
-        adjacent = same_dev and all(t.is_contiguous() for t in tens) and all(
-            a.data_ptr() + 4 * a.numel() == b.data_ptr() for a, b in zip(tens[:-1], tens[1:]))
-        if adjacent:
-            # the usual case: consecutive slices of one label buffer (DeviceChunks.labels): one copy, no per-chunk kernels
-            base = tens[0]
-            whole = torch.as_strided(base, (mine,), (1,)) if len(tens) > 1 else base
-            flat[:mine] = whole
-        else:
-            flat[:mine] = torch.cat([t.reshape(-1).to(dtype=torch.int32) for t in tens]).to(device)
-    allflat = torch.empty(world * pad, dtype=torch.int32, device=device)
-    dist.all_gather_into_tensor(allflat, flat, group=group)
-    allflat_h = allflat.cpu().numpy().reshape(world, pad)
-    out = [None] * num_chunks
-    for r in range(world):
-        o = 0
-        for cid, ln in metas_h[r]:
-            if cid < 0:
-                continue
-            out[int(cid)] = allflat_h[r, o:o + int(ln)].copy()
-            o += int(ln)
-    return out
+    g = LabelGather(local_ids, [int(len(lab)) for lab in local_labels], num_chunks, group=group, device=device, dst=None)
+    return [a.copy() for a in g.gather(local_labels)]

@@ -211,12 +211,14 @@ def make_chunk(chunk_id: int = 0, n_target: int = 8192, features: str = "tarl_di
     return ch
 
 
-def make_map(n_chunks: int = 8, n_per_chunk: int = 4096, features: str = "tarl", seed: int = 77,
+def make_map(n_chunks: int = 8, n_per_chunk=4096, features: str = "tarl", seed: int = 77,
              background_facades: bool = True, attach_prob: float = 0.4, feature_noise: float = 0.5) -> list[Chunk]:
     """Synthetic "first map": ONE scene along a straight 25 m wide corridor, voxelised once at 0.35 m, then
     cut into 25 m cubes every 22 m (`chunk_generation.py:123-137`, OVERLAP = 3 m, `config.py:58`), so that
     neighbouring chunks share instances and, in the 3 m overlap, exactly the same points — what the
     reference's merge relies on (`point_cloud_utils.py:387-491`).
+    `n_per_chunk`: target major points per chunk, or a (lo, hi) pair: the object density then varies along the
+    corridor so that the chunk sizes spread over about [lo, hi] (BASELINE.json config 4: N in [3 k, 12 k]).
     Facades are "stuff": their GT instance id is 0 (background) when background_facades is set, like
     buildings in SemanticKITTI; they exercise `remove_semantics`.
     Chunk.instance holds the map-level GT instance id (0 = background)."""
@@ -225,7 +227,24 @@ def make_map(n_chunks: int = 8, n_per_chunk: int = 4096, features: str = "tarl",
     length = 22.0 * (n_chunks - 1) + CHUNK_EDGE
     kinds = ["facade", "car", "car", "veg", "car", "veg", "car", "car"]
     per_kind = {"facade": 900.0, "car": 285.0, "veg": 520.0}
-    target = n_per_chunk * length / CHUNK_EDGE
+    varying = isinstance(n_per_chunk, (tuple, list))
+    if varying:
+        n_lo, n_hi = float(n_per_chunk[0]), float(n_per_chunk[1])
+        want = rng.uniform(n_lo, n_hi, size=n_chunks)               # target size of every chunk
+        edges = np.concatenate(([0.0], 22.0 * np.arange(1, n_chunks), [length]))
+        mass = want / CHUNK_EDGE * np.diff(edges)                   # expected points per 22 m stride cell
+        n_per_chunk = n_lo
+    else:
+        edges = np.array([0.0, length])
+        mass = np.array([n_per_chunk * length / CHUNK_EDGE])
+    target = float(mass.sum())
+    cell_p = mass / mass.sum()
+
+    def draw_x():
+        if not varying:
+            return rng.uniform(0.5, length - 0.5)                   # (same random stream as the committed fixtures)
+        c = int(rng.choice(len(cell_p), p=cell_p))
+        return rng.uniform(max(edges[c], 0.5), min(edges[c + 1], length - 0.5))
     pts, inst, boxes, is_bg, obj_kind = [], [], [], [], []
     total, o = 0.0, 0
     while total < 0.9 * target and o < 100000:
@@ -246,7 +265,7 @@ def make_map(n_chunks: int = 8, n_per_chunk: int = 4096, features: str = "tarl",
                 shift[oa] = rng.uniform(min(a_, b_), max(a_, b_))
                 shift[2] = hl[2] - lo0[2]
             else:
-                shift = np.array([rng.uniform(0.5, length - 0.5), rng.uniform(-half + 0.5, half - 0.5),
+                shift = np.array([draw_x(), rng.uniform(-half + 0.5, half - 0.5),
                                   rng.uniform(-half + 0.3, half - 0.3)]) - (lo0 + hi0) / 2
                 shift[2] = rng.uniform(-half + 0.3, half - 0.3 - (hi0[2] - lo0[2])) - lo0[2]
             lo, hi = lo0 + shift, hi0 + shift

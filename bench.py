@@ -2,27 +2,32 @@
 """Benchmark of the NCuts hot path (BASELINE.json metric: NCuts chunks/sec).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--config tarl_spatial|spatial|tarl_spatial_dino] [--workload batch|map]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-Workload (BASELINE.json configs[1]): config_tarl_spatial (alpha 1.0, theta 0.5, T 0.03) on synthetic
-SemanticKITTI-shaped chunks of about 8192 major points with random 96-d TARL features.  One step =
-one pass of the whole path (affinity -> degrees -> Lanczos -> N-cut scan -> partition, recursively,
--> labels) over one batch of `--batch` chunks per GPU.  Multi-GPU is weak scaling: every rank gets
-its own batch of chunks; after segmenting, the ranks all-gather the label arrays (NCCL), as the map
-merge needs them.
+Default workload (BASELINE.json configs[1]): config_tarl_spatial (alpha 1.0, theta 0.5, T 0.03) on synthetic
+SemanticKITTI-shaped chunks of about 8192 major points with random 96-d TARL features.  One step = one pass of the
+whole path (affinity -> degrees -> Lanczos -> N-cut scan -> partition, recursively, -> labels) over one batch of
+`--batch` chunks per GPU.  Multi-GPU is weak scaling: every rank segments the SAME batch (identical per-GPU work, so
+the max over ranks is not a straggler lottery); after segmenting, the ranks all-gather the label arrays (NCCL) and
+rank 0 takes them to the host, as the map merge needs them.
+`--workload map` is BASELINE.json configs[3]: ONE synthetic first map of 40 chunks (N in [3 k, 12 k]) sharded
+longest-first over the ranks (strong scaling), labels gathered once, merged and scored on rank 0.
 
 The JSON line carries: value (inputs resident in HBM), e2e (host buffers through the C ABI entry
-`ancuts_segment_chunks_host`: H2D of points+features and D2H of labels inside the timed region),
-roofline (matvec kernel, CUDA events around every launch, algorithmic bytes of SURVEY.md §8d),
-cpu_baseline (the oracle port of the reference's CPU path on the host cores), clocks.
-`--impl reference` times only the CPU oracle port (the reference is pure Python; `oracle/` is its
-restatement, checked against the unmodified reference by oracle/make_golden.py).
+`ancuts_segment_chunks_host`: H2D of points+features and D2H of labels inside the timed region), roofline (dominant
+kernel: the dense matvec of the persistent Lanczos kernels, CUDA events around every level launch, algorithmic bytes
+of SURVEY.md §8d, with the sparse lower bound next to it), cpu_baseline (the oracle port of the reference's CPU path
+on one host core, whose pinned labels also give `parity_ok` for that chunk), clocks.
+`--impl reference` times only the CPU oracle port on all host cores (the reference is pure Python; `oracle/` is its
+restatement, proven bit-equal to the unmodified reference by oracle/make_golden.py).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import platform
 import subprocess
 import sys
 import tempfile
@@ -35,7 +40,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "ncuts_chunks_per_sec"
 UNIT = "chunks/s"
-CONFIG_NAME = "tarl_spatial"
+FEATURES = {"spatial": "", "tarl_spatial": "tarl", "tarl_spatial_dino": "tarl_dino"}
 
 
 def peaks():
@@ -46,53 +51,179 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def make_batch(batch, n_target, seed0):
+def make_batch(batch, n_target, seed0, config):
     from autoinst_b200.synthetic import make_chunk
-    return [make_chunk(seed0 + i, n_target=n_target, features="tarl") for i in range(batch)]
+    return [make_chunk(seed0 + i, n_target=n_target, features=FEATURES[config] or "tarl") for i in range(batch)]
+
+
+def config_block(args):
+    """The `config` object: identical in the b200 and the reference arm (the driver compares them)."""
+    from autoinst_b200.synthetic import CONFIGS
+    cfg = CONFIGS[args.config]
+    feat = {"spatial": "no features", "tarl_spatial": "96-d TARL features",
+            "tarl_spatial_dino": "96-d TARL + 384-d DINOv2 features"}[args.config]
+    if args.workload == "map":
+        w = (f"config_{args.config} NCuts (alpha {cfg['alpha']}, theta {cfg['theta']}, gamma {cfg['gamma']}, T {cfg['T']}), "
+             f"one synthetic first map: {args.map_chunks} chunks of {args.map_lo}-{args.map_hi} major points, {feat}")
+    else:
+        w = (f"config_{args.config} NCuts (alpha {cfg['alpha']}, theta {cfg['theta']}, T {cfg['T']}), "
+             f"synthetic SemanticKITTI-shaped chunks n_target={args.n_target}, {feat}")
+    return {"workload": w}
+
+
+def host_info():
+    info = {"os_cpu_count": os.cpu_count(), "python": platform.python_version()}
+    try:
+        info["sched_affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    try:
+        out = subprocess.run(["lscpu"], capture_output=True, text=True, timeout=10).stdout
+        for line in out.splitlines():
+            if line.startswith("Model name"):
+                info["lscpu_model"] = line.split(":", 1)[1].strip()
+                break
+    except Exception:
+        pass
+    try:
+        import psutil
+        vm = psutil.virtual_memory()
+        info["ram_total_gb"] = round(vm.total / 2 ** 30, 1)
+        info["ram_available_gb"] = round(vm.available / 2 ** 30, 1)
+    except Exception:
+        pass
+    try:
+        import scipy
+        info["numpy"], info["scipy"] = np.__version__, scipy.__version__
+    except Exception:
+        pass
+    return info
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU side: the oracle port of the reference path, one chunk per call
+# CPU side: the oracle port of the reference path, one chunk per call.  Only what the reference's ncuts_chunk
+# computes is timed (affinity -> csr_matrix -> normalized_cut, ncuts_utils.py:56-174): inputs are in memory.
 # ------------------------------------------------------------------------------------------------
-def _cpu_one_chunk(args):
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    seed, n_target, faithful = args
+def _cpu_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    os.environ["MKL_NUM_THREADS"] = "1"
+    import scipy.sparse  # noqa: F401
+    import scipy.sparse.linalg  # noqa: F401
+    import scipy.spatial.distance  # noqa: F401
+    from oracle import affinity_ref, ncut_ref  # noqa: F401
+
+
+def _cpu_compute(task):
+    """task = (points, tarl, dino, config name, pinned).  Returns (seconds, n, labels)."""
+    pts, tarl, dino, name, pinned = task
+    import contextlib
     import scipy.sparse as sp
-    from autoinst_b200.synthetic import CONFIGS, make_chunk
+    from autoinst_b200.synthetic import CONFIGS
+    from oracle import ncut_ref as R
     from oracle.affinity_ref import affinity_ref, drop_isolated
-    from oracle.ncut_ref import normalized_cut_ref
-    cfg = CONFIGS[CONFIG_NAME]
-    ch = make_chunk(seed, n_target=n_target, features="tarl")
+    cfg = CONFIGS[name]
+    n = pts.shape[0]
     t0 = time.perf_counter()
-    A = affinity_ref(ch.points, ch.tarl, None, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
+    A = affinity_ref(pts, tarl, dino, alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
     _keep, A = drop_isolated(A)
     w = sp.csr_matrix(A)
-    groups = normalized_cut_ref(w, ch.n, np.arange(ch.n), T=cfg["T"], split_lim=0.01, faithful=faithful)
-    return time.perf_counter() - t0, ch.n, len(groups)
+    with (R.pinned_eigsh() if pinned else contextlib.nullcontext()):
+        groups = R.normalized_cut_ref(w, n, np.arange(n), T=cfg["T"], split_lim=0.01, faithful=True)
+    dt = time.perf_counter() - t0
+    return dt, n, R.labels_from_groups(groups, n)
 
 
-def cpu_sample(seeds, n_target, workers, faithful=True):
-    """Run the oracle port over the given chunk seeds with `workers` processes; returns (wall s, points)."""
-    t0 = time.perf_counter()
-    if workers <= 1:
-        res = [_cpu_one_chunk((s, n_target, faithful)) for s in seeds]
-    else:
-        import multiprocessing as mp
-        with mp.get_context("spawn").Pool(workers) as pool:
-            res = pool.map(_cpu_one_chunk, [(s, n_target, faithful) for s in seeds])
-    wall = time.perf_counter() - t0
-    return wall, sum(r[1] for r in res), [r[0] for r in res]
+def chunk_task(ch, name, pinned=False):
+    from autoinst_b200.synthetic import CONFIGS
+    cfg = CONFIGS[name]
+    return (ch.points, ch.tarl if cfg["theta"] else None, ch.dino if cfg["gamma"] else None, name, pinned)
 
 
-def host_workers(n_target):
-    cores = os.cpu_count() or 1
+def host_workers(n_points):
+    """Worker processes for the all-core figure: every core the process may use, bounded by RAM
+    (about 10 live dense float64 N x N arrays per worker)."""
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
     try:
         import psutil
         avail = psutil.virtual_memory().available
     except Exception:
         avail = 64 << 30
-    per_worker = 10 * 8 * (n_target * 1.15) ** 2          # ~10 live dense float64 N x N arrays (SURVEY §6.2)
-    return int(max(1, min(cores, avail * 0.6 // per_worker, 16)))
+    per_worker = 10 * 8 * float(n_points) ** 2
+    return int(max(1, min(cores, avail * 0.7 // per_worker)))
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation (oracle port, `kind: "port"`; oracle/make_golden.py proves it
+    bit-equal to the unmodified pipeline/ncuts code) on ALL host cores.  A persistent pool of single-threaded workers is
+    created, warmed up and handed the pre-generated chunks BEFORE the clock starts; the K steps are submitted back to
+    back (a worker that finishes a chunk takes the next one, no per-step barrier), ms_per_step = wall / K."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cfgb = config_block(args)
+    if args.workload == "map":
+        from autoinst_b200.synthetic import make_map
+        chunks = make_map(args.map_chunks, (args.map_lo, args.map_hi), features=FEATURES[args.config] or "tarl", seed=args.seed)
+        nmax = max(c.n for c in chunks)
+        workers = host_workers(nmax)
+        per_step = len(chunks)
+    else:
+        nmax = int(args.n_target * 1.15)
+        workers = host_workers(nmax)
+        per_step = args.ref_chunks if args.ref_chunks > 0 else workers       # upper bound; trimmed to the time budget below
+        chunks = make_batch(per_step, args.n_target, args.seed, args.config)
+    tasks = [chunk_task(c, args.config) for c in chunks]
+    pool = mp.get_context("spawn").Pool(workers, initializer=_cpu_init)
+    try:
+        # warm-up: imports and page-in on every worker (tiny chunks), then ONE full-size chunk alone on an otherwise idle
+        # machine = the 1-core figure (what run_pipeline.py does: one chunk after the other on one core)
+        from autoinst_b200.synthetic import make_chunk
+        tiny = chunk_task(make_chunk(1, n_target=600, features=FEATURES[args.config] or "tarl"), args.config)
+        for _ in range(max(args.warmup, 1)):
+            pool.map(_cpu_compute, [tiny] * workers, chunksize=1)
+        one = None
+        if not args.no_one_core:
+            dt1, n1, _ = pool.apply(_cpu_compute, (tasks[0],))
+            one = {"value": 1.0 / dt1, "unit": UNIT, "cores": 1, "seconds_per_chunk": dt1, "points": n1}
+        if args.workload != "map" and args.ref_chunks <= 0:
+            # bounded sample: K steps must end within --ref-budget-s.  A chunk takes about twice its idle-machine time when
+            # every core runs one (memory-bound dense ncut_cost); `rounds` chunks per worker fit the budget.
+            t_c = 2.0 * (one["seconds_per_chunk"] if one else 25.0)
+            rounds = max(1, int(args.ref_budget_s // t_c))
+            per_step = int(min(workers, max(1, rounds * workers // max(args.steps, 1))))
+            chunks, tasks = chunks[:per_step], tasks[:per_step]
+        pts_step = int(sum(c.n for c in chunks))
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_compute, tasks * args.steps, chunksize=1)
+        wall = time.perf_counter() - t0
+    finally:
+        pool.terminate()
+    ms = 1e3 * wall / args.steps
+    value = per_step * args.steps / wall
+    each = [r[0] for r in res]
+    sample = (f"{per_step} chunk(s) per step ({pts_step} major points), {args.steps} steps submitted back to back to a "
+              f"persistent pool of {workers} single-threaded worker processes (pool start, imports and chunk generation "
+              f"outside the clock); oracle port with the reference's dense ncut_cost (faithful=True); "
+              f"mean {np.mean(each):.1f} s per chunk under load")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong" if args.workload == "map" else "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": cfgb,
+        "detail": {"chunks_per_step": per_step, "points_per_sec": pts_step * args.steps / wall,
+                   "seconds_per_chunk_under_load": {"mean": float(np.mean(each)), "min": float(np.min(each)),
+                                                    "max": float(np.max(each))},
+                   "cpu_seconds_total": float(np.sum(each)), "one_core": one, "host": host_info()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "one_core_value": one["value"] if one else None},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -154,14 +285,15 @@ class ClockSampler:
         return out
 
 
-TRAFFIC_FILE = "r1c_cluster_dram_b128.csv"        # written by tools/gpu_final_s3.sh (ncu, same build)
+TRAFFIC_FILE = "r2_cluster_dram_b128.csv"        # ncu DRAM bytes of the cluster kernels, same build (tools/gpu_evidence.sh)
 
 
-def measured_traffic(batch, n_target, launches_per_step):
-    """DRAM bytes per timed launch of the dominant kernel from the committed ncu list (profiles/r1c_cluster_dram_b128.csv:
-    two passes over 128 chunks of n_target 8192), or None when the workload differs."""
+def measured_traffic(args, launches_per_step):
+    """DRAM bytes per timed launch of the dominant kernel from the committed ncu list (two passes over 128 chunks of
+    n_target 8192, config_tarl_spatial, dense matvec), or None when the workload differs."""
     path = os.path.join(ROOT, "profiles", TRAFFIC_FILE)
-    if batch != 128 or n_target != 8192 or not os.path.exists(path) or launches_per_step <= 0:
+    if (args.batch != 128 or args.n_target != 8192 or args.config != "tarl_spatial" or args.workload != "batch"
+            or not os.path.exists(path) or launches_per_step <= 0):
         return None
     total = 0.0
     for line in open(path):
@@ -169,43 +301,6 @@ def measured_traffic(batch, n_target, launches_per_step):
         if len(f) >= 7 and f[0].startswith("k_lanczos_cluster"):      # the kernel name itself contains a comma
             total += (float(f[-2]) + float(f[-1])) * 1e9
     return total / 2.0 / launches_per_step if total else None
-
-
-def workload_string(n_target):
-    from autoinst_b200.synthetic import CONFIGS
-    cfg = CONFIGS[CONFIG_NAME]
-    return (f"config_{CONFIG_NAME} NCuts (alpha {cfg['alpha']}, theta {cfg['theta']}, T {cfg['T']}), "
-            f"synthetic SemanticKITTI-shaped chunks n_target={n_target}, 96-d TARL features")
-
-
-def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation (oracle port) on the host cores."""
-    if rank != 0:
-        return
-    workers = host_workers(args.n_target)
-    per_step = workers if args.ref_chunks <= 0 else args.ref_chunks
-    seeds = [args.seed + i for i in range(per_step)]
-    for _ in range(args.warmup):
-        cpu_sample(seeds[:1], min(args.n_target, 1024), 1)          # warm-up: imports, page-in (tiny chunk)
-    walls, pts = [], 0
-    for _ in range(args.steps):
-        wall, p, _each = cpu_sample(seeds, args.n_target, workers)
-        walls.append(wall)
-        pts = p
-    ms = 1e3 * float(np.mean(walls))
-    value = per_step / (ms / 1e3)
-    sample = (f"{per_step} chunk(s) of n_target={args.n_target} ({pts} major points) per step, oracle port with the "
-              f"reference's dense ncut_cost (faithful=True), {workers} worker process(es), 1 thread each")
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_string(args.n_target), "chunks_per_step": per_step, "points_per_sec": pts / (ms / 1e3)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    emit(line)
 
 
 _REAL_STDOUT = None
@@ -227,143 +322,207 @@ def emit(line: dict):
     out.flush()
 
 
-def main():
-    protect_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="chunks per GPU per step")
-    ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
-    ap.add_argument("--seed", type=int, default=1000)
-    ap.add_argument("--cpu-chunks", type=int, default=1, help="chunks in the cpu_baseline sample (0 = skip)")
-    ap.add_argument("--ref-chunks", type=int, default=0, help="--impl reference: chunks per step (0 = one per worker)")
-    ap.add_argument("--no-stats", action="store_true")
-    args = ap.parse_args()
+class Dist:
+    """Rank bookkeeping + the timing helper of the contract (barrier + synchronize on both sides, CUDA events on the
+    current stream, MAX over ranks; min / mean over ranks reported next to it)."""
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-
-    import torch
-    import torch.distributed as dist
-    from autoinst_b200 import api, sharding
-    from autoinst_b200.synthetic import CONFIGS
-
-    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = CONFIGS[CONFIG_NAME]
-    kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"], T=cfg["T"])
-
-    chunks = make_batch(args.batch, args.n_target, args.seed + rank * args.batch)
-    packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"], pin=True)
-    dev_chunks = packed.to_device(dev)
-    hd = api.Handle.get(dev)
-    local_ids = [rank * args.batch + i for i in range(args.batch)]
-    total_chunks = args.batch * world
-
-    def barrier():
-        if world > 1:
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
             dist.barrier()
-        torch.cuda.synchronize(dev)
+        self.torch.cuda.synchronize(self.dev)
 
-    def gather(labels_dev):
-        if world > 1:
-            parts = [labels_dev[a:b] for a, b in zip(packed.off[:-1], packed.off[1:])]
-            sharding.gather_labels(local_ids, parts, total_chunks, device=dev)
+    def over_ranks(self, x):
+        """(max, min, mean) of a per-rank scalar."""
+        if self.world == 1:
+            return float(x), float(x), float(x)
+        import torch.distributed as dist
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        all_ = self.torch.empty(self.world, dtype=self.torch.float64, device=self.dev)
+        dist.all_gather_into_tensor(all_, t)
+        a = all_.cpu().numpy()
+        return float(a.max()), float(a.min()), float(a.mean())
 
-    def step_resident():
-        api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
-        gather(dev_chunks.labels)
-
-    def step_e2e():
-        res = api.segment_packed(packed, device=dev, **kw)
-        if world > 1:
-            sharding.gather_labels(local_ids, res.labels, total_chunks, device=dev)
-        return res
-
-    def timed(fn, steps):
-        barrier()
+    def timed(self, fn, steps):
+        torch = self.torch
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        barrier()
+        self.barrier()
         ms = e0.elapsed_time(e1) / steps
-        if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return self.over_ranks(ms)
 
-    sampler = ClockSampler(local_rank)
+    def close(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+
+
+def sparse_bound(stats, nnz_per_row):
+    """SURVEY.md §8d last sentence: bytes per chunk a sparse matvec would move for the same Lanczos steps,
+    (4 + 4) bytes per stored entry, next to the dense 4 n^2 + 8 n."""
+    if stats is None or nnz_per_row is None:
+        return None
+    n = stats["n"].astype(np.float64)
+    k = stats["steps"].astype(np.float64)
+    return float((k * 8.0 * nnz_per_row * n).sum())
+
+
+def run_batch(args):
+    import torch
+    from autoinst_b200 import api, sharding
+    from autoinst_b200._lib import OPT_MATVEC
+    from autoinst_b200.synthetic import CONFIGS
+    D = Dist()
+    rank, world, dev = D.rank, D.world, D.dev
+    cfg = CONFIGS[args.config]
+    kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"], T=cfg["T"])
+
+    chunks = make_batch(args.batch, args.n_target, args.seed, args.config)       # the same batch on every rank
+    packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks] if cfg["theta"] else None,
+                              [c.dino for c in chunks] if cfg["gamma"] else None, theta=cfg["theta"], gamma=cfg["gamma"],
+                              pin=True)
+    local_ids = [rank * args.batch + i for i in range(args.batch)]
+    total_chunks = args.batch * world
+    gat = sharding.LabelGather(local_ids, packed.sizes, total_chunks, device=dev, dst=0) if world > 1 else None
+    dev_chunks = packed.to_device(dev, labels=gat.send_view() if gat else None)
+    hd = api.Handle.get(dev)
+    hd.set_option(OPT_MATVEC, args.matvec)
+    gather_host_ms = []
+
+    def gather():
+        if gat is None:
+            return
+        t0 = time.perf_counter()
+        gat.start()
+        gat.finish()
+        gather_host_ms.append(1e3 * (time.perf_counter() - t0))
+
+    def step_resident():
+        api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
+        gather()
+
+    def step_e2e():
+        res = api.segment_packed(packed, device=dev, **kw)
+        if gat is not None:
+            gat.load_flat(packed.labels)
+            gather()
+        return res
+
+    sampler = ClockSampler(D.local_rank)
     if rank == 0:
         sampler.start()                 # nvidia-smi needs ~1 s before its first sample: start before the warm-up
-    # warm-up (also sizes the workspace)
-    for _ in range(args.warmup):
+    for _ in range(args.warmup):        # warm-up (also sizes the workspace)
         step_resident()
     step_e2e()
     t_begin = time.time()
-    # timed region 1: inputs resident in HBM.  CUDA events around every matvec launch (timing mode 2)
-    # give the roofline of the dominant kernel over exactly this region.
+    # timed region 1: inputs resident in HBM.  CUDA events around every level launch of the Lanczos kernels (timing
+    # mode 2) give the roofline of the dominant kernel over exactly this region.
     hd.set_stage_timing(2)
     hd.launch_count(reset=True)
-    mv_bytes = mv_ms = 0.0
-    mv_launches = 0
+    mv = dict(bytes=0.0, ms=0.0, launches=0)
     acc_all = {s: dict(bytes=0.0, launches=0) for s in api.STAGES}
 
     def step_resident_acct():
-        nonlocal mv_bytes, mv_ms, mv_launches
         step_resident()
         acc = hd.accounting()
-        mv_bytes += acc["matvec"]["bytes"]; mv_ms += acc["matvec"]["ms"]; mv_launches += acc["matvec"]["launches"]
+        for k in mv:
+            mv[k] += acc["matvec"][k]
         for s in api.STAGES:
             acc_all[s]["bytes"] += acc[s]["bytes"]; acc_all[s]["launches"] += acc[s]["launches"]
 
-    ms_step = timed(step_resident_acct, args.steps)
+    gather_host_ms.clear()
+    ms_step, ms_min, ms_mean = D.timed(step_resident_acct, args.steps)
     launches = hd.launch_count(reset=True)
     hd.set_stage_timing(0)
+    g_res = list(gather_host_ms)
+    gather_host_ms.clear()
     # timed region 2: the same steps through the host-buffer entry point
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e, ms_e2e_min, ms_e2e_mean = D.timed(step_e2e, args.steps)
+    g_e2e = list(gather_host_ms)
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    gmax = D.over_ranks(float(np.mean(g_res)) if g_res else 0.0)
 
-    # parity spot check + node statistics outside the timed regions
+    # outside the timed regions: node statistics, per-stage shares, the Python-list surface, the parity spot check
     res = api.segment_packed(packed, device=dev, want_stats=True, **kw)
     stats = res.stats
-    # per-stage time shares from one fully instrumented step (events around every launch)
     hd.set_stage_timing(1)
     api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
     stage_ms = {s: v["ms"] for s, v in hd.accounting().items()}
     hd.set_stage_timing(0)
+    py_ms = None
+    if rank == 0 and not args.no_python_surface:
+        lists = ([c.points for c in chunks], [c.tarl for c in chunks] if cfg["theta"] else None,
+                 [c.dino for c in chunks] if cfg["gamma"] else None)
+        api.segment_chunks(*lists, device=dev, **kw)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for _ in range(2):
+            api.segment_chunks(*lists, device=dev, **kw)
+        py_ms = 1e3 * (time.perf_counter() - t0) / 2
 
     if rank == 0:
         peak, peak_src = peaks()
         value = total_chunks / (ms_step / 1e3)
         pts_total = int(packed.off[-1]) * world
-        achieved = (mv_bytes / mv_launches) / ((mv_ms / mv_launches) * 1e-3) / 1e9 if mv_launches else 0.0
+        achieved = (mv["bytes"] / mv["launches"]) / ((mv["ms"] / mv["launches"]) * 1e-3) / 1e9 if mv["launches"] else 0.0
         cpu = None
+        parity = None
+        nnz_row = None
         if args.cpu_chunks > 0:
-            wall, pts, each = cpu_sample([args.seed + i for i in range(args.cpu_chunks)], args.n_target, 1)
-            cpu = {"value": args.cpu_chunks / wall, "unit": UNIT, "cores": 1, "kind": "port",
-                   "sample": f"{args.cpu_chunks} chunk(s) of the same batch (seed {args.seed}.., {pts} major points), oracle port "
-                             f"with the reference's dense ncut_cost (faithful=True), single thread, {wall:.1f} s"}
+            # the oracle port on one host core, pinned eigsh start vector: its labels are also the parity spot check of the
+            # timed batch (same chunks, GPU labels of the e2e call above)
+            t0 = time.perf_counter()
+            outs = [_cpu_compute(chunk_task(chunks[i], args.config, pinned=True)) for i in range(args.cpu_chunks)]
+            wall = time.perf_counter() - t0
+            from oracle import ncut_ref as R
+            ok = [bool(R.same_partition(res.labels[i], outs[i][2])) for i in range(args.cpu_chunks)]
+            parity = {"parity_ok": all(ok), "chunks_checked": len(ok), "identical": int(sum(ok)),
+                      "against": "oracle port under the eigsh pin (v0 = ones), partition equality up to label permutation"}
+            from oracle.affinity_ref import affinity_ref
+            c0 = chunks[0]
+            A = affinity_ref(c0.points, c0.tarl if cfg["theta"] else None, c0.dino if cfg["gamma"] else None,
+                             alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"])
+            nnz_row = float(np.count_nonzero(A)) / c0.n
+            compute_s = float(sum(o[0] for o in outs))
+            cpu = {"value": args.cpu_chunks / compute_s, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{args.cpu_chunks} chunk(s) of the timed batch (seed {args.seed}.., {sum(o[1] for o in outs)} major "
+                             f"points), oracle port with the reference's dense ncut_cost (faithful=True), single thread, "
+                             f"{compute_s:.1f} s of affinity + csr + normalized_cut",
+                   "host": host_info()}
+        sp_bytes = sparse_bound(stats, nnz_row)
+        dense_bytes = float(((4.0 * stats["n"].astype(np.float64) ** 2 + 8.0 * stats["n"]) * stats["steps"]).sum()) if stats is not None else None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_string(args.n_target),
-                       "chunks_per_gpu_per_step": args.batch, "points_per_step": pts_total,
+            "data": "synthetic", "config": config_block(args),
+            "detail": {"chunks_per_gpu_per_step": args.batch, "points_per_step": pts_total,
                        "points_per_sec": pts_total / (ms_step / 1e3),
+                       "ms_per_step_over_ranks": {"max": ms_step, "min": ms_min, "mean": ms_mean},
+                       "gather_ms": {"host_timer_mean_rank0": float(np.mean(g_res)) if g_res else 0.0,
+                                     "max_over_ranks": gmax[0], "e2e_mean_rank0": float(np.mean(g_e2e)) if g_e2e else 0.0,
+                                     "what": "one all_gather_into_tensor of the padded label buffers + one async D2H into "
+                                             "pinned memory on rank 0; tables exchanged once before the clock"},
+                       "matvec_form": "dense blocks streamed from HBM every Lanczos step" if args.matvec == 0 else
+                                      "row slices compressed into shared memory once per node",
                        "l2": "inputs larger than L2: every step rebuilds the float32 affinity blocks of all recursion nodes "
                              "(%.1f GB per GPU, 126 MB of L2) and streams them from HBM once per Lanczos step"
                              % (acc_all["degree"]["bytes"] / max(args.steps, 1) / 1e9),
@@ -371,30 +530,179 @@ def main():
                        "segments_per_chunk": float(np.mean(res.num_segments)),
                        "eig_nodes_per_chunk": (len(stats) / args.batch) if stats is not None else None,
                        "lanczos_steps_per_chunk": (float(stats["steps"].sum()) / args.batch) if stats is not None else None,
-                       "unconverged_nodes": int((stats["converged"] == 0).sum()) if stats is not None else None,
+                       "unconverged_nodes": int(res.unconverged),
                        "stage_ms_one_step": stage_ms,
-                       "stage_algorithmic_gb_per_step": {s: acc_all[s]["bytes"] / args.steps / 1e9 for s in api.STAGES}},
+                       "stage_algorithmic_gb_per_step": {s: acc_all[s]["bytes"] / args.steps / 1e9 for s in api.STAGES},
+                       "python_list_surface": None if py_ms is None else {
+                           "value": args.batch / (py_ms / 1e3), "unit": UNIT, "ms_per_step": py_ms,
+                           "what": "api.segment_chunks(lists of numpy arrays): packing into host buffers (float64 -> float32 "
+                                   "features, pageable) + the C ABI host call, rank 0 alone, outside the timed regions"}},
+            "parity": parity,
             "e2e": {"value": total_chunks / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "ms_per_step_over_ranks": {"max": ms_e2e, "min": ms_e2e_min, "mean": ms_e2e_mean},
                     "h2d_bytes_per_step": packed.h2d_bytes() * world, "d2h_bytes_per_step": packed.d2h_bytes() * world},
             "gpu_launches": int(launches) * world,
-            "roofline": {"bound": "hbm", "kernel": "k_lanczos_cluster<C> (matvec of the persistent Lanczos kernels, one timed launch = the concurrent kernels of one recursion level)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak,
-                         "traffic": measured_traffic(args.batch, args.n_target, mv_launches / max(args.steps, 1)),
+            "roofline": {"bound": "hbm", "kernel": "k_lanczos_cluster<C, 6> (dense matvec of the persistent Lanczos kernels, one timed "
+                                                    "launch = the concurrent kernels of one recursion level)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(args, mv["launches"] / max(args.steps, 1)),
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the cluster kernels, "
                                            "profiles/" + TRAFFIC_FILE + ", per level like achieved",
                          "peak_source": peak_src,
-                         "launches_timed": mv_launches, "avg_launch_us": 1e3 * mv_ms / max(mv_launches, 1),
-                         "algorithmic_bytes_per_launch": mv_bytes / max(mv_launches, 1),
-                         "note": "algorithmic bytes = sum over running nodes of 4 n^2 + 8 n per Lanczos step (SURVEY.md §8d), summed over "
-                                 "the steps the kernels of one level take; the blocks of small nodes stay in L2, so the DRAM "
-                                 "traffic is below the algorithmic bytes"},
+                         "launches_timed": mv["launches"], "avg_launch_us": 1e3 * mv["ms"] / max(mv["launches"], 1),
+                         "algorithmic_bytes_per_launch": mv["bytes"] / max(mv["launches"], 1),
+                         "dense_matvec_bytes_per_chunk": dense_bytes / args.batch if dense_bytes else None,
+                         "sparse_lower_bound_bytes_per_chunk": sp_bytes / args.batch if sp_bytes else None,
+                         "dense_over_sparse": (dense_bytes / sp_bytes) if (dense_bytes and sp_bytes) else None,
+                         "nnz_per_row": nnz_row,
+                         "note": "algorithmic bytes = sum over running nodes of 4 n^2 + 8 n per Lanczos step (SURVEY.md §8d), summed "
+                                 "over the steps the kernels of one level take; the blocks of small nodes stay in L2, so the DRAM "
+                                 "traffic is below the algorithmic bytes.  The sparse lower bound is (4+4) bytes per stored entry "
+                                 "per step for the same steps: the fraction of the HBM peak says how well the DENSE design "
+                                 "streams, not that streaming zeros is optimal"},
             "cpu_baseline": cpu,
             "clocks": clocks,
         }
         emit(line)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    D.close()
+
+
+def run_map(args):
+    """BASELINE.json configs[3]: one synthetic first map, chunks sharded longest-first over the ranks (strong scaling),
+    labels gathered once per pass to rank 0, merged (N2) and scored (N4) there on the device."""
+    import torch
+    from autoinst_b200 import api, sharding
+    from autoinst_b200._lib import OPT_MATVEC
+    from autoinst_b200.synthetic import CONFIGS, make_map
+    D = Dist()
+    rank, world, dev = D.rank, D.world, D.dev
+    cfg = CONFIGS[args.config]
+    kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"], T=cfg["T"])
+    chunks = make_map(args.map_chunks, (args.map_lo, args.map_hi), features=FEATURES[args.config] or "tarl", seed=args.seed)
+    sizes = [c.n for c in chunks]
+    shards = sharding.shard_chunks(sizes, world)
+    mine = shards[rank]
+    loc = [chunks[i] for i in mine]
+    packed = api.PackedChunks([c.points for c in loc], [c.tarl for c in loc] if cfg["theta"] else None,
+                              [c.dino for c in loc] if cfg["gamma"] else None, theta=cfg["theta"], gamma=cfg["gamma"], pin=True)
+    gat = sharding.LabelGather(mine, packed.sizes, len(chunks), device=dev, dst=0)
+    dev_chunks = packed.to_device(dev, labels=gat.send_view())
+    hd = api.Handle.get(dev)
+    hd.set_option(OPT_MATVEC, args.matvec)
+    post = api.MapPost(chunks, device=dev, min_points=args.min_points) if rank == 0 else None
+    last = {}
+    src_index = None
+    if rank == 0:
+        # where every chunk's labels sit in the gathered buffer (rank r's padded segment), in chunk order
+        where = {}
+        for r, (ids, szs) in enumerate(gat.tables):
+            o = r * gat.pad
+            for cid, n in zip(ids, szs):
+                where[cid] = (o, n)
+                o += n
+        src_index = torch.as_tensor(np.concatenate([np.arange(where[c][0], where[c][0] + where[c][1]) for c in range(len(chunks))]),
+                                    dtype=torch.int64).to(dev)
+
+    def finish(labels):
+        if rank == 0:
+            # merge + metrics consume the gathered labels where the collective left them (device); the host copy of
+            # LabelGather is what a caller that writes the map to disk would take
+            last["metrics"] = post.merge_and_score(gat.recv[src_index])
+
+    def step_resident():
+        api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
+        gat.start()
+        finish(gat.finish())
+
+    def step_e2e():
+        api.segment_packed(packed, device=dev, **kw)
+        gat.load_flat(packed.labels)
+        gat.start()
+        finish(gat.finish())
+
+    sampler = ClockSampler(D.local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step_resident()
+    step_e2e()
+    t_begin = time.time()
+    hd.launch_count(reset=True)
+    ms_step, ms_min, ms_mean = D.timed(step_resident, args.steps)
+    launches = hd.launch_count(reset=True)
+    ms_e2e, ms_e2e_min, ms_e2e_mean = D.timed(step_e2e, args.steps)
+    t_end = time.time()
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    # single-chunk latency through the array-level call the drop-in ncuts_chunk makes (one chunk per call)
+    lat = None
+    if rank == 0:
+        c = chunks[int(np.argsort(sizes)[len(sizes) // 2])]
+        for _ in range(2):
+            api.segment_chunk(c.points, c.tarl if cfg["theta"] else None, c.dino if cfg["gamma"] else None, device=dev, **kw)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            api.segment_chunk(c.points, c.tarl if cfg["theta"] else None, c.dino if cfg["gamma"] else None, device=dev, **kw)
+        lat = {"ms": 1e3 * (time.perf_counter() - t0) / 5, "n": c.n,
+               "what": "api.segment_chunk (host arrays in, host labels out), the call ncuts.ncuts_utils.ncuts_chunk makes"}
+    load = D.over_ranks(float(sum(sizes[i] ** 2 for i in mine)))
+    if rank == 0:
+        pts_total = int(sum(sizes))
+        line = {
+            "metric": METRIC, "value": len(chunks) / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_block(args),
+            "detail": {"chunks": len(chunks), "points": pts_total, "points_per_sec": pts_total / (ms_step / 1e3),
+                       "chunk_sizes": {"min": int(min(sizes)), "max": int(max(sizes)), "mean": float(np.mean(sizes))},
+                       "chunks_per_rank": [len(s) for s in shards],
+                       "load_n2_over_ranks": {"max": load[0], "min": load[1], "mean": load[2]},
+                       "ms_per_step_over_ranks": {"max": ms_step, "min": ms_min, "mean": ms_mean},
+                       "step": "segment the rank's shard -> all-gather labels -> D2H on rank 0 -> merge + metrics on rank 0"
+                               + (" (device: ancuts_merge_chunks / ancuts_instance_metrics)" if post is not None else
+                                  " (merge/metrics not in this build)"),
+                       "metrics": last.get("metrics"), "single_chunk_latency": lat},
+            "e2e": {"value": len(chunks) / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "ms_per_step_over_ranks": {"max": ms_e2e, "min": ms_e2e_min, "mean": ms_e2e_mean},
+                    "h2d_bytes_per_step": int(D.over_ranks(packed.h2d_bytes())[2] * world),
+                    "d2h_bytes_per_step": int(4 * pts_total)},
+            "gpu_launches": int(launches) * world, "roofline": None, "cpu_baseline": None, "clocks": clocks,
+        }
+        emit(line)
+    D.close()
+
+
+def main():
+    protect_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="tarl_spatial", choices=list(FEATURES))
+    ap.add_argument("--workload", default="batch", choices=["batch", "map"])
+    ap.add_argument("--batch", type=int, default=128, help="chunks per GPU per step")
+    ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
+    ap.add_argument("--seed", type=int, default=1000)
+    ap.add_argument("--matvec", type=int, default=0, help="ANCUTS_OPT_MATVEC: 0 dense from HBM, 1 shared-memory slices")
+    ap.add_argument("--cpu-chunks", type=int, default=1, help="chunks in the cpu_baseline sample / parity check (0 = skip)")
+    ap.add_argument("--ref-chunks", type=int, default=0, help="--impl reference: chunks per step (0 = half the workers)")
+    ap.add_argument("--no-one-core", action="store_true", help="--impl reference: skip the separate 1-core measurement")
+    ap.add_argument("--ref-budget-s", dest="ref_budget_s", type=float, default=420.0,
+                    help="--impl reference: wall-clock budget of the timed steps (bounded sample)")
+    ap.add_argument("--no-python-surface", action="store_true")
+    ap.add_argument("--map-chunks", type=int, default=40)
+    ap.add_argument("--map-lo", type=int, default=3000)
+    ap.add_argument("--map-hi", type=int, default=12000)
+    ap.add_argument("--min-points", type=int, default=20, help="map workload: Metrics min_points at the major level")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    elif args.workload == "map":
+        run_map(args)
+    else:
+        run_batch(args)
 
 
 if __name__ == "__main__":

@@ -170,6 +170,44 @@ int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, 
                         const double* h_box_min, const double* h_box_max, int normalise, double* d_out,
                         int32_t* d_out_count, void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* "Next" row N2 — replaces merge_chunks_unite_instances2 (pipeline/utils/point_cloud/point_cloud_utils.py:387-491; caller
+ * pipeline/run_pipeline.py:197-199): the chunk labelings of one map, chunks in file-name order, are united into one map
+ * labeling.  Chunk c owns points [h_chunk_off[c], h_chunk_off[c+1]) of d_points (P x 3 float64) and d_labels (P int32,
+ * 0 = background / "black", :428; every other value names an instance and must not be negative).  Per new chunk:
+ * crop of the merge so far to the cube h_centers[c] +/- crop_half_side (20.0, inclusive, :405-417; the centre is the mean
+ * of the chunk's points, :397-403, computed by the caller with the reference's own expression), per-instance bounding
+ * boxes (:447-448), points of every new instance inside them (:452-455), union = number of DISTINCT SCALAR coordinate
+ * values of both instances (np.unique without axis, :457), iou > min_iou (0.01, :459), every new instance keeps the
+ * cropped instance with the largest iou in (id1, id2) ascending order with strict replacement (:465-477), recolour
+ * (:479-481), append and drop exact-coordinate duplicates keeping the first occurrence (:488-489).
+ * d_out_labels[P]: label of every slot after the association; d_out_index: indices of the surviving points in order
+ * (capacity P; may be NULL); *h_num_kept their number.  Blocks until done. */
+int ancuts_merge_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off, const double* d_points,
+                        const int32_t* d_labels, const double* h_centers, double crop_half_side, double min_iou,
+                        int32_t* d_out_labels, int64_t* d_out_index, int64_t* h_num_kept, void* stream);
+
+/* Glue of run_pipeline.py:216-218 for integer labels: per-chunk segment ids (0 .. n_c - 1, as the segment calls write
+ * them) -> labels unique across the map, ((c + 1) << id_shift) + r + 1 with r = rank of the segment by first occurrence
+ * in the chunk's point order (the reference's colours are random; its greedy rules depend on the order of the label
+ * values, so both sides of a comparison need the same, labeling-independent numbering). */
+int ancuts_map_labels(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off, const int32_t* d_seg_labels,
+                      int id_shift, int32_t* d_out_labels, void* stream);
+
+/* remove_semantics(labels, preds, threshold) (point_cloud_utils.py:253-287; caller run_pipeline.py:223): a predicted
+ * label with more than `threshold` (0.8) of its points on ground-truth background (gt == 0) becomes 0.  Asynchronous. */
+int ancuts_remove_semantics(ancuts_handle* h, int64_t n, const int32_t* d_gt_labels, const int32_t* d_pred_labels,
+                            double threshold, int32_t* d_out_labels, void* stream);
+
+/* "Next" row N4 — Metrics(...).update_stats(all_labels, pred_labels, gt_labels) of a fresh Metrics object for one map
+ * (pipeline/metrics/metrics_class.py:137-179): filter_labels (:302-309, fewer than min_points points -> 0) on both
+ * prediction arrays, IoU table of the co-occurring (pred, gt) pairs (:296-300), greedy first-unused-GT matching in
+ * np.unique order at IoU 0.5 for P / R / F1 (:61-117,315-340) and at the 11 overlaps of :40 for AP with constant
+ * confidence (:181-235, np.trapz with the sentinels), and the association term of modified_LSTQ.py:23-80 on all_labels.
+ * h_out (21 doubles): [0..6] p, r, f1, ap, ap0.25, ap0.5, S_assoc (the keys of sequence_stats, :262-269);
+ * [7..9] true positives, n_pred, n_gt at IoU 0.5; [10..20] AP per overlap.  Labels must not be negative.  Blocks. */
+int ancuts_instance_metrics(ancuts_handle* h, int64_t n, const int32_t* d_all_labels, const int32_t* d_pred_labels,
+                            const int32_t* d_gt_labels, int min_points, double* h_out, void* stream);
+
 /* Eigensolver nodes of the handle's last segment call (ancuts_segment_chunks / _host / _dense_f32) that stopped at
  * lanczos_max_steps without meeting the residual test.  Their cut used the unconverged Ritz vector; the reference's
  * eigsh (normalized_cut.py:49) raises ArpackNoConvergence in that situation, so callers must look at this count
@@ -187,6 +225,10 @@ int ancuts_last_unconverged(ancuts_handle* h);
 #define ANCUTS_OPT_MATVEC        2
 #define ANCUTS_OPT_COUNT         3
 int ancuts_set_option(ancuts_handle* h, int option, int value);
+
+/* Shared-memory sparse matvec form (ANCUTS_OPT_MATVEC = 1), last segment call: out2[0] = sum over the nodes it ran of
+ * Lanczos steps x stored entries (what the sparse lower bound of SURVEY.md §8d multiplies by 8 bytes), out2[1] = entries. */
+int ancuts_last_sparse_accounting(ancuts_handle* h, double* out2);
 
 /* Counters for bench.py: kernels launched by this handle since the last reset, and the per-kernel
  * CUDA-event time of the kernels named by ancuts_timing_select(). */

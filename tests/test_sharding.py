@@ -46,9 +46,24 @@ def _worker(rank, world, port, sizes, q, adjacent=False):
             flat = torch.from_numpy(np.concatenate(labels)) if labels else torch.zeros(0, dtype=torch.int32)
             offs = np.cumsum([0] + [sizes[i] for i in mine])
             labels = [flat[a:b] for a, b in zip(offs[:-1], offs[1:])]
+        expect = [np.full(sizes[i], i, dtype=np.int32) + np.arange(sizes[i], dtype=np.int32) % 3 for i in range(len(sizes))]
         out = sharding.gather_labels(mine, labels, len(sizes))
-        ok = all(np.array_equal(out[i], np.full(sizes[i], i, dtype=np.int32) + np.arange(sizes[i], dtype=np.int32) % 3)
-                 for i in range(len(sizes)))
+        ok = all(np.array_equal(out[i], expect[i]) for i in range(len(sizes)))
+        # the persistent form bench.py uses: table exchanged once, labels written straight into the send buffer, two
+        # passes, the host copy on rank 0 only
+        g = sharding.LabelGather(mine, [sizes[i] for i in mine], len(sizes), dst=0)
+        for rep in range(2):
+            view = g.send_view()
+            o = 0
+            for i in mine:
+                view[o:o + sizes[i]] = torch.from_numpy(expect[i] + rep)
+                o += sizes[i]
+            g.start()
+            got = g.finish()
+            if rank == 0:
+                ok = ok and all(np.array_equal(got[i], expect[i] + rep) for i in range(len(sizes)))
+            else:
+                ok = ok and got is None
         q.put((rank, ok, [len(o) for o in out]))
     finally:
         dist.destroy_process_group()
