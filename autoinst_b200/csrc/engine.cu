@@ -76,6 +76,8 @@ struct Plan {
     std::vector<size_t> qoff;              // deferred: first queue entry of chunk c
     std::vector<int> qcap_c;               // deferred: queue capacity of chunk c
     int* pg_cells = nullptr; int* pg_sorted = nullptr; double* pg_spts = nullptr; PairGrid* pg_grid = nullptr;   // deferred: cell grids of the pair search
+    int* c_tile0 = nullptr; double* tbox = nullptr; long long* d_qoff = nullptr; int* d_qcap = nullptr;          // cell-sorted sweep
+    std::vector<int> tile0; int max_tiles = 0;
     bool grid_pairs = false;
     ancuts_node_stat* stats;
     Eng e;
@@ -164,6 +166,17 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
             pl.pg_sorted = ar.take<int>((size_t)P);
             pl.pg_spts = ar.take<double>((size_t)P * 3);
             pl.pg_grid = ar.take<PairGrid>((size_t)B);
+            pl.tile0.assign(B + 1, 0);
+            pl.max_tiles = 0;
+            for (int c = 0; c < B; ++c) {
+                const int t = (pl.n[c] + PS_T - 1) / PS_T;
+                pl.tile0[c + 1] = pl.tile0[c] + t;
+                pl.max_tiles = std::max(pl.max_tiles, t);
+            }
+            pl.c_tile0 = ar.take<int>((size_t)B + 1);
+            pl.tbox = ar.take<double>((size_t)pl.tile0[B] * 6);
+            pl.d_qoff = ar.take<long long>((size_t)B);
+            pl.d_qcap = ar.take<int>((size_t)B);
         }
     }
     pl.hW0.assign(B, nullptr); pl.hW1.assign(B, nullptr);
@@ -374,19 +387,6 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
         dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
         if (defer_chunk >= 0) {
             // deferred: pairs and root-level components only; W is written after the root split (run_rebuild)
-            if (pl.grid_pairs) {
-                const int c = defer_chunk;
-                int* cells = pl.pg_cells + (size_t)c * PG_STRIDE;
-                int* sorted = pl.pg_sorted + pos0;
-                double* spts = pl.pg_spts + (size_t)pos0 * 3;
-                LAUNCH(SG_AFFINITY, k_pair_grid<<<1, 1024, PG_CELLS * sizeof(int), st>>>(n, pts, p->proximity, cells, sorted, spts,
-                                                                                      pl.pg_grid + c));
-                LAUNCH(SG_AFFINITY, k_pair_search<<<(n + 7) / 8, 256, 0, st>>>(n, spts, p->alpha, p->proximity, pl.pg_grid + c,
-                                                                                 cells, sorted, pl.pairq + pl.qoff[c],
-                                                                                 pl.qcap_c[c], qctr, parent, pos0));
-                ANCUTS_CUDA(cudaGetLastError());
-                return ANCUTS_OK;
-            }
             LAUNCH(SG_AFFINITY, k_affinity_pairs<<<grid, 256, 0, st>>>(n, pts, p->alpha, p->proximity, nullptr, ld,
                                                                        pl.pairq + pl.qoff[defer_chunk], pl.qcap_c[defer_chunk],
                                                                        qctr, parent, pos0));
@@ -819,6 +819,7 @@ int ancuts_destroy(ancuts_handle* h) {
     if (h->post_ws) cudaFree(h->post_ws);
     if (h->h_post) cudaFreeHost(h->h_post);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; ++i) if (h->ev_host[i]) cudaEventDestroy(h->ev_host[i]);
     for (auto ev : h->copy_ev) cudaEventDestroy(ev);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_acct) cudaFreeHost(h->h_acct);
@@ -1290,12 +1291,39 @@ int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, 
     return ANCUTS_OK;
 }
 
+// Pair stage of the deferred affinity for ALL chunks of the call in four launches (ANCUTS_OPT_PAIR_SEARCH = 1):
+// cell sort, tile boxes, tile-pair sweep, root-level unions.  Needs the points only.
+static int run_pairs_batched(ancuts_handle* h, Plan& pl, const double* d_points, const float* d_tarl, const ancuts_params* p,
+                             cudaStream_t st) {
+    const int B = pl.B;
+    std::vector<long long> qo(B);
+    for (int c = 0; c < B; ++c) qo[c] = (long long)pl.qoff[c];
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.c_tile0, pl.tile0.data(), (B + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.d_qoff, qo.data(), B * sizeof(long long), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaMemcpyAsync(pl.d_qcap, pl.qcap_c.data(), B * sizeof(int), cudaMemcpyHostToDevice, st));
+    ANCUTS_CUDA(cudaStreamSynchronize(st));              // qo is a local
+    if (h->ev_points) ANCUTS_CUDA(cudaStreamWaitEvent(st, h->ev_points, 0));    // host entry: the coordinates have arrived
+    LAUNCH(SG_AFFINITY, k_pair_grid_b<<<B, 1024, PG_CELLS * sizeof(int), st>>>(pl.c_n, pl.c_base, d_points, p->proximity,
+                                                                              pl.pg_cells, pl.pg_sorted, pl.pg_spts, pl.pg_grid));
+    LAUNCH(SG_AFFINITY, k_tile_boxes<<<dim3(pl.max_tiles, B), PS_T, 0, st>>>(pl.c_n, pl.c_base, pl.c_tile0, pl.pg_spts, pl.tbox));
+    const int npair = pl.max_tiles * (pl.max_tiles + 1) / 2;
+    LAUNCH(SG_AFFINITY, k_pair_sweep<<<dim3(npair, B), 256, 0, st>>>(pl.c_n, pl.c_base, pl.c_tile0, pl.pg_spts, pl.pg_sorted, pl.tbox,
+                                                                     p->alpha, p->proximity, pl.pairq, pl.d_qoff, pl.d_qcap, pl.qctr));
+    LAUNCH(SG_AFFINITY, k_pair_unions<<<dim3(32, B), 256, 0, st>>>(pl.pairq, pl.d_qoff, pl.d_qcap, pl.qctr, pl.c_base, pl.e.parent));
+    if (h->ev_feats) ANCUTS_CUDA(cudaStreamWaitEvent(st, h->ev_feats, 0));      // host entry: the features have arrived
+    if (p->theta != 0.0 && d_tarl)
+        LAUNCH(SG_AFFINITY, k_zero_rows<<<(pl.P + 7) / 8, 256, 0, st>>>(pl.P, d_tarl, p->tarl_dim, pl.tarl_zero));
+    ANCUTS_CUDA(cudaGetLastError());
+    return ANCUTS_OK;
+}
+
 static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chunk_off, const double* d_points,
                           const float* d_tarl, const float* d_dino, const float* d_W_dense, int64_t ld_dense,
                           int num_points_orig, const ancuts_params* p, int32_t* d_labels, int32_t* h_num_segments,
                           ancuts_node_stat* h_stats, int32_t stats_cap, int32_t* h_num_stats, cudaStream_t st) {
     const cudaEvent_t* wait_ev = h ? h->wait_ev : nullptr;      // per-chunk "inputs have arrived" events of the host entry point
     if (h) h->wait_ev = nullptr;                                 // consumed by this call
+    struct EvReset { ancuts_handle* h; ~EvReset() { if (h) { h->ev_points = nullptr; h->ev_feats = nullptr; } } } ev_reset{h};
     int rc = check_params(p);
     if (rc) return rc;
     if (!h || num_chunks <= 0 || !h_chunk_off || !d_labels) { set_error("bad argument to segment"); return ANCUTS_EINVAL; }
@@ -1318,7 +1346,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && feats && aform != 2;
     pl.deferred = pl.want_pairq && aform == 0;                 // W written block by block after the root split
     pl.grid_pairs = pl.deferred && h->opt[ANCUTS_OPT_PAIR_SEARCH] == 1;     // pairs from a cell grid instead of the tile sweep
-    if (pl.grid_pairs) ANCUTS_CUDA(cudaFuncSetAttribute(k_pair_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PG_CELLS * sizeof(int))));
+    if (pl.grid_pairs) ANCUTS_CUDA(cudaFuncSetAttribute(k_pair_grid_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PG_CELLS * sizeof(int))));
     bool root_forest = pl.want_pairq;
     bool deferred = pl.deferred;
     size_t bytes = layout(pl, nullptr, stats_cap, p->tarl_dim, p->dino_dim, need_tc);
@@ -1349,7 +1377,14 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
             const int gP = (pl.P + 255) / 256;
             LAUNCH(SG_PARTITION, k_cc_init<<<gP, 256, 0, st>>>(pl.e));          // forest of the root-level components
         }
-        for (int c = 0; c < num_chunks; ++c) {
+        if (pl.grid_pairs) {
+            rc = run_pairs_batched(h, pl, d_points, d_tarl, p, st);
+            if (rc) return rc;
+            for (int c = 0; c < num_chunks; ++c)
+                aff_bytes += 4.0 * n[c] * (double)n[c] +
+                             4.0 * n[c] * (3 + (p->theta != 0 ? p->tarl_dim : 0) + (p->gamma != 0 ? p->dino_dim : 0));
+        }
+        for (int c = 0; c < num_chunks && !pl.grid_pairs; ++c) {
             int64_t o = h_chunk_off[c] - off0;
             const float* tz = d_tarl ? d_tarl + (size_t)(h_chunk_off[c]) * p->tarl_dim : nullptr;
             const float* dz = d_dino ? d_dino + (size_t)(h_chunk_off[c]) * p->dino_dim : nullptr;
@@ -1448,7 +1483,22 @@ int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* 
     }
     cudaError_t ce = cudaEventRecord(h->copy_ev[num_chunks], st);           // earlier work on st may still read the staging area
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->copy_stream, h->copy_ev[num_chunks], 0);
-    for (int c = 0; c < num_chunks && ce == cudaSuccess; ++c) {
+    const bool feats_on = use_t || use_d;
+    const bool batched = feats_on && p->affinity_impl == 0 && h->opt[ANCUTS_OPT_AFFINITY_FORM] == 0 && h->opt[ANCUTS_OPT_PAIR_SEARCH] == 1;
+    if (batched && ce == cudaSuccess) {
+        // the batched pair stage needs every chunk's coordinates at once and no features: coordinates first (one copy), then
+        // the features, which arrive while the pair stage and the root split run
+        if (!h->ev_host[0]) {
+            for (int i = 0; i < 2; ++i) ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_host[i], cudaEventDisableTiming));
+        }
+        ce = cudaMemcpyAsync(d_points, h_points, bp, cudaMemcpyHostToDevice, h->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_host[0], h->copy_stream);
+        if (ce == cudaSuccess && use_t) ce = cudaMemcpyAsync(d_tarl, h_tarl, bt, cudaMemcpyHostToDevice, h->copy_stream);
+        if (ce == cudaSuccess && use_d) ce = cudaMemcpyAsync(d_dino, h_dino, bd, cudaMemcpyHostToDevice, h->copy_stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_host[1], h->copy_stream);
+        if (ce == cudaSuccess) { h->ev_points = h->ev_host[0]; h->ev_feats = h->ev_host[1]; }
+    }
+    for (int c = 0; c < num_chunks && ce == cudaSuccess && !batched; ++c) {
         const size_t o = (size_t)h_chunk_off[c], m = (size_t)(h_chunk_off[c + 1] - h_chunk_off[c]);
         ce = cudaMemcpyAsync(d_points + o * 3, h_points + o * 3, m * 3 * sizeof(double), cudaMemcpyHostToDevice, h->copy_stream);
         if (ce == cudaSuccess && use_t)
@@ -1458,7 +1508,7 @@ int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* 
         if (ce == cudaSuccess) ce = cudaEventRecord(h->copy_ev[c], h->copy_stream);
     }
     if (ce != cudaSuccess) { set_error("H2D copy failed: %s", cudaGetErrorString(ce)); rc = ANCUTS_ECUDA; cudaStreamSynchronize(h->copy_stream); }
-    if (rc == ANCUTS_OK) h->wait_ev = h->copy_ev.data();
+    if (rc == ANCUTS_OK && !batched) h->wait_ev = h->copy_ev.data();
     if (rc == ANCUTS_OK)
         rc = segment_common(h, num_chunks, h_chunk_off, d_points, d_tarl, d_dino, nullptr, 0, 0, p, d_labels,
                             h_num_segments, h_stats, stats_cap, h_num_stats, st);

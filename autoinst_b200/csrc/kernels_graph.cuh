@@ -318,13 +318,11 @@ k_affinity_pairs(int n, const double* __restrict__ pts, double alpha, double pro
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pass 1 of the deferred affinity without the N^2 tile sweep: the in-mask pairs are the pairs closer than `prox`,
-// so they are found with a cell grid of pitch >= prox (at most PG_DIM cells per axis): one CTA bins the points of a
-// chunk by counting sort in shared memory (k_pair_grid), then one thread per point walks the 3 x 3 runs of three
-// x-adjacent cells around it (k_pair_search).  About 150 float64 distance tests per point instead of N / 2 float32
-// pre-filter tests: the tile sweep was issue-bound at ~95 us per 8.4 k-point chunk even without its stores.
-// Same inclusive float64 test and operation order as k_affinity_pairs (ncuts_utils.py:60-61); every pair i < j is
-// queued exactly once; queue order is arbitrary (as before), W and the union-find forest do not depend on it.
+// Cell grid of the cell-sorted pair search below: pitch >= prox, at most PG_DIM cells per axis (one CTA bins the points
+// of a chunk by counting sort in shared memory).  Same inclusive float64 test and operation order as k_affinity_pairs
+// (ncuts_utils.py:60-61); every pair is queued exactly once; queue order is arbitrary, W and the union-find forest do
+// not depend on it.  (Round 1 walked the 27 neighbour cells with one warp per point and one union per found pair:
+// 190 us per chunk, union-find bound; replaced by the tile sweep over the sorted points.)
 // ---------------------------------------------------------------------------------------------
 constexpr int PG_DIM = 25;
 constexpr int PG_CELLS = PG_DIM * PG_DIM * PG_DIM;       // 15625 counters = 61 KB of shared memory
@@ -336,14 +334,37 @@ __device__ __forceinline__ int pg_cell1(const PairGrid& g, double x, int a) {
     return max(0, min(g.n[a] - 1, c));
 }
 
-// one CTA of 1024 threads per launch (one chunk); dynamic shared memory: PG_CELLS ints
+// ---------------------------------------------------------------------------------------------
+// Pair search on the CELL-SORTED points (ANCUTS_OPT_PAIR_SEARCH = 1), batched over the chunks of a call:
+//   k_pair_grid_b   one CTA per chunk: counting sort into cells of pitch >= prox (x fastest), points stored in cell order
+//   k_tile_boxes    bounding box of every run of PS_T consecutive sorted points ("tile")
+//   k_pair_sweep    one CTA per tile pair (ti <= tj) of a chunk: pairs of tiles whose boxes are farther apart than prox
+//                   exit at once (in cell order a tile covers a few adjacent cell rows, so only ~1/5 of the tile pairs
+//                   survive), the others take the float32 pre-filter in registers (64 pairs per thread) and the exact
+//                   float64 test of k_affinity_pairs; hits go to the chunk's queue with their ORIGINAL indices
+//   k_pair_unions   root-level components: one union per queued pair, visited in a scattered order (in queue order
+//                   neighbouring threads would hook into the same component at the same time: the first cell-grid
+//                   search of round 1 spent 75 % of its stall samples in uf_find for that reason)
+// Same pairs, same float64 distances as the shuffled 64 x 64 sweep (k_affinity_pairs walks all N^2 / 2 pairs in 8.7 k
+// CTAs per chunk of 16 pairs per thread and is bound by its per-CTA overhead: 96 us per 8.4 k-point chunk).
+// ---------------------------------------------------------------------------------------------
+constexpr int PS_T = 128;                              // points per tile side
+
 __global__ void __launch_bounds__(1024)
-k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict__ cell_start, int* __restrict__ sorted,
-            double* __restrict__ spts, PairGrid* __restrict__ gout) {
+k_pair_grid_b(const int* __restrict__ c_n, const int* __restrict__ c_base, const double* __restrict__ pts_all, double prox,
+              int* __restrict__ cells_all, int* __restrict__ sorted_all, double* __restrict__ spts_all,
+              PairGrid* __restrict__ grids) {
     extern __shared__ int hist[];
     __shared__ double red[6][32];
     __shared__ PairGrid g;
     __shared__ int wsum[32];
+    const int chunk = blockIdx.x;
+    const int n = c_n[chunk];
+    const size_t pos0 = (size_t)c_base[chunk];
+    const double* pts = pts_all + pos0 * 3;
+    int* cell_start = cells_all + (size_t)chunk * PG_STRIDE;
+    int* sorted = sorted_all + pos0;
+    double* spts = spts_all + pos0 * 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
     for (int i = tid; i < n; i += 1024) {
@@ -369,7 +390,7 @@ k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict_
         g.inv_h = 1.0 / pitch;
         for (int a = 0; a < 3; ++a) g.n[a] = min(PG_DIM, (int)floor((red[3 + a][0] - g.lo[a]) * g.inv_h) + 1);
         g.pad = 0;
-        *gout = g;
+        grids[chunk] = g;
     }
     __syncthreads();
     for (int i = tid; i < n; i += 1024) {
@@ -378,8 +399,7 @@ k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict_
         atomicAdd(&hist[c], 1);
     }
     __syncthreads();
-    // exclusive scan over the cells: 16 consecutive cells per thread, then a scan of the 1024 partial sums
-    constexpr int PER = (PG_CELLS + 1023) / 1024;          // 16
+    constexpr int PER = (PG_CELLS + 1023) / 1024;          // 16 consecutive cells per thread, then a scan of the partial sums
     const int c0 = tid * PER;
     int loc[PER];
     int s = 0;
@@ -395,7 +415,7 @@ k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict_
         int wi = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
-        wsum[lane] = wi - w;                               // exclusive prefix of the warp totals
+        wsum[lane] = wi - w;
     }
     __syncthreads();
     const int base = wsum[warp] + incl - s;
@@ -406,6 +426,7 @@ k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict_
     }
     if (tid == 0) cell_start[PG_CELLS] = n;
     __syncthreads();
+    // The position inside a cell follows the atomics: any order gives the same pairs (the queue order is arbitrary anyway).
     for (int i = tid; i < n; i += 1024) {
         const int c = (pg_cell1(g, pts[(size_t)i * 3 + 2], 2) * g.n[1] + pg_cell1(g, pts[(size_t)i * 3 + 1], 1)) * g.n[0]
                       + pg_cell1(g, pts[(size_t)i * 3], 0);
@@ -417,79 +438,162 @@ k_pair_grid(int n, const double* __restrict__ pts, double prox, int* __restrict_
     }
 }
 
-// one WARP per point (in cell order), lanes over the candidates of a run: coordinates and indices of the candidates are
-// read in cell order (coalesced: k_pair_grid also stores the points sorted by cell).  Count, reserve with one atomic per
-// CTA, write.  (A first version with one thread per point and scattered candidate loads ran 1.5 ms per chunk: a chain of
-// dependent L2 round trips on 8 warps per SM.)
+// grid: (tiles of the largest chunk, chunks), PS_T threads
+__global__ void __launch_bounds__(PS_T)
+k_tile_boxes(const int* __restrict__ c_n, const int* __restrict__ c_base, const int* __restrict__ c_tile0,
+             const double* __restrict__ spts_all, double* __restrict__ tbox) {
+    __shared__ double red[6][PS_T / 32];
+    const int chunk = blockIdx.y, t = blockIdx.x;
+    const int n = c_n[chunk];
+    if (t * PS_T >= n) return;
+    const int i = min(t * PS_T + (int)threadIdx.x, n - 1);              // the last tile repeats its last point
+    const double* q = spts_all + ((size_t)c_base[chunk] + i) * 3;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double lo = warp_min(q[a]), hi = warp_max(q[a]);
+        if (lane == 0) { red[a][warp] = lo; red[3 + a][warp] = hi; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        const int a = threadIdx.x;
+        double v = red[a][0];
+        for (int w = 1; w < PS_T / 32; ++w) v = (a < 3) ? fmin(v, red[a][w]) : fmax(v, red[a][w]);
+        tbox[((size_t)c_tile0[chunk] + t) * 6 + a] = v;
+    }
+}
+
+// grid: (tile pairs of the largest chunk, chunks), 256 threads; tile pair L -> (ti <= tj) with L = tj (tj + 1) / 2 + ti
 __global__ void __launch_bounds__(256)
-k_pair_search(int n, const double* __restrict__ spts, double alpha, double prox, const PairGrid* __restrict__ gp,
-              const int* __restrict__ cell_start, const int* __restrict__ sorted, PairQ* __restrict__ q, int qcap,
-              int* __restrict__ qctr, int* parent, int pos0) {
-    __shared__ int wtot[8];
-    __shared__ int qbase;
-    const PairGrid g = *gp;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t = blockIdx.x * 8 + warp;                 // sorted position of this warp's point
-    const bool live = t < n;
-    const int tt = live ? t : 0;
-    const int i = sorted[tt];
-    const double px = spts[(size_t)tt * 3], py = spts[(size_t)tt * 3 + 1], pz = spts[(size_t)tt * 3 + 2];
-    const int cx = pg_cell1(g, px, 0), cy = pg_cell1(g, py, 1), cz = pg_cell1(g, pz, 2);
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.n[0] - 1);
-    // run bounds: lane r < 9 looks up the run (dy, dz) = (r % 3 - 1, r / 3 - 1)
-    int rlo = 0, rhi = 0;
+k_pair_sweep(const int* __restrict__ c_n, const int* __restrict__ c_base, const int* __restrict__ c_tile0,
+             const double* __restrict__ spts_all, const int* __restrict__ sorted_all, const double* __restrict__ tbox,
+             double alpha, double prox, PairQ* __restrict__ q_all, const long long* __restrict__ q_off,
+             const int* __restrict__ q_cap, int* __restrict__ qctr_all) {
+    const int chunk = blockIdx.y;
+    const int n = c_n[chunk];
+    const int T = (n + PS_T - 1) / PS_T;
+    const int L = blockIdx.x;
+    int tj = (int)((sqrt(8.0 * (double)L + 1.0) - 1.0) * 0.5);
+    while ((tj + 1) * (tj + 2) / 2 <= L) ++tj;                           // guard the float square root
+    while (tj * (tj + 1) / 2 > L) --tj;
+    const int ti = L - tj * (tj + 1) / 2;
+    if (tj >= T) return;
     {
-        const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
-        if (live && lane < 9 && y >= 0 && y < g.n[1] && z >= 0 && z < g.n[2]) {
-            const int rowc = (z * g.n[1] + y) * g.n[0];
-            rlo = cell_start[rowc + x0];
-            rhi = cell_start[rowc + x1 + 1];
+        const double* ba = tbox + ((size_t)c_tile0[chunk] + ti) * 6;
+        const double* bb = tbox + ((size_t)c_tile0[chunk] + tj) * 6;
+        double g2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double d = fmax(0.0, fmax(ba[a] - bb[3 + a], bb[a] - ba[3 + a]));
+            g2 += d * d;
+        }
+        if (g2 > prox * prox * 1.000001) return;                         // no pair of the two tiles can be inside the mask
+    }
+    __shared__ double pr[PS_T][3];
+    __shared__ double pc[PS_T][3];
+    __shared__ float pr32[PS_T][3];
+    __shared__ float pc32[PS_T][3];
+    __shared__ unsigned short queue[PS_T * PS_T];
+    __shared__ int qn, qbase;
+    const int tid = threadIdx.x;
+    const size_t pos0 = (size_t)c_base[chunk];
+    const double* sp = spts_all + pos0 * 3;
+    const int row0 = ti * PS_T, col0 = tj * PS_T;
+    if (tid == 0) qn = 0;
+    for (int i = tid; i < PS_T * 3; i += 256) {
+        const int pnt = i / 3, k = i % 3;
+        const int gr = row0 + pnt, gc = col0 + pnt;
+        const double org = sp[(size_t)row0 * 3 + k];
+        const double a = gr < n ? sp[(size_t)gr * 3 + k] : 1e30;        // padding points are far from everything
+        const double b = gc < n ? sp[(size_t)gc * 3 + k] : -1e30;
+        pr[pnt][k] = a; pc[pnt][k] = b;
+        pr32[pnt][k] = (float)(a - org); pc32[pnt][k] = (float)(b - org);
+    }
+    __syncthreads();
+    const float lim32 = (float)((prox + 1e-2) * (prox + 1e-2) * 1.001);     // see k_affinity_exact
+    const int rg = (tid >> 4) * 8, cg = (tid & 15) * 8;                 // 8 x 8 pairs per thread
+    float cx[8], cy[8], cz[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { cx[c] = pc32[cg + c][0]; cy[c] = pc32[cg + c][1]; cz[c] = pc32[cg + c][2]; }
+    const bool diag = (ti == tj);
+    const int lane = tid & 31;
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+        const float rx = pr32[rg + r][0], ry = pr32[rg + r][1], rz = pr32[rg + r][2];
+        unsigned cand = 0;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float fx = rx - cx[c], fy = ry - cy[c], fz = rz - cz[c];
+            if (!(fx * fx + fy * fy + fz * fz > lim32)) cand |= 1u << c;
+        }
+        unsigned hits = 0;
+        const int row = rg + r;
+        while (cand) {
+            const int c = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const int col = cg + c;
+            if (diag && col <= row) continue;                            // every pair once
+            const double dx = pr[row][0] - pc[col][0], dy = pr[row][1] - pc[col][1], dz = pr[row][2] - pc[col][2];
+            const double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (__dsqrt_rn(s2) <= prox) hits |= 1u << c;                 // ncuts_utils.py:61, inclusive
+        }
+        // append this row's hits: exclusive prefix over the warp, one shared-memory atomic per warp
+        const int cnt = __popc(hits);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+        int wbase = 0;
+        if (lane == 31 && wtot > 0) wbase = atomicAdd(&qn, wtot);
+        wbase = __shfl_sync(0xffffffffu, wbase, 31);
+        int pos = wbase + incl - cnt;
+        while (hits) {
+            const int c = __ffs(hits) - 1;
+            hits &= hits - 1;
+            queue[pos++] = (unsigned short)(row * PS_T + cg + c);
         }
     }
-    int off = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        int cnt = 0;                                     // warp-uniform
-        for (int r = 0; r < 9; ++r) {
-            const int lo = __shfl_sync(0xffffffffu, rlo, r), hi = __shfl_sync(0xffffffffu, rhi, r);
-            for (int s0 = lo; s0 < hi; s0 += 32) {
-                const int sidx = s0 + lane;
-                bool hit = false;
-                int j = 0;
-                double sd = 0.0;
-                if (sidx < hi) {
-                    j = sorted[sidx];
-                    if (j > i) {                                                    // every pair once, i < j
-                        double dx = px - spts[(size_t)sidx * 3], dy2 = py - spts[(size_t)sidx * 3 + 1], dz2 = pz - spts[(size_t)sidx * 3 + 2];
-                        double s2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy2, dy2)), __dmul_rn(dz2, dz2));
-                        sd = __dsqrt_rn(s2);
-                        hit = sd <= prox;                                           // ncuts_utils.py:61, inclusive
-                    }
-                }
-                const unsigned mask = __ballot_sync(0xffffffffu, hit);
-                if (pass == 1 && hit) {
-                    PairQ e;
-                    e.i = i; e.j = j;
-                    e.a = alpha != 0.0 ? alpha * sd : 0.0;                          // ncuts_utils.py:63-66
-                    q[off + cnt + __popc(mask & ((1u << lane) - 1u))] = e;
-                    if (parent) uf_union(parent, pos0 + i, pos0 + j);
-                }
-                cnt += __popc(mask);
-            }
-        }
-        if (pass == 1) break;
-        if (lane == 0) wtot[warp] = cnt;
-        __syncthreads();
-        int wbase = 0, total = 0;
-#pragma unroll
-        for (int w = 0; w < 8; ++w) { if (w < warp) wbase += wtot[w]; total += wtot[w]; }
-        if (tid == 0) {
-            int b = total > 0 ? atomicAdd(&qctr[0], total) : 0;
-            if (b + total > qcap) { atomicExch(&qctr[1], 1); b = -1; }              // the caller falls back to the dense form
-            qbase = b;
-        }
-        __syncthreads();
-        if (qbase < 0 || total == 0) return;
-        off = qbase + wbase;
+    __syncthreads();
+    const int total = qn;
+    if (total == 0) return;
+    int* qctr = qctr_all + 2 * chunk;
+    if (tid == 0) {
+        int b = atomicAdd(&qctr[0], total);
+        if (b + total > q_cap[chunk]) { atomicExch(&qctr[1], 1); b = -1; }   // the caller falls back to the dense form
+        qbase = b;
+    }
+    __syncthreads();
+    const int base = qbase;
+    if (base < 0) return;
+    PairQ* q = q_all + q_off[chunk];
+    const int* sorted = sorted_all + pos0;
+    for (int t = tid; t < total; t += 256) {
+        const int idx = queue[t];
+        const int r = idx / PS_T, c = idx % PS_T;
+        const double dx = pr[r][0] - pc[c][0], dy = pr[r][1] - pc[c][1], dz = pr[r][2] - pc[c][2];
+        const double sd = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+        PairQ e;
+        const int i0 = sorted[row0 + r], j0 = sorted[col0 + c];
+        e.i = min(i0, j0); e.j = max(i0, j0);
+        e.a = alpha != 0.0 ? alpha * sd : 0.0;                           // ncuts_utils.py:63-66
+        q[base + t] = e;
+    }
+}
+
+// grid: (blocks, chunks).  Entry t of the chunk's queue is visited as (t * 2147483629) mod total: a bijection for every
+// total below 2^31 (the multiplier is prime), and neighbouring threads land in unrelated components.
+__global__ void __launch_bounds__(256)
+k_pair_unions(const PairQ* __restrict__ q_all, const long long* __restrict__ q_off, const int* __restrict__ q_cap,
+              const int* __restrict__ qctr_all, const int* __restrict__ c_base, int* parent) {
+    const int chunk = blockIdx.y;
+    if (qctr_all[2 * chunk + 1]) return;
+    const long long total = min(qctr_all[2 * chunk], q_cap[chunk]);
+    const PairQ* q = q_all + q_off[chunk];
+    const int pos0 = c_base[chunk];
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long idx = (long long)(((unsigned long long)t * 2147483629ull) % (unsigned long long)total);
+        const PairQ e = q[idx];
+        uf_union(parent, pos0 + e.i, pos0 + e.j);
     }
 }
 

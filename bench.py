@@ -388,7 +388,7 @@ def sparse_bound(stats, nnz_per_row):
 def run_batch(args):
     import torch
     from autoinst_b200 import api, sharding
-    from autoinst_b200._lib import OPT_MATVEC
+    from autoinst_b200._lib import OPT_MATVEC, OPT_PAIR_SEARCH
     from autoinst_b200.synthetic import CONFIGS
     D = Dist()
     rank, world, dev = D.rank, D.world, D.dev
@@ -405,6 +405,7 @@ def run_batch(args):
     dev_chunks = packed.to_device(dev, labels=gat.send_view() if gat else None)
     hd = api.Handle.get(dev)
     hd.set_option(OPT_MATVEC, args.matvec)
+    hd.set_option(OPT_PAIR_SEARCH, args.pairs)
     gather_host_ms = []
 
     def gather():
@@ -572,7 +573,7 @@ def run_map(args):
     labels gathered once per pass to rank 0, merged (N2) and scored (N4) there on the device."""
     import torch
     from autoinst_b200 import api, sharding
-    from autoinst_b200._lib import OPT_MATVEC
+    from autoinst_b200._lib import OPT_MATVEC, OPT_PAIR_SEARCH
     from autoinst_b200.synthetic import CONFIGS, make_map
     D = Dist()
     rank, world, dev = D.rank, D.world, D.dev
@@ -589,6 +590,7 @@ def run_map(args):
     dev_chunks = packed.to_device(dev, labels=gat.send_view())
     hd = api.Handle.get(dev)
     hd.set_option(OPT_MATVEC, args.matvec)
+    hd.set_option(OPT_PAIR_SEARCH, args.pairs)
     post = api.MapPost(chunks, device=dev, min_points=args.min_points) if rank == 0 else None
     last = {}
     src_index = None
@@ -683,6 +685,7 @@ def main():
     ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--matvec", type=int, default=0, help="ANCUTS_OPT_MATVEC: 0 dense from HBM, 1 shared-memory slices")
+    ap.add_argument("--pairs", type=int, default=0, help="ANCUTS_OPT_PAIR_SEARCH: 0 shuffled tile sweep, 1 cell-sorted sweep")
     ap.add_argument("--cpu-chunks", type=int, default=1, help="chunks in the cpu_baseline sample / parity check (0 = skip)")
     ap.add_argument("--ref-chunks", type=int, default=0, help="--impl reference: chunks per step (0 = half the workers)")
     ap.add_argument("--no-one-core", action="store_true", help="--impl reference: skip the separate 1-core measurement")

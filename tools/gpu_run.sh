@@ -16,6 +16,7 @@ for stage in "$@"; do
     bench)    timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; tail -c 600 $OUT/${TAG}_bench.json ;;
     bench20)  timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench20.json 2> $OUT/${TAG}_bench20.err; tail -c 400 $OUT/${TAG}_bench20.json ;;
     benchsp)  timeout 900 python bench.py --steps 5 --warmup 3 --matvec 1 --cpu-chunks 0 > $OUT/${TAG}_bench_sparse.json 2> $OUT/${TAG}_bench_sparse.err; tail -c 400 $OUT/${TAG}_bench_sparse.json ;;
+    ab)       for v in "0 0" "1 0" "0 1" "1 1"; do set -- $v; timeout 600 python bench.py --steps 4 --warmup 3 --pairs $1 --matvec $2 --cpu-chunks 0 --no-python-surface > $OUT/${TAG}_ab_p$1_m$2.json 2> $OUT/${TAG}_ab_p$1_m$2.err; python -c "import json;d=json.load(open('$OUT/${TAG}_ab_p$1_m$2.json'));print('pairs',$1,'matvec',$2,round(d['value'],1),round(d['e2e']['value'],1),d['detail']['stage_ms_one_step'])"; done ;;
     configs)  for c in spatial tarl_spatial_dino; do timeout 900 python bench.py --steps 3 --warmup 3 --config $c --cpu-chunks 0 > $OUT/${TAG}_bench_$c.json 2> $OUT/${TAG}_bench_$c.err; tail -c 300 $OUT/${TAG}_bench_$c.json; done ;;
     small)    for b in 40 16 5 1; do timeout 600 python bench.py --steps 5 --warmup 3 --batch $b --cpu-chunks 0 --no-python-surface > $OUT/${TAG}_bench_b$b.json 2> $OUT/${TAG}_bench_b$b.err; python -c "import json;d=json.load(open('$OUT/${TAG}_bench_b$b.json'));print('batch',$b,d['value'],d['e2e']['value'],d['roofline']['frac'])"; done ;;
     map)      timeout 900 python bench.py --workload map --steps 3 --warmup 2 > $OUT/${TAG}_bench_map.json 2> $OUT/${TAG}_bench_map.err; tail -c 900 $OUT/${TAG}_bench_map.json ;;
