@@ -139,6 +139,7 @@ struct Eng {
     double* deg; double* sinv; double* wbuf; double* ybuf; double* ev;
     double* zbuf;           // S wbuf (input of the matvec), P + 4 entries
     uint8_t* bucket; uint8_t* side;
+    int* rownnz;            // stored (non-zero) entries of every row inside its node's block, written by k_degree
     int* parent; int* croot;
     unsigned long long* key; unsigned long long* key2; int* val; int* val2; int* flag; int* incl;
     double* V;              // (kmax+2) rows of P

@@ -106,7 +106,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     e.rid = ar.take<int>(P); e.rid2 = ar.take<int>(P); e.perm = ar.take<int>(P); e.perm2 = ar.take<int>(P);
     e.deg = ar.take<double>(P); e.sinv = ar.take<double>(P); e.wbuf = ar.take<double>(P);
     e.ybuf = ar.take<double>(P); e.ev = ar.take<double>(P); e.zbuf = ar.take<double>(P + 4);
-    e.bucket = ar.take<uint8_t>(P); e.side = ar.take<uint8_t>(P);
+    e.bucket = ar.take<uint8_t>(P); e.side = ar.take<uint8_t>(P); e.rownnz = ar.take<int>(P);
     e.parent = ar.take<int>(P); e.croot = ar.take<int>(P);
     e.key = ar.take<unsigned long long>(P); e.key2 = ar.take<unsigned long long>(P);
     e.val = ar.take<int>(P); e.val2 = ar.take<int>(P); e.flag = ar.take<int>(P); e.incl = ar.take<int>(P);
@@ -624,6 +624,7 @@ struct DeferredAffinity {
     const float* tarl;      // all chunks, input order
     const float* dino;
     const int64_t* chunk_off;
+    const cudaEvent_t* feat_ev;    // host entry with the batched pair stage: chunk c's features have arrived at feat_ev[c]
 };
 
 static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int max_split_n, bool components,
@@ -681,6 +682,12 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
         for (int c = 0; c < e.B; ++c) {
             const size_t o = (size_t)df->chunk_off[c];
             float* dst = cur ? pl.hW0[c] : pl.hW1[c];
+            if (df->feat_ev) {
+                ANCUTS_CUDA(cudaStreamWaitEvent(st, df->feat_ev[c], 0));
+                if (use_tarl)
+                    LAUNCH(SG_AFFINITY, k_zero_rows<<<(pl.n[c] + 7) / 8, 256, 0, st>>>(pl.n[c], df->tarl + o * p->tarl_dim, p->tarl_dim,
+                                                                                      pl.tarl_zero + (o - (size_t)df->chunk_off[0])));
+            }
             LAUNCH(SG_AFFINITY, k_affinity_feats<<<148 * 4, 256, 0, st>>>(
                 pl.pairq + pl.qoff[c], pl.qctr + 2 * c, pl.qcap_c[c], use_tarl ? df->tarl + o * p->tarl_dim : nullptr, p->tarl_dim,
                 use_dino ? df->dino + o * p->dino_dim : nullptr, p->dino_dim, pl.tarl_zero + (o - (size_t)df->chunk_off[0]),
@@ -1310,8 +1317,9 @@ static int run_pairs_batched(ancuts_handle* h, Plan& pl, const double* d_points,
     LAUNCH(SG_AFFINITY, k_pair_sweep<<<dim3(npair, B), 256, 0, st>>>(pl.c_n, pl.c_base, pl.c_tile0, pl.pg_spts, pl.pg_sorted, pl.tbox,
                                                                      p->alpha, p->proximity, pl.pairq, pl.d_qoff, pl.d_qcap, pl.qctr));
     LAUNCH(SG_AFFINITY, k_pair_unions<<<dim3(32, B), 256, 0, st>>>(pl.pairq, pl.d_qoff, pl.d_qcap, pl.qctr, pl.c_base, pl.e.parent));
-    if (h->ev_feats) ANCUTS_CUDA(cudaStreamWaitEvent(st, h->ev_feats, 0));      // host entry: the features have arrived
-    if (p->theta != 0.0 && d_tarl)
+    // host entry: the features arrive chunk by chunk while this stage and the root split run; the zero-row flags are then
+    // taken per chunk right before its feature pass (run_rebuild)
+    if (!h->feat_ev && p->theta != 0.0 && d_tarl)
         LAUNCH(SG_AFFINITY, k_zero_rows<<<(pl.P + 7) / 8, 256, 0, st>>>(pl.P, d_tarl, p->tarl_dim, pl.tarl_zero));
     ANCUTS_CUDA(cudaGetLastError());
     return ANCUTS_OK;
@@ -1323,7 +1331,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
                           ancuts_node_stat* h_stats, int32_t stats_cap, int32_t* h_num_stats, cudaStream_t st) {
     const cudaEvent_t* wait_ev = h ? h->wait_ev : nullptr;      // per-chunk "inputs have arrived" events of the host entry point
     if (h) h->wait_ev = nullptr;                                 // consumed by this call
-    struct EvReset { ancuts_handle* h; ~EvReset() { if (h) { h->ev_points = nullptr; h->ev_feats = nullptr; } } } ev_reset{h};
+    struct EvReset { ancuts_handle* h; ~EvReset() { if (h) { h->ev_points = nullptr; h->feat_ev = nullptr; } } } ev_reset{h};
     int rc = check_params(p);
     if (rc) return rc;
     if (!h || num_chunks <= 0 || !h_chunk_off || !d_labels) { set_error("bad argument to segment"); return ANCUTS_EINVAL; }
@@ -1409,6 +1417,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
                 deferred = false;
                 for (int c = 0; c < num_chunks; ++c) {
                     int64_t o = h_chunk_off[c] - off0;
+                    if (h->feat_ev) ANCUTS_CUDA(cudaStreamWaitEvent(st, h->feat_ev[c], 0));     // batched host path: features
                     const float* tz = d_tarl ? d_tarl + (size_t)(h_chunk_off[c]) * p->tarl_dim : nullptr;
                     const float* dz = d_dino ? d_dino + (size_t)(h_chunk_off[c]) * p->dino_dim : nullptr;
                     rc = run_affinity(h, pl, n[c], d_points + (size_t)h_chunk_off[c] * 3, tz, dz, p, pl.hW0[c], pl.ld[c],
@@ -1419,7 +1428,7 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
         }
         h->stage_bytes[SG_AFFINITY] = aff_bytes;
     }
-    DeferredAffinity df{p, d_tarl, d_dino, h_chunk_off};
+    DeferredAffinity df{p, d_tarl, d_dino, h_chunk_off, (deferred && pl.grid_pairs) ? h->feat_ev : nullptr};
     rc = run_levels(h, pl, p, 0, d_labels, h_num_segments, st, root_forest, deferred ? &df : nullptr);
     if (rc) return rc;
     rc = copy_stats(h, pl, h_stats, stats_cap, h_num_stats, st);
@@ -1488,15 +1497,17 @@ int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* 
     if (batched && ce == cudaSuccess) {
         // the batched pair stage needs every chunk's coordinates at once and no features: coordinates first (one copy), then
         // the features, which arrive while the pair stage and the root split run
-        if (!h->ev_host[0]) {
-            for (int i = 0; i < 2; ++i) ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_host[i], cudaEventDisableTiming));
-        }
+        if (!h->ev_host[0]) ANCUTS_CUDA(cudaEventCreateWithFlags(&h->ev_host[0], cudaEventDisableTiming));
         ce = cudaMemcpyAsync(d_points, h_points, bp, cudaMemcpyHostToDevice, h->copy_stream);
         if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_host[0], h->copy_stream);
-        if (ce == cudaSuccess && use_t) ce = cudaMemcpyAsync(d_tarl, h_tarl, bt, cudaMemcpyHostToDevice, h->copy_stream);
-        if (ce == cudaSuccess && use_d) ce = cudaMemcpyAsync(d_dino, h_dino, bd, cudaMemcpyHostToDevice, h->copy_stream);
-        if (ce == cudaSuccess) ce = cudaEventRecord(h->ev_host[1], h->copy_stream);
-        if (ce == cudaSuccess) { h->ev_points = h->ev_host[0]; h->ev_feats = h->ev_host[1]; }
+        for (int c = 0; c < num_chunks && ce == cudaSuccess; ++c) {
+            const size_t o = (size_t)h_chunk_off[c], m = (size_t)(h_chunk_off[c + 1] - h_chunk_off[c]);
+            if (use_t) ce = cudaMemcpyAsync(d_tarl + o * p->tarl_dim, h_tarl + o * p->tarl_dim, m * p->tarl_dim * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream);
+            if (ce == cudaSuccess && use_d)
+                ce = cudaMemcpyAsync(d_dino + o * p->dino_dim, h_dino + o * p->dino_dim, m * p->dino_dim * sizeof(float), cudaMemcpyHostToDevice, h->copy_stream);
+            if (ce == cudaSuccess) ce = cudaEventRecord(h->copy_ev[c], h->copy_stream);
+        }
+        if (ce == cudaSuccess) { h->ev_points = h->ev_host[0]; h->feat_ev = h->copy_ev.data(); }
     }
     for (int c = 0; c < num_chunks && ce == cudaSuccess && !batched; ++c) {
         const size_t o = (size_t)h_chunk_off[c], m = (size_t)(h_chunk_off[c + 1] - h_chunk_off[c]);

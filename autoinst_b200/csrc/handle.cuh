@@ -40,8 +40,9 @@ struct ancuts_handle {
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call
     const cudaEvent_t* wait_ev = nullptr;    // set by the host entry point for segment_common (chunk c waits for wait_ev[c])
-    cudaEvent_t ev_host[2] = {nullptr, nullptr};     // batched pair stage: all coordinates / all features have arrived
-    cudaEvent_t ev_points = nullptr, ev_feats = nullptr;   // = ev_host[...] for the call in flight, else NULL
+    cudaEvent_t ev_host[2] = {nullptr, nullptr};     // batched pair stage: all coordinates have arrived ([1] unused)
+    cudaEvent_t ev_points = nullptr;                 // = ev_host[0] for the call in flight, else NULL
+    const cudaEvent_t* feat_ev = nullptr;            // per-chunk "features have arrived" events of the call in flight, else NULL
     unsigned long long* dbg = nullptr;       // device, 32 entries: phase cycles of the cluster kernel (ANCUTS_PHASES=1)
     char* post_ws = nullptr;                 // map_post.cu (merge / metrics): growable device workspace
     size_t post_ws_bytes = 0;

@@ -28,16 +28,18 @@ constexpr int CL_THREADS = 512;          // 1024 threads (64 registers, 2 KB rin
 constexpr int CL_WARPS = CL_THREADS / 32;
 constexpr int CL_HALF = CL_THREADS / 2;     // shifts per eigenvalue and bisection round
 constexpr int CL_CLASSES = 6;            // node size bins (kernels_graph.cuh::cluster_class); cluster sizes 1, 2, 4, 8
-constexpr int CL_DYN_SMEM = 195 * 1024;  // z for the whole node + as many basis rows of the slice as fit
+constexpr int CL_DYN_SMEM = 194 * 1024;  // z for the whole node + as many basis rows of the slice as fit
                                          // (one CTA per SM; 256 threads x 2 CTAs per SM measured 25 % slower)
 
 struct ClusterShared {
-    double hpart[2][CL_KS];      // this CTA's partial dots (pass 1 / pass 2), read by the peers
+    double hpart[CL_KS];         // this CTA's partial dots of the Gram-Schmidt pass, read by the peers
     double npart[2];             // partial squared norm of the slice
     double spart[4];             // at the end: partial (sum, min, max, sum of squares) of the Ritz vector
     double hs[CL_KS];            // reduced projection coefficients
     double alpha[CL_KS], beta[CL_KS];
-    double be2[CL_KS], dd[CL_KS], yv[CL_KS];
+    double be2[CL_KS], dd[CL_KS], du[CL_KS], yv[CL_KS];
+    short hexp[CL_KS], pexp[CL_KS];   // exponent offsets of dd / du (cluster_tridiag_vec)
+    double prev_th[2];           // the two eigenvalues at the previous check (seed of the next multisection)
     double ysl[2][CL_RPMAX];     // this CTA's slice of the current vector (ping) and of the matvec result (pong)
     double wred[CL_WARPS];       // per-warp partials of the fused reductions (alpha in the matvec, norm in the update)
     double sv[CL_RPMAX];         // D^-1/2 of the slice
@@ -122,108 +124,141 @@ __device__ __forceinline__ int sturm_count_poly(const double* al, const double* 
     return cnt;     // number of eigenvalues < x
 }
 
-// tridiagonal analysis by the whole CTA (512 threads): top two eigenvalues by multisection with 256
-// shifts each (257^8 > 2^64), eigenvector of the largest by a twisted factorisation (thread 0).
-// Returns the residual estimate beta_{k-1} |y_{k-1}|; th[0], th[1] = eigenvalues; S.yv = eigenvector.
-__device__ double cluster_tridiag(ClusterShared& S, int k, double* th, bool poly, int sh) {
+// Tridiagonal analysis by the whole CTA (512 threads), part 1: the two largest eigenvalues of the k x k tridiagonal by
+// multisection with CL_SHIFTS shifts per eigenvalue and round, until the brackets are one float64 step wide
+// (129^8 > 2^56: eight rounds from the Gershgorin bracket).  From the second check of a node on, round 0 is SEEDED:
+// the eigenvalues of T_k interlace those of T_{k'} for k' < k, so theta_i(k) >= theta_i(k'), and after the first few
+// dozen steps they move by less than 1e-6 between checks; the shifts of round 0 then sit at prev + (hi - prev) 2^(-0.4 j),
+// which brackets the new value to 30 % of the distance it moved, and 3-5 uniform rounds finish instead of 8.
+// th[0], th[1] = eigenvalues (also kept in S.prev_th for the next check).
+constexpr int CL_SHIFTS = CL_HALF / 2;              // 128: half as many warps on the FP64 pipe as with 256, same 8 rounds
+
+__device__ __forceinline__ double cl_shift(double lo, double hi, int t, bool seeded) {
+    if (t < 0) return lo;
+    if (t >= CL_SHIFTS) return hi;
+    if (!seeded) return lo + (hi - lo) * ((double)(t + 1) * (1.0 / (double)(CL_SHIFTS + 1)));
+    return lo + (hi - lo) * exp2(-0.4 * (double)(CL_SHIFTS - t));      // t = CL_SHIFTS - 1 -> 0.76 (hi - lo); the bound hi follows
+}
+
+__device__ void cluster_tridiag_eigs(ClusterShared& S, int k, double* th) {
     const int tid = threadIdx.x;
-    // Gershgorin bracket of the spectrum and the pivot floor, by the whole CTA
-    double lo_t = 1e300, hi_t = -1e300, bm_t = 0.0;
+    // Gershgorin bracket of the spectrum, by the whole CTA
+    double lo_t = 1e300, hi_t = -1e300;
     for (int i = tid; i < k; i += CL_THREADS) {
         const double b = S.beta[i];
         S.be2[i] = b * b;
         const double rad = (i > 0 ? fabs(S.beta[i - 1]) : 0.0) + (i < k - 1 ? fabs(b) : 0.0);
         lo_t = fmin(lo_t, S.alpha[i] - rad);
         hi_t = fmax(hi_t, S.alpha[i] + rad);
-        if (i < k - 1) bm_t = fmax(bm_t, b * b);
     }
     lo_t = block_min_512(lo_t, S.red);
     hi_t = -block_min_512(-hi_t, S.red);
-    bm_t = -block_min_512(-bm_t, S.red);
+    const bool seeded = S.prev_k > 0;
     if (tid == 0) {
-        double w = fmax(fmax(fabs(lo_t), fabs(hi_t)), 1e-300);
+        const double w = fmax(fmax(fabs(lo_t), fabs(hi_t)), 1e-300);
         S.gb[0] = lo_t - 1e-10 * w;
         S.gb[1] = hi_t + 1e-10 * w;
-        S.gb[2] = fmax(bm_t, 1.0) * 1.0020841800044864e-292;
+        S.gb[2] = 0x1p-52 * w;                       // bracket width at which the multisection stops
+        for (int e = 0; e < 2; ++e) {
+            S.bounds[2 * e] = seeded ? fmax(S.prev_th[e] - 1e-12 * w, lo_t - 1e-10 * w) : lo_t - 1e-10 * w;
+            S.bounds[2 * e + 1] = hi_t + 1e-10 * w;
+        }
     }
     __syncthreads();
-    const double glo = S.gb[0], ghi = S.gb[1], pivmin = S.gb[2];
-    {
-        // sh shifts per eigenvalue and round.  256 (all 512 threads) resolves 8 bits per round, 128 resolves 7:
-        // 129^8 > 2^56 still brackets a float64 in 8 rounds, with half as many warps competing for the FP64 pipe.
-        const int which = tid / sh, t256 = tid % sh;
-        const bool act = which < 2;
-        const int m = k - 1 - which;
-        double lo = glo, hi = ghi;
-        const int rounds = 8;                       // full float64 resolution (the residual estimate below is only
-                                                    // as good as the eigenvalue)
-        const double den = 1.0 / (double)(sh + 1);
-        for (int round = 0; round < rounds; ++round) {
-            if (act) {
-                double x = lo + (hi - lo) * ((double)(t256 + 1) * den);
-                S.cnts[tid] = (m < 0) ? 0 : poly ? sturm_count_poly(S.alpha, S.be2, k, x) : sturm_count(S.alpha, S.be2, k, x, pivmin);
-            }
-            __syncthreads();
-            if (act && t256 < 32) {          // one warp per eigenvalue finds the last shift with count <= m
-                int best = -1;
-                for (int i = t256; i < sh; i += 32) if (S.cnts[which * sh + i] <= m) best = max(best, i);
+    const double eps = S.gb[2];
+    const int which = tid / CL_SHIFTS, ts = tid % CL_SHIFTS;
+    const bool act = which < 2 && (k - 1 - which) >= 0;
+    const int m = k - 1 - which;
+    for (int round = 0; round < 12; ++round) {
+        const bool sd = seeded && round == 0;
+        double lo = 0.0, hi = 0.0;
+        if (which < 2) { lo = S.bounds[2 * which]; hi = S.bounds[2 * which + 1]; }
+        if (act) S.cnts[tid] = sturm_count_poly(S.alpha, S.be2, k, cl_shift(lo, hi, ts, sd));
+        __syncthreads();
+        if (act && ts < 32) {                // one warp per eigenvalue finds the last shift with count <= m
+            int best = -1;
+            for (int i = ts; i < CL_SHIFTS; i += 32) if (S.cnts[which * CL_SHIFTS + i] <= m) best = max(best, i);
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-                if (t256 == 0) {
-                    S.bounds[2 * which] = (best >= 0) ? lo + (hi - lo) * ((double)(best + 1) * den) : lo;
-                    S.bounds[2 * which + 1] = (best < sh - 1) ? lo + (hi - lo) * ((double)(best + 2) * den) : hi;
-                }
+            for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+            if (ts == 0) {
+                S.bounds[2 * which] = cl_shift(lo, hi, best, sd);
+                S.bounds[2 * which + 1] = cl_shift(lo, hi, best + 1, sd);
             }
-            __syncthreads();
-            if (act) { lo = S.bounds[2 * which]; hi = S.bounds[2 * which + 1]; }
-            __syncthreads();
         }
+        __syncthreads();
+        // every thread sees the same four bounds: uniform exit
+        const bool done0 = (S.bounds[1] - S.bounds[0]) <= eps;
+        const bool done1 = (k < 2) || (S.bounds[3] - S.bounds[2]) <= eps;
+        if (done0 && done1) break;
     }
     const double th1 = 0.5 * (S.bounds[0] + S.bounds[1]);
     const double th2 = (k > 1) ? 0.5 * (S.bounds[2] + S.bounds[3]) : -1e300;
-    if (tid == 0) {
-        S.tmark = clock64();
-        // Eigenvector of th1 from the factorisation of T - th1 I twisted at the FIRST index: bottom-up
-        // pivots p_k = a_k - th, p_i = a_i - th - b_i^2 / p_{i+1}.  The trailing blocks of T do not contain
-        // the converged part of the Krylov space, their eigenvalues stay below th1 (interlacing), so every
-        // pivot is safely negative and the recurrence z_1 = 1, z_{i+1} = -b_i z_i / p_{i+1} is stable; it
-        // replaces a pivoted LU plus inverse iteration (2k divisions, agreement with LAPACK to 1e-14).
-        // S.dd holds the RECIPROCAL pivots, so the vector recurrence below has no division of its own.
-        double d = S.alpha[k - 1] - th1;
-        if (fabs(d) < pivmin) d = -pivmin;
-        double r = 1.0 / d;
-        S.dd[k - 1] = r;
-        for (int i = k - 2; i >= 0; --i) {
-            d = fma(-S.be2[i], r, S.alpha[i] - th1);
-            if (fabs(d) < pivmin) d = -pivmin;
-            r = 1.0 / d;
-            S.dd[i] = r;
-        }
-        double z = 1.0, ss = 1.0;
-        S.yv[0] = 1.0;
-        for (int i = 0; i < k - 1; ++i) {
-            z = -(S.beta[i] * S.dd[i + 1]) * z;
-            if (fabs(z) > 1e150) {                       // start vector almost orthogonal to the Ritz vector
-                for (int j = 0; j <= i; ++j) S.yv[j] *= 1e-150;
-                z *= 1e-150;
-                ss *= 1e-300;
-            }
-            S.yv[i + 1] = z;
-            ss = fma(z, z, ss);
-        }
-        S.gb[1] = 1.0 / sqrt(ss);
-    }
     __syncthreads();
-    {
-        const double inv = S.gb[1];
-        for (int i = tid; i < k; i += CL_THREADS) S.yv[i] *= inv;
-    }
-    __syncthreads();
-    if (tid == 0) S.gb[0] = fabs(S.beta[k - 1] * S.yv[k - 1]);
-    __syncthreads();
+    if (tid == 0) { S.prev_th[0] = th1; S.prev_th[1] = (k > 1) ? th2 : S.gb[0]; S.tmark = clock64(); }
     th[0] = th1;
     th[1] = th2;
-    return S.gb[0];
+}
+
+// Part 2: eigenvector of th1 from the factorisation of T - th1 I twisted at the FIRST index, division-free.
+// Bottom-up determinants of the trailing blocks, r_k = 1, r_{k-1} = a_{k-1} - th, r_i = (a_i - th) r_{i+1} - b_i^2 r_{i+2}:
+// the trailing blocks of T do not contain the converged part of the Krylov space, their eigenvalues stay below th1
+// (interlacing), so consecutive r have opposite signs and both terms of the recurrence add up (no cancellation; the
+// forward recurrence from the first index cancels catastrophically once the Ritz value has converged).  The pivots of
+// the twisted factorisation are r_i / r_{i+1} and the vector is z_i = (prod_{j<i} -b_j) r_{i+1} / r_1: ONE dependent
+// FMA and one multiply per element instead of a float64 division (a ~30-instruction dependent sequence; the serial
+// part of a check was 2 % of the CTA time in the dense form and a quarter of it in the shared-memory sparse form).
+// Thread 0 runs the r chain, thread 32 the product chain (exponents tracked separately so that neither overflows),
+// then all threads form z and the norm.  Agreement with LAPACK on every component: 1e-14 (numpy model, 160 steps).
+// Returns the residual estimate beta_{k-1} |y_{k-1}|; S.yv = unit eigenvector.
+__device__ double cluster_tridiag_vec(ClusterShared& S, int k, double th1) {
+    const int tid = threadIdx.x;
+    // S.dd[i] = r_{i+1} (scaled), S.hexp[i] = its exponent offset; S.du[i] = prod_{j<i} -b_j (scaled), S.pexp[i]
+    if (tid == 0) {
+        double rp = 1.0, rc = S.alpha[k - 1] - th1;          // r_k, r_{k-1}
+        int e = 0;
+        S.dd[k - 1] = 1.0; S.hexp[k - 1] = 0;                // r_k goes with z_{k-1}
+        if (k >= 2) { S.dd[k - 2] = rc; S.hexp[k - 2] = 0; } // r_{k-1} goes with z_{k-2}
+        for (int i = k - 2; i >= 0; --i) {                   // r_i from r_{i+1} = rc, r_{i+2} = rp
+            const double rn = fma(S.alpha[i] - th1, rc, -(S.be2[i] * rp));
+            rp = rc; rc = rn;
+            const int ex = (__double2hiint(rc) >> 20) & 0x7ff;
+            if (ex > 1023 + 256) { rc *= 0x1p-256; rp *= 0x1p-256; e += 256; }
+            else if (ex < 1023 - 256 && ex != 0) { rc *= 0x1p256; rp *= 0x1p256; e -= 256; }
+            if (i >= 1) { S.dd[i - 1] = rc; S.hexp[i - 1] = e; }     // r_i goes with z_{i-1}
+        }
+        (void)rc;                                            // r_0 = the twist pivot's numerator: only a common factor
+    } else if (tid == 32) {
+        double p = 1.0;
+        int f = 0;
+        for (int i = 0; i < k; ++i) {
+            S.du[i] = p; S.pexp[i] = f;
+            if (i < k - 1) {
+                p *= -S.beta[i];
+                const int ex = (__double2hiint(p) >> 20) & 0x7ff;
+                if (ex < 1023 - 256 && ex != 0) { p *= 0x1p256; f -= 256; }
+            }
+        }
+    }
+    __syncthreads();
+    // z_i = P_i r_{i+1} up to a common factor.  The largest recorded exponent is the reference, so that nothing overflows
+    // even when the start vector was almost orthogonal to the Ritz vector (z_0 tiny against later components); anything
+    // 2^-1000 below the largest component is zero for the Ritz sum.
+    double emax_t = -1e9;
+    for (int i = tid; i < k; i += CL_THREADS) emax_t = fmax(emax_t, (double)(S.pexp[i] + S.hexp[i]));
+    const int emax = (int)(-block_min_512(-emax_t, S.red));
+    double ss = 0.0;
+    for (int i = tid; i < k; i += CL_THREADS) {
+        const int ex = S.pexp[i] + S.hexp[i] - emax;
+        double z = S.du[i] * S.dd[i];
+        z = (ex < -1000) ? 0.0 : ldexp(z, ex);
+        S.yv[i] = z;
+        ss = fma(z, z, ss);
+    }
+    ss = block_sum_512(ss, S.red);
+    const double inv = 1.0 / sqrt(ss);
+    for (int i = tid; i < k; i += CL_THREADS) S.yv[i] *= inv;
+    __syncthreads();
+    return fabs(S.beta[k - 1] * S.yv[k - 1]);
 }
 
 template <int C>
@@ -262,7 +297,7 @@ __device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const double* 
 #pragma unroll
         for (int m = 0; m < M; ++m) s += t[m] * yr[m];
         s = warp_sum(s);
-        if (lane == 0) S.hpart[buf][j] = s;
+        if (lane == 0) S.hpart[j] = s;
     }
 }
 
@@ -272,9 +307,9 @@ __device__ __forceinline__ void cl_reduce_h(cg::cluster_group& cl, ClusterShared
         double h = 0.0;
         if (C > 1) {
 #pragma unroll
-            for (int r = 0; r < C; ++r) h += cl.map_shared_rank(&S.hpart[buf][0], r)[j];     // rank order
+            for (int r = 0; r < C; ++r) h += cl.map_shared_rank(&S.hpart[0], r)[j];     // rank order
         } else {
-            h = S.hpart[buf][j];
+            h = S.hpart[j];
         }
         S.hs[j] = h;
     }
@@ -287,12 +322,19 @@ __device__ __forceinline__ double cl_update_norm(ClusterShared& S, double* __res
     for (int i = threadIdx.x; i < nr; i += CL_THREADS) {
         double v = y[i];
         int j = 0;
-        for (; j + 8 <= rows; j += 8) {
-            double t[8];
+        for (; j + 12 <= rows; j += 12) {                 // 12 basis rows in flight: the rows behind the shared-memory part come
+            double t[12];                                 // from L2 / HBM while other SMs stream W, one round trip per group
 #pragma unroll
-            for (int u = 0; u < 8; ++u) t[u] = B.row(j + u)[i];
+            for (int u = 0; u < 12; ++u) t[u] = B.row(j + u)[i];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v -= S.hs[j + u] * t[u];
+            for (int u = 0; u < 12; ++u) v -= S.hs[j + u] * t[u];
+        }
+        for (; j + 4 <= rows; j += 4) {
+            double t[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) t[u] = B.row(j + u)[i];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v -= S.hs[j + u] * t[u];
         }
         for (; j < rows; ++j) v -= S.hs[j] * B.row(j)[i];
         y[i] = v;
@@ -496,9 +538,9 @@ __device__ __forceinline__ double cl_matvec_ring(ClusterShared& S, const double*
 
 // ---- shared-memory sparse matvec (MODE 7, ANCUTS_OPT_MATVEC = 1): W is 99.5 % zeros (27-66 stored entries per row
 // against n <= 4096 columns), yet the dense form streams every block from HBM once per Lanczos step.  Here the CTA reads
-// its row slice of the dense block TWICE at the start of the node (count, then fill) and keeps it as CSR in shared memory
-// (float32 value + uint16 column, rows in slice order, columns ascending) for all the steps: 8 n^2 bytes per node instead
-// of k (4 n^2 + 8 n).  No ring, so the basis rows get the shared memory the ring took.  Same float64 products; the sum of a
+// its row slice of the dense block ONCE at the start of the node (the entries per row were counted by k_degree on its own
+// pass) and keeps it as CSR in shared memory (float32 value + uint16 column, rows in slice order, columns ascending) for
+// all the steps: 4 n^2 bytes per node instead of k (4 n^2 + 8 n).  No ring, so the basis rows get the shared memory the ring took.  Same float64 products; the sum of a
 // row is taken by four lanes over its entries round-robin and combined (l0 + l1) + (l2 + l3): a fixed order, but not
 // the dense kernels' order, so alpha/beta differ from the dense form in the last bits (parity is against the oracle).
 // A slice that does not fit (dense little nodes far above 100 entries per row) sends the node to the grid-wide path.
@@ -507,30 +549,40 @@ struct SparseSlice {
 };
 constexpr int SP_LANES = 4;
 
-// entries of row `rowp` inside the block's aligned window, counted (FILL = false) or written (FILL = true) by one warp
-template <bool FILL>
-__device__ __forceinline__ int sp_scan_row(const float* __restrict__ rowp, int a0, int c_lo, int c_hi, int lane,
-                                           float* val, unsigned short* col, int base) {
-    int total = 0;
-    for (int c = a0 + lane * 4; c - lane * 4 < c_hi; c += 128) {          // warp-uniform trip count
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < c_hi) w = ld_stream4(rowp + c);
-        const float in[4] = {w.x, w.y, w.z, w.w};
-        unsigned m = 0;
+// Entries of TWO rows inside the block's aligned window, written by one warp: eight 128-bit loads in flight per lane
+// (512 columns of both rows) before the first use.  Entries of a row keep the column order.  A row pointer may be NULL.
+__device__ __forceinline__ void sp_fill_rows(const float* __restrict__ rowa, const float* __restrict__ rowb, int a0, int c_lo,
+                                             int c_hi, int lane, float* val, unsigned short* col, int basea, int baseb) {
+    for (int c0 = a0; c0 < c_hi; c0 += 512) {
+        float4 w[2][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) m |= (in[q] != 0.0f && c + q >= c_lo && c + q < c_hi) ? (1u << q) : 0u;
-        const int cnt = __popc(m);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        if (FILL) {
-            int pos = base + total + incl - cnt;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (m & (1u << q)) { val[pos] = in[q]; col[pos] = (unsigned short)(c + q - c_lo); ++pos; }
+        for (int g = 0; g < 4; ++g) {
+            const int c = c0 + 128 * g + lane * 4;
+            w[0][g] = (rowa && c < c_hi) ? ld_stream4(rowa + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            w[1][g] = (rowb && c < c_hi) ? ld_stream4(rowb + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        total += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (c0 + 128 * g >= c_hi) break;                              // warp-uniform
+                const int c = c0 + 128 * g + lane * 4;
+                const float in[4] = {w[rr][g].x, w[rr][g].y, w[rr][g].z, w[rr][g].w};
+                unsigned m = 0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) m |= (in[q] != 0.0f && c + q >= c_lo && c + q < c_hi) ? (1u << q) : 0u;
+                const int cnt = __popc(m);
+                int incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                int& base = rr ? baseb : basea;
+                int pos = base + incl - cnt;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (m & (1u << q)) { val[pos] = in[q]; col[pos] = (unsigned short)(c + q - c_lo); ++pos; }
+                base += __shfl_sync(0xffffffffu, incl, 31);
+            }
+        }
     }
-    return total;
 }
 
 // returns (every lane) the thread's share of alpha = v . (M v), v_i = yin_i * invb; the caller reduces it over the warp
@@ -586,16 +638,10 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     sp.val = nullptr; sp.col = nullptr; sp.ptr = nullptr; sp.nnz = 0;
     int sp_doubles = 0;
     if (SP) {
-        // ---- build the CSR slice: count the entries per row, scan, fill (two passes over the slice) ----
+        // ---- build the CSR slice: entries per row (counted by k_degree on its pass over the block), scan, fill ----
         const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
-        int* rowcnt = S.cnts;                          // free until the first convergence check
         __shared__ int sp_wtot[CL_WARPS + 1];
-        for (int i = warp; i < nr; i += CL_WARPS) {
-            const int t = sp_scan_row<false>(v.W + (size_t)(v.ro + r0 + i) * v.ld, a0, c_lo, c_hi, lane, nullptr, nullptr, 0);
-            if (lane == 0) rowcnt[i] = t;
-        }
-        __syncthreads();
-        const int mine = (tid < nr) ? rowcnt[tid] : 0;
+        const int mine = (tid < nr) ? e.rownnz[g0 + tid] : 0;      // stored entries per row, counted by k_degree
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -630,8 +676,11 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         if (tid < nr) ptr[tid] = sp_wtot[warp] + incl - mine;
         if (tid == 0) ptr[nr] = total;
         __syncthreads();
-        for (int i = warp; i < nr; i += CL_WARPS)
-            sp_scan_row<true>(v.W + (size_t)(v.ro + r0 + i) * v.ld, a0, c_lo, c_hi, lane, val, col, ptr[i]);
+        for (int i = warp; i < nr; i += 2 * CL_WARPS) {
+            const int i2 = i + CL_WARPS;
+            sp_fill_rows(v.W + (size_t)(v.ro + r0 + i) * v.ld, i2 < nr ? v.W + (size_t)(v.ro + r0 + i2) * v.ld : nullptr, a0, c_lo,
+                         c_hi, lane, val, col, ptr[i], i2 < nr ? ptr[i2] : 0);
+        }
         sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total;
         __syncthreads();
     }
@@ -771,8 +820,9 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         CL_PHASE(6);
         const bool breakdown = beta < 1e-13;
         if (breakdown || k >= kcap || k == S.next_check) {
-            double res = cluster_tridiag(S, k, th, true, CL_HALF / 2);
+            cluster_tridiag_eigs(S, k, th);
             if (prof) { tph[3] += S.tmark - tlast; tlast = S.tmark; }     // slot 3: multisection part of the check
+            const double res = cluster_tridiag_vec(S, k, th[0]);
             double gap = fmax(th[0] - th[1], 1e-300);
             bool c1 = (k >= n - 1) || breakdown || (res <= e.tol * gap);
             if (c1) { conv = 1; break; }
@@ -838,7 +888,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             if (!SP) atomicAdd(&e.acct[SG_MATVEC], (unsigned long long)k * (4ull * n * n + 8ull * n));
         }
         if (SP && tid == 0) {      // what this form really moves: the slice twice from HBM, then k sweeps over its entries
-            atomicAdd(&e.acct[SG_MATVEC], 8ull * (unsigned long long)nr * n);
+            atomicAdd(&e.acct[SG_MATVEC], 4ull * (unsigned long long)nr * n);
             atomicAdd(&e.acct[SG_SPARSE_STEPS], (unsigned long long)k * (unsigned long long)sp.nnz);
             atomicAdd(&e.acct[SG_SPARSE_NNZ], (unsigned long long)sp.nnz);
         }

@@ -650,21 +650,29 @@ k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int 
 // Stage 2: degrees of W = w + I for every active node:  d_i = 1 + sum_j w_ij  (float64)
 //   normalized_cut.py:38,42-43.  One warp per row, aligned 128-bit window loads.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double row_sum_window(const float* __restrict__ rowp, int c_lo, int c_hi, int lane) {
+__device__ __forceinline__ double row_sum_window(const float* __restrict__ rowp, int c_lo, int c_hi, int lane,
+                                                 int* nnz_out = nullptr) {
     double acc = 0.0;
+    int nz = 0;
     int a0 = c_lo & ~3;
     for (int c = a0 + lane * 4; c < c_hi; c += 128) {
         float4 w = ld_stream4(rowp + c);
         double s = 0.0;
         if (c >= c_lo && c + 3 < c_hi) {
             s = ((double)w.x + (double)w.y) + ((double)w.z + (double)w.w);
+            nz += (w.x != 0.0f) + (w.y != 0.0f) + (w.z != 0.0f) + (w.w != 0.0f);
         } else {
-            if (c >= c_lo && c < c_hi) s += (double)w.x;
-            if (c + 1 >= c_lo && c + 1 < c_hi) s += (double)w.y;
-            if (c + 2 >= c_lo && c + 2 < c_hi) s += (double)w.z;
-            if (c + 3 >= c_lo && c + 3 < c_hi) s += (double)w.w;
+            if (c >= c_lo && c < c_hi) { s += (double)w.x; nz += (w.x != 0.0f); }
+            if (c + 1 >= c_lo && c + 1 < c_hi) { s += (double)w.y; nz += (w.y != 0.0f); }
+            if (c + 2 >= c_lo && c + 2 < c_hi) { s += (double)w.z; nz += (w.z != 0.0f); }
+            if (c + 3 >= c_lo && c + 3 < c_hi) { s += (double)w.w; nz += (w.w != 0.0f); }
         }
         acc += s;
+    }
+    if (nnz_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        *nnz_out = nz;
     }
     return warp_sum(acc);
 }
@@ -677,11 +685,13 @@ k_degree(Eng e, int cur) {
     int row = blockIdx.x * 8 + warp;
     if (row >= v.n) return;
     const float* rowp = v.W + (size_t)(v.ro + row) * v.ld;
-    double s = row_sum_window(rowp, v.ro, v.ro + v.n, lane);
+    int nnz = 0;
+    double s = row_sum_window(rowp, v.ro, v.ro + v.n, lane, &nnz);
     if (lane == 0) {
         double d = 1.0 + s;                         // + identity (normalized_cut.py:38)
         e.deg[v.start + row] = d;
         e.sinv[v.start + row] = 1.0 / sqrt(d);      // :43
+        e.rownnz[v.start + row] = nnz;              // stored entries of the row inside its block (shared-memory sparse matvec)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         atomicAdd(&e.acct[SG_DEGREE], 4ull * v.n * v.n);

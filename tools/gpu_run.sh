@@ -21,6 +21,7 @@ for stage in "$@"; do
     small)    for b in 40 16 5 1; do timeout 600 python bench.py --steps 5 --warmup 3 --batch $b --cpu-chunks 0 --no-python-surface > $OUT/${TAG}_bench_b$b.json 2> $OUT/${TAG}_bench_b$b.err; python -c "import json;d=json.load(open('$OUT/${TAG}_bench_b$b.json'));print('batch',$b,d['value'],d['e2e']['value'],d['roofline']['frac'])"; done ;;
     map)      timeout 900 python bench.py --workload map --steps 3 --warmup 2 > $OUT/${TAG}_bench_map.json 2> $OUT/${TAG}_bench_map.err; tail -c 900 $OUT/${TAG}_bench_map.json ;;
     levels)   ANCUTS_PHASES=1 timeout 600 python tools/level_profile.py --batch 128 --out $OUT/${TAG}_levels_b128.json > $OUT/${TAG}_levels.log 2>&1; grep "cluster size" $OUT/${TAG}_levels.log ;;
+    levelsp)  ANCUTS_PHASES=1 timeout 600 python tools/level_profile.py --batch 128 --matvec 1 --pairs 1 --out $OUT/${TAG}_levels_b128_sparse.json > $OUT/${TAG}_levels_sparse.log 2>&1; grep "cluster size" $OUT/${TAG}_levels_sparse.log; python -c "import json;d=json.load(open('$OUT/${TAG}_levels_b128_sparse.json'));print([(l['active'],round(l['ms'],2)) for l in d['levels']])" ;;
     refarm)   timeout 1200 python bench.py --impl reference --steps ${REF_STEPS:-4} --warmup 1 > $OUT/${TAG}_bench_reference.json 2> $OUT/${TAG}_bench_reference.err; tail -c 1200 $OUT/${TAG}_bench_reference.json ;;
     ncu_list) timeout 300 python tools/one_step.py --batch 128 --passes 2 > $OUT/${TAG}_one_step.log 2>&1 && \
               timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 6000 --csv \

@@ -16,6 +16,8 @@ def main():
     ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--out", default="gpurun_out/levels.json")
+    ap.add_argument("--matvec", type=int, default=0)
+    ap.add_argument("--pairs", type=int, default=0)
     args = ap.parse_args()
     import torch
     from autoinst_b200 import api
@@ -27,6 +29,9 @@ def main():
     packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"])
     devc = packed.to_device(dev)
     hd = api.Handle.get(dev)
+    from autoinst_b200._lib import OPT_MATVEC, OPT_PAIR_SEARCH
+    hd.set_option(OPT_MATVEC, args.matvec)
+    hd.set_option(OPT_PAIR_SEARCH, args.pairs)
     for _ in range(2):
         api.segment_packed(packed, dev_chunks=devc, **kw)
     hd.set_stage_timing(2)
