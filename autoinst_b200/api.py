@@ -56,8 +56,8 @@ class Handle:
 
     def set_option(self, option: int, value: int):
         """Alternative implementations behind the same results (`ancuts_set_option`): _lib.OPT_AFFINITY_FORM
-        (0 deferred, 1 dense two-pass, 2 dense one-kernel), OPT_PAIR_SEARCH (0 tile sweep, 1 cell grid),
-        OPT_MATVEC (0 dense blocks from HBM, 1 slices compressed into shared memory)."""
+        (0 deferred, 1 dense two-pass, 2 dense one-kernel), OPT_PAIR_SEARCH (0 cell-sorted sweep, 1 shuffled sweep),
+        OPT_MATVEC (0 slices compressed into shared memory, 1 dense blocks from HBM), OPT_CLUSTER_MAP (tuning)."""
         check(self.lib.ancuts_set_option(self.h, int(option), int(value)))
 
     def sparse_accounting(self) -> dict:
@@ -487,31 +487,66 @@ def plan_batches(sizes, budget_bytes, max_steps=0):
     return batches
 
 
-def _pack_host(points_list, tarl_list, dino_list, use_t, use_d, pin=True):
+class _PinnedPool:
+    """Grow-only pinned host buffers reused across calls (cudaHostAlloc of hundreds of MB costs more than the copy)."""
+    _bufs: dict = {}
+
+    @classmethod
+    def take(cls, name, shape, dtype, pin):
+        if not pin:
+            return torch.empty(shape, dtype=dtype)
+        need = int(np.prod(shape))
+        key = (name, dtype)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(max(need, 1), dtype=dtype).pin_memory()
+            cls._bufs[key] = buf
+        return buf[:need].view(shape)
+
+
+def _pack_host(points_list, tarl_list, dino_list, use_t, use_d, pin=True, reuse=False):
+    """Concatenate the chunks into (pinned) host buffers: float64 coordinates, float32 features.  The float64 -> float32
+    conversion of the features (the reference hands float64 means, chunk_generation.py:252) goes straight into the buffer,
+    chunks in parallel on a few threads (numpy releases the GIL)."""
     sizes = [int(np.asarray(p).shape[0]) for p in points_list]
     off = np.zeros(len(sizes) + 1, dtype=np.int64)
     off[1:] = np.cumsum(sizes)
     total = int(off[-1])
 
-    def mk(shape, dtype):
+    def mk(name, shape, dtype):
+        if reuse:
+            return _PinnedPool.take(name, shape, dtype, pin)
         t = torch.empty(shape, dtype=dtype)
         return t.pin_memory() if pin else t
-    hp = mk((total, 3), torch.float64)
-    ht = mk((total, np.asarray(tarl_list[0]).shape[1]), torch.float32) if use_t else None
-    hd_ = mk((total, np.asarray(dino_list[0]).shape[1]), torch.float32) if use_d else None
-    for c, (a, b) in enumerate(zip(off[:-1], off[1:])):
-        hp[a:b] = torch.as_tensor(np.asarray(points_list[c], dtype=np.float64))
+    hp = mk("points", (total, 3), torch.float64)
+    ht = mk("tarl", (total, np.asarray(tarl_list[0]).shape[1]), torch.float32) if use_t else None
+    hd_ = mk("dino", (total, np.asarray(dino_list[0]).shape[1]), torch.float32) if use_d else None
+    hp_n = hp.numpy()
+    ht_n = ht.numpy() if use_t else None
+    hd_n = hd_.numpy() if use_d else None
+
+    def put(c):
+        a, b = int(off[c]), int(off[c + 1])
+        np.copyto(hp_n[a:b], np.asarray(points_list[c]), casting="same_kind")
         if use_t:
-            ht[a:b] = torch.as_tensor(np.asarray(tarl_list[c], dtype=np.float32))
+            np.copyto(ht_n[a:b], np.asarray(tarl_list[c]), casting="same_kind")
         if use_d:
-            hd_[a:b] = torch.as_tensor(np.asarray(dino_list[c], dtype=np.float32))
+            np.copyto(hd_n[a:b], np.asarray(dino_list[c]), casting="same_kind")
+    if len(sizes) >= 4 and total * (3 + (ht_n.shape[1] if use_t else 0) + (hd_n.shape[1] if use_d else 0)) > (1 << 22):
+        from concurrent.futures import ThreadPoolExecutor
+        import os as _os
+        with ThreadPoolExecutor(max_workers=min(8, len(sizes), _os.cpu_count() or 1)) as ex:
+            list(ex.map(put, range(len(sizes))))
+    else:
+        for c in range(len(sizes)):
+            put(c)
     return sizes, off, hp, ht, hd_
 
 
 class PackedChunks:
     """Inputs of a batch of chunks packed once into pinned host buffers (what a data loader hands over)."""
 
-    def __init__(self, points_list, tarl_list=None, dino_list=None, *, theta=0.0, gamma=0.0, pin=True):
+    def __init__(self, points_list, tarl_list=None, dino_list=None, *, theta=0.0, gamma=0.0, pin=True, reuse=False):
         self.use_t = bool(theta) and tarl_list is not None
         self.use_d = bool(gamma) and dino_list is not None
         if theta and tarl_list is None:
@@ -519,10 +554,13 @@ class PackedChunks:
         if gamma and dino_list is None:
             raise ValueError("The length should be longer than 0!")
         self.sizes, self.off, self.points, self.tarl, self.dino = _pack_host(
-            points_list, tarl_list, dino_list, self.use_t, self.use_d, pin)
-        self.labels = torch.empty(int(self.off[-1]), dtype=torch.int32)
-        if pin:
-            self.labels = self.labels.pin_memory()
+            points_list, tarl_list, dino_list, self.use_t, self.use_d, pin, reuse)
+        if reuse:      # buffers of the module-level pool: valid until the next PackedChunks(reuse=True)
+            self.labels = _PinnedPool.take("labels", (int(self.off[-1]),), torch.int32, pin)
+        else:
+            self.labels = torch.empty(int(self.off[-1]), dtype=torch.int32)
+            if pin:
+                self.labels = self.labels.pin_memory()
         self.tarl_dim = self.tarl.shape[1] if self.use_t else 0
         self.dino_dim = self.dino.shape[1] if self.use_d else 0
 
@@ -653,7 +691,7 @@ def segment_chunks(points_list, tarl_list=None, dino_list=None, *, alpha=1.0, th
         pk = PackedChunks([points_list[i] for i in batch],
                           [tarl_list[i] for i in batch] if tarl_list is not None else None,
                           [dino_list[i] for i in batch] if dino_list is not None else None,
-                          theta=theta, gamma=gamma, pin=False)
+                          theta=theta, gamma=gamma, pin=True, reuse=True)      # pooled pinned buffers; labels are copied out below
         res = segment_packed(pk, alpha=alpha, theta=theta, gamma=gamma, T=T, proximity=proximity,
                              split_lim=split_lim, device=device, want_stats=want_stats, **kw)
         unconv += res.unconverged

@@ -382,7 +382,7 @@ static int run_affinity(ancuts_handle* h, Plan& pl, int n, const double* pts, co
                                     p->dino_dim, tarl_zero, p->alpha, p->theta, p->gamma, p->proximity, W, ld,
                                     pl.tc_scratch, pl.tc_scratch_bytes, st);
         if (rc != ANCUTS_OK) return rc;
-    } else if (qctr && (use_tarl || use_dino)) {
+    } else if (qctr) {
         // two-pass form: distances + zero fill + pair queue, then the queued pairs spread over the whole grid
         dim3 grid((unsigned)((ld + AT - 1) / AT), (n + AT - 1) / AT);
         if (defer_chunk >= 0) {
@@ -500,13 +500,25 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
     // node do the same work with fewer cluster barriers.
     static const int c_latency[CL_CLASSES] = {1, 2, 2, 4, 8, 8};
     static const int c_throughput[CL_CLASSES] = {1, 1, 2, 2, 4, 8};
-    // shared-memory sparse form (ANCUTS_OPT_MATVEC = 1): slices of at most 256-320 rows, so that the CSR slice AND most of the
-    // basis fit the CTA's shared memory; nodes above 2048 points keep the dense form (their slices do not fit)
-    static const int c_sparse[CL_CLASSES] = {1, 2, 2, 4, 8, 8};
-    const bool sparse_on = h->opt[ANCUTS_OPT_MATVEC] == 1 && cluster_mode(e) == 6;
+    // Shared-memory sparse form (ANCUTS_OPT_MATVEC = 0, the default): the same two mappings.  Its steps are short, the fixed
+    // costs per CTA (cluster barriers, the redundant convergence checks) count, and a level is bound by SM time: the mapping
+    // with the fewest CTAs per node measured 2858 chunks/s against 2351 with {1,2,2,4,8,8} (profiles/r2e_cmap_*.json); with
+    // 512-row slices most of the basis then sits behind the CSR slice in L2.  Nodes above 2048 points keep the dense form
+    // (their slices do not fit the shared memory).
+    const bool sparse_on = h->opt[ANCUTS_OPT_MATVEC] == 0 && cluster_mode(e) == 6;
     int ctas = 0;
     for (int b = 0; b < CL_CLASSES; ++b) ctas += class_cnt[b] * c_latency[b];
-    const int* cmap = sparse_on ? c_sparse : (ctas <= 148) ? c_latency : c_throughput;
+    const int* cmap = (ctas <= 148) ? c_latency : c_throughput;
+    int c_user[CL_CLASSES];
+    if (h->opt[ANCUTS_OPT_CLUSTER_MAP] > 0) {                   // tuning: six decimal digits, CTAs per node for the six size bins
+        int d = h->opt[ANCUTS_OPT_CLUSTER_MAP];
+        bool ok = true;
+        for (int b = CL_CLASSES - 1; b >= 0; --b) { c_user[b] = d % 10; d /= 10; ok &= (c_user[b] == 1 || c_user[b] == 2 || c_user[b] == 4 || c_user[b] == 8); }
+        // a slice has at most CL_RPMAX rows
+        static const int nmax[CL_CLASSES] = {320, 512, 640, 1024, 2048, 4096};
+        for (int b = 0; b < CL_CLASSES; ++b) ok &= ((nmax[b] + c_user[b] - 1) / c_user[b] <= CL_RPMAX);
+        if (ok && d == 0) cmap = c_user;
+    }
     for (int cls = CL_CLASSES - 1; cls >= 0; --cls) {          // largest nodes first
         int cnt = class_cnt[cls];
         if (cnt <= 0) continue;
@@ -1351,9 +1363,10 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
     const bool need_tc = (p->affinity_impl == 1) && !d_W_dense;
     const bool feats = (p->theta != 0.0 && d_tarl) || (p->gamma != 0.0 && d_dino);
     const int aform = h->opt[ANCUTS_OPT_AFFINITY_FORM];        // 0 deferred (default), 1 dense two-pass, 2 dense one-kernel
-    pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && feats && aform != 2;
+    (void)feats;                                               // spatial-only configs take the deferred form too (pass 2 = exp(-alpha d))
+    pl.want_pairq = !d_W_dense && p->affinity_impl == 0 && aform != 2;
     pl.deferred = pl.want_pairq && aform == 0;                 // W written block by block after the root split
-    pl.grid_pairs = pl.deferred && h->opt[ANCUTS_OPT_PAIR_SEARCH] == 1;     // pairs from a cell grid instead of the tile sweep
+    pl.grid_pairs = pl.deferred && h->opt[ANCUTS_OPT_PAIR_SEARCH] == 0;     // cell-sorted, batched sweep (default) or the shuffled one
     if (pl.grid_pairs) ANCUTS_CUDA(cudaFuncSetAttribute(k_pair_grid_b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PG_CELLS * sizeof(int))));
     bool root_forest = pl.want_pairq;
     bool deferred = pl.deferred;
@@ -1493,7 +1506,8 @@ int ancuts_segment_chunks_host(ancuts_handle* h, int num_chunks, const int64_t* 
     cudaError_t ce = cudaEventRecord(h->copy_ev[num_chunks], st);           // earlier work on st may still read the staging area
     if (ce == cudaSuccess) ce = cudaStreamWaitEvent(h->copy_stream, h->copy_ev[num_chunks], 0);
     const bool feats_on = use_t || use_d;
-    const bool batched = feats_on && p->affinity_impl == 0 && h->opt[ANCUTS_OPT_AFFINITY_FORM] == 0 && h->opt[ANCUTS_OPT_PAIR_SEARCH] == 1;
+    (void)feats_on;
+    const bool batched = p->affinity_impl == 0 && h->opt[ANCUTS_OPT_AFFINITY_FORM] == 0 && h->opt[ANCUTS_OPT_PAIR_SEARCH] == 0;
     if (batched && ce == cudaSuccess) {
         // the batched pair stage needs every chunk's coordinates at once and no features: coordinates first (one copy), then
         // the features, which arrive while the pair stage and the root split run

@@ -322,21 +322,23 @@ __device__ __forceinline__ double cl_update_norm(ClusterShared& S, double* __res
     for (int i = threadIdx.x; i < nr; i += CL_THREADS) {
         double v = y[i];
         int j = 0;
+        double c0 = 0.0, c1 = 0.0;                        // the correction sum_j hs[j] V[j][i] in two chains (fixed order)
         for (; j + 12 <= rows; j += 12) {                 // 12 basis rows in flight: the rows behind the shared-memory part come
             double t[12];                                 // from L2 / HBM while other SMs stream W, one round trip per group
 #pragma unroll
             for (int u = 0; u < 12; ++u) t[u] = B.row(j + u)[i];
 #pragma unroll
-            for (int u = 0; u < 12; ++u) v -= S.hs[j + u] * t[u];
+            for (int u = 0; u < 12; u += 2) { c0 = fma(S.hs[j + u], t[u], c0); c1 = fma(S.hs[j + u + 1], t[u + 1], c1); }
         }
         for (; j + 4 <= rows; j += 4) {
             double t[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) t[u] = B.row(j + u)[i];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v -= S.hs[j + u] * t[u];
+            for (int u = 0; u < 4; u += 2) { c0 = fma(S.hs[j + u], t[u], c0); c1 = fma(S.hs[j + u + 1], t[u + 1], c1); }
         }
-        for (; j < rows; ++j) v -= S.hs[j] * B.row(j)[i];
+        for (; j < rows; ++j) c0 = fma(S.hs[j], B.row(j)[i], c0);
+        v -= c0 + c1;
         y[i] = v;
         q = fma(v, v, q);
     }
@@ -796,8 +798,19 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         CL_PHASE(4);
         // ---- update, squared norm, z = S y for the next matvec ----
         double q = cl_update_norm(S, yn, B, rows, nr);
-        if (C > 1) { for (int i = tid; i < nr; i += CL_THREADS) e.zbuf[g0 + i] = S.sv[i] * yn[i]; }
-        else { for (int i = tid; i < nr; i += CL_THREADS) zs[i + pad] = S.sv[i] * yn[i]; }
+        // z = S y for the next matvec: every CTA PUSHES its slice into the z vector of all CTAs of the cluster through
+        // distributed shared memory (every matvec of this step has ended before the barrier of the Gram-Schmidt exchange
+        // above, so the peers' z is free; the barrier of the norm exchange below publishes the stores).  Round 1 went through
+        // global memory: slice written, barrier, whole vector read back from L2 by every CTA.
+        if (C > 1) {
+            for (int i = tid; i < nr; i += CL_THREADS) {
+                const double zv = S.sv[i] * yn[i];
+#pragma unroll
+                for (int r = 0; r < C; ++r) cl.map_shared_rank(zs, r)[r0 + i + pad] = zv;
+            }
+        } else {
+            for (int i = tid; i < nr; i += CL_THREADS) zs[i + pad] = S.sv[i] * yn[i];
+        }
         q = cl_block_sum1(S, q);
         CL_PHASE(5);
         double nn = q;
@@ -807,9 +820,6 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             nn = 0.0;
 #pragma unroll
             for (int r = 0; r < C; ++r) nn += cl.map_shared_rank(&S.npart[0], r)[0];
-            // z of the whole node.  (Through global memory: a CTA reads its peers' slices from L2 at ~64 B/clk, distributed
-            // shared memory moves 17-21 B/clk per SM, B300_MICROARCH.md; the cluster barrier above orders the two sides.)
-            for (int i = tid; i < n; i += CL_THREADS) zs[i + pad] = __ldcg(e.zbuf + v.start + i);
         }
         const double beta = sqrt(nn);
         if (tid == 0) { S.alpha[k] = a1 + a2; S.beta[k] = beta; }

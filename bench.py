@@ -388,7 +388,7 @@ def sparse_bound(stats, nnz_per_row):
 def run_batch(args):
     import torch
     from autoinst_b200 import api, sharding
-    from autoinst_b200._lib import OPT_MATVEC, OPT_PAIR_SEARCH
+    from autoinst_b200._lib import MATVEC_DENSE, MATVEC_SPARSE, OPT_CLUSTER_MAP, OPT_MATVEC, OPT_PAIR_SEARCH
     from autoinst_b200.synthetic import CONFIGS
     D = Dist()
     rank, world, dev = D.rank, D.world, D.dev
@@ -404,8 +404,9 @@ def run_batch(args):
     gat = sharding.LabelGather(local_ids, packed.sizes, total_chunks, device=dev, dst=0) if world > 1 else None
     dev_chunks = packed.to_device(dev, labels=gat.send_view() if gat else None)
     hd = api.Handle.get(dev)
-    hd.set_option(OPT_MATVEC, args.matvec)
-    hd.set_option(OPT_PAIR_SEARCH, args.pairs)
+    hd.set_option(OPT_MATVEC, MATVEC_DENSE if args.matvec == "dense" else MATVEC_SPARSE)
+    hd.set_option(OPT_PAIR_SEARCH, 1 if args.pairs == "shuffled" else 0)
+    hd.set_option(OPT_CLUSTER_MAP, args.cluster_map)
     gather_host_ms = []
 
     def gather():
@@ -450,9 +451,18 @@ def run_batch(args):
             acc_all[s]["bytes"] += acc[s]["bytes"]; acc_all[s]["launches"] += acc[s]["launches"]
 
     gather_host_ms.clear()
+    sparse_acc = dict(entry_steps=0.0, entries=0.0)
+    _plain_acct = step_resident_acct
+
+    def step_resident_acct():        # noqa: F811  (adds the sparse-form counters of every step)
+        _plain_acct()
+        sa = hd.sparse_accounting()
+        sparse_acc["entry_steps"] += sa["entry_steps"]; sparse_acc["entries"] += sa["entries"]
+
     ms_step, ms_min, ms_mean = D.timed(step_resident_acct, args.steps)
     launches = hd.launch_count(reset=True)
     hd.set_stage_timing(0)
+    mv_default = dict(mv)
     g_res = list(gather_host_ms)
     gather_host_ms.clear()
     # timed region 2: the same steps through the host-buffer entry point
@@ -462,6 +472,25 @@ def run_batch(args):
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     gmax = D.over_ranks(float(np.mean(g_res)) if g_res else 0.0)
 
+    # roofline leg: the north-star DENSE matvec form (W streamed from HBM every Lanczos step) on the same batch, same process,
+    # CUDA events around every level launch.  When the timed region itself ran the dense form this is that region.
+    roof_src = "the timed region (value)"
+    roof_steps_used = args.steps
+    if args.matvec != "dense" and args.roof_steps > 0:
+        roof_steps_used = args.roof_steps
+        hd.set_option(OPT_MATVEC, MATVEC_DENSE)
+        api.segment_packed(packed, dev_chunks=dev_chunks, **kw)              # warm-up of the dense kernels
+        hd.set_stage_timing(2)
+        for k in mv:
+            mv[k] = 0.0
+        for _ in range(args.roof_steps):
+            api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
+            acc = hd.accounting()
+            for k in mv:
+                mv[k] += acc["matvec"][k]
+        hd.set_stage_timing(0)
+        hd.set_option(OPT_MATVEC, MATVEC_SPARSE)
+        roof_src = f"a separate leg of {args.roof_steps} steps with ANCUTS_OPT_MATVEC = dense after the timed regions (the default form keeps W in shared memory)"
     # outside the timed regions: node statistics, per-stage shares, the Python-list surface, the parity spot check
     res = api.segment_packed(packed, device=dev, want_stats=True, **kw)
     stats = res.stats
@@ -522,8 +551,9 @@ def run_batch(args):
                                      "max_over_ranks": gmax[0], "e2e_mean_rank0": float(np.mean(g_e2e)) if g_e2e else 0.0,
                                      "what": "one all_gather_into_tensor of the padded label buffers + one async D2H into "
                                              "pinned memory on rank 0; tables exchanged once before the clock"},
-                       "matvec_form": "dense blocks streamed from HBM every Lanczos step" if args.matvec == 0 else
-                                      "row slices compressed into shared memory once per node",
+                       "matvec_form": "dense blocks streamed from HBM every Lanczos step" if args.matvec == "dense" else
+                                      "row slices compressed into shared memory once per node (nodes <= 2048 points)",
+                       "pair_search": args.pairs,
                        "l2": "inputs larger than L2: every step rebuilds the float32 affinity blocks of all recursion nodes "
                              "(%.1f GB per GPU, 126 MB of L2) and streams them from HBM once per Lanczos step"
                              % (acc_all["degree"]["bytes"] / max(args.steps, 1) / 1e9),
@@ -543,10 +573,22 @@ def run_batch(args):
                     "ms_per_step_over_ranks": {"max": ms_e2e, "min": ms_e2e_min, "mean": ms_e2e_mean},
                     "h2d_bytes_per_step": packed.h2d_bytes() * world, "d2h_bytes_per_step": packed.d2h_bytes() * world},
             "gpu_launches": int(launches) * world,
+            "sparse": None if args.matvec == "dense" else {
+                "what": "default matvec form: the CTA's row slice as CSR (float32 value + uint16 column) in shared memory, built once "
+                        "per node from the dense block; its Lanczos kernels over the timed region (value)",
+                "entry_steps_per_step": sparse_acc["entry_steps"] / max(args.steps, 1),
+                "lower_bound_bytes_per_step": 8.0 * sparse_acc["entry_steps"] / max(args.steps, 1),
+                "hbm_bytes_per_step": mv_default["bytes"] / max(args.steps, 1),
+                "lanczos_ms_per_step": mv_default["ms"] / max(args.steps, 1),
+                "lower_bound_gbs": (8.0 * sparse_acc["entry_steps"] / (mv_default["ms"] * 1e-3) / 1e9) if mv_default["ms"] else None,
+                "note": "the sparse matvec reads shared memory, not HBM: its Lanczos phase is bound by Gram-Schmidt, barriers and the "
+                        "convergence checks (profiles/), not by a memory roofline; lower_bound_gbs is the (4+4)-byte-per-entry "
+                        "bound of SURVEY.md §8d divided by the measured Lanczos time"},
             "roofline": {"bound": "hbm", "kernel": "k_lanczos_cluster<C, 6> (dense matvec of the persistent Lanczos kernels, one timed "
                                                     "launch = the concurrent kernels of one recursion level)",
+                         "measured_over": roof_src,
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(args, mv["launches"] / max(args.steps, 1)),
+                         "traffic": measured_traffic(args, mv["launches"] / max(roof_steps_used, 1)),
                          "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum of the cluster kernels, "
                                            "profiles/" + TRAFFIC_FILE + ", per level like achieved",
                          "peak_source": peak_src,
@@ -573,7 +615,7 @@ def run_map(args):
     labels gathered once per pass to rank 0, merged (N2) and scored (N4) there on the device."""
     import torch
     from autoinst_b200 import api, sharding
-    from autoinst_b200._lib import OPT_MATVEC, OPT_PAIR_SEARCH
+    from autoinst_b200._lib import MATVEC_DENSE, MATVEC_SPARSE, OPT_CLUSTER_MAP, OPT_MATVEC, OPT_PAIR_SEARCH
     from autoinst_b200.synthetic import CONFIGS, make_map
     D = Dist()
     rank, world, dev = D.rank, D.world, D.dev
@@ -589,8 +631,9 @@ def run_map(args):
     gat = sharding.LabelGather(mine, packed.sizes, len(chunks), device=dev, dst=0)
     dev_chunks = packed.to_device(dev, labels=gat.send_view())
     hd = api.Handle.get(dev)
-    hd.set_option(OPT_MATVEC, args.matvec)
-    hd.set_option(OPT_PAIR_SEARCH, args.pairs)
+    hd.set_option(OPT_MATVEC, MATVEC_DENSE if args.matvec == "dense" else MATVEC_SPARSE)
+    hd.set_option(OPT_PAIR_SEARCH, 1 if args.pairs == "shuffled" else 0)
+    hd.set_option(OPT_CLUSTER_MAP, args.cluster_map)
     post = api.MapPost(chunks, device=dev, min_points=args.min_points) if rank == 0 else None
     last = {}
     src_index = None
@@ -635,6 +678,22 @@ def run_map(args):
     ms_e2e, ms_e2e_min, ms_e2e_mean = D.timed(step_e2e, args.steps)
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    # where one resident pass spends its time (host timer with a device synchronisation after every part, one extra pass)
+    D.barrier()
+    t0 = time.perf_counter()
+    api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
+    torch.cuda.synchronize(dev)
+    t1 = time.perf_counter()
+    gat.start()
+    lab_h = gat.finish()
+    torch.cuda.synchronize(dev)
+    t2 = time.perf_counter()
+    finish(lab_h)
+    torch.cuda.synchronize(dev)
+    t3 = time.perf_counter()
+    seg_ms = D.over_ranks(1e3 * (t1 - t0))
+    breakdown = {"segment_ms_max_over_ranks": seg_ms[0], "segment_ms_min_over_ranks": seg_ms[1],
+                 "gather_ms_rank0": 1e3 * (t2 - t1), "merge_metrics_ms_rank0": 1e3 * (t3 - t2)}
     # single-chunk latency through the array-level call the drop-in ncuts_chunk makes (one chunk per call)
     lat = None
     if rank == 0:
@@ -661,6 +720,7 @@ def run_map(args):
                        "step": "segment the rank's shard -> all-gather labels -> D2H on rank 0 -> merge + metrics on rank 0"
                                + (" (device: ancuts_merge_chunks / ancuts_instance_metrics)" if post is not None else
                                   " (merge/metrics not in this build)"),
+                       "breakdown_one_pass": breakdown,
                        "metrics": last.get("metrics"), "single_chunk_latency": lat},
             "e2e": {"value": len(chunks) / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "ms_per_step_over_ranks": {"max": ms_e2e, "min": ms_e2e_min, "mean": ms_e2e_mean},
@@ -684,8 +744,12 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="chunks per GPU per step")
     ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
     ap.add_argument("--seed", type=int, default=1000)
-    ap.add_argument("--matvec", type=int, default=0, help="ANCUTS_OPT_MATVEC: 0 dense from HBM, 1 shared-memory slices")
-    ap.add_argument("--pairs", type=int, default=0, help="ANCUTS_OPT_PAIR_SEARCH: 0 shuffled tile sweep, 1 cell-sorted sweep")
+    ap.add_argument("--matvec", default="sparse", choices=["sparse", "dense"],
+                    help="ANCUTS_OPT_MATVEC: row slices in shared memory (default) or dense blocks from HBM every step")
+    ap.add_argument("--pairs", default="sorted", choices=["sorted", "shuffled"], help="ANCUTS_OPT_PAIR_SEARCH")
+    ap.add_argument("--cluster-map", dest="cluster_map", type=int, default=0, help="ANCUTS_OPT_CLUSTER_MAP (tuning)")
+    ap.add_argument("--roof-steps", dest="roof_steps", type=int, default=3,
+                    help="steps of the dense-matvec leg that measures the roofline of the north-star kernel (0 = skip)")
     ap.add_argument("--cpu-chunks", type=int, default=1, help="chunks in the cpu_baseline sample / parity check (0 = skip)")
     ap.add_argument("--ref-chunks", type=int, default=0, help="--impl reference: chunks per step (0 = half the workers)")
     ap.add_argument("--no-one-core", action="store_true", help="--impl reference: skip the separate 1-core measurement")

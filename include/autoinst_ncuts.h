@@ -214,16 +214,21 @@ int ancuts_instance_metrics(ancuts_handle* h, int64_t n, const int32_t* d_all_la
  * (the Python drop-in raises, the array-level API warns). */
 int ancuts_last_unconverged(ancuts_handle* h);
 
-/* Alternative implementations behind the same results (each one parity-tested; defaults = 0):
+/* Alternative implementations behind the same results (each one parity-tested; 0 = the default):
  *   ANCUTS_OPT_AFFINITY_FORM  0 deferred (pairs queued, W written block by block after the root split),
  *                             1 dense two-pass (pairs + feature pass on the full N x N matrix), 2 dense one-kernel
- *   ANCUTS_OPT_PAIR_SEARCH    0 upper-triangle tile sweep, 1 cell grid (deferred form only)
- *   ANCUTS_OPT_MATVEC         0 dense blocks streamed from HBM every Lanczos step (north-star form),
- *                             1 the cluster's row slices compressed into shared memory once per node */
+ *   ANCUTS_OPT_PAIR_SEARCH    0 cell-sorted tile sweep, all chunks of the call in one launch, tile pairs pruned by their boxes,
+ *                             1 shuffled 64 x 64 tile sweep over the whole upper triangle, one launch per chunk
+ *   ANCUTS_OPT_MATVEC         0 the cluster's row slices compressed into shared memory once per node (nodes <= 2048 points),
+ *                             1 dense blocks streamed from HBM every Lanczos step (the north-star form; bench.py measures
+ *                               its roofline)
+ *   ANCUTS_OPT_CLUSTER_MAP    0 built-in; otherwise six decimal digits (1, 2, 4 or 8 each) = CTAs per node for the size bins
+ *                             <= 320, 512, 640, 1024, 2048, 4096 points (tuning) */
 #define ANCUTS_OPT_AFFINITY_FORM 0
 #define ANCUTS_OPT_PAIR_SEARCH   1
 #define ANCUTS_OPT_MATVEC        2
-#define ANCUTS_OPT_COUNT         3
+#define ANCUTS_OPT_CLUSTER_MAP   3
+#define ANCUTS_OPT_COUNT         4
 int ancuts_set_option(ancuts_handle* h, int option, int value);
 
 /* Shared-memory sparse matvec form (ANCUTS_OPT_MATVEC = 1), last segment call: out2[0] = sum over the nodes it ran of

@@ -26,8 +26,17 @@ torch = pytest.importorskip("torch")
 FIX = np.load(os.path.join(GOLDEN, "parity_bench_size.npz"))
 
 
-def run_set(device, name, n_target, seed0, count, clutter):
+def run_set(device, name, n_target, seed0, count, clutter, dense_matvec=False):
     from autoinst_b200 import api
+    from autoinst_b200._lib import MATVEC_DENSE, MATVEC_SPARSE, OPT_MATVEC
+    api.Handle.get(device).set_option(OPT_MATVEC, MATVEC_DENSE if dense_matvec else MATVEC_SPARSE)
+    try:
+        return _run_set(api, device, name, n_target, seed0, count, clutter)
+    finally:
+        api.Handle.get(device).set_option(OPT_MATVEC, MATVEC_SPARSE)
+
+
+def _run_set(api, device, name, n_target, seed0, count, clutter):
     cfg = CONFIGS[name]
     feats = "tarl_dino" if cfg["gamma"] else "tarl"
     seeds = list(range(seed0, seed0 + count))
@@ -52,6 +61,14 @@ def test_labels_identical_at_bench_size(cuda_device, name, n_target, seed0, coun
     stable = [r for r in rows if r[4]]
     assert len(stable) >= max(3, count - 1), "too few oracle-stable chunks in the fixture"
     bad = [s for s, ch, lab, ref, _ in stable if not R.same_partition(lab, ref)]
+    assert not bad, f"partitions differ from the reference on seeds {bad}"
+
+
+def test_labels_identical_at_bench_size_dense_matvec(cuda_device):
+    """The north-star dense form (W streamed from HBM every Lanczos step, ANCUTS_OPT_MATVEC = 1) on the bench workload."""
+    name, n_target, seed0, count, clutter = [s for s in SETS if s[0] == "tarl_spatial" and s[1] == 8192 and s[4] == 0][0]
+    rows = run_set(cuda_device, name, n_target, seed0, count, clutter, dense_matvec=True)
+    bad = [s for s, ch, lab, ref, st in rows if st and not R.same_partition(lab, ref)]
     assert not bad, f"partitions differ from the reference on seeds {bad}"
 
 

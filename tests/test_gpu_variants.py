@@ -36,10 +36,12 @@ def check_affinity(W, A):
 
 
 # include/autoinst_ncuts.h: ANCUTS_OPT_AFFINITY_FORM 0 (0 deferred, 1 dense two-pass, 2 dense one-kernel),
-# ANCUTS_OPT_PAIR_SEARCH 1 (0 tile sweep, 1 cell grid), ANCUTS_OPT_MATVEC 2 (0 dense from HBM, 1 shared-memory slices)
-AFF, PAIRS, MATVEC = 0, 1, 2
-VARIANTS = {"default": {}, "grid_pairs": {PAIRS: 1}, "dense_two_pass_affinity": {AFF: 1}, "one_kernel_affinity": {AFF: 2},
-            "smem_sparse_matvec": {MATVEC: 1}, "smem_sparse_matvec_grid_pairs": {MATVEC: 1, PAIRS: 1}}
+# ANCUTS_OPT_PAIR_SEARCH 1 (0 cell-sorted sweep, 1 shuffled sweep), ANCUTS_OPT_MATVEC 2 (0 shared-memory slices, 1 dense from
+# HBM), ANCUTS_OPT_CLUSTER_MAP 3 (CTAs per node and size bin)
+AFF, PAIRS, MATVEC, CMAP = 0, 1, 2, 3
+VARIANTS = {"default": {}, "shuffled_pairs": {PAIRS: 1}, "dense_two_pass_affinity": {AFF: 1}, "one_kernel_affinity": {AFF: 2},
+            "dense_matvec": {MATVEC: 1}, "dense_matvec_shuffled_pairs": {MATVEC: 1, PAIRS: 1},
+            "sparse_matvec_few_ctas": {CMAP: 112248}, "dense_matvec_many_ctas": {MATVEC: 1, CMAP: 224888}}
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
@@ -148,16 +150,25 @@ def test_level_trace(cuda_device):
     packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"])
     devc = packed.to_device(cuda_device)
     hd = api.Handle.get(cuda_device)
-    hd.set_stage_timing(2)
-    try:
-        res = api.segment_packed(packed, dev_chunks=devc, alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"], want_stats=True)
-        lv = hd.levels()
-        acc = hd.accounting()
-    finally:
-        hd.set_stage_timing(0)
-    assert len(lv) >= 1 and all(l["ms"] > 0 for l in lv)
-    assert sum(sum(l["bins"]) + l["big"] for l in lv) == len(res.stats)
-    assert abs(sum(l["ms"] for l in lv) - acc["matvec"]["ms"]) < 1e-3 * max(acc["matvec"]["ms"], 1.0) + 1e-3
-    n = res.stats["n"].astype(np.float64)
-    k = res.stats["steps"].astype(np.float64)
-    assert acc["matvec"]["bytes"] == pytest.approx(float((k * (4 * n * n + 8 * n)).sum()), rel=1e-12)
+    for dense in (1, 0):
+        hd.set_option(MATVEC, dense)
+        hd.set_stage_timing(2)
+        try:
+            res = api.segment_packed(packed, dev_chunks=devc, alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"], want_stats=True)
+            lv = hd.levels()
+            acc = hd.accounting()
+            sa = hd.sparse_accounting()
+        finally:
+            hd.set_stage_timing(0)
+            hd.set_option(MATVEC, 0)
+        assert len(lv) >= 1 and all(l["ms"] > 0 for l in lv)
+        assert sum(sum(l["bins"]) + l["big"] for l in lv) == len(res.stats)
+        assert abs(sum(l["ms"] for l in lv) - acc["matvec"]["ms"]) < 1e-3 * max(acc["matvec"]["ms"], 1.0) + 1e-3
+        n = res.stats["n"].astype(np.float64)
+        k = res.stats["steps"].astype(np.float64)
+        if dense:      # algorithmic bytes of the dense form: every block once per Lanczos step
+            assert acc["matvec"]["bytes"] == pytest.approx(float((k * (4 * n * n + 8 * n)).sum()), rel=1e-12)
+            assert sa["entries"] == 0
+        else:          # shared-memory form: every block read once, then steps x stored entries from shared memory
+            assert acc["matvec"]["bytes"] == pytest.approx(float((4 * n * n).sum()), rel=1e-12)
+            assert 3 * n.sum() <= sa["entries"] <= (n * n).sum() and sa["entry_steps"] >= sa["entries"]

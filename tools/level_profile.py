@@ -16,8 +16,8 @@ def main():
     ap.add_argument("--n-target", dest="n_target", type=int, default=8192)
     ap.add_argument("--seed", type=int, default=1000)
     ap.add_argument("--out", default="gpurun_out/levels.json")
-    ap.add_argument("--matvec", type=int, default=0)
-    ap.add_argument("--pairs", type=int, default=0)
+    ap.add_argument("--matvec", type=int, default=0, help="ANCUTS_OPT_MATVEC: 0 shared-memory sparse (default), 1 dense")
+    ap.add_argument("--pairs", type=int, default=0, help="ANCUTS_OPT_PAIR_SEARCH: 0 cell-sorted (default), 1 shuffled")
     args = ap.parse_args()
     import torch
     from autoinst_b200 import api
