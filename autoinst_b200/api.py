@@ -306,6 +306,51 @@ def feature_pool(major_points, scan_points, scan_features, radius, box_min, box_
     return (out, cnt) if return_count else out
 
 
+def dino_mean_views(major_points, views, max_dist, *, feat_dim=384, device=None, return_count=False):
+    """DINOv2 features of the major points averaged over the views that see them (`image_based_features_per_patch`
+    behind its visibility bookkeeping + `dinov2_mean`, image_utils.py:264-346,363-371; C ABI `ancuts_dino_view_pixels`,
+    `ancuts_dino_mean`).  views: list of None (a view the reference skips) or dicts with T_pcd2cam (4 x 4), visible_cam
+    ((M, 3) float64: the view's visible chunk points in the camera frame), K (3 x 3), img_hw (h, w), feature_map
+    ((Hp, Wp, F) float32, numpy or a CUDA tensor).  Returns (N, F) float64 on the device."""
+    device = _dev(device)
+    hd = Handle.get(device)
+    major = np.ascontiguousarray(major_points, dtype=np.float64)
+    n = major.shape[0]
+    V = len(views)
+    pix = torch.full((max(V, 1), n), -1, dtype=torch.int32, device=device)
+    maps, keep = [], []
+    hom = np.concatenate([major, np.ones((n, 1))], axis=1)
+    with torch.cuda.device(device):
+        for v, view in enumerate(views):
+            if view is None:
+                maps.append(None)
+                continue
+            fm = view["feature_map"]
+            fm = fm.to(device=device, dtype=torch.float32).contiguous() if isinstance(fm, torch.Tensor) else \
+                torch.as_tensor(np.ascontiguousarray(fm, dtype=np.float32)).to(device)
+            if fm.shape[2] != feat_dim:
+                raise ValueError("feature map depth differs from feat_dim")
+            keep.append(fm)
+            maps.append(fm)
+            T = np.asarray(view["T_pcd2cam"], dtype=np.float64)
+            cam = hom @ T.T                                        # Open3D PointCloud.transform (:264): homogeneous product,
+            cam = np.ascontiguousarray(cam[:, :3] / cam[:, 3:4])  # division by w
+            d_cam = torch.as_tensor(cam).to(device)
+            vis = _as_dev(view["visible_cam"], torch.float64, device).reshape(-1, 3)
+            K = np.ascontiguousarray(view["K"], dtype=np.float64).reshape(9)
+            h_img, w_img = int(view["img_hw"][0]), int(view["img_hw"][1])
+            check(hd.lib.ancuts_dino_view_pixels(hd.h, n, _ptr(d_cam), int(vis.shape[0]), _ptr(vis) if vis.shape[0] else None,
+                                                 float(max_dist), K.ctypes.data_as(C.POINTER(C.c_double)), h_img, w_img,
+                                                 int(fm.shape[0]), int(fm.shape[1]), _ptr(pix[v]), _stream(device)))
+            keep.extend([d_cam, vis])
+        out = torch.empty((n, feat_dim), dtype=torch.float64, device=device)
+        cnt = torch.empty(n, dtype=torch.int32, device=device)
+        ptrs = (C.c_void_p * max(V, 1))(*[(m.data_ptr() if m is not None else (keep[0].data_ptr() if keep else 0)) for m in maps] or [0])
+        check(hd.lib.ancuts_dino_mean(hd.h, n, V, _ptr(pix), ptrs, int(feat_dim), _ptr(out), _ptr(cnt), _stream(device)))
+        torch.cuda.current_stream(device).synchronize()           # `keep` may go away
+    return (out, cnt) if return_count else out
+
+
 # ------------------------------------------------------------------------------------------------
 # map level: merge (N2), remove_semantics, instance metrics (N4)
 # ------------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@
 #include "kernels_ncut.cuh"
 #include "kernels_cluster.cuh"
 #include "kernels_pool.cuh"
+#include "kernels_dino.cuh"
 
 namespace ancuts {
 
@@ -1333,6 +1334,51 @@ static int run_pairs_batched(ancuts_handle* h, Plan& pl, const double* d_points,
     // taken per chunk right before its feature pass (run_rebuild)
     if (!h->feat_ev && p->theta != 0.0 && d_tarl)
         LAUNCH(SG_AFFINITY, k_zero_rows<<<(pl.P + 7) / 8, 256, 0, st>>>(pl.P, d_tarl, p->tarl_dim, pl.tarl_zero));
+    ANCUTS_CUDA(cudaGetLastError());
+    return ANCUTS_OK;
+}
+
+// ---- next row N3 (DINOv2 half): per-view feature-map pixel of every major point, then the mean over views ----
+int ancuts_dino_view_pixels(ancuts_handle* h, int num_major, const double* d_major_cam, int num_visible,
+                            const double* d_visible_cam, double max_dist, const double* h_K, int img_h, int img_w,
+                            int map_h, int map_w, int32_t* d_out_pixel, void* stream) {
+    if (!h || num_major <= 0 || !d_major_cam || num_visible < 0 || (num_visible > 0 && !d_visible_cam) || !h_K ||
+        img_h <= 0 || img_w <= 0 || map_h <= 0 || map_w <= 0 || !d_out_pixel) {
+        set_error("bad argument to ancuts_dino_view_pixels");
+        return ANCUTS_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    LAUNCH(SG_AFFINITY, k_dino_view_pixels<<<(num_major + 255) / 256, 256, 0, st>>>(
+        num_major, d_major_cam, num_visible, d_visible_cam, max_dist, h_K[0], h_K[1], h_K[2], h_K[3], h_K[4], h_K[5], h_K[6],
+        h_K[7], h_K[8], img_h, img_w, map_h, map_w, d_out_pixel));
+    ANCUTS_CUDA(cudaGetLastError());
+    return ANCUTS_OK;
+}
+
+int ancuts_dino_mean(ancuts_handle* h, int num_major, int num_views, const int32_t* d_view_pixel,
+                     const float* const* h_feature_maps, int feat_dim, double* d_out, int32_t* d_out_count, void* stream) {
+    if (!h || num_major <= 0 || num_views < 0 || (num_views > 0 && (!d_view_pixel || !h_feature_maps)) || feat_dim <= 0 ||
+        feat_dim > 384 || !d_out) {
+        set_error("bad argument to ancuts_dino_mean (feat_dim 1 .. 384)");
+        return ANCUTS_EINVAL;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    ANCUTS_CUDA(cudaSetDevice(h->device));
+    const float** d_maps = nullptr;
+    if (num_views > 0) {
+        int rc = ensure_ws(h, (size_t)num_views * sizeof(float*) + 256);      // the table of map pointers lives in the workspace
+        if (rc) return rc;
+        d_maps = reinterpret_cast<const float**>(h->ws);
+        ANCUTS_CUDA(cudaMemcpyAsync(d_maps, h_feature_maps, (size_t)num_views * sizeof(float*), cudaMemcpyHostToDevice, st));
+        ANCUTS_CUDA(cudaStreamSynchronize(st));                              // h_feature_maps is the caller's
+    }
+    const int blocks = (num_major + 7) / 8;
+    const int fpl = (feat_dim + 31) / 32;
+#define DINO_CASE(F) LAUNCH(SG_AFFINITY, k_dino_mean<F><<<blocks, 256, 0, st>>>(num_major, num_views, d_view_pixel, d_maps, feat_dim, \
+                                                                           d_out, d_out_count))
+    if (fpl <= 1) DINO_CASE(1); else if (fpl <= 3) DINO_CASE(3); else if (fpl <= 4) DINO_CASE(4); else DINO_CASE(12);
+#undef DINO_CASE
     ANCUTS_CUDA(cudaGetLastError());
     return ANCUTS_OK;
 }

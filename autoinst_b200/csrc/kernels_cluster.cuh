@@ -277,6 +277,12 @@ struct SliceBasis {
     __device__ __forceinline__ double* row(int j) const {
         return (j < rows_s) ? smem + (size_t)j * nrp : glob + (size_t)j * P;
     }
+    __device__ __forceinline__ double get(int j, int i) const {
+        return (j < rows_s) ? smem[(size_t)j * nrp + i] : glob[(size_t)j * P + i];
+    }
+    __device__ __forceinline__ void put(int j, int i, double v) const {
+        row(j)[i] = v;
+    }
 };
 
 // partial dots of the slice vector y with basis rows [0, rows): S.hpart[buf][j].  One warp per row,
@@ -289,8 +295,8 @@ __device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const double* 
 #pragma unroll
     for (int m = 0; m < M; ++m) { int i = lane + 32 * m; yr[m] = (i < nr) ? y[i] : 0.0; }
     for (int j = warp; j < rows; j += CL_WARPS) {
-        const double* vr = B.row(j);
         double t[M];
+        const double* vr = B.row(j);
 #pragma unroll
         for (int m = 0; m < M; ++m) { int i = lane + 32 * m; t[m] = (i < nr) ? vr[i] : 0.0; }
         double s = 0.0;
@@ -326,18 +332,18 @@ __device__ __forceinline__ double cl_update_norm(ClusterShared& S, double* __res
         for (; j + 12 <= rows; j += 12) {                 // 12 basis rows in flight: the rows behind the shared-memory part come
             double t[12];                                 // from L2 / HBM while other SMs stream W, one round trip per group
 #pragma unroll
-            for (int u = 0; u < 12; ++u) t[u] = B.row(j + u)[i];
+            for (int u = 0; u < 12; ++u) t[u] = B.get(j + u, i);
 #pragma unroll
             for (int u = 0; u < 12; u += 2) { c0 = fma(S.hs[j + u], t[u], c0); c1 = fma(S.hs[j + u + 1], t[u + 1], c1); }
         }
         for (; j + 4 <= rows; j += 4) {
             double t[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) t[u] = B.row(j + u)[i];
+            for (int u = 0; u < 4; ++u) t[u] = B.get(j + u, i);
 #pragma unroll
             for (int u = 0; u < 4; u += 2) { c0 = fma(S.hs[j + u], t[u], c0); c1 = fma(S.hs[j + u + 1], t[u + 1], c1); }
         }
-        for (; j < rows; ++j) c0 = fma(S.hs[j], B.row(j)[i], c0);
+        for (; j < rows; ++j) c0 = fma(S.hs[j], B.get(j, i), c0);
         v -= c0 + c1;
         y[i] = v;
         q = fma(v, v, q);
@@ -423,7 +429,7 @@ __device__ __forceinline__ double cl_matvec_guard(ClusterShared& S, const double
 }
 
 // ---- TMA-fed matvec (MODE 4 / 6): every warp owns a ring of RING_ST stages in shared memory; a stage holds up to
-// RING_COLS columns of the warp's two current rows (4 KB).  Lane 0 issues one bulk copy per row and stage
+// RING_COLS columns of the warp's RING_R current rows (4 KB).  Lane 0 issues one bulk copy per row and stage
 // (cp.async.bulk, completion counted on the stage's mbarrier); the warp waits for the stage, multiplies it with z
 // from shared memory and hands the slot back.  Registers limit a register-staged form to 4 KB per warp in flight and
 // only in bursts (issue 8 loads, wait, multiply: ncu put 32 % of that kernel's stall samples on the first use of the
@@ -433,20 +439,27 @@ __device__ __forceinline__ double cl_matvec_guard(ClusterShared& S, const double
 // The blocks come from k_gather_blocks_cur / k_zero_blocks, which zero the <= 3-column fringe of every block, and
 // zs is zero there: no selects.  (Measured and dropped, DESIGN.md 5a: 1 KB stages x 4, register-staged loads with L2
 // bulk prefetch, per-lane prefetch, L2 prefetch of the next matvec's stages, all loads of a stage hoisted.)
+#ifndef ANCUTS_RING_ROWS
+#define ANCUTS_RING_ROWS 4
+#endif
 constexpr int RING_ST = 2;
-constexpr int RING_COLS = 512;                               // floats per row and stage
-constexpr int RING_STAGE_FLOATS = 2 * RING_COLS;
+constexpr int RING_R = ANCUTS_RING_ROWS;                     // rows per stage.  4: every z value read from shared memory serves
+                                                             // four rows (0.713 of the HBM peak against 0.684 with 2, profiles/r2i_lib_*)
+constexpr int RING_COLS = 1024 / RING_R;                     // floats per row and stage (a stage is 4 KB)
+constexpr int RING_STAGE_FLOATS = RING_R * RING_COLS;
 constexpr int RING_WARP_FLOATS = RING_ST * RING_STAGE_FLOATS;
 constexpr int RING_BYTES = CL_WARPS * RING_WARP_FLOATS * 4;      // 128 KB
 
-struct RingGeom { int a0, width, nseg, npass, T; };
+struct RingGeom {
+    int a0, width, nseg, npass, T;
+};
 __device__ __forceinline__ RingGeom ring_geom(const NodeView& v, int nr) {
     RingGeom q;
     const int warp = threadIdx.x >> 5;
     q.a0 = v.ro & ~3;
     q.width = (v.ro + v.n - q.a0 + 3) & ~3;            // columns fetched per row (multiple of 4)
     q.nseg = (q.width + RING_COLS - 1) / RING_COLS;
-    q.npass = (warp * 2 < nr) ? (nr - warp * 2 + CL_WARPS * 2 - 1) / (CL_WARPS * 2) : 0;
+    q.npass = (warp * RING_R < nr) ? (nr - warp * RING_R + CL_WARPS * RING_R - 1) / (CL_WARPS * RING_R) : 0;
     q.T = q.npass * q.nseg;
     return q;
 }
@@ -454,15 +467,18 @@ __device__ __forceinline__ RingGeom ring_geom(const NodeView& v, int nr) {
 __device__ __forceinline__ void ring_issue(const NodeView& v, const RingGeom& q, int r0, int nr, int p, int sg,
                                            float* ring_w, uint64_t* bars_w, uint32_t gi) {
     const int warp = threadIdx.x >> 5;
-    const int rb = warp * 2 + p * (CL_WARPS * 2);
+    const int rb = warp * RING_R + p * (CL_WARPS * RING_R);
     const int c = sg * RING_COLS;
     const uint32_t bytes = (uint32_t)min(RING_COLS, q.width - c) * 4u;
     const uint32_t slot = gi % RING_ST;
     float* dst = ring_w + slot * RING_STAGE_FLOATS;
     uint64_t* bar = bars_w + slot;
-    mbarrier_expect_tx(bar, 2u * bytes);
-    bulk_copy_g2s(dst, v.W + (size_t)(v.ro + r0 + min(rb, nr - 1)) * v.ld + q.a0 + c, bytes, bar);
-    bulk_copy_g2s(dst + RING_COLS, v.W + (size_t)(v.ro + r0 + min(rb + 1, nr - 1)) * v.ld + q.a0 + c, bytes, bar);
+    mbarrier_expect_tx(bar, (uint32_t)RING_R * bytes);
+#pragma unroll
+    for (int rr = 0; rr < RING_R; ++rr) {
+        const float* src = v.W + (size_t)(v.ro + r0 + min(rb + rr, nr - 1)) * v.ld + q.a0 + c;
+        bulk_copy_g2s(dst + rr * RING_COLS, src, bytes, bar);
+    }
 }
 // the first min(RING_ST, T) stages of a matvec (before the first step and after every matvec)
 __device__ __forceinline__ void ring_prologue(const NodeView& v, const RingGeom& q, int r0, int nr, float* ring_w,
@@ -491,27 +507,26 @@ __device__ __forceinline__ double cl_matvec_ring(ClusterShared& S, const double*
     int t = 0;
     double pa = 0.0;
     for (int p = 0; p < q.npass; ++p) {
-        double acc0 = 0.0, acb0 = 0.0, acc1 = 0.0, acb1 = 0.0;
+        double acc[RING_R], acb[RING_R];               // two FMA chains per row: one FP64 instruction per element
+#pragma unroll
+        for (int rr = 0; rr < RING_R; ++rr) { acc[rr] = 0.0; acb[rr] = 0.0; }
         for (int sg = 0; sg < q.nseg; ++sg, ++t) {
             const uint32_t slot = g % RING_ST;
             mbarrier_wait(bars_w + slot, (g / RING_ST) & 1u);
             const float* buf = ring_w + slot * RING_STAGE_FLOATS;
-            auto fma8 = [&](const float4& wa, const float4& wb, const double2& z0, const double2& z1) {
-                acc0 = fma((double)wa.x, z0.x, acc0); acb0 = fma(widen_alt<MIX>(wa.y), z0.y, acb0);
-                acc0 = fma((double)wa.z, z1.x, acc0); acb0 = fma(widen_alt<MIX>(wa.w), z1.y, acb0);
-                acc1 = fma((double)wb.x, z0.x, acc1); acb1 = fma(widen_alt<MIX>(wb.y), z0.y, acb1);
-                acc1 = fma((double)wb.z, z1.x, acc1); acb1 = fma(widen_alt<MIX>(wb.w), z1.y, acb1);
-            };
 #pragma unroll
             for (int gq = 0; gq < RING_COLS / 128; ++gq) {
                 const int cs = 128 * gq + 4 * lane;                // column inside the stage
                 const int cofs = sg * RING_COLS + cs;              // column - a0
                 if (cofs < q.width) {
-                    const float4 wa = *reinterpret_cast<const float4*>(buf + cs);
-                    const float4 wb = *reinterpret_cast<const float4*>(buf + RING_COLS + cs);
                     const double2 z0 = *reinterpret_cast<const double2*>(&zs[cofs]);
                     const double2 z1 = *reinterpret_cast<const double2*>(&zs[cofs + 2]);
-                    fma8(wa, wb, z0, z1);
+#pragma unroll
+                    for (int rr = 0; rr < RING_R; ++rr) {
+                        const float4 w = *reinterpret_cast<const float4*>(buf + rr * RING_COLS + cs);
+                        acc[rr] = fma((double)w.x, z0.x, acc[rr]); acb[rr] = fma(widen_alt<MIX>(w.y), z0.y, acb[rr]);
+                        acc[rr] = fma((double)w.z, z1.x, acc[rr]); acb[rr] = fma(widen_alt<MIX>(w.w), z1.y, acb[rr]);
+                    }
                 }
             }
             __syncwarp();
@@ -521,16 +536,18 @@ __device__ __forceinline__ double cl_matvec_ring(ClusterShared& S, const double*
                 if (++isg == q.nseg) { isg = 0; ++ip; }
             }
         }
-        const int rb = warp * 2 + p * (CL_WARPS * 2);
-        const double t0 = warp_sum(acc0 + acb0), t1 = warp_sum(acc1 + acb1);
+        const int rb = warp * RING_R + p * (CL_WARPS * RING_R);
+        double tsum[RING_R];
+#pragma unroll
+        for (int rr = 0; rr < RING_R; ++rr) tsum[rr] = warp_sum(acc[rr] + acb[rr]);
         if (lane == 0) {
-            const double y0 = S.sv[rb] * invb * (t0 + zs[r0 + rb + pad]);               // (w + I) z
-            yout[rb] = y0;
-            pa = fma(yin[rb] * invb, y0, pa);
-            if (rb + 1 < nr) {
-                const double y1 = S.sv[rb + 1] * invb * (t1 + zs[r0 + rb + 1 + pad]);
-                yout[rb + 1] = y1;
-                pa = fma(yin[rb + 1] * invb, y1, pa);
+#pragma unroll
+            for (int rr = 0; rr < RING_R; ++rr) {
+                if (rb + rr < nr) {
+                    const double y = S.sv[rb + rr] * invb * (tsum[rr] + zs[r0 + rb + rr + pad]);      // (w + I) z
+                    yout[rb + rr] = y;
+                    pa = fma(yin[rb + rr] * invb, y, pa);
+                }
             }
         }
     }
@@ -736,7 +753,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
     for (int i = tid; i < nr; i += CL_THREADS) {
         int j = r0 + i;
         double u = sqrt(e.deg[v.start + j]) * ivol;
-        B.row(0)[i] = u;                                 // basis row 0 = u1
+        B.put(0, i, u);                                  // basis row 0 = u1
         yc[i] = sv0.at(v.start + j, j) - dot * u;
         S.sv[i] = e.sinv[v.start + j];
     }
@@ -786,8 +803,9 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         //      loses orthogonality within dozens of steps (measured in round 1 and again in the model). ----
         {
             const double bk = (k > 0) ? S.beta[k - 1] : 0.0;
-            const double* vp = B.row(k);                                                // v_{k-1} (u1 when k = 0: bk = 0)
-            for (int i = tid; i < nr; i += CL_THREADS) yn[i] = (yn[i] - a1 * vk[i]) - bk * vp[i];   // own elements of vk, vp
+            // own elements of v_k and v_{k-1} (u1 when k = 0: bk = 0)
+            const double* vp = B.row(k);
+            for (int i = tid; i < nr; i += CL_THREADS) yn[i] = (yn[i] - a1 * vk[i]) - bk * vp[i];
         }
         __syncthreads();
         CL_PHASE(2);
@@ -868,7 +886,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         double xs = 0.0, xq = 0.0, xmn = 1e300, xmx = -1e300;
         for (int i = tid; i < nr; i += CL_THREADS) {
             double x = 0.0;
-            for (int j = 0; j < k; ++j) x += S.yv[j] * B.row(j + 1)[i];
+            for (int j = 0; j < k; ++j) x += S.yv[j] * B.get(j + 1, i);
             e.ev[g0 + i] = x;
             xs += x; xq += x * x; xmn = fmin(xmn, x); xmx = fmax(xmx, x);
         }

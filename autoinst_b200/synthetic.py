@@ -380,3 +380,50 @@ def make_scans(chunk: Chunk, n_scans: int = 21, pts_per_major: float = 3.0, seed
         order = rng.permutation(per_scan + n_out)
         scans.append((np.concatenate((p, po))[order], np.concatenate((f, fo))[order]))
     return scans
+
+
+def make_camera_scene(seed: int = 31, n_views: int = 5, minor_per_major: int = 6, visible_frac: float = 0.10,
+                      map_hw=(7, 23), fdim: int = 384):
+    """Synthetic inputs of the DINOv2 half of the feature row (`image_utils.py:91-371`): a small chunk
+    ~12 m in front of a forward-moving KITTI-like camera, a 5 cm "minor" map cloud (jittered copies of the major points
+    plus points elsewhere in the map), per-view visibility masks over the map cloud (what hidden point removal would
+    give; view 3 sees nothing), poses, calibration and random feature maps with 15 % feature-less pixels.
+    Returns a dict of plain arrays and a `dataset` object with the getters the reference calls."""
+    rng = np.random.default_rng(seed)
+    ch = small_chunk(seed + 2, n_obj=3, pts_per_obj=260, features="tarl")
+    major = ch.points + np.array([12.0, 0.0, 0.0])
+    n = major.shape[0]
+    minor_chunk = np.repeat(major, minor_per_major, axis=0) + rng.uniform(-0.12, 0.12, size=(minor_per_major * n, 3))
+    elsewhere = rng.uniform([-30, -30, -2], [-10, 30, 4], size=(400, 3))
+    pcd_pts = np.concatenate([elsewhere[:200], minor_chunk, elsewhere[200:]])
+    chunk_indices = np.arange(200, 200 + minor_chunk.shape[0])
+
+    def pose(i):                                               # lidar pose of frame i in the world (x forward, z up)
+        a = 0.06 * i
+        T = np.eye(4)
+        T[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+        T[:3, 3] = [1.2 * i, 0.15 * i, 0.0]
+        return T
+    T_lidar2cam = np.array([[0.0, -1.0, 0.0, 0.05], [0.0, 0.0, -1.0, -0.08], [1.0, 0.0, 0.0, -0.27], [0, 0, 0, 1.0]])
+    K = np.array([[718.856, 0.0, 607.1928], [0.0, 718.856, 185.2157], [0.0, 0.0, 1.0]])
+    img_w, img_h = 1241, 376
+    fmaps = []
+    for _ in range(n_views):
+        f = rng.normal(size=(map_hw[0], map_hw[1], fdim)).astype(np.float32)
+        f[rng.random(map_hw) < 0.15] = 0.0
+        fmaps.append(f)
+    hpr_masks = rng.random((n_views, pcd_pts.shape[0])) < visible_frac
+    if n_views > 3:
+        hpr_masks[3] = False
+
+    class Image:
+        size = (img_w, img_h)
+
+    class Dataset:
+        def get_image(self, cam, i): return Image()
+        def get_pose(self, i): return pose(i)
+        def get_calibration_matrices(self, cam): return T_lidar2cam, K
+        def get_dinov2_features(self, cam, i): return fmaps[i]
+    return dict(major=major, pcd_points=pcd_pts, chunk_indices=chunk_indices, T_pcd2world=np.eye(4), cam_indices=list(range(n_views)),
+                hpr_masks=hpr_masks, K=K, T_lidar2cam=T_lidar2cam, img_hw=(img_h, img_w), feature_maps=fmaps, pose=pose,
+                dataset=Dataset())

@@ -336,8 +336,10 @@ class Dist:
         torch.cuda.set_device(self.local_rank)
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
+            import datetime
             import torch.distributed as dist
-            dist.init_process_group("nccl", device_id=self.dev)
+            # a mismatched collective must fail in minutes, not hold the box for the default 10-minute watchdog
+            dist.init_process_group("nccl", device_id=self.dev, timeout=datetime.timedelta(seconds=180))
 
     def barrier(self):
         if self.world > 1:
@@ -706,6 +708,7 @@ def run_map(args):
         lat = {"ms": 1e3 * (time.perf_counter() - t0) / 5, "n": c.n,
                "what": "api.segment_chunk (host arrays in, host labels out), the call ncuts.ncuts_utils.ncuts_chunk makes"}
     load = D.over_ranks(float(sum(sizes[i] ** 2 for i in mine)))
+    h2d_mean = D.over_ranks(packed.h2d_bytes())[2]          # (collectives on every rank, outside the rank-0 block)
     if rank == 0:
         pts_total = int(sum(sizes))
         line = {
@@ -724,7 +727,7 @@ def run_map(args):
                        "metrics": last.get("metrics"), "single_chunk_latency": lat},
             "e2e": {"value": len(chunks) / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "ms_per_step_over_ranks": {"max": ms_e2e, "min": ms_e2e_min, "mean": ms_e2e_mean},
-                    "h2d_bytes_per_step": int(D.over_ranks(packed.h2d_bytes())[2] * world),
+                    "h2d_bytes_per_step": int(h2d_mean * world),
                     "d2h_bytes_per_step": int(4 * pts_total)},
             "gpu_launches": int(launches) * world, "roofline": None, "cpu_baseline": None, "clocks": clocks,
         }

@@ -170,6 +170,24 @@ int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, 
                         const double* h_box_min, const double* h_box_max, int normalise, double* d_out,
                         int32_t* d_out_count, void* d_workspace, int64_t workspace_bytes, void* stream);
 
+/* "Next" row N3 (DINOv2 half) — replaces the per-view part of image_based_features_per_patch behind the visibility
+ * bookkeeping (pipeline/utils/image/image_utils.py:264-346, called at ncuts_utils.py:81-110) and dinov2_mean (:363-371).
+ * ancuts_dino_view_pixels, one call per view: every major point (d_major_cam, N x 3 float64, already in the view's camera
+ * frame, :264) looks up its nearest visible chunk point (d_visible_cam, M x 3 float64, same frame, :262-263) and is kept
+ * if that distance is strictly below max_dist (MAJOR_VOXEL_SIZE / 2, :271-276); kept points are projected with the 3 x 3
+ * intrinsics h_K (row-major, HOST array): K p, division by the depth, np.round, inside the img_h x img_w image and depth > 0
+ * (point_to_pixels.py:21-30); d_out_pixel[i] = int(map_h / img_h * row) * map_w + int(map_w / img_w * col) (:255-256,
+ * 341-346) or -1.  ancuts_dino_mean: d_view_pixel is num_views x N (views the reference skips, :183-191,:212-214, hold -1
+ * everywhere), h_feature_maps a HOST array of num_views device pointers to map_h x map_w x feat_dim float32 maps; a view
+ * counts for a point if its looked-up feature vector has any non-zero entry; d_out (N x feat_dim float64) = the mean over
+ * those views in view order, zero row if none; d_out_count their number (may be NULL).  Asynchronous on `stream`
+ * (ancuts_dino_mean synchronises once to read the pointer table). */
+int ancuts_dino_view_pixels(ancuts_handle* h, int num_major, const double* d_major_cam, int num_visible,
+                            const double* d_visible_cam, double max_dist, const double* h_K, int img_h, int img_w,
+                            int map_h, int map_w, int32_t* d_out_pixel, void* stream);
+int ancuts_dino_mean(ancuts_handle* h, int num_major, int num_views, const int32_t* d_view_pixel,
+                     const float* const* h_feature_maps, int feat_dim, double* d_out, int32_t* d_out_count, void* stream);
+
 /* "Next" row N2 — replaces merge_chunks_unite_instances2 (pipeline/utils/point_cloud/point_cloud_utils.py:387-491; caller
  * pipeline/run_pipeline.py:197-199): the chunk labelings of one map, chunks in file-name order, are united into one map
  * labeling.  Chunk c owns points [h_chunk_off[c], h_chunk_off[c+1]) of d_points (P x 3 float64) and d_labels (P int32,

@@ -70,7 +70,7 @@ def ncuts_chunk(dataset, chunk_downsample_dict, pcd_nonground_minor, T_pcd, samp
     from utils.point_cloud.point_cloud_utils import get_subpcd, get_statistical_inlier_indices
     from autoinst_b200 import api
     from utils.visualization_utils import generate_random_colors
-    from utils.image.image_utils import dinov2_mean, image_based_features_per_patch
+    from autoinst_b200.dino import dinov2_mean_per_patch          # per-view look-up and mean on the GPU (ancuts_dino_*)
     from utils.point_cloud.chunk_generation import get_indices_feature_reprojection
     from autoinst_b200.pooling import tarl_features_per_patch      # radius-mean pooling on the GPU (ancuts_feature_pool)
 
@@ -90,9 +90,8 @@ def ncuts_chunk(dataset, chunk_downsample_dict, pcd_nonground_minor, T_pcd, samp
     # feature producers stay the reference's (out of scope)
     dino_list = None
     if CONFIG["gamma"]:
-        point2dino_list, _ = image_based_features_per_patch(dataset, pcd_nonground_minor, d["indices"][sequence], major,
-                                                            T_pcd, cam_ids, sam=False, dino=True, pcd_chunk=pcd_chunk)
-        dino_list = [dinov2_mean(p2d) for p2d in point2dino_list]
+        # image_based_features_per_patch(..., sam=False, dino=True) + dinov2_mean per camera (ncuts_utils.py:81-110)
+        dino_list = dinov2_mean_per_patch(dataset, pcd_nonground_minor, d["indices"][sequence], major, T_pcd, cam_ids)
     tarl = None
     if CONFIG["theta"]:
         tarl = tarl_features_per_patch(dataset, major, T_pcd, d["center_positions"][sequence], tarl_ids)

@@ -211,6 +211,7 @@ def main():
     golden_metrics()
     golden_pooling()
     golden_merge()
+    golden_dino()
 
 
 class _O3dCloud:
@@ -471,3 +472,107 @@ def golden_metrics():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# row N3, DINOv2 half: image_based_features_per_patch (sam=False, dino=True, hpr_masks given) + dinov2_mean
+# ---------------------------------------------------------------------------------------------------------------------
+class _O3dCloudFull(_O3dCloud):
+    """PointCloud stand-in for image_utils.py: points, transform, statistical outlier removal (stand-in: k-NN mean
+    distance against mean + std_ratio * std, Open3D's published rule) — the outlier filter is NOT part of the restated
+    path, it only has to give the reference function a deterministic index list."""
+    def remove_statistical_outlier(self, nb_neighbors=20, std_ratio=2.0):
+        from scipy.spatial import cKDTree
+        P = np.asarray(self.points, dtype=np.float64)
+        k = min(nb_neighbors, P.shape[0])
+        d, _ = cKDTree(P).query(P, k=k)
+        avg = d.reshape(P.shape[0], -1).mean(axis=1)
+        keep = np.where(avg < avg.mean() + std_ratio * avg.std())[0]
+        return None, keep
+
+
+class _O3dKDTreeKnn(_O3dKDTree):
+    def search_knn_vector_3d(self, query, k):
+        d, idx = self.tree.query(np.asarray(query, dtype=np.float64), k=k)
+        idx = np.atleast_1d(idx)
+        d = np.atleast_1d(d)
+        return int(idx.size), idx, d * d
+
+
+def golden_dino():
+    """Run the reference's image_based_features_per_patch + dinov2_mean on a synthetic scene; oracle.dino_ref must match."""
+    from autoinst_b200.synthetic import small_chunk
+    from oracle.dino_ref import dino_mean_ref, transform_points
+    for name in ["open3d", "open3d.geometry", "open3d.utility", "open3d.io", "open3d.pipelines",
+                 "open3d.pipelines.registration", "matplotlib", "matplotlib.pyplot"]:
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    o3d = sys.modules["open3d"]
+    o3d.geometry = sys.modules["open3d.geometry"]
+    o3d.utility = sys.modules["open3d.utility"]
+    o3d.pipelines = sys.modules["open3d.pipelines"]
+    o3d.pipelines.registration = sys.modules["open3d.pipelines.registration"]
+    o3d.geometry.PointCloud = _O3dCloudFull
+    o3d.geometry.KDTreeFlann = _O3dKDTreeKnn
+    o3d.geometry.KDTreeSearchParamHybrid = lambda **kw: None
+    o3d.utility.Vector3dVector = lambda a: np.asarray(a, dtype=np.float64)
+    plt = sys.modules["matplotlib.pyplot"]
+    sys.modules["matplotlib"].pyplot = plt
+    if not hasattr(plt, "cm"):
+        plt.cm = types.SimpleNamespace(viridis=lambda x: np.zeros((len(x), 4)))
+    cwd = os.getcwd()
+    os.chdir(REF)
+    sys.path.insert(0, REF)
+    stash = {m: sys.modules.pop(m) for m in [k for k in sys.modules if k == "config" or k == "utils" or k.startswith("utils.")]}
+    try:
+        import utils.image.image_utils as iu
+        assert iu.__file__.startswith(REF)
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+    from autoinst_b200.synthetic import make_camera_scene
+    sc = make_camera_scene(31)
+    major, pcd_pts, chunk_indices, T_pcd2world = sc["major"], sc["pcd_points"], sc["chunk_indices"], sc["T_pcd2world"]
+    n, n_views, hpr_masks, K, T_lidar2cam, fmaps, pose = major.shape[0], len(sc["cam_indices"]), sc["hpr_masks"], sc["K"], \
+        sc["T_lidar2cam"], sc["feature_maps"], sc["pose"]
+    img_h, img_w = sc["img_hw"]
+    Dataset = lambda: sc["dataset"]      # noqa: E731
+    pcd = _O3dCloudFull()
+    pcd.points = pcd_pts
+    chunk_nc = _O3dCloudFull()
+    chunk_nc.points = major
+    cam_indices = list(range(n_views))
+    lists, _vis = iu.image_based_features_per_patch(Dataset(), pcd, chunk_indices, chunk_nc, T_pcd2world, cam_indices,
+                                                    hpr_masks=hpr_masks, sam=False, dino=True)
+    assert len(lists) == 1
+    ref = iu.dinov2_mean(lists[0])
+    # the same views as plain arrays: what the restated path (and the CUDA path) takes
+    sub = _O3dCloudFull()
+    sub.points = pcd_pts[chunk_indices]
+    _, inl = sub.remove_statistical_outlier(nb_neighbors=20, std_ratio=2.0)
+    chunk_and_inlier = set(chunk_indices[inl].tolist())
+    views = []
+    for i in cam_indices:
+        T_pcd2cam = T_lidar2cam @ np.linalg.inv(pose(i)) @ T_pcd2world                  # image_utils.py:150-154
+        frame = list(set(np.where(hpr_masks[i])[0].tolist()) & chunk_and_inlier)        # :206-209 (the reference's own order)
+        if len(frame) == 0:
+            views.append(None)
+            continue
+        views.append(dict(T_pcd2cam=T_pcd2cam, visible_cam=transform_points(pcd_pts, T_pcd2cam)[frame], K=K,
+                          img_hw=(img_h, img_w), feature_map=fmaps[i]))
+    mine = dino_mean_ref(major, views, max_dist=iu.MAJOR_VOXEL_SIZE / 2, fdim=iu.NUM_DINO_FEATURES)
+    if not np.array_equal(ref, mine):
+        raise SystemExit(f"oracle DINO mean differs from the reference: max abs diff {np.abs(ref - mine).max()}")
+    seen = np.count_nonzero(ref.any(axis=1))
+    assert 0 < seen < n and views[3] is None
+    out = dict(major=major, n_views=np.int64(n_views), K=K, img_hw=np.array([img_h, img_w]), out=ref,
+               max_dist=np.float64(iu.MAJOR_VOXEL_SIZE / 2))
+    for i, v in enumerate(views):
+        out[f"skip{i}"] = np.bool_(v is None)
+        if v is not None:
+            out[f"T{i}"] = v["T_pcd2cam"]; out[f"vis{i}"] = v["visible_cam"]; out[f"fmap{i}"] = v["feature_map"]
+    np.savez_compressed(os.path.join(OUT, "dino.npz"), **out)
+    print(f"dino.npz: {n} major points, {n_views} views, {seen} points with features")
+    for m_ in [k for k in sys.modules if k == "config" or k == "utils" or k.startswith("utils.")]:
+        sys.modules.pop(m_)
+    sys.modules.update(stash)

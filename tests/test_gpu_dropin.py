@@ -63,18 +63,10 @@ def install_fake_reference_modules(monkeypatch, chunk):
     pcu.get_statistical_inlier_indices = lambda pcd, nb_neighbors=20, std_ratio=2.0: np.arange(len(pcd.points))
     vis = types.ModuleType("utils.visualization_utils")
     vis.generate_random_colors = lambda n: [((37 * i) % 255 + 1, (91 * i) % 256, (53 * i) % 256) for i in range(n)]
-    img = types.ModuleType("utils.image.image_utils")
-    img.image_based_features_per_patch = lambda *a, **k: ([chunk.dino[:, None, :]], None)
-
-    def dinov2_mean(p):                                                  # image_utils.py:363-371
-        out = np.zeros((p.shape[0], p.shape[2]))
-        nz = p.any(axis=2)
-        for i in range(p.shape[0]):
-            f = p[i][nz[i]]
-            if f.shape[0]:
-                out[i] = f.mean(axis=0)
-        return out
-    img.dinov2_mean = dinov2_mean
+    # the DINOv2 means come from autoinst_b200.dino (tests/test_dino.py checks that path against the reference's own
+    # functions); here the per-camera result is the synthetic array
+    import autoinst_b200.dino as dino_mod
+    monkeypatch.setattr(dino_mod, "dinov2_mean_per_patch", lambda *a, **k: [chunk.dino])
     cg = types.ModuleType("utils.point_cloud.chunk_generation")      # tarl_features_per_patch is autoinst_b200.pooling's now
 
     def get_indices_feature_reprojection(global_indices, first_id, adjacent_frames=(8, 5)):
@@ -84,7 +76,7 @@ def install_fake_reference_modules(monkeypatch, chunk):
     cg.get_indices_feature_reprojection = get_indices_feature_reprojection
     for name, mod in {"open3d": o3d, "utils": types.ModuleType("utils"), "utils.point_cloud": types.ModuleType("utils.point_cloud"),
                       "utils.image": types.ModuleType("utils.image"), "utils.point_cloud.point_cloud_utils": pcu,
-                      "utils.visualization_utils": vis, "utils.image.image_utils": img,
+                      "utils.visualization_utils": vis,
                       "utils.point_cloud.chunk_generation": cg}.items():
         monkeypatch.setitem(sys.modules, name, mod)
 
@@ -130,5 +122,6 @@ def test_ncuts_chunk_drop_in(cuda_device, monkeypatch, name):
     assert R.same_partition(got.reshape(-1), ref_major[nn])
     with pytest.raises(ValueError):
         monkeypatch.setattr(nu, "CONFIG", dict(cfg, gamma=0.1))
-        sys.modules["utils.image.image_utils"].image_based_features_per_patch = lambda *a, **k: ([], None)
+        import autoinst_b200.dino as dino_mod
+        monkeypatch.setattr(dino_mod, "dinov2_mean_per_patch", lambda *a, **k: [])
         nu.ncuts_chunk(FakeDataset(), d, None, np.eye(4), list(range(40)), sequence=0, patchwise_indices=[[5]])

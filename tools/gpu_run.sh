@@ -17,6 +17,10 @@ for stage in "$@"; do
     bench20)  timeout 900 python bench.py --steps 20 --warmup 5 > $OUT/${TAG}_bench20.json 2> $OUT/${TAG}_bench20.err; tail -c 400 $OUT/${TAG}_bench20.json ;;
     benchdense) timeout 900 python bench.py --steps 5 --warmup 3 --matvec dense --cpu-chunks 0 > $OUT/${TAG}_bench_dense.json 2> $OUT/${TAG}_bench_dense.err; tail -c 400 $OUT/${TAG}_bench_dense.json ;;
     ab)       for v in "shuffled dense" "sorted dense" "shuffled sparse" "sorted sparse"; do set -- $v; timeout 600 python bench.py --steps 4 --warmup 3 --pairs $1 --matvec $2 --cpu-chunks 0 --no-python-surface --roof-steps 0 > $OUT/${TAG}_ab_$1_$2.json 2> $OUT/${TAG}_ab_$1_$2.err; python -c "import json;d=json.load(open('$OUT/${TAG}_ab_$1_$2.json'));print('pairs','$1','matvec','$2',round(d['value'],1),round(d['e2e']['value'],1),d['roofline']['frac'],d['detail']['stage_ms_one_step'])"; done ;;
+    libab)    for v in ${LIBS:-default r4 hints r4hints}; do L=""; [ $v != default ] && L="autoinst_b200/lib_ab/libautoinst_ncuts_$v.so"; for mv in ${LIBAB_MV:-dense}; do ANCUTS_LIB_PATH=$L timeout 600 python bench.py --steps 4 --warmup 3 --matvec $mv --cpu-chunks 0 --no-python-surface --roof-steps 0 > $OUT/${TAG}_lib_${v}_$mv.json 2> $OUT/${TAG}_lib_${v}_$mv.err; python -c "import json;d=json.load(open('$OUT/${TAG}_lib_${v}_$mv.json'));print('lib','$v','matvec','$mv',round(d['value'],1),round(d['e2e']['value'],1),d['roofline']['frac'],d['detail']['stage_ms_one_step']['matvec'])"; done; done ;;
+    tc)       timeout 600 python tools/tc_crossover.py --out $OUT/${TAG}_tc_crossover.json > $OUT/${TAG}_tc_crossover.log 2>&1; tail -8 $OUT/${TAG}_tc_crossover.log | cut -c1-250; \
+              timeout 200 python tools/tc_crossover.py --only-tc 8192 > $OUT/${TAG}_tc_plain.log 2>&1 && \
+              timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_affinity_tc -s 2 -c 1 -o $OUT/${TAG}_prof_affinity_tc -f python tools/tc_crossover.py --only-tc 8192 > $OUT/${TAG}_tc_ncu.log 2>&1; tail -2 $OUT/${TAG}_tc_ncu.log ;;
     cmaps)    for m in ${CMAPS:-122488 112488 112248 122448 124488}; do timeout 600 python bench.py --steps 4 --warmup 3 --cluster-map $m --cpu-chunks 0 --no-python-surface --roof-steps 0 > $OUT/${TAG}_cmap_$m.json 2> $OUT/${TAG}_cmap_$m.err; python -c "import json;d=json.load(open('$OUT/${TAG}_cmap_$m.json'));print('cmap',$m,round(d['value'],1),round(d['e2e']['value'],1),d['detail']['stage_ms_one_step']['matvec'])"; done ;;
     configs)  for c in spatial tarl_spatial_dino; do timeout 900 python bench.py --steps 3 --warmup 3 --config $c --cpu-chunks 0 > $OUT/${TAG}_bench_$c.json 2> $OUT/${TAG}_bench_$c.err; tail -c 300 $OUT/${TAG}_bench_$c.json; done ;;
     small)    for b in 40 16 5 1; do timeout 600 python bench.py --steps 5 --warmup 3 --batch $b --cpu-chunks 0 --no-python-surface > $OUT/${TAG}_bench_b$b.json 2> $OUT/${TAG}_bench_b$b.err; python -c "import json;d=json.load(open('$OUT/${TAG}_bench_b$b.json'));print('batch',$b,d['value'],d['e2e']['value'],d['roofline']['frac'])"; done ;;
