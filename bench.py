@@ -519,7 +519,7 @@ def run_batch(args):
         cpu = None
         parity = None
         nnz_row = None
-        if args.cpu_chunks > 0:
+        if args.cpu_chunks > 0 and world == 1:          # the CPU leg (and with it the parity spot check) runs at N = 1 only
             # the oracle port on one host core, pinned eigsh start vector: its labels are also the parity spot check of the
             # timed batch (same chunks, GPU labels of the e2e call above)
             t0 = time.perf_counter()
