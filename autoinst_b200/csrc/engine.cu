@@ -504,8 +504,7 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
     // Shared-memory sparse form (ANCUTS_OPT_MATVEC = 0, the default): the same two mappings.  Its steps are short, the fixed
     // costs per CTA (cluster barriers, the redundant convergence checks) count, and a level is bound by SM time: the mapping
     // with the fewest CTAs per node measured 2858 chunks/s against 2351 with {1,2,2,4,8,8} (profiles/r2e_cmap_*.json); with
-    // 512-row slices most of the basis then sits behind the CSR slice in L2.  Nodes above 2048 points keep the dense form
-    // (their slices do not fit the shared memory).
+    // 512-row slices most of the basis then sits behind the CSR slice in L2.
     const bool sparse_on = h->opt[ANCUTS_OPT_MATVEC] == 0 && cluster_mode(e) == 6;
     int ctas = 0;
     for (int b = 0; b < CL_CLASSES; ++b) ctas += class_cnt[b] * c_latency[b];
@@ -529,7 +528,7 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
         cudaError_t err = cudaSuccess;
         {
             h->launches_total++;
-            const bool sp = sparse_on && cls < CL_CLASSES - 1;
+            const bool sp = sparse_on;       // every bin: a slice that does not fit streams W inside the same kernel
             switch (cmap[cls]) {
                 case 1: err = launch_cluster<1>(e, cur, ids, cnt, s, sp); break;
                 case 2: err = launch_cluster<2>(e, cur, ids, cnt, s, sp); break;

@@ -687,21 +687,23 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             cl.sync();                                                       // peers have read the flag: the slot is free again
         }
         if (misfit != 0.0) {
-            if (rank == 0 && tid == 0) { e.a_done[a] = DONE_NO; e.a_path[a] = 1; atomicAdd(&e.ctr[4], 1); }
-            return;                                                          // grid-wide path (kernels_lanczos.cuh)
+            // a slice that does not fit (dense little graphs far above 100 entries per row, 512-row slices of the largest
+            // nodes): this node streams W with the register-staged matvec instead, in the same kernel
+            sp_doubles = 0;
+        } else {
+            float* val = reinterpret_cast<float*>(zs + nz + ptr_d);
+            unsigned short* col = reinterpret_cast<unsigned short*>(zs + nz + ptr_d + val_d);
+            if (tid < nr) ptr[tid] = sp_wtot[warp] + incl - mine;
+            if (tid == 0) ptr[nr] = total;
+            __syncthreads();
+            for (int i = warp; i < nr; i += 2 * CL_WARPS) {
+                const int i2 = i + CL_WARPS;
+                sp_fill_rows(v.W + (size_t)(v.ro + r0 + i) * v.ld, i2 < nr ? v.W + (size_t)(v.ro + r0 + i2) * v.ld : nullptr, a0,
+                             c_lo, c_hi, lane, val, col, ptr[i], i2 < nr ? ptr[i2] : 0);
+            }
+            sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total;
+            __syncthreads();
         }
-        float* val = reinterpret_cast<float*>(zs + nz + ptr_d);
-        unsigned short* col = reinterpret_cast<unsigned short*>(zs + nz + ptr_d + val_d);
-        if (tid < nr) ptr[tid] = sp_wtot[warp] + incl - mine;
-        if (tid == 0) ptr[nr] = total;
-        __syncthreads();
-        for (int i = warp; i < nr; i += 2 * CL_WARPS) {
-            const int i2 = i + CL_WARPS;
-            sp_fill_rows(v.W + (size_t)(v.ro + r0 + i) * v.ld, i2 < nr ? v.W + (size_t)(v.ro + r0 + i2) * v.ld : nullptr, a0, c_lo,
-                         c_hi, lane, val, col, ptr[i], i2 < nr ? ptr[i2] : 0);
-        }
-        sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total;
-        __syncthreads();
     }
     SliceBasis B;
     {
@@ -779,7 +781,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         // ---- matvec of the slice; alpha = v_k . (M v_k) rides on its epilogue ----
         double pa;
         if (RING) pa = cl_matvec_ring<MODE == 6>(S, zs, yc, yn, v, rq, r0, nr, pad, invb, ring_w, bars_w, ring_g);
-        else if (SP) pa = warp_sum(cl_matvec_sparse(S, zs, yc, yn, sp, r0, nr, pad, invb));
+        else if (SP && sp.ptr) pa = warp_sum(cl_matvec_sparse(S, zs, yc, yn, sp, r0, nr, pad, invb));
         else pa = cl_matvec_guard(S, zs, yc, yn, v, r0, nr, pad, invb);
         if (lane == 0) S.wred[warp] = pa;
         __syncthreads();
@@ -913,9 +915,9 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             e.a_theta[2 * a + 1] = th[1];
             e.a_done[a] = DONE_YES;
             e.a_path[a] = 0;                    // Ritz vector and statistics are already in place
-            if (!SP) atomicAdd(&e.acct[SG_MATVEC], (unsigned long long)k * (4ull * n * n + 8ull * n));
+            if (!SP || !sp.ptr) atomicAdd(&e.acct[SG_MATVEC], (unsigned long long)k * (4ull * n * n + 8ull * n));
         }
-        if (SP && tid == 0) {      // what this form really moves: the slice twice from HBM, then k sweeps over its entries
+        if (SP && sp.ptr && tid == 0) {      // what this form really moves: the slice once from HBM, then k sweeps over its entries
             atomicAdd(&e.acct[SG_MATVEC], 4ull * (unsigned long long)nr * n);
             atomicAdd(&e.acct[SG_SPARSE_STEPS], (unsigned long long)k * (unsigned long long)sp.nnz);
             atomicAdd(&e.acct[SG_SPARSE_NNZ], (unsigned long long)sp.nnz);
