@@ -29,7 +29,7 @@ EXPORTS = [
 ]
 
 # ancuts_set_option (include/autoinst_ncuts.h)
-OPT_AFFINITY_FORM, OPT_PAIR_SEARCH, OPT_MATVEC, OPT_CLUSTER_MAP = 0, 1, 2, 3
+OPT_AFFINITY_FORM, OPT_PAIR_SEARCH, OPT_MATVEC, OPT_CLUSTER_MAP, OPT_FUSED_CUT = 0, 1, 2, 3, 4
 PAIRS_SORTED, PAIRS_SHUFFLED = 0, 1
 MATVEC_SPARSE, MATVEC_DENSE = 0, 1
 

@@ -147,6 +147,8 @@ struct Eng {
     int* split_ids;       // ranges that split at this level (input of the next rebuild)
     int* a_rid; int* a_k; int* a_kcap; int* a_done; int* a_conv; int* a_slot0; int* a_nch;
     int* a_path;          // 1 = multi-launch Lanczos path (k_ritz needed), 0 = finished by the cluster kernel
+    int* a_fused;         // 1 = the cluster kernel also took the cut decision of the node (cl_fused_cut): the cut kernels skip it
+    int fuse_cut;         // segment calls: the sparse-form cluster kernels may fuse the cut
     int* cl_ids;          // [class][active_cap] active slots per cluster-size class
     int active_cap;
     double* a_alpha; double* a_beta;     // [slot][KS]

@@ -128,6 +128,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     e.p_norm = ar.take<double>(C); e.p_stat = ar.take<double>((size_t)C * 4); e.p_vol = ar.take<double>((size_t)C * NB);
     e.ctr = ar.take<int>(CTR_COUNT);
     e.a_path = ar.take<int>(A);
+    e.a_fused = ar.take<int>(A);
     e.cl_ids = ar.take<int>((size_t)CL_CLASSES * A);
     e.active_cap = A;
     e.acct = ar.take<unsigned long long>(SG_ACCT);
@@ -566,7 +567,8 @@ static int run_lanczos_all(ancuts_handle* h, Eng& e, int cur, int num_active, in
 }
 
 // Ritz vector, sign, thresholds, buckets, cut scan, decision, side flags
-static int run_cut(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n, bool ritz, cudaStream_t st) {
+static int run_cut(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n, bool ritz, cudaStream_t st,
+                   bool reset_split_list = true) {
     const int nch_max = (max_n + CH - 1) / CH;
     dim3 gc(nch_max, num_active);
     if (ritz) {
@@ -574,8 +576,10 @@ static int run_cut(ancuts_handle* h, Eng& e, int cur, int num_active, int max_n,
     }
     LAUNCH(SG_SCAN, k_ev_final<<<(num_active + 127) / 128, 128, 0, st>>>(e, num_active));
     LAUNCH(SG_SCAN, k_bucket<<<gc, 256, 0, st>>>(e));
-    ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 5, 0, sizeof(int), st));
-    ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 7, 0, sizeof(int), st));
+    if (reset_split_list) {
+        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 5, 0, sizeof(int), st));
+        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 7, 0, sizeof(int), st));
+    }
     dim3 gs((max_n + 7) / 8, num_active);
     LAUNCH(SG_SCAN, k_scan<<<gs, 256, 0, st>>>(e, cur));
     LAUNCH(SG_SCAN, k_decide<<<(num_active + 127) / 128, 128, 0, st>>>(e, num_active));
@@ -641,12 +645,13 @@ struct DeferredAffinity {
 
 static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int max_split_n, bool components,
                        cudaStream_t st, int* class_cnt = nullptr, int* big_cnt = nullptr, bool forest_ready = false,
-                       const DeferredAffinity* df = nullptr) {
+                       const DeferredAffinity* df = nullptr, bool forest_inited = false) {
     Eng& e = pl.e;
     const int P = e.P;
     const int tb = 256, gP = (P + tb - 1) / tb;
     // forest_ready: the affinity pass already joined every in-mask pair of the (root) ranges in e.parent
-    if (!forest_ready) LAUNCH(SG_PARTITION, k_cc_init<<<gP, tb, 0, st>>>(e));
+    // forest_inited: the level loop reset the forest before the Lanczos launch (the fused cut joins components into it)
+    if (!forest_ready && !forest_inited) LAUNCH(SG_PARTITION, k_cc_init<<<gP, tb, 0, st>>>(e));
     if (!forest_ready && components && num_split > 0) {
         dim3 g((max_split_n + 7) / 8, num_split);
         LAUNCH(SG_PARTITION, k_cc_union<<<g, 256, 0, st>>>(e, cur, e.split_ids));
@@ -738,16 +743,22 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
     while (num_split > 0) {
         int class_cnt[CL_CLASSES] = {0}, big_cnt = 0;
         rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt, root_forest_ready && guard == 0,
-                         guard == 0 ? df : nullptr);
+                         guard == 0 ? df : nullptr, guard > 0);
         if (rc) return rc;
         int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
         if (num_active == 0) break;
         dim3 gdeg((max_n + 7) / 8, num_active);
         LAUNCH(SG_DEGREE, k_degree<<<gdeg, 256, 0, st>>>(e, cur));
+        // the split list and the component forest of this level start empty BEFORE the Lanczos launch: cluster kernels that
+        // hold their node as CSR slices decide the cut and join the components themselves (cl_fused_cut)
+        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 5, 0, sizeof(int), st));
+        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 7, 0, sizeof(int), st));
+        LAUNCH(SG_PARTITION, k_cc_init<<<(P + 255) / 256, 256, 0, st>>>(e));
+        e.fuse_cut = (h->opt[ANCUTS_OPT_FUSED_CUT] == 0) ? 1 : 0;
         if (p->lanczos_impl == 1) rc = run_lanczos(h, e, cur, num_active, max_n, st);
         else rc = run_lanczos_all(h, e, cur, num_active, max_n, class_cnt, big_cnt, st);
         if (rc) return rc;
-        rc = run_cut(h, e, cur, num_active, max_n, true, st);
+        rc = run_cut(h, e, cur, num_active, max_n, true, st, false);
         if (rc) return rc;
         rc = read_ctr(h, e, st);
         if (rc) return rc;
@@ -1060,6 +1071,8 @@ static int setup_nodes(ancuts_handle* h, Plan& pl, int n_total, float* W0, float
         }
         ANCUTS_CUDA(cudaMemcpyAsync(e.a_done, zeros.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
         ANCUTS_CUDA(cudaMemcpyAsync(e.a_path, ones.data(), num_nodes * sizeof(int), cudaMemcpyHostToDevice, st));
+        ANCUTS_CUDA(cudaMemsetAsync(e.a_fused, 0, num_nodes * sizeof(int), st));
+        e.fuse_cut = 0;                        // stage entries return the eigenvectors; the cut is its own stage
         ANCUTS_CUDA(cudaMemcpyAsync(e.cl_ids, cl.data(), cl.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         ANCUTS_CUDA(cudaStreamSynchronize(st));
         for (int i = 0; i < CL_CLASSES; ++i) h->h_ctr[8 + i] = cnt[8 + i];

@@ -35,7 +35,7 @@ struct ancuts_handle {
     size_t pool_used = 0;
     bool attrs_set = false;
     // Code paths with more than one implementation behind the same results (ancuts_set_option; every one is parity-tested):
-    int opt[ANCUTS_OPT_COUNT] = {0, 0, 0, 0};
+    int opt[ANCUTS_OPT_COUNT] = {0, 0, 0, 0, 0};
     int last_unconverged = 0;                // eigensolver nodes of the last segment call that stopped at lanczos_max_steps
     cudaStream_t copy_stream = nullptr;      // host entry point: per-chunk H2D copies run ahead of the affinity kernels
     std::vector<cudaEvent_t> copy_ev;        // one per chunk of the current host call

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "kernels_graph.cuh"
 #include "kernels_lanczos.cuh"
+#include "kernels_ncut.cuh"
 
 namespace ancuts {
 namespace cg = cooperative_groups;
@@ -40,6 +41,11 @@ struct ClusterShared {
     double be2[CL_KS], dd[CL_KS], du[CL_KS], yv[CL_KS];
     short hexp[CL_KS], pexp[CL_KS];   // exponent offsets of dd / du (cluster_tridiag_vec)
     double prev_th[2];           // the two eigenvalues at the previous check (seed of the next multisection)
+    unsigned long long fdiff[NB + 1];   // fused cut: this CTA's difference array of cut weights, read by the peers
+    unsigned long long fsum[NB + 1];    //            the node's difference array
+    double fvol[NB];                    //            volume per bucket
+    int fcnt[NB];                       //            points per bucket
+    int fdec[4];                        //            decision: best threshold, split, side 0 passes, side 1 passes
     double ysl[2][CL_RPMAX];     // this CTA's slice of the current vector (ping) and of the matvec result (pong)
     double wred[CL_WARPS];       // per-warp partials of the fused reductions (alpha in the matvec, norm in the update)
     double sv[CL_RPMAX];         // D^-1/2 of the slice
@@ -628,6 +634,181 @@ __device__ __forceinline__ double cl_matvec_sparse(ClusterShared& S, const doubl
     return pa;
 }
 
+// ---- fused cut (segment calls, nodes whose CSR slice is in shared memory): what k_ev_final, k_bucket, k_scan, k_decide,
+// k_sides and, for the next rebuild, k_cc_union do in six launches and two dense passes over the node's block
+// (get_min_ncut / ncut_cost / cut_cost, normalized_cut.py:4-34, the decision :56 and the component split of DESIGN.md 4.2)
+// happens here from the CSR slice: the Ritz vector of the whole node was pushed into every CTA's z buffer, every CTA derives
+// sign, thresholds, buckets and volumes redundantly (identical values), the ten cut weights come from the slice's stored
+// entries with the same fixed-point integer atomics as k_scan (identical sums), and after the decision the entries whose
+// end points share a side that goes on are joined in the union-find forest.  The cut weights are bit-equal to the separate
+// kernels'; the volumes are summed in another (fixed) order, so costs may differ in the last bits.
+template <int C>
+__device__ void cl_fused_cut(cg::cluster_group& cl, ClusterShared& S, const Eng& e, const double* zs, const SparseSlice& sp,
+                             const NodeView& v, int a, int rank, int r0, int nr, int pad, int steps, const double* th) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = v.n;
+    const int r = e.a_rid[a];
+    // statistics of the Ritz vector in rank order (S.spart of every CTA is complete: the caller synchronised the cluster)
+    double ts = 0.0, tmn = 1e300, tmx = -1e300, tq = 0.0;
+#pragma unroll
+    for (int q = 0; q < C; ++q) {
+        const double* np_ = (C > 1) ? cl.map_shared_rank(&S.spart[0], q) : &S.spart[0];
+        ts += np_[0]; tmn = fmin(tmn, np_[1]); tmx = fmax(tmx, np_[2]); tq += np_[3];
+    }
+    // k_ev_final: unit norm, sign sum(ev) >= 0, np.allclose(min, max), np.linspace(endpoint=False)
+    const double scale = 1.0 / sqrt(tq);
+    const double sg = (ts < 0.0) ? -scale : scale;
+    double mn = tmn, mx = tmx;
+    if (ts < 0.0) { const double t = mn; mn = -mx; mx = -t; }
+    mn *= scale; mx *= scale;
+    const bool nocut = fabs(mn - mx) <= 1e-8 + 1e-5 * fabs(mx);
+    const double step = (mx - mn) / (double)NCUT;
+    double thr[NCUT];
+#pragma unroll
+    for (int q = 0; q < NCUT; ++q) thr[q] = __dadd_rn(__dmul_rn((double)q, step), mn);
+    // k_bucket: bucket of every point of the node (all CTAs), signed unit-norm ev and bucket of the slice to global memory
+    unsigned char* bk = reinterpret_cast<unsigned char*>(&S.ysl[0][0]);       // 8 KB: n <= 4096 buckets
+    double volp[NB];
+    int cntp[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { volp[b] = 0.0; cntp[b] = 0; }
+    for (int j = tid; j < n; j += CL_THREADS) {
+        const double x = zs[j + pad] * sg;
+        int b = 0;
+#pragma unroll
+        for (int q = 0; q < NCUT; ++q) b += (x > thr[q]) ? 1 : 0;
+        bk[j] = (unsigned char)b;
+        const double dg = e.deg[v.start + j];
+#pragma unroll
+        for (int b2 = 0; b2 < NB; ++b2) { volp[b2] += (b == b2) ? dg : 0.0; cntp[b2] += (b == b2) ? 1 : 0; }
+        if (j >= r0 && j < r0 + nr) { e.ev[v.start + j] = x; e.bucket[v.start + j] = (uint8_t)b; }
+    }
+    // block reduction of the 11 volumes and counts in a fixed order: S.du = 16 x 11 doubles, S.cnts = 16 x 11 ints
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const double vs = warp_sum(volp[b]);
+        int cs = cntp[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cs += __shfl_xor_sync(0xffffffffu, cs, o);
+        if (lane == 0) { S.du[warp * NB + b] = vs; S.cnts[warp * NB + b] = cs; }
+    }
+    if (tid <= NB) S.fdiff[tid] = 0ull;
+    __syncthreads();
+    if (tid < NB) {
+        double vs = 0.0; int cs = 0;
+        for (int w = 0; w < CL_WARPS; ++w) { vs += S.du[w * NB + tid]; cs += S.cnts[w * NB + tid]; }
+        S.fvol[tid] = vs; S.fcnt[tid] = cs;
+    }
+    __syncthreads();
+    double vtot = 0.0;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) vtot += S.fvol[b];
+    const int shift = fix_shift(vtot);
+    const double fscale = ldexp(1.0, shift);
+    // k_scan on the CSR slice: every stored entry of the upper triangle adds its weight to the difference array
+    if (!nocut) {
+        for (int base = 0; base < nr; base += CL_THREADS / SP_LANES) {
+            const int i = base + tid / SP_LANES;
+            if (i < nr) {
+                const int gi = r0 + i, bi = bk[gi];
+                for (int q = sp.ptr[i] + (tid & (SP_LANES - 1)); q < sp.ptr[i + 1]; q += SP_LANES) {
+                    const int c = sp.col[q];
+                    if (c > gi) {
+                        const int bj = bk[c];
+                        if (bj != bi) {
+                            const long long w = __double2ll_rn((double)sp.val[q] * fscale);
+                            atomicAdd(&S.fdiff[min(bi, bj)], (unsigned long long)w);
+                            atomicAdd(&S.fdiff[max(bi, bj)], (unsigned long long)(-w));
+                        }
+                    }
+                }
+            }
+        }
+    }
+    cl_sync<C>(cl);
+    if (tid <= NB) {
+        unsigned long long t = 0ull;
+#pragma unroll
+        for (int q = 0; q < C; ++q) t += (C > 1) ? cl.map_shared_rank(&S.fdiff[0], q)[tid] : S.fdiff[tid];
+        S.fsum[tid] = t;
+    }
+    __syncthreads();
+    // k_decide (every CTA, identical inputs): N-cut value of the ten cuts, first strictly smallest, mcut < T, side sizes
+    if (tid == 0) {
+        int best = -1;
+        double bestc = INFINITY;
+        double costs[NCUT];
+        if (!nocut) {
+            const double unfix = ldexp(1.0, -shift);
+            long long run = 0;
+            for (int q = 0; q < NCUT; ++q) {
+                run += (long long)S.fsum[q];
+                const double cut = (double)run * unfix;
+                double assoc_b = 0.0, assoc_a = 0.0;
+                for (int b = 0; b <= q; ++b) assoc_b += S.fvol[b];
+                for (int b = q + 1; b < NB; ++b) assoc_a += S.fvol[b];
+                const double cost = (cut / assoc_a) + (cut / assoc_b);
+                costs[q] = cost;
+                if (cost < bestc) { bestc = cost; best = q; }
+            }
+        } else {
+            for (int q = 0; q < NCUT; ++q) costs[q] = INFINITY;
+        }
+        const bool split = (best >= 0) && (bestc < e.T);
+        int n_a = 0;
+        if (best >= 0) for (int b = best + 1; b < NB; ++b) n_a += S.fcnt[b];
+        const int n_b = n - n_a;
+        const double no = (double)e.c_norig[v.chunk] + 1e-8;
+        const int p0 = (split && n_a > 2 && (double)n_a / no > CHILD_SPLIT_LIM) ? 1 : 0;
+        const int p1 = (split && n_b > 2 && (double)n_b / no > CHILD_SPLIT_LIM) ? 1 : 0;
+        S.fdec[0] = best; S.fdec[1] = split ? 1 : 0; S.fdec[2] = p0; S.fdec[3] = p1;
+        if (rank == 0) {
+            e.a_bestk[a] = best;
+            e.a_mcut[a] = bestc;
+            for (int q = 0; q < NCUT; ++q) e.a_costs[a * NCUT + q] = costs[q];
+            if (split) {
+                e.r_pass[2 * r + 0] = p0 ? 2 : 0;            // 2 = passes and its components are already joined (k_cc_union skips it)
+                e.r_pass[2 * r + 1] = p1 ? 2 : 0;
+                e.r_status[r] = ST_SPLIT;
+                const int s_ = atomicAdd(&e.ctr[5], 1);
+                e.split_ids[s_] = r;
+                atomicMax(&e.ctr[7], n);
+            } else {
+                e.r_status[r] = ST_LEAF;
+            }
+            if (e.stats != nullptr) {
+                const int s_ = atomicAdd(&e.ctr[6], 1);
+                if (s_ < e.stats_cap) {
+                    ancuts_node_stat st;
+                    st.chunk = v.chunk; st.n = n; st.steps = steps; st.converged = 1;
+                    st.best_k = best; st.split = split ? 1 : 0; st.level = e.r_level[r]; st.n_side = n_a;
+                    st.lambda2 = 1.0 - th[0]; st.mcut = bestc;
+                    e.stats[s_] = st;
+                }
+            }
+            e.a_fused[a] = 1;
+        }
+    }
+    __syncthreads();
+    if (!S.fdec[1]) return;
+    // k_sides + k_cc_union on the slice: side 0 = mask side (ev > t); entries inside a side that goes on are joined
+    const int best = S.fdec[0];
+    for (int i = tid; i < nr; i += CL_THREADS) e.side[v.start + r0 + i] = (bk[r0 + i] > best) ? 0 : 1;
+    for (int base = 0; base < nr; base += CL_THREADS / SP_LANES) {
+        const int i = base + tid / SP_LANES;
+        if (i < nr) {
+            const int gi = r0 + i;
+            const int si = (bk[gi] > best) ? 0 : 1;
+            if (S.fdec[2 + si]) {
+                for (int q = sp.ptr[i] + (tid & (SP_LANES - 1)); q < sp.ptr[i + 1]; q += SP_LANES) {
+                    const int c = sp.col[q];
+                    if (c > gi && ((bk[c] > best) ? 0 : 1) == si) uf_union(e.parent, v.start + gi, v.start + c);
+                }
+            }
+        }
+    }
+}
+
 // grid: count * C CTAs, cluster (C,1,1); ids[cluster index] = active slot.
 // MODE 0: guarded register-staged matvec (caller's W read in place); 4: TMA ring; 6: TMA ring + integer widening of
 // every second element (weights in {0} U [2^-126, 2): the library's own affinities); 7: row slice as CSR in shared memory.
@@ -885,12 +1066,21 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
 #undef CL_PHASE
     // ---- Ritz vector of the slice, statistics for the cut kernels ----
     if (conv) {
+        const bool fuse = SP && sp.ptr != nullptr && e.fuse_cut != 0;
         double xs = 0.0, xq = 0.0, xmn = 1e300, xmx = -1e300;
         for (int i = tid; i < nr; i += CL_THREADS) {
             double x = 0.0;
             for (int j = 0; j < k; ++j) x += S.yv[j] * B.get(j + 1, i);
             e.ev[g0 + i] = x;
             xs += x; xq += x * x; xmn = fmin(xmn, x); xmx = fmax(xmx, x);
+            if (fuse) {                               // the whole node's Ritz vector into every CTA's z buffer (no matvec follows)
+                if (C > 1) {
+#pragma unroll
+                    for (int q = 0; q < C; ++q) cl.map_shared_rank(zs, q)[r0 + i + pad] = x;
+                } else {
+                    zs[i + pad] = x;
+                }
+            }
         }
         double sm_ = block_sum_512(xs, S.red);
         double sq = block_sum_512(xq, S.red);
@@ -922,6 +1112,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             atomicAdd(&e.acct[SG_SPARSE_STEPS], (unsigned long long)k * (unsigned long long)sp.nnz);
             atomicAdd(&e.acct[SG_SPARSE_NNZ], (unsigned long long)sp.nnz);
         }
+        if (fuse) cl_fused_cut<C>(cl, S, e, zs, sp, v, a, rank, r0, nr, pad, k, th);
     } else if (rank == 0 && tid == 0) {
         e.a_done[a] = DONE_NO;                  // left for the multi-launch path (more steps)
         e.a_path[a] = 1;

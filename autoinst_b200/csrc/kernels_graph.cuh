@@ -791,7 +791,7 @@ k_cc_union(Eng e, int cur, const int* __restrict__ split_ids) {
     if (row >= v.n) return;
     int gi = v.start + row;
     int si = e.side[gi];
-    if (!e.r_pass[2 * r + si]) return;             // a side at or below the size limit stays whole
+    if (e.r_pass[2 * r + si] != 1) return;         // 0: a side at or below the size limit stays whole; 2: joined by cl_fused_cut
     const float* rowp = v.W + (size_t)(v.ro + row) * v.ld;
     int c_lo = v.ro + row + 1, c_hi = v.ro + v.n;  // upper triangle only (w is symmetric)
     int a0 = c_lo & ~3;
@@ -885,6 +885,7 @@ __global__ void k_finish_ranges(Eng e, int num_ranges) {
         atomicMax(&e.ctr[2], n);
         e.a_done[a] = DONE_NO;
         e.a_path[a] = 1;
+        e.a_fused[a] = 0;
         int cls = cluster_class(n);
         if (cls >= 0) e.cl_ids[cls * e.active_cap + atomicAdd(&e.ctr[8 + cls], 1)] = a;
         else atomicAdd(&e.ctr[14], 1);

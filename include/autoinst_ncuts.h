@@ -237,19 +237,24 @@ int ancuts_last_unconverged(ancuts_handle* h);
  *                             1 dense two-pass (pairs + feature pass on the full N x N matrix), 2 dense one-kernel
  *   ANCUTS_OPT_PAIR_SEARCH    0 cell-sorted tile sweep, all chunks of the call in one launch, tile pairs pruned by their boxes,
  *                             1 shuffled 64 x 64 tile sweep over the whole upper triangle, one launch per chunk
- *   ANCUTS_OPT_MATVEC         0 the cluster's row slices compressed into shared memory once per node (nodes <= 2048 points),
+ *   ANCUTS_OPT_MATVEC         0 the cluster's row slices compressed (CSR) into shared memory once per node; a node whose
+ *                               slices do not fit falls back, inside the kernel, to the dense form,
  *                             1 dense blocks streamed from HBM every Lanczos step (the north-star form; bench.py measures
  *                               its roofline)
  *   ANCUTS_OPT_CLUSTER_MAP    0 built-in; otherwise six decimal digits (1, 2, 4 or 8 each) = CTAs per node for the size bins
- *                             <= 320, 512, 640, 1024, 2048, 4096 points (tuning) */
+ *                             <= 320, 512, 640, 1024, 2048, 4096 points (tuning)
+ *   ANCUTS_OPT_FUSED_CUT      0 a cluster kernel that holds its node as CSR slices also takes the node's cut decision (sign,
+ *                               thresholds, buckets, N-cut scan, decision, side flags, component unions) in its epilogue,
+ *                             1 the cut always runs as its own kernels after the eigensolver */
 #define ANCUTS_OPT_AFFINITY_FORM 0
 #define ANCUTS_OPT_PAIR_SEARCH   1
 #define ANCUTS_OPT_MATVEC        2
 #define ANCUTS_OPT_CLUSTER_MAP   3
-#define ANCUTS_OPT_COUNT         4
+#define ANCUTS_OPT_FUSED_CUT     4
+#define ANCUTS_OPT_COUNT         5
 int ancuts_set_option(ancuts_handle* h, int option, int value);
 
-/* Shared-memory sparse matvec form (ANCUTS_OPT_MATVEC = 1), last segment call: out2[0] = sum over the nodes it ran of
+/* Shared-memory sparse matvec form (ANCUTS_OPT_MATVEC = 0), last segment call: out2[0] = sum over the nodes it ran of
  * Lanczos steps x stored entries (what the sparse lower bound of SURVEY.md §8d multiplies by 8 bytes), out2[1] = entries. */
 int ancuts_last_sparse_accounting(ancuts_handle* h, double* out2);
 

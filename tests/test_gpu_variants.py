@@ -37,11 +37,13 @@ def check_affinity(W, A):
 
 # include/autoinst_ncuts.h: ANCUTS_OPT_AFFINITY_FORM 0 (0 deferred, 1 dense two-pass, 2 dense one-kernel),
 # ANCUTS_OPT_PAIR_SEARCH 1 (0 cell-sorted sweep, 1 shuffled sweep), ANCUTS_OPT_MATVEC 2 (0 shared-memory slices, 1 dense from
-# HBM), ANCUTS_OPT_CLUSTER_MAP 3 (CTAs per node and size bin)
-AFF, PAIRS, MATVEC, CMAP = 0, 1, 2, 3
+# HBM), ANCUTS_OPT_CLUSTER_MAP 3 (CTAs per node and size bin), ANCUTS_OPT_FUSED_CUT 4 (0 cut decision inside the sparse-form
+# eigensolver kernel, 1 its own kernels)
+AFF, PAIRS, MATVEC, CMAP, FUSED = 0, 1, 2, 3, 4
 VARIANTS = {"default": {}, "shuffled_pairs": {PAIRS: 1}, "dense_two_pass_affinity": {AFF: 1}, "one_kernel_affinity": {AFF: 2},
             "dense_matvec": {MATVEC: 1}, "dense_matvec_shuffled_pairs": {MATVEC: 1, PAIRS: 1},
-            "sparse_matvec_few_ctas": {CMAP: 112248}, "dense_matvec_many_ctas": {MATVEC: 1, CMAP: 224888}}
+            "sparse_matvec_few_ctas": {CMAP: 112248}, "dense_matvec_many_ctas": {MATVEC: 1, CMAP: 224888},
+            "separate_cut_kernels": {FUSED: 1}, "separate_cut_few_ctas": {FUSED: 1, CMAP: 112248}}
 
 
 @pytest.mark.parametrize("variant", list(VARIANTS))
@@ -59,6 +61,32 @@ def test_variants_give_oracle_labels(cuda_device, variant):
         with R.pinned_eigsh():
             g = R.normalized_cut_ref(sp.csr_matrix(A), ch.n, np.arange(ch.n), T=cfg["T"])
         assert R.same_partition(lab, R.labels_from_groups(g, ch.n)), variant
+
+
+def test_fused_cut_takes_the_decisions_of_the_cut_kernels(cuda_device):
+    """The cut fused into the sparse-form eigensolver kernel (default) and the separate cut kernels decide every node of the
+    tree alike: same labels, same node records (size, best threshold, split, side size), N-cut values equal to rounding
+    (the bucket volumes are summed in another order; the cut weights are integer sums and equal)."""
+    api = _api()
+    cfg = CONFIGS["tarl_spatial"]
+    chunks = [make_chunk(330 + i, n_target=2500 + 900 * i, features="tarl") for i in range(3)]
+    packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"])
+    kw = dict(device=cuda_device, alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"], want_stats=True)
+    fused = api.segment_packed(packed, lane=0, **kw)
+    sep = api.segment_packed(packed, lane=variant_lane(cuda_device, {FUSED: 1}, 31), **kw)
+    for a, b in zip(fused.labels, sep.labels):
+        assert np.array_equal(a, b)
+
+    def table(st):
+        order = np.lexsort((st["n_side"], st["n"], st["level"], st["chunk"]))
+        return {k: np.asarray(st[k])[order] for k in ("chunk", "level", "n", "n_side", "best_k", "split", "steps", "mcut")}
+    tf, ts = table(fused.stats), table(sep.stats)
+    assert len(tf["n"]) == len(ts["n"]) > 20
+    for k in ("chunk", "level", "n", "n_side", "best_k", "split", "steps"):
+        assert np.array_equal(tf[k], ts[k]), k
+    fin = np.isfinite(ts["mcut"])
+    assert np.array_equal(fin, np.isfinite(tf["mcut"]))
+    assert np.allclose(tf["mcut"][fin], ts["mcut"][fin], rtol=1e-12, atol=0)
 
 
 def test_non_convergence_is_never_silent(cuda_device):
