@@ -170,6 +170,7 @@ struct Eng {
     int* ctr;             // CTR_COUNT ints: [0]=numRanges [1]=numActive [2]=maxActiveN [3]=cslots [4]=notDone [5]=numSplit [6]=statCount
                           // [7]=maxSplitN [8..13]=nodes per cluster class [14]=nodes for the multi-launch path
                           // [16]=eigensolver nodes that stopped unconverged (whole call, never reset between levels)
+                          // [17]=nodes of the level whose cut was decided inside the cluster kernel (cl_fused_cut)
     unsigned long long* acct;   // [SG_COUNT] algorithmic bytes
     ancuts_node_stat* stats; int stats_cap;
     int w_own;            // 1 = W holds the library's own affinities (0 or [2^-126, 2)): the matvec may widen on the integer pipe

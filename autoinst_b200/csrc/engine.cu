@@ -691,8 +691,7 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
     if (num_active > 0 && df) {
         // deferred affinity: there is no matrix to gather from.  Zero the blocks of the active ranges (unit diagonal)
         // and scatter the queued pairs of every chunk to the positions their points have now.
-        dim3 g((max_n + 255) / 256, (max_n + 15) / 16, num_active);
-        LAUNCH(SG_AFFINITY, k_zero_blocks<<<g, 256, 0, st>>>(e, cur));
+        LAUNCH(SG_AFFINITY, k_zero_blocks<<<dim3(ZB_BLOCKS, num_active), 256, 0, st>>>(e, cur));
         LAUNCH(SG_PARTITION, k_inverse_positions<<<gP, tb, 0, st>>>(e, e.val));
         const ancuts_params* p = df->p;
         const bool use_tarl = p->theta != 0.0 && df->tarl, use_dino = p->gamma != 0.0 && df->dino;
@@ -753,15 +752,21 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
         // hold their node as CSR slices decide the cut and join the components themselves (cl_fused_cut)
         ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 5, 0, sizeof(int), st));
         ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 7, 0, sizeof(int), st));
+        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 17, 0, sizeof(int), st));       // nodes decided inside the cluster kernels
         LAUNCH(SG_PARTITION, k_cc_init<<<(P + 255) / 256, 256, 0, st>>>(e));
         e.fuse_cut = (h->opt[ANCUTS_OPT_FUSED_CUT] == 0) ? 1 : 0;
+        h->h_ctr[17] = 0;
         if (p->lanczos_impl == 1) rc = run_lanczos(h, e, cur, num_active, max_n, st);
         else rc = run_lanczos_all(h, e, cur, num_active, max_n, class_cnt, big_cnt, st);
         if (rc) return rc;
-        rc = run_cut(h, e, cur, num_active, max_n, true, st, false);
-        if (rc) return rc;
-        rc = read_ctr(h, e, st);
-        if (rc) return rc;
+        // every node of the level decided by cl_fused_cut (the usual case): the counters read back after the cluster kernels
+        // already hold the split list, no cut kernel and no second read-back
+        if (h->h_ctr[17] != num_active) {
+            rc = run_cut(h, e, cur, num_active, max_n, true, st, false);
+            if (rc) return rc;
+            rc = read_ctr(h, e, st);
+            if (rc) return rc;
+        }
         num_split = h->h_ctr[5];
         max_split_n = h->h_ctr[7];
         if (++guard > 100000) { set_error("internal: recursion did not terminate"); return ANCUTS_EINVAL; }

@@ -787,6 +787,7 @@ __device__ void cl_fused_cut(cg::cluster_group& cl, ClusterShared& S, const Eng&
                 }
             }
             e.a_fused[a] = 1;
+            atomicAdd(&e.ctr[17], 1);
         }
     }
     __syncthreads();
