@@ -686,6 +686,92 @@ def segment_packed(packed: PackedChunks, *, alpha=1.0, theta=0.0, gamma=0.0, T=0
     return SegmentResult(labels=labels, num_segments=nseg, stats=stats, unconverged=unconv)
 
 
+class SegmentStream:
+    """Batches through host buffers with the upload of the NEXT batch overlapping the cut of the current one.
+
+    `segment_packed(packed)` on host buffers is one synchronous C call: upload, cut, labels back.  A caller that has a
+    sequence of batches (the chunks of successive maps) loses the upload time of every batch (0.44 GB per 128 chunks with
+    TARL features, 8 ms of PCIe) unless the next upload runs while the GPU works.  Here two sets of device input buffers
+    alternate: `submit(packed)` starts the upload on a side stream, `result()` cuts the oldest submitted batch with the
+    device entry point (`ancuts_segment_chunks`) as soon as its upload event has fired, copies the labels into the
+    batch's pinned `packed.labels` and returns them.  Depth 2: at most one batch uploads while one is cut.
+    """
+
+    def __init__(self, device=None, lane: int = 0, strict: bool = False, **kw):
+        self.device = _dev(device)
+        self.lane, self.strict, self.kw = lane, strict, kw
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.slots = [dict(points=None, tarl=None, dino=None, labels=None, ev=None) for _ in range(2)]
+        self.queue = []                 # (slot index, packed) in submission order
+        self.next_slot = 0
+
+    @staticmethod
+    def _fit(t, src, device):
+        if src is None:
+            return None
+        if t is None or t.numel() < src.numel() or t.dtype != src.dtype:
+            t = torch.empty(src.numel(), dtype=src.dtype, device=device)
+        return t
+
+    def submit(self, packed: "PackedChunks"):
+        if len(self.queue) >= 2:
+            raise RuntimeError("SegmentStream: two batches are already in flight; call result() first")
+        i = self.next_slot
+        self.next_slot ^= 1
+        sl = self.slots[i]
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            # buffers are allocated (and later read by the kernels) on the caller's stream; only the copies run aside
+            sl["points"] = self._fit(sl["points"], packed.points, self.device)
+            sl["tarl"] = self._fit(sl["tarl"], packed.tarl if packed.use_t else None, self.device)
+            sl["dino"] = self._fit(sl["dino"], packed.dino if packed.use_d else None, self.device)
+            sl["labels"] = self._fit(sl["labels"], packed.labels, self.device)
+            self.copy_stream.wait_stream(cur)          # the slot's previous batch has been cut (stream order)
+            with torch.cuda.stream(self.copy_stream):
+                for key, src in (("points", packed.points), ("tarl", packed.tarl if packed.use_t else None),
+                                 ("dino", packed.dino if packed.use_d else None)):
+                    if src is not None:
+                        sl[key][:src.numel()].view(src.shape).copy_(src, non_blocking=True)
+                sl["ev"] = torch.cuda.Event()
+                sl["ev"].record(self.copy_stream)
+        self.queue.append((i, packed))
+
+    def result(self, want_stats: bool = False) -> "SegmentResult":
+        if not self.queue:
+            raise RuntimeError("SegmentStream: nothing submitted")
+        i, packed = self.queue.pop(0)
+        sl = self.slots[i]
+        total = int(packed.off[-1])
+        torch.cuda.current_stream(self.device).wait_event(sl["ev"])
+        dc = DeviceChunks.__new__(DeviceChunks)
+        dc.packed, dc.device = packed, self.device
+        dc.points = sl["points"][:packed.points.numel()].view(packed.points.shape)
+        dc.tarl = sl["tarl"][:packed.tarl.numel()].view(packed.tarl.shape) if packed.use_t else None
+        dc.dino = sl["dino"][:packed.dino.numel()].view(packed.dino.shape) if packed.use_d else None
+        dc.labels = sl["labels"][:total]
+        res = segment_packed(packed, dev_chunks=dc, want_stats=want_stats, lane=self.lane, strict=self.strict, **self.kw)
+        packed.labels[:total].copy_(dc.labels, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        arr = packed.labels.numpy()
+        res.labels = [arr[a:b].copy() for a, b in zip(packed.off[:-1], packed.off[1:])]
+        return res
+
+
+def segment_stream(batches, *, device=None, lane: int = 0, strict: bool = False, **kw):
+    """Generator over `SegmentResult`s of an iterable of PackedChunks (see SegmentStream): batch k+1 uploads while batch k
+    is cut.  `kw`: the parameters of `segment_packed` (alpha, theta, gamma, T, ...)."""
+    ss = SegmentStream(device=device, lane=lane, strict=strict, **kw)
+    it = iter(batches)
+    first = next(it, None)
+    if first is None:
+        return
+    ss.submit(first)
+    for nxt in it:
+        ss.submit(nxt)
+        yield ss.result()
+    yield ss.result()
+
+
 def segment_packed_lanes(packed_lanes, dev_lanes=None, **kw):
     """Run several packed batches CONCURRENTLY on one device, one host thread + CUDA stream + library handle
     per batch ("lane").  The recursion of one batch is level-synchronous and its later levels leave most SMs

@@ -423,8 +423,20 @@ def run_batch(args):
         api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
         gather()
 
-    def step_e2e():
+    def step_single_call():             # host buffers through ONE synchronous C call: upload, cut, labels back
         res = api.segment_packed(packed, device=dev, **kw)
+        if gat is not None:
+            gat.load_flat(packed.labels)
+            gather()
+        return res
+
+    # e2e: successive batches through api.SegmentStream -- every step uploads one batch from pinned host memory (for the
+    # NEXT step, on a side stream, while this step's batch is cut), cuts one batch and reads its labels back to the host
+    stream = api.SegmentStream(device=dev, **kw)
+
+    def step_e2e():
+        stream.submit(packed)
+        res = stream.result()
         if gat is not None:
             gat.load_flat(packed.labels)
             gather()
@@ -435,6 +447,8 @@ def run_batch(args):
         sampler.start()                 # nvidia-smi needs ~1 s before its first sample: start before the warm-up
     for _ in range(args.warmup):        # warm-up (also sizes the workspace)
         step_resident()
+    step_single_call()
+    stream.submit(packed)               # prime the pipeline: from here on one batch is always uploaded ahead
     step_e2e()
     t_begin = time.time()
     # timed region 1: inputs resident in HBM.  CUDA events around every level launch of the Lanczos kernels (timing
@@ -470,6 +484,8 @@ def run_batch(args):
     # timed region 2: the same steps through the host-buffer entry point
     ms_e2e, ms_e2e_min, ms_e2e_mean = D.timed(step_e2e, args.steps)
     g_e2e = list(gather_host_ms)
+    res_last = stream.result()          # drain the batch uploaded by the last timed step (outside the region)
+    ms_single, _, _ = D.timed(step_single_call, min(args.steps, 3))
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     gmax = D.over_ranks(float(np.mean(g_res)) if g_res else 0.0)
@@ -496,6 +512,8 @@ def run_batch(args):
     # outside the timed regions: node statistics, per-stage shares, the Python-list surface, the parity spot check
     res = api.segment_packed(packed, device=dev, want_stats=True, **kw)
     stats = res.stats
+    if not all(np.array_equal(a, b) for a, b in zip(res.labels, res_last.labels)):
+        raise SystemExit("bench: labels of the streamed e2e path differ from the single host call")
     hd.set_stage_timing(1)
     api.segment_packed(packed, dev_chunks=dev_chunks, **kw)
     stage_ms = {s: v["ms"] for s, v in hd.accounting().items()}
@@ -573,7 +591,14 @@ def run_batch(args):
             "parity": parity,
             "e2e": {"value": total_chunks / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "ms_per_step_over_ranks": {"max": ms_e2e, "min": ms_e2e_min, "mean": ms_e2e_mean},
-                    "h2d_bytes_per_step": packed.h2d_bytes() * world, "d2h_bytes_per_step": packed.d2h_bytes() * world},
+                    "h2d_bytes_per_step": packed.h2d_bytes() * world, "d2h_bytes_per_step": packed.d2h_bytes() * world,
+                    "how": "api.SegmentStream: every step uploads one batch from pinned host memory on a side stream (the batch "
+                           "the next step cuts), cuts the batch uploaded one step earlier through the C ABI and copies its labels "
+                           "to pinned host memory; K uploads, K cuts, K read-backs inside the K timed steps",
+                    "single_call": {"value": total_chunks / (ms_single / 1e3), "unit": UNIT, "ms_per_step": ms_single,
+                                    "steps": min(args.steps, 3),
+                                    "what": "ancuts_segment_chunks_host, one synchronous call per batch: upload, cut and "
+                                            "read-back in sequence (points first, features overlap the pair stage)"}},
             "gpu_launches": int(launches) * world,
             "sparse": None if args.matvec == "dense" else {
                 "what": "default matvec form: the CTA's row slice as CSR (float32 value + uint16 column) in shared memory, built once "
@@ -661,8 +686,17 @@ def run_map(args):
         gat.start()
         finish(gat.finish())
 
-    def step_e2e():
+    def step_single_call():
         api.segment_packed(packed, device=dev, **kw)
+        gat.load_flat(packed.labels)
+        gat.start()
+        finish(gat.finish())
+
+    stream = api.SegmentStream(device=dev, **kw)      # successive maps: the next map's chunks upload while this one is cut
+
+    def step_e2e():
+        stream.submit(packed)
+        stream.result()
         gat.load_flat(packed.labels)
         gat.start()
         finish(gat.finish())
@@ -672,12 +706,16 @@ def run_map(args):
         sampler.start()
     for _ in range(args.warmup):
         step_resident()
+    step_single_call()
+    stream.submit(packed)
     step_e2e()
     t_begin = time.time()
     hd.launch_count(reset=True)
     ms_step, ms_min, ms_mean = D.timed(step_resident, args.steps)
     launches = hd.launch_count(reset=True)
     ms_e2e, ms_e2e_min, ms_e2e_mean = D.timed(step_e2e, args.steps)
+    stream.result()
+    ms_single, _, _ = D.timed(step_single_call, min(args.steps, 3))
     t_end = time.time()
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     # where one resident pass spends its time (host timer with a device synchronisation after every part, one extra pass)
@@ -728,7 +766,12 @@ def run_map(args):
             "e2e": {"value": len(chunks) / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "ms_per_step_over_ranks": {"max": ms_e2e, "min": ms_e2e_min, "mean": ms_e2e_mean},
                     "h2d_bytes_per_step": int(h2d_mean * world),
-                    "d2h_bytes_per_step": int(4 * pts_total)},
+                    "d2h_bytes_per_step": int(4 * pts_total),
+                    "how": "api.SegmentStream: the chunks of the next map upload on a side stream while this map is cut; every "
+                           "step uploads one map, cuts one map and reads its labels back",
+                    "single_call": {"value": len(chunks) / (ms_single / 1e3), "unit": UNIT, "ms_per_step": ms_single,
+                                    "steps": min(args.steps, 3),
+                                    "what": "one synchronous ancuts_segment_chunks_host call per map"}},
             "gpu_launches": int(launches) * world, "roofline": None, "cpu_baseline": None, "clocks": clocks,
         }
         emit(line)

@@ -148,3 +148,32 @@ def test_map_level_metrics_match_oracle(cuda_device):
     for k in ("p", "r", "f1", "ap", "ap0.25", "ap0.5", "S_assoc"):
         assert abs(got[k] - ref[k]) <= 1e-3, (k, got[k], ref[k])    # 0.1 points
     assert ref["S_assoc"] > 0.3 and ref["ap0.25"] > 0.2              # the comparison is not vacuous
+
+
+def test_segment_stream_equals_single_calls(cuda_device):
+    """api.segment_stream (upload of batch k+1 overlaps the cut of batch k, two alternating sets of device input buffers)
+    returns, batch by batch, the labels of the synchronous host call -- batches of different sizes and feature sets of
+    one config, so that the slots are re-used with other shapes."""
+    api = _api()
+    cfg = CONFIGS["tarl_spatial"]
+    kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], gamma=cfg["gamma"], T=cfg["T"])
+    batches = []
+    for b, (count, n) in enumerate([(3, 1400), (1, 2600), (4, 900), (2, 2000), (1, 700)]):
+        chunks = [make_chunk(900 + 10 * b + i, n_target=n, features="tarl") for i in range(count)]
+        batches.append(api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"]))
+    want = [[l.copy() for l in api.segment_packed(pk, device=cuda_device, **kw).labels] for pk in batches]
+    got = list(api.segment_stream(batches, device=cuda_device, **kw))
+    assert len(got) == len(batches)
+    for res, ref, pk in zip(got, want, batches):
+        assert len(res.labels) == len(pk.sizes)
+        for a, b in zip(res.labels, ref):
+            assert np.array_equal(a, b)
+    # the explicit form: never more than two batches in flight
+    ss = api.SegmentStream(device=cuda_device, **kw)
+    ss.submit(batches[0]); ss.submit(batches[1])
+    with pytest.raises(RuntimeError):
+        ss.submit(batches[2])
+    assert np.array_equal(ss.result().labels[0], want[0][0])
+    assert np.array_equal(ss.result().labels[0], want[1][0])
+    with pytest.raises(RuntimeError):
+        ss.result()
