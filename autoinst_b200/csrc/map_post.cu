@@ -140,12 +140,15 @@ struct MergeState {
     int* inter;                   // [G][n2max] points of instance 2 inside the box of instance 1
     double* iou;                  // [G][n2max]
     int* match;                   // [n2max] rank of the instance the new instance is united with, or -1
-    unsigned long long* kval; unsigned long long* kval2;   // scalar keys (value) and their instance ids (side 2: G + local)
-    int* kid; int* kid2;
-    int* kflag; int* kincl;
-    unsigned long long* uval;     // compacted distinct (instance, value) entries, grouped by instance, ascending
-    int* ustart; int* usz;        // [G + n2max]
-    long long* ctr;               // [4]: [0] number of scalar keys of the step
+    // distinct scalar values per instance (the reference's np.union1d / intersect1d of FLATTENED coordinates, :457): one
+    // open-addressing set per instance that takes part in a candidate pair, all sets of a step in one table
+    unsigned long long* sv;       // set slots (f64_key of a coordinate, SET_EMPTY = free)
+    long long* ustart;            // [G + n2max] first slot of the instance's set (side 2: G + local)
+    int* ucap;                    // [G + n2max] slots of the set (a power of two, >= 4/3 of the values it can receive), 0 = none
+    int* usz;                     // [G + n2max] distinct values in the set
+    int* need;                    // [G + n2max] the instance is in a pair with a non-empty box intersection
+    int* pairs;                   // [G][n2max] candidate pairs (r * n2 + j) of the step, in no particular order
+    long long* ctr;               // [4]: [1] slots in use in this step, [2] candidate pairs
     int* htab; long long hmask;   // open-addressing table of point indices (first occurrence wins)
     const int* chunk_rank0;       // [B+1] offsets into chunk_ranks
     const int* chunk_ranks;       // sorted original instance ranks of every chunk
@@ -165,108 +168,219 @@ __global__ void k_merge_reset(MergeState m, int n2) {
         m.cnt1[i] = 0;
         for (int k = 0; k < 3; ++k) { m.box1[i * 6 + k] = 1e300; m.box1[i * 6 + 3 + k] = -1e300; }
     }
-    if (i < (long long)m.G + n2) { m.ustart[i] = 0; m.usz[i] = 0; }
+    if (i < (long long)m.G + n2) { m.ustart[i] = 0; m.ucap[i] = 0; m.usz[i] = 0; m.need[i] = 0; }
     if (i < n2) { m.cnt2[i] = 0; m.match[i] = -1; }
     if (i < (long long)m.G * n2) { m.inter[i] = 0; m.iou[i] = 0.0; }
-    if (i == 0) m.ctr[0] = 0;
+    if (i == 0) { m.ctr[0] = 0; m.ctr[1] = 0; m.ctr[2] = 0; }
 }
 
-// side 1: alive points of the earlier chunks inside the crop box (inclusive, :405-417) -> instance sizes, boxes
-// (:447-448) and the scalar keys of the "union" (:457)
+constexpr unsigned long long SET_EMPTY = 0xFFFFFFFFFFFFFFFFull;      // f64_key never yields it (a NaN pattern)
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ bool in_crop(const MergeState& m, long long p, double lx, double ly, double lz, double hx, double hy,
+                                        double hz) {
+    const double x = m.pts[p * 3], y = m.pts[p * 3 + 1], z = m.pts[p * 3 + 2];
+    return x >= lx && x <= hx && y >= ly && y <= hy && z >= lz && z <= hz;
+}
+// side 1: alive points of the earlier chunks inside the crop box (inclusive, :405-417) -> instance sizes and boxes (:447-448)
 __global__ void k_merge_crop(MergeState m, long long p1, double lx, double ly, double lz, double hx, double hy, double hz) {
     long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= p1 || !m.alive[p]) return;
     int r = m.rank[p];
     if (r < 0) return;                                          // black = ground / background (:428)
+    if (!in_crop(m, p, lx, ly, lz, hx, hy, hz)) return;
     const double x = m.pts[p * 3], y = m.pts[p * 3 + 1], z = m.pts[p * 3 + 2];
-    if (!(x >= lx && x <= hx && y >= ly && y <= hy && z >= lz && z <= hz)) return;
     atomicAdd(&m.cnt1[r], 1);
     atomic_min_f64(&m.box1[r * 6 + 0], x); atomic_min_f64(&m.box1[r * 6 + 1], y); atomic_min_f64(&m.box1[r * 6 + 2], z);
     atomic_max_f64(&m.box1[r * 6 + 3], x); atomic_max_f64(&m.box1[r * 6 + 4], y); atomic_max_f64(&m.box1[r * 6 + 5], z);
-    long long k = (long long)atomicAdd((unsigned long long*)&m.ctr[0], 3ull);
-    m.kval[k] = f64_key(x); m.kval[k + 1] = f64_key(y); m.kval[k + 2] = f64_key(z);
-    m.kid[k] = r; m.kid[k + 1] = r; m.kid[k + 2] = r;
 }
 // side 2: the new chunk's instances (all of their points, :434-442)
-__global__ void k_merge_chunk_keys(MergeState m, long long a, long long b) {
+__global__ void k_merge_cnt2(MergeState m, long long a, long long b) {
     long long p = a + blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= b) return;
     int j = m.local[p];
-    if (j < 0) return;
-    atomicAdd(&m.cnt2[j], 1);
-    long long k = (long long)atomicAdd((unsigned long long*)&m.ctr[0], 3ull);
-    const int id = m.G + j;
-    m.kval[k] = f64_key(m.pts[p * 3]); m.kval[k + 1] = f64_key(m.pts[p * 3 + 1]); m.kval[k + 2] = f64_key(m.pts[p * 3 + 2]);
-    m.kid[k] = id; m.kid[k + 1] = id; m.kid[k + 2] = id;
+    if (j >= 0) atomicAdd(&m.cnt2[j], 1);
 }
-// keys sorted by (instance, value): distinct entries
-__global__ void k_merge_uflag(MergeState m, long long nk, const unsigned long long* __restrict__ val, const int* __restrict__ id) {
-    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < nk) m.kflag[i] = (i == 0 || id[i] != id[i - 1] || val[i] != val[i - 1]) ? 1 : 0;
+// one block: slots of the sets of the instances that are in a candidate pair (3 scalar values per point, load <= 3/4)
+__global__ void __launch_bounds__(1024)
+k_merge_regions(MergeState m, int n2) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = m.G + n2;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += 1024) {
+        const int id = base + tid;
+        int cap = 0;
+        if (id < total && m.need[id]) {
+            const int cnt = (id < m.G) ? m.cnt1[id] : m.cnt2[id - m.G];
+            cap = 4;
+            while (cap < 4 * cnt) cap <<= 1;
+        }
+        long long v = cap;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+        if (lane == 31) wsum[warp] = v;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const long long before = carry + (warp ? wsum[warp - 1] : 0) + v - cap;
+        if (id < total) { m.ustart[id] = before; m.ucap[id] = cap; }
+        __syncthreads();
+        if (tid == 1023) carry = before + cap;
+        __syncthreads();
+    }
+    if (tid == 0) m.ctr[1] = carry;
 }
-__global__ void k_merge_ucompact(MergeState m, long long nk, const unsigned long long* __restrict__ val, const int* __restrict__ id) {
+__global__ void k_merge_set_clear(MergeState m, long long bound) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= nk || !m.kflag[i]) return;
-    const int pos = m.kincl[i] - 1;
-    m.uval[pos] = val[i];
-    atomicAdd(&m.usz[id[i]], 1);
-    if (i == 0 || id[i] != id[i - 1]) m.ustart[id[i]] = pos;
+    if (i < bound && i < m.ctr[1]) m.sv[i] = SET_EMPTY;
+}
+__device__ __forceinline__ void set_insert(const MergeState& m, int id, unsigned long long v) {
+    const unsigned mask = (unsigned)m.ucap[id] - 1u;
+    unsigned long long* T = m.sv + m.ustart[id];
+    unsigned s = (unsigned)mix64(v) & mask;
+    while (true) {
+        const unsigned long long old = atomicCAS(&T[s], SET_EMPTY, v);
+        if (old == SET_EMPTY) { atomicAdd(&m.usz[id], 1); return; }
+        if (old == v) return;
+        s = (s + 1u) & mask;
+    }
+}
+__device__ __forceinline__ bool set_has(const MergeState& m, int id, unsigned long long v) {
+    const unsigned mask = (unsigned)m.ucap[id] - 1u;
+    const unsigned long long* T = m.sv + m.ustart[id];
+    unsigned s = (unsigned)mix64(v) & mask;
+    while (true) {
+        const unsigned long long cur = T[s];
+        if (cur == v) return true;
+        if (cur == SET_EMPTY) return false;
+        s = (s + 1u) & mask;
+    }
+}
+// the three coordinates of every point of a needed instance go into the instance's set; side 1 = [0, p1) cropped, side 2
+// = the chunk [a, b)
+__global__ void k_merge_set_fill(MergeState m, long long p1, long long b, double lx, double ly, double lz, double hx, double hy,
+                                 double hz) {
+    long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (p >= b) return;
+    int id;
+    if (p < p1) {
+        if (!m.alive[p]) return;
+        id = m.rank[p];
+        if (id < 0 || !m.need[id] || !in_crop(m, p, lx, ly, lz, hx, hy, hz)) return;
+    } else {
+        const int j = m.local[p];
+        if (j < 0 || !m.need[m.G + j]) return;
+        id = m.G + j;
+    }
+    set_insert(m, id, f64_key(m.pts[p * 3]));
+    set_insert(m, id, f64_key(m.pts[p * 3 + 1]));
+    set_insert(m, id, f64_key(m.pts[p * 3 + 2]));
 }
 // points of every new instance inside the box of every cropped instance (:452-455)
-__global__ void k_merge_inter(MergeState m, long long a, long long b, int n2) {
-    long long p = a + blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (p >= b) return;
-    int j = m.local[p];
-    if (j < 0) return;
-    const double x = m.pts[p * 3], y = m.pts[p * 3 + 1], z = m.pts[p * 3 + 2];
-    for (int r = 0; r < m.G; ++r) {
-        if (m.cnt1[r] == 0) continue;
-        const double* bx = m.box1 + (size_t)r * 6;
-        if (x >= bx[0] && y >= bx[1] && z >= bx[2] && x <= bx[3] && y <= bx[4] && z <= bx[5])
-            atomicAdd(&m.inter[(size_t)r * n2 + j], 1);
+__global__ void __launch_bounds__(256)
+k_merge_inter(MergeState m, long long a, long long b, int n2) {
+    // few of the map's G instances have points in the crop: the block compacts the boxes of those into shared memory
+    // (256 candidates per round) and every point tests only them
+    __shared__ double sbox[256][6];
+    __shared__ int sr[256];
+    __shared__ int sn;
+    const long long p = a + blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int j = (p < b) ? m.local[p] : -1;
+    double x = 0.0, y = 0.0, z = 0.0;
+    if (j >= 0) { x = m.pts[p * 3]; y = m.pts[p * 3 + 1]; z = m.pts[p * 3 + 2]; }
+    for (int base = 0; base < m.G; base += 256) {
+        if (threadIdx.x == 0) sn = 0;
+        __syncthreads();
+        const int rc = base + threadIdx.x;
+        if (rc < m.G && m.cnt1[rc] > 0) {
+            const int k = atomicAdd(&sn, 1);
+            sr[k] = rc;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) sbox[k][q] = m.box1[(size_t)rc * 6 + q];
+        }
+        __syncthreads();
+        if (j >= 0) {
+            const int cnt = sn;
+            for (int k = 0; k < cnt; ++k) {
+                const double* bx = sbox[k];
+                if (x >= bx[0] && y >= bx[1] && z >= bx[2] && x <= bx[3] && y <= bx[4] && z <= bx[5]) {
+                    const int r = sr[k];
+                    if (atomicAdd(&m.inter[(size_t)r * n2 + j], 1) == 0) {      // first point of the pair: it becomes a candidate
+                        m.pairs[atomicAdd((unsigned long long*)&m.ctr[2], 1ull)] = r * n2 + j;
+                        m.need[r] = 1; m.need[m.G + j] = 1;
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
 }
-// one warp per (cropped instance r, new instance j) with a non-empty intersection: |U1 n U2| by binary search of the
-// smaller distinct-value list in the larger one; union = |U1| + |U2| - common; iou = float(inter) / float(union) (:457-458)
+// one block per candidate pair (cropped instance r, new instance j): |U1 n U2| by looking the values of the smaller set up
+// in the larger one, four look-ups in flight per thread; union = |U1| + |U2| - common; iou = float(inter) / float(union)
+// (:457-458)
+constexpr int IOU_BLOCKS = 296;
 __global__ void __launch_bounds__(256)
 k_merge_iou(MergeState m, int n2, double min_iou) {
-    const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= (long long)m.G * n2) return;
-    const int r = (int)(w / n2), j = (int)(w % n2);
-    const int it = m.inter[w];
-    if (it <= 0) return;
-    int ia = r, ib = m.G + j;
-    if (m.usz[ia] > m.usz[ib]) { int t = ia; ia = ib; ib = t; }          // search the elements of the smaller list
-    const unsigned long long* A = m.uval + m.ustart[ia];
-    const unsigned long long* Bv = m.uval + m.ustart[ib];
-    const int na = m.usz[ia], nb = m.usz[ib];
-    int common = 0;
-    for (int i = lane; i < na; i += 32) {
-        const unsigned long long v = A[i];
-        int lo = 0, hi = nb;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (Bv[mid] < v) lo = mid + 1; else hi = mid; }
-        common += (lo < nb && Bv[lo] == v) ? 1 : 0;
-    }
+    __shared__ int red[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int npairs = (int)m.ctr[2];
+    for (int pi = blockIdx.x; pi < npairs; pi += gridDim.x) {
+        const int w = m.pairs[pi];
+        const int r = w / n2, j = w % n2;
+        int ia = r, ib = m.G + j;
+        if (m.usz[ia] > m.usz[ib]) { int t = ia; ia = ib; ib = t; }
+        const unsigned long long* A = m.sv + m.ustart[ia];
+        const int capa = m.ucap[ia];
+        int common = 0;
+        for (int i = tid; i < capa; i += 4 * 256) {
+            unsigned long long v[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) common += __shfl_xor_sync(0xffffffffu, common, o);
-    if (lane == 0) {
-        const int uni = na + nb - common;
-        const double v = (double)it / (double)uni;
-        m.iou[w] = (v > min_iou) ? v : 0.0;                              // :459
+            for (int u = 0; u < 4; ++u) v[u] = (i + 256 * u < capa) ? A[i + 256 * u] : SET_EMPTY;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (v[u] != SET_EMPTY && set_has(m, ib, v[u])) ++common;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) common += __shfl_xor_sync(0xffffffffu, common, o);
+        if (lane == 0) red[warp] = common;
+        __syncthreads();
+        if (tid == 0) {
+            int c = 0;
+            for (int k = 0; k < 8; ++k) c += red[k];
+            const int uni = m.usz[ia] + m.usz[ib] - c;
+            const double v = (double)m.inter[w] / (double)uni;
+            m.iou[w] = (v > min_iou) ? v : 0.0;                          // :459
+        }
+        __syncthreads();
     }
 }
 // every new instance keeps the cropped instance with the largest iou; pairs come in (id1, id2) ascending order and a
 // later pair replaces an earlier one only if strictly larger (:465-477)
 __global__ void k_merge_resolve(MergeState m, int n2) {
-    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per new instance: largest iou, the smallest rank among equals (what "strictly larger replaces" leaves)
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (j >= n2) return;
     double best = 0.0; int br = -1;
-    for (int r = 0; r < m.G; ++r) {
+    for (int r = lane; r < m.G; r += 32) {
         const double v = m.iou[(size_t)r * n2 + j];
         if (v > 0.0 && (br < 0 || v > best)) { best = v; br = r; }
     }
-    m.match[j] = br;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int orr = __shfl_xor_sync(0xffffffffu, br, o);
+        if (orr >= 0 && (br < 0 || ob > best || (ob == best && orr < br))) { best = ob; br = orr; }
+    }
+    if (lane == 0) m.match[j] = br;
 }
 __global__ void k_merge_apply(MergeState m, long long a, long long b) {
     long long p = a + blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -392,8 +506,6 @@ int ancuts_merge_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk
     cub::DeviceRadixSort::SortKeys(nullptr, cubA, (int*)nullptr, (int*)nullptr, (int)P, 0, 32);
     cub::DeviceScan::InclusiveSum(nullptr, cubB, (int*)nullptr, (int*)nullptr, (int)P);
     cub::DeviceRadixSort::SortKeys(nullptr, cubC, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)P, 0, 64);
-    cub::DeviceRadixSort::SortPairs(nullptr, cubD, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int*)nullptr,
-                                    (int*)nullptr, (int)(3 * P), 0, 64);
     size_t cubE = 0;
     cub::DeviceSelect::If(nullptr, cubE, cub::CountingInputIterator<long long>(0), (long long*)nullptr, (long long*)nullptr,
                           (long long)P, IsAlive{nullptr});
@@ -405,7 +517,7 @@ int ancuts_merge_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk
     auto layoutA = [&](PArena& a, int*& sorted, int*& flag, int*& incl, int*& uniq, long long*& dctr, int*& rank, int*& local,
                        unsigned char*& alive, int*& chunk_of, unsigned long long*& ckey, unsigned long long*& ckey2,
                        int*& chunk_ranks, int*& chunk_cnt, long long*& d_off, int*& htab, void*& cub_tmp) {
-        sorted = a.take<int>(P); flag = a.take<int>(3 * P); incl = a.take<int>(3 * P); uniq = a.take<int>(P);
+        sorted = a.take<int>(P); flag = a.take<int>(P); incl = a.take<int>(P); uniq = a.take<int>(P);
         dctr = a.take<long long>(8); rank = a.take<int>(P); local = a.take<int>(P); alive = a.take<unsigned char>(P);
         chunk_of = a.take<int>(P); ckey = a.take<unsigned long long>(P); ckey2 = a.take<unsigned long long>(P);
         chunk_ranks = a.take<int>(P); chunk_cnt = a.take<int>(B + 1); d_off = a.take<long long>(B + 1);
@@ -414,10 +526,11 @@ int ancuts_merge_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk
     int *sorted, *flag, *incl, *uniq, *rank, *local, *chunk_of, *chunk_ranks, *chunk_cnt, *htab;
     long long *dctr, *d_off; unsigned char* alive; unsigned long long *ckey, *ckey2; void* cub_tmp;
     layoutA(ar, sorted, flag, incl, uniq, dctr, rank, local, alive, chunk_of, ckey, ckey2, chunk_ranks, chunk_cnt, d_off, htab, cub_tmp);
-    // phase B buffers sized after G / n2max are known: reserve generously now (keys 3P each) and tables later
+    // phase B buffers sized after G / n2max are known: reserve the set table now (3 values per point, sets at most 8/3 of
+    // their values: 8 slots per point) and the instance tables later
     const size_t fixed_bytes = ar.off;
-    // scalar keys
-    size_t keys_bytes = pa_align(3 * P * 8) * 3 + pa_align(3 * P * 4) * 2 + 4096;
+    const long long set_slots = 8 * P + 64;
+    size_t keys_bytes = pa_align((size_t)set_slots * 8) + 4096;
     int rc = post_ws(h, fixed_bytes + keys_bytes + (64u << 20));
     if (rc) return rc;
     ar = PArena{h->post_ws};
@@ -479,9 +592,10 @@ int ancuts_merge_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk
     auto layoutB = [&](PArena& a, MergeState& m) {
         m.cnt1 = a.take<int>(Gs); m.box1 = a.take<double>((size_t)Gs * 6); m.cnt2 = a.take<int>(n2max);
         m.inter = a.take<int>(table); m.iou = a.take<double>(table); m.match = a.take<int>(n2max);
-        m.kval = a.take<unsigned long long>(3 * P); m.kval2 = a.take<unsigned long long>(3 * P);
-        m.kid = a.take<int>(3 * P); m.kid2 = a.take<int>(3 * P);
-        m.uval = a.take<unsigned long long>(3 * P); m.ustart = a.take<int>((size_t)Gs + n2max); m.usz = a.take<int>((size_t)Gs + n2max);
+        m.pairs = a.take<int>(table);
+        m.sv = a.take<unsigned long long>((size_t)set_slots);
+        m.ustart = a.take<long long>((size_t)Gs + n2max); m.ucap = a.take<int>((size_t)Gs + n2max);
+        m.usz = a.take<int>((size_t)Gs + n2max); m.need = a.take<int>((size_t)Gs + n2max);
     };
     MergeState m;
     memset(&m, 0, sizeof(m));
@@ -505,7 +619,7 @@ int ancuts_merge_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk
     br.off = fixed_bytes;
     layoutB(br, m);
     m.P = P; m.G = G; m.n2max = n2max; m.pts = d_points; m.rank = rank; m.local = local; m.alive = alive;
-    m.kflag = flag; m.kincl = incl; m.ctr = dctr + 2; m.htab = htab; m.hmask = hsize - 1;
+    m.ctr = dctr + 2; m.htab = htab; m.hmask = hsize - 1;
     m.chunk_rank0 = d_rank0; m.chunk_ranks = chunk_ranks;
 
     PLAUNCH(k_fill_i32<<<grid(hsize), tb, 0, st>>>(htab, hsize, -1));
@@ -527,28 +641,17 @@ int ancuts_merge_chunks(ancuts_handle* h, int num_chunks, const int64_t* h_chunk
             const double hx = ctr[0] + crop_half_side, hy = ctr[1] + crop_half_side, hz = ctr[2] + crop_half_side;
             const long long tbl = std::max<long long>((long long)G * n2, (long long)G + n2);
             PLAUNCH(k_merge_reset<<<grid(tbl), tb, 0, st>>>(m, n2));
+            // no read-back inside the loop: sizes of the step stay on the device
             PLAUNCH(k_merge_crop<<<grid(a), tb, 0, st>>>(m, a, lx, ly, lz, hx, hy, hz));
-            PLAUNCH(k_merge_chunk_keys<<<grid(b - a), tb, 0, st>>>(m, a, b));
-            ANCUTS_CUDA(cudaMemcpyAsync(h->h_post, m.ctr, sizeof(long long), cudaMemcpyDeviceToHost, st));
-            ANCUTS_CUDA(cudaStreamSynchronize(st));
-            const long long nk = h->h_post[0];
-            if (nk > 0) {
-                int idbits = 1;
-                while ((1ll << idbits) < (long long)G + n2 + 1) ++idbits;
-                size_t tmp = cub_bytes;
-                h->launches_total += 3;
-                ANCUTS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, m.kval, m.kval2, m.kid, m.kid2, (int)nk, 0, 64, st));
-                tmp = cub_bytes;     // stable second pass by instance id: grouped by instance, values ascending inside
-                ANCUTS_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, tmp, m.kid2, m.kid, m.kval2, m.kval, (int)nk, 0, idbits, st));
-                PLAUNCH(k_merge_uflag<<<grid(nk), tb, 0, st>>>(m, nk, m.kval, m.kid));
-                tmp = cub_bytes;
-                ANCUTS_CUDA(cub::DeviceScan::InclusiveSum(cub_tmp, tmp, m.kflag, m.kincl, (int)nk, st));
-                PLAUNCH(k_merge_ucompact<<<grid(nk), tb, 0, st>>>(m, nk, m.kval, m.kid));
-                PLAUNCH(k_merge_inter<<<grid(b - a), tb, 0, st>>>(m, a, b, n2));
-                PLAUNCH(k_merge_iou<<<grid((long long)G * n2 * 32), tb, 0, st>>>(m, n2, min_iou));
-                PLAUNCH(k_merge_resolve<<<grid(n2), tb, 0, st>>>(m, n2));
-                PLAUNCH(k_merge_apply<<<grid(b - a), tb, 0, st>>>(m, a, b));
-            }
+            PLAUNCH(k_merge_cnt2<<<grid(b - a), tb, 0, st>>>(m, a, b));
+            PLAUNCH(k_merge_inter<<<grid(b - a), tb, 0, st>>>(m, a, b, n2));
+            PLAUNCH(k_merge_regions<<<1, 1024, 0, st>>>(m, n2));
+            const long long bound = std::min<long long>(set_slots, 8 * b + 64);
+            PLAUNCH(k_merge_set_clear<<<grid(bound), tb, 0, st>>>(m, bound));
+            PLAUNCH(k_merge_set_fill<<<grid(b), tb, 0, st>>>(m, a, b, lx, ly, lz, hx, hy, hz));
+            PLAUNCH(k_merge_iou<<<IOU_BLOCKS, 256, 0, st>>>(m, n2, min_iou));
+            PLAUNCH(k_merge_resolve<<<grid((long long)n2 * 32), tb, 0, st>>>(m, n2));
+            PLAUNCH(k_merge_apply<<<grid(b - a), tb, 0, st>>>(m, a, b));
         }
         PLAUNCH(k_merge_hash_insert<<<grid(b - a), tb, 0, st>>>(m, a, b));
         // remove_duplicated_points (:489): a new point never displaces an earlier owner (larger index), so only the new chunk
