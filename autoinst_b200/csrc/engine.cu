@@ -76,7 +76,7 @@ struct Plan {
     bool deferred = false;                 // per-chunk pair queues kept until the root split (deferred affinity)
     std::vector<size_t> qoff;              // deferred: first queue entry of chunk c
     std::vector<int> qcap_c;               // deferred: queue capacity of chunk c
-    int* pg_cells = nullptr; int* pg_sorted = nullptr; double* pg_spts = nullptr; PairGrid* pg_grid = nullptr;   // deferred: cell grids of the pair search
+    int* pg_cells = nullptr; int* pg_sorted = nullptr; int* pg_tmp = nullptr; double* pg_spts = nullptr; PairGrid* pg_grid = nullptr;   // deferred: cell grids of the pair search
     int* c_tile0 = nullptr; double* tbox = nullptr; long long* d_qoff = nullptr; int* d_qcap = nullptr;          // cell-sorted sweep
     std::vector<int> tile0; int max_tiles = 0;
     bool grid_pairs = false;
@@ -166,6 +166,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
         if (pl.deferred) {
             pl.pg_cells = ar.take<int>((size_t)B * PG_STRIDE);
             pl.pg_sorted = ar.take<int>((size_t)P);
+            pl.pg_tmp = ar.take<int>((size_t)P);
             pl.pg_spts = ar.take<double>((size_t)P * 3);
             pl.pg_grid = ar.take<PairGrid>((size_t)B);
             pl.tile0.assign(B + 1, 0);
@@ -320,13 +321,15 @@ __global__ void k_init_roots(Eng e, double split_lim, double T) {
     if (g < e.P) e.side[g] = 0;
 }
 
-__global__ void k_init_positions(Eng e) {
+// order != NULL: position g of a chunk holds the point order[g] (cell-sorted order of the batched pair search: neighbours in
+// space are neighbours in every node, the stored entries of a row come in runs of consecutive columns)
+__global__ void k_init_positions(Eng e, const int* __restrict__ order) {
     int c = blockIdx.y;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < e.c_n[c]) {
         int g = e.c_base[c] + i;
         e.rid[g] = c;
-        e.perm[g] = i;
+        e.perm[g] = order ? order[g] : i;
     }
 }
 
@@ -641,6 +644,7 @@ struct DeferredAffinity {
     const float* dino;
     const int64_t* chunk_off;
     const cudaEvent_t* feat_ev;    // host entry with the batched pair stage: chunk c's features have arrived at feat_ev[c]
+    const int* order;              // batched pair stage: the queue holds cell-sorted ranks, order[base + rank] = input index
 };
 
 static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int max_split_n, bool components,
@@ -707,7 +711,8 @@ static int run_rebuild(ancuts_handle* h, Plan& pl, int& cur, int num_split, int 
             LAUNCH(SG_AFFINITY, k_affinity_feats<<<148 * 4, 256, 0, st>>>(
                 pl.pairq + pl.qoff[c], pl.qctr + 2 * c, pl.qcap_c[c], use_tarl ? df->tarl + o * p->tarl_dim : nullptr, p->tarl_dim,
                 use_dino ? df->dino + o * p->dino_dim : nullptr, p->dino_dim, pl.tarl_zero + (o - (size_t)df->chunk_off[0]),
-                p->theta, p->gamma, dst, pl.ld[c], e.val, pl.base[c], e.rid, e.r_status));
+                p->theta, p->gamma, dst, pl.ld[c], e.val, pl.base[c], e.rid, e.r_status,
+                df->order ? df->order + pl.base[c] : nullptr));
         }
         ANCUTS_CUDA(cudaGetLastError());
         cur ^= 1;
@@ -731,7 +736,7 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
         int nmax = 0;
         for (int c = 0; c < B; ++c) nmax = std::max(nmax, pl.n[c]);
         dim3 g((nmax + 255) / 256, B);
-        LAUNCH(SG_PARTITION, k_init_positions<<<g, 256, 0, st>>>(e));
+        LAUNCH(SG_PARTITION, k_init_positions<<<g, 256, 0, st>>>(e, df ? df->order : nullptr));
         int m = std::max(P, B);
         LAUNCH(SG_PARTITION, k_init_roots<<<(m + 255) / 256, 256, 0, st>>>(e, p->split_lim, p->T));
     }
@@ -1341,10 +1346,10 @@ static int run_pairs_batched(ancuts_handle* h, Plan& pl, const double* d_points,
     ANCUTS_CUDA(cudaStreamSynchronize(st));              // qo is a local
     if (h->ev_points) ANCUTS_CUDA(cudaStreamWaitEvent(st, h->ev_points, 0));    // host entry: the coordinates have arrived
     LAUNCH(SG_AFFINITY, k_pair_grid_b<<<B, 1024, PG_CELLS * sizeof(int), st>>>(pl.c_n, pl.c_base, d_points, p->proximity,
-                                                                              pl.pg_cells, pl.pg_sorted, pl.pg_spts, pl.pg_grid));
+                                                                              pl.pg_cells, pl.pg_sorted, pl.pg_tmp, pl.pg_spts, pl.pg_grid));
     LAUNCH(SG_AFFINITY, k_tile_boxes<<<dim3(pl.max_tiles, B), PS_T, 0, st>>>(pl.c_n, pl.c_base, pl.c_tile0, pl.pg_spts, pl.tbox));
     const int npair = pl.max_tiles * (pl.max_tiles + 1) / 2;
-    LAUNCH(SG_AFFINITY, k_pair_sweep<<<dim3(npair, B), 256, 0, st>>>(pl.c_n, pl.c_base, pl.c_tile0, pl.pg_spts, pl.pg_sorted, pl.tbox,
+    LAUNCH(SG_AFFINITY, k_pair_sweep<<<dim3(npair, B), 256, 0, st>>>(pl.c_n, pl.c_base, pl.c_tile0, pl.pg_spts, pl.tbox,
                                                                      p->alpha, p->proximity, pl.pairq, pl.d_qoff, pl.d_qcap, pl.qctr));
     LAUNCH(SG_AFFINITY, k_pair_unions<<<dim3(32, B), 256, 0, st>>>(pl.pairq, pl.d_qoff, pl.d_qcap, pl.qctr, pl.c_base, pl.e.parent));
     // host entry: the features arrive chunk by chunk while this stage and the root split run; the zero-row flags are then
@@ -1504,7 +1509,8 @@ static int segment_common(ancuts_handle* h, int num_chunks, const int64_t* h_chu
         }
         h->stage_bytes[SG_AFFINITY] = aff_bytes;
     }
-    DeferredAffinity df{p, d_tarl, d_dino, h_chunk_off, (deferred && pl.grid_pairs) ? h->feat_ev : nullptr};
+    DeferredAffinity df{p, d_tarl, d_dino, h_chunk_off, (deferred && pl.grid_pairs) ? h->feat_ev : nullptr,
+                        (deferred && pl.grid_pairs) ? pl.pg_sorted : nullptr};
     rc = run_levels(h, pl, p, 0, d_labels, h_num_segments, st, root_forest, deferred ? &df : nullptr);
     if (rc) return rc;
     rc = copy_stats(h, pl, h_stats, stats_cap, h_num_stats, st);

@@ -341,7 +341,8 @@ __device__ __forceinline__ int pg_cell1(const PairGrid& g, double x, int a) {
 //   k_pair_sweep    one CTA per tile pair (ti <= tj) of a chunk: pairs of tiles whose boxes are farther apart than prox
 //                   exit at once (in cell order a tile covers a few adjacent cell rows, so only ~1/5 of the tile pairs
 //                   survive), the others take the float32 pre-filter in registers (64 pairs per thread) and the exact
-//                   float64 test of k_affinity_pairs; hits go to the chunk's queue with their ORIGINAL indices
+//                   float64 test of k_affinity_pairs; hits go to the chunk's queue with their CELL-SORTED ranks, which are
+//                   the positions of the points at the root of the tree (k_init_positions takes the sorted order)
 //   k_pair_unions   root-level components: one union per queued pair, visited in a scattered order (in queue order
 //                   neighbouring threads would hook into the same component at the same time: the first cell-grid
 //                   search of round 1 spent 75 % of its stall samples in uf_find for that reason)
@@ -352,8 +353,8 @@ constexpr int PS_T = 128;                              // points per tile side
 
 __global__ void __launch_bounds__(1024)
 k_pair_grid_b(const int* __restrict__ c_n, const int* __restrict__ c_base, const double* __restrict__ pts_all, double prox,
-              int* __restrict__ cells_all, int* __restrict__ sorted_all, double* __restrict__ spts_all,
-              PairGrid* __restrict__ grids) {
+              int* __restrict__ cells_all, int* __restrict__ sorted_all, int* __restrict__ tmp_all,
+              double* __restrict__ spts_all, PairGrid* __restrict__ grids) {
     extern __shared__ int hist[];
     __shared__ double red[6][32];
     __shared__ PairGrid g;
@@ -364,6 +365,7 @@ k_pair_grid_b(const int* __restrict__ c_n, const int* __restrict__ c_base, const
     const double* pts = pts_all + pos0 * 3;
     int* cell_start = cells_all + (size_t)chunk * PG_STRIDE;
     int* sorted = sorted_all + pos0;
+    int* tmp = tmp_all + pos0;
     double* spts = spts_all + pos0 * 3;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
@@ -426,11 +428,22 @@ k_pair_grid_b(const int* __restrict__ c_n, const int* __restrict__ c_base, const
     }
     if (tid == 0) cell_start[PG_CELLS] = n;
     __syncthreads();
-    // The position inside a cell follows the atomics: any order gives the same pairs (the queue order is arbitrary anyway).
+    // The slot inside a cell follows the atomics; the sorted order is the order of the points in every node of the tree
+    // (k_init_positions), so it has to be the same in every run: a second pass ranks the points of a cell by input index.
     for (int i = tid; i < n; i += 1024) {
         const int c = (pg_cell1(g, pts[(size_t)i * 3 + 2], 2) * g.n[1] + pg_cell1(g, pts[(size_t)i * 3 + 1], 1)) * g.n[0]
                       + pg_cell1(g, pts[(size_t)i * 3], 0);
-        const int pos = atomicAdd(&hist[c], 1);
+        tmp[atomicAdd(&hist[c], 1)] = i;
+    }
+    __syncthreads();
+    for (int q = tid; q < n; q += 1024) {
+        const int i = tmp[q];
+        const int c = (pg_cell1(g, pts[(size_t)i * 3 + 2], 2) * g.n[1] + pg_cell1(g, pts[(size_t)i * 3 + 1], 1)) * g.n[0]
+                      + pg_cell1(g, pts[(size_t)i * 3], 0);
+        const int start = cell_start[c], end = hist[c];            // hist[c] has advanced to the end of the cell
+        int rank = 0;
+        for (int t = start; t < end; ++t) rank += (tmp[t] < i) ? 1 : 0;
+        const int pos = start + rank;
         sorted[pos] = i;
         spts[(size_t)pos * 3] = pts[(size_t)i * 3];
         spts[(size_t)pos * 3 + 1] = pts[(size_t)i * 3 + 1];
@@ -466,7 +479,7 @@ k_tile_boxes(const int* __restrict__ c_n, const int* __restrict__ c_base, const 
 // grid: (tile pairs of the largest chunk, chunks), 256 threads; tile pair L -> (ti <= tj) with L = tj (tj + 1) / 2 + ti
 __global__ void __launch_bounds__(256)
 k_pair_sweep(const int* __restrict__ c_n, const int* __restrict__ c_base, const int* __restrict__ c_tile0,
-             const double* __restrict__ spts_all, const int* __restrict__ sorted_all, const double* __restrict__ tbox,
+             const double* __restrict__ spts_all, const double* __restrict__ tbox,
              double alpha, double prox, PairQ* __restrict__ q_all, const long long* __restrict__ q_off,
              const int* __restrict__ q_cap, int* __restrict__ qctr_all) {
     const int chunk = blockIdx.y;
@@ -566,15 +579,13 @@ k_pair_sweep(const int* __restrict__ c_n, const int* __restrict__ c_base, const 
     const int base = qbase;
     if (base < 0) return;
     PairQ* q = q_all + q_off[chunk];
-    const int* sorted = sorted_all + pos0;
     for (int t = tid; t < total; t += 256) {
         const int idx = queue[t];
         const int r = idx / PS_T, c = idx % PS_T;
         const double dx = pr[r][0] - pc[c][0], dy = pr[r][1] - pc[c][1], dz = pr[r][2] - pc[c][2];
         const double sd = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
         PairQ e;
-        const int i0 = sorted[row0 + r], j0 = sorted[col0 + c];
-        e.i = min(i0, j0); e.j = max(i0, j0);
+        e.i = row0 + r; e.j = col0 + c;                                  // cell-sorted ranks (ti <= tj, col > row on the diagonal): i < j
         e.a = alpha != 0.0 ? alpha * sd : 0.0;                           // ncuts_utils.py:63-66
         q[base + t] = e;
     }
@@ -604,7 +615,8 @@ k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int 
                  const uint8_t* __restrict__ tarl_zero, double theta, double gamma,
                  float* __restrict__ W, long long ld,
                  const int* __restrict__ inv = nullptr, int base = 0, const int* __restrict__ rid = nullptr,
-                 const int* __restrict__ r_status = nullptr) {
+                 const int* __restrict__ r_status = nullptr, const int* __restrict__ order = nullptr) {
+    // order != NULL: the queue holds cell-sorted ranks (= root positions); order[rank] = input index, where the features are
     // inv != NULL (deferred mode): the pair is written at the positions its points have AFTER the root split
     // (inv[old global position] = new global position), and only if their range goes on to the eigensolver.
     const int total = min(qctr[0], qcap);
@@ -619,14 +631,15 @@ k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int 
         int gi = 0, gj = 0;
         double a = 0.0;
         if (live) { PairQ e = q[idx]; gi = e.i; gj = e.j; a = e.a; }
+        const int fi = order ? order[gi] : gi, fj = order ? order[gj] : gj;
         double arg = 0.0;
         if (theta != 0.0 && tarl != nullptr) {
-            double td = feat_dist8(tarl + (size_t)gi * tdim, tarl + (size_t)gj * tdim, tdim, lane8);
-            if (tarl_zero[gi] | tarl_zero[gj]) td = 0.0;                 // ncuts_utils.py:145-146
+            double td = feat_dist8(tarl + (size_t)fi * tdim, tarl + (size_t)fj * tdim, tdim, lane8);
+            if (tarl_zero[fi] | tarl_zero[fj]) td = 0.0;                 // ncuts_utils.py:145-146
             arg += theta * td;
         }
         if (gamma != 0.0 && dino != nullptr) {
-            double dd = feat_dist8(dino + (size_t)gi * ddim, dino + (size_t)gj * ddim, ddim, lane8);
+            double dd = feat_dist8(dino + (size_t)fi * ddim, dino + (size_t)fj * ddim, ddim, lane8);
             arg += gamma * dd;                                           // :129-133
         }
         if (live && lane8 == 0) {
