@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/levels.json")
     ap.add_argument("--matvec", type=int, default=0, help="ANCUTS_OPT_MATVEC: 0 shared-memory sparse (default), 1 dense")
     ap.add_argument("--pairs", type=int, default=0, help="ANCUTS_OPT_PAIR_SEARCH: 0 cell-sorted (default), 1 shuffled")
+    ap.add_argument("--map", type=int, default=0, help="chunks of one synthetic map (N in [3 k, 12 k]) instead of --batch equal chunks")
     args = ap.parse_args()
     import torch
     from autoinst_b200 import api
@@ -25,7 +26,11 @@ def main():
     dev = torch.device("cuda", 0)
     cfg = CONFIGS["tarl_spatial"]
     kw = dict(alpha=cfg["alpha"], theta=cfg["theta"], T=cfg["T"])
-    chunks = [make_chunk(args.seed + i, n_target=args.n_target, features="tarl") for i in range(args.batch)]
+    if args.map:
+        from autoinst_b200.synthetic import make_map
+        chunks = make_map(args.map, (3000, 12000), features="tarl", seed=args.seed)
+    else:
+        chunks = [make_chunk(args.seed + i, n_target=args.n_target, features="tarl") for i in range(args.batch)]
     packed = api.PackedChunks([c.points for c in chunks], [c.tarl for c in chunks], None, theta=cfg["theta"])
     devc = packed.to_device(dev)
     hd = api.Handle.get(dev)
@@ -68,6 +73,7 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(out, open(args.out, "w"), indent=1)
     print("total matvec ms", acc["matvec"]["ms"], "levels", out["stat_levels"])
+    print("stage ms", {k: round(v["ms"], 3) for k, v in acc.items()})
 
 
 if __name__ == "__main__":
