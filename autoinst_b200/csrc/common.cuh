@@ -149,6 +149,8 @@ struct Eng {
     int* a_path;          // 1 = multi-launch Lanczos path (k_ritz needed), 0 = finished by the cluster kernel
     int* a_fused;         // 1 = the cluster kernel also took the cut decision of the node (cl_fused_cut): the cut kernels skip it
     int fuse_cut;         // segment calls: the sparse-form cluster kernels may fuse the cut
+    int* unfused;         // active slots the cluster kernels ran but did not decide (ctr[18] entries)
+    const int* sel;       // cut kernels: the slots to work on (blockIdx.y / thread index -> slot), NULL = all active slots
     int* cl_ids;          // [class][active_cap] active slots per cluster-size class
     int active_cap;
     double* a_alpha; double* a_beta;     // [slot][KS]
@@ -171,6 +173,7 @@ struct Eng {
                           // [7]=maxSplitN [8..13]=nodes per cluster class [14]=nodes for the multi-launch path
                           // [16]=eigensolver nodes that stopped unconverged (whole call, never reset between levels)
                           // [17]=nodes of the level whose cut was decided inside the cluster kernel (cl_fused_cut)
+                          // [18]=nodes of the level the cluster kernels ran but left to the cut kernels (Eng::unfused)
     unsigned long long* acct;   // [SG_COUNT] algorithmic bytes
     ancuts_node_stat* stats; int stats_cap;
     int w_own;            // 1 = W holds the library's own affinities (0 or [2^-126, 2)): the matvec may widen on the integer pipe

@@ -81,7 +81,7 @@ struct Plan {
     std::vector<int> tile0; int max_tiles = 0;
     bool grid_pairs = false;
     ancuts_node_stat* stats;
-    Eng e;
+    Eng e{};            // zero: optional pointers (sel, unfused, dbg, stats) are NULL unless a call sets them
 };
 
 static size_t cub_temp_bytes(int P) {
@@ -129,6 +129,7 @@ static size_t layout(Plan& pl, char* base, int stats_cap, int tdim, int ddim, bo
     e.ctr = ar.take<int>(CTR_COUNT);
     e.a_path = ar.take<int>(A);
     e.a_fused = ar.take<int>(A);
+    e.unfused = ar.take<int>(A);
     e.cl_ids = ar.take<int>((size_t)CL_CLASSES * A);
     e.active_cap = A;
     e.acct = ar.take<unsigned long long>(SG_ACCT);
@@ -744,9 +745,10 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
     if (rc) return rc;
     int num_split = h->h_ctr[5], max_split_n = h->h_ctr[7];
     int guard = 0;
+    bool all_fused = false;            // previous level: every node joined its components inside the cluster kernel
     while (num_split > 0) {
         int class_cnt[CL_CLASSES] = {0}, big_cnt = 0;
-        rc = run_rebuild(h, pl, cur, num_split, max_split_n, true, st, class_cnt, &big_cnt, root_forest_ready && guard == 0,
+        rc = run_rebuild(h, pl, cur, num_split, max_split_n, !all_fused, st, class_cnt, &big_cnt, root_forest_ready && guard == 0,
                          guard == 0 ? df : nullptr, guard > 0);
         if (rc) return rc;
         int num_active = h->h_ctr[1], max_n = h->h_ctr[2];
@@ -757,17 +759,24 @@ static int run_levels(ancuts_handle* h, Plan& pl, const ancuts_params* p, int cu
         // hold their node as CSR slices decide the cut and join the components themselves (cl_fused_cut)
         ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 5, 0, sizeof(int), st));
         ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 7, 0, sizeof(int), st));
-        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 17, 0, sizeof(int), st));       // nodes decided inside the cluster kernels
+        ANCUTS_CUDA(cudaMemsetAsync(e.ctr + 17, 0, 2 * sizeof(int), st));   // nodes decided inside / left over by the cluster kernels
         LAUNCH(SG_PARTITION, k_cc_init<<<(P + 255) / 256, 256, 0, st>>>(e));
         e.fuse_cut = (h->opt[ANCUTS_OPT_FUSED_CUT] == 0) ? 1 : 0;
-        h->h_ctr[17] = 0;
+        h->h_ctr[17] = 0; h->h_ctr[18] = 0;
         if (p->lanczos_impl == 1) rc = run_lanczos(h, e, cur, num_active, max_n, st);
         else rc = run_lanczos_all(h, e, cur, num_active, max_n, class_cnt, big_cnt, st);
         if (rc) return rc;
         // every node of the level decided by cl_fused_cut (the usual case): the counters read back after the cluster kernels
         // already hold the split list, no cut kernel and no second read-back
-        if (h->h_ctr[17] != num_active) {
-            rc = run_cut(h, e, cur, num_active, max_n, true, st, false);
+        all_fused = (h->h_ctr[17] == num_active);
+        if (!all_fused) {
+            // the few nodes the cluster kernels left over (slices that did not fit, more steps needed) are on a list: the cut
+            // kernels run over those only; levels with nodes the cluster kernels never saw (> 4096 points) take every slot
+            const int left = num_active - h->h_ctr[17];
+            const bool listed = p->lanczos_impl != 1 && big_cnt == 0 && h->h_ctr[18] == left;
+            e.sel = listed ? e.unfused : nullptr;
+            rc = run_cut(h, e, cur, listed ? left : num_active, max_n, true, st, false);
+            e.sel = nullptr;
             if (rc) return rc;
             rc = read_ctr(h, e, st);
             if (rc) return rc;

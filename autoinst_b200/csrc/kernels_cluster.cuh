@@ -1114,10 +1114,12 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             atomicAdd(&e.acct[SG_SPARSE_NNZ], (unsigned long long)sp.nnz);
         }
         if (fuse) cl_fused_cut<C>(cl, S, e, zs, sp, v, a, rank, r0, nr, pad, k, th);
+        else if (rank == 0 && tid == 0 && e.unfused) e.unfused[atomicAdd(&e.ctr[18], 1)] = a;     // the cut kernels take it
     } else if (rank == 0 && tid == 0) {
         e.a_done[a] = DONE_NO;                  // left for the multi-launch path (more steps)
         e.a_path[a] = 1;
         atomicAdd(&e.ctr[4], 1);
+        if (e.unfused) e.unfused[atomicAdd(&e.ctr[18], 1)] = a;
     }
     cl_sync<C>(cl);                             // peers may still be reading this CTA's shared memory
 }

@@ -460,7 +460,7 @@ k_ritz(Eng e) {
     extern __shared__ double sm[];      // y[KS] | red[3*8]
     double* ys = sm;
     double* red = sm + e.KS;
-    int a = blockIdx.y;
+    int a = e.sel ? e.sel[blockIdx.y] : blockIdx.y;
     if (e.a_path[a] == 0) return;                // the cluster kernel already wrote ev and its statistics
     int nch = e.a_nch[a];
     int ch = blockIdx.x;

@@ -26,6 +26,7 @@ __device__ __forceinline__ int fix_shift(double vol) {
 __global__ void k_ev_final(Eng e, int num_active) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= num_active) return;
+    if (e.sel) a = e.sel[a];
     if (e.a_fused[a]) return;                  // decided inside the cluster kernel (cl_fused_cut)
     int s0 = e.a_slot0[a], nch = e.a_nch[a];
     double sum = 0.0, mn = 1e300, mx = -1e300, q = 0.0;
@@ -57,7 +58,7 @@ k_bucket(Eng e) {
     __shared__ double red[8];
     __shared__ int scnt[NB];
     __shared__ double thr[NCUT];
-    int a = blockIdx.y;
+    int a = e.sel ? e.sel[blockIdx.y] : blockIdx.y;
     if (e.a_fused[a]) return;
     int nch = e.a_nch[a];
     int ch = blockIdx.x;
@@ -103,7 +104,7 @@ k_scan(Eng e, int cur) {
     __shared__ unsigned long long sdiff[NB + 1];
     __shared__ double svol[NB];
     __shared__ double sscale;
-    int a = blockIdx.y;
+    int a = e.sel ? e.sel[blockIdx.y] : blockIdx.y;
     if (e.a_fused[a] || e.a_nocut[a]) return;
     NodeView v = node_view(e, e.a_rid[a], cur);
     int row0 = blockIdx.x * 8;
@@ -161,6 +162,7 @@ k_scan(Eng e, int cur) {
 __global__ void k_decide(Eng e, int num_active) {
     int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= num_active) return;
+    if (e.sel) a = e.sel[a];
     if (e.a_fused[a]) return;
     int r = e.a_rid[a];
     int n = e.r_n[r], c = e.r_chunk[r];
@@ -225,7 +227,7 @@ __global__ void k_decide(Eng e, int num_active) {
 // grid: (chunks, active)
 __global__ void __launch_bounds__(256)
 k_sides(Eng e) {
-    int a = blockIdx.y;
+    int a = e.sel ? e.sel[blockIdx.y] : blockIdx.y;
     int r = e.a_rid[a];
     if (e.a_fused[a] || e.r_status[r] != ST_SPLIT) return;
     int start = e.r_start[r], n = e.r_n[r];
