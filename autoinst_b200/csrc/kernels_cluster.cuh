@@ -47,7 +47,8 @@ struct ClusterShared {
     int fcnt[NB];                       //            points per bucket
     int fdec[4];                        //            decision: best threshold, split, side 0 passes, side 1 passes
     double ysl[2][CL_RPMAX];     // this CTA's slice of the current vector (ping) and of the matvec result (pong)
-    double wred[CL_WARPS];       // per-warp partials of the fused reductions (alpha in the matvec, norm in the update)
+    double wred[CL_WARPS];       // per-warp partials of alpha (matvec epilogue)
+    double wred2[CL_WARPS];      // per-warp partials of the norm (update): its own array, no barrier separates the two uses
     double sv[CL_RPMAX];         // D^-1/2 of the slice
     double red[32];
     double bounds[4];
@@ -291,10 +292,13 @@ struct SliceBasis {
     }
 };
 
-// partial dots of the slice vector y with basis rows [0, rows): S.hpart[buf][j].  One warp per row,
+// partial dots of the slice vector y with basis rows [0, rows): S.hpart[j].  One warp per row,
 // all loads of a row in flight at once (nr <= CL_RPMAX = 16 * 32).
+// (Forming the three-term values inside this pass -- every warp from yraw, v_k, v_{k-1}, no barrier in between -- was built
+// and measured: bit-identical results, 3 % SLOWER: sixteen warps re-read v_k and v_{k-1}, from L2 once the basis has outgrown
+// its shared-memory part.)
 __device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const double* __restrict__ y, const SliceBasis& B,
-                                                int rows, int nr, int buf) {
+                                                int rows, int nr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int M = (CL_RPMAX + 31) / 32;
     double yr[M];
@@ -329,27 +333,53 @@ __device__ __forceinline__ void cl_reduce_h(cg::cluster_group& cl, ClusterShared
 }
 
 // y_i -= sum_j hs[j] V[j][i] for the slice; returns this thread's share of |y|^2 (the norm rides on the update pass)
-__device__ __forceinline__ double cl_update_norm(ClusterShared& S, double* __restrict__ y, const SliceBasis& B, int rows, int nr) {
+__device__ __forceinline__ double cl_update_norm(const double* __restrict__ hs, double* __restrict__ y, const SliceBasis& B,
+                                                 int rows, int nr) {
+    // Rows [0, rows_s) of the basis sit in shared memory (stride nrp), the rest in global memory (stride P).  A group of
+    // rows that lies on one side is walked with a stepping pointer; B.get's per-element select and two 64-bit address
+    // products were 22 % of all instructions the kernel executed (ncu source view).  Same groups, same two chains, same
+    // order as before: bit-identical sums.
     double q = 0.0;
+    const int rs = B.rows_s;
     for (int i = threadIdx.x; i < nr; i += CL_THREADS) {
         double v = y[i];
         int j = 0;
         double c0 = 0.0, c1 = 0.0;                        // the correction sum_j hs[j] V[j][i] in two chains (fixed order)
         for (; j + 12 <= rows; j += 12) {                 // 12 basis rows in flight: the rows behind the shared-memory part come
             double t[12];                                 // from L2 / HBM while other SMs stream W, one round trip per group
+            if (j + 12 <= rs) {
+                const double* p = B.smem + (size_t)j * B.nrp + i;
 #pragma unroll
-            for (int u = 0; u < 12; ++u) t[u] = B.get(j + u, i);
+                for (int u = 0; u < 12; ++u) { t[u] = *p; p += B.nrp; }
+            } else if (j >= rs) {
+                const double* p = B.glob + (size_t)j * B.P + i;
 #pragma unroll
-            for (int u = 0; u < 12; u += 2) { c0 = fma(S.hs[j + u], t[u], c0); c1 = fma(S.hs[j + u + 1], t[u + 1], c1); }
+                for (int u = 0; u < 12; ++u) { t[u] = *p; p += B.P; }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 12; ++u) t[u] = B.get(j + u, i);
+            }
+#pragma unroll
+            for (int u = 0; u < 12; u += 2) { c0 = fma(hs[j + u], t[u], c0); c1 = fma(hs[j + u + 1], t[u + 1], c1); }
         }
         for (; j + 4 <= rows; j += 4) {
             double t[4];
+            if (j + 4 <= rs) {
+                const double* p = B.smem + (size_t)j * B.nrp + i;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) t[u] = B.get(j + u, i);
+                for (int u = 0; u < 4; ++u) { t[u] = *p; p += B.nrp; }
+            } else if (j >= rs) {
+                const double* p = B.glob + (size_t)j * B.P + i;
 #pragma unroll
-            for (int u = 0; u < 4; u += 2) { c0 = fma(S.hs[j + u], t[u], c0); c1 = fma(S.hs[j + u + 1], t[u + 1], c1); }
+                for (int u = 0; u < 4; ++u) { t[u] = *p; p += B.P; }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) t[u] = B.get(j + u, i);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) { c0 = fma(hs[j + u], t[u], c0); c1 = fma(hs[j + u + 1], t[u + 1], c1); }
         }
-        for (; j < rows; ++j) c0 = fma(S.hs[j], B.get(j, i), c0);
+        for (; j < rows; ++j) c0 = fma(hs[j], B.get(j, i), c0);
         v -= c0 + c1;
         y[i] = v;
         q = fma(v, v, q);
@@ -357,14 +387,14 @@ __device__ __forceinline__ double cl_update_norm(ClusterShared& S, double* __res
     return q;
 }
 
-// sum over the CTA of one value per thread: warp partials in S.wred, ONE block barrier, fixed order
+// sum over the CTA of one value per thread: warp partials in S.wred2, ONE block barrier, fixed order
 __device__ __forceinline__ double cl_block_sum1(ClusterShared& S, double v) {
     v = warp_sum(v);
-    if ((threadIdx.x & 31) == 0) S.wred[threadIdx.x >> 5] = v;
+    if ((threadIdx.x & 31) == 0) S.wred2[threadIdx.x >> 5] = v;
     __syncthreads();
     double t = 0.0;
 #pragma unroll
-    for (int i = 0; i < CL_WARPS; ++i) t += S.wred[i];
+    for (int i = 0; i < CL_WARPS; ++i) t += S.wred2[i];
     return t;
 }
 
@@ -984,7 +1014,9 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         //      full pass only removes rounding-level components and plays the role of the SECOND pass of "twice is
         //      enough": orthogonality stays at 2e-15 like CGS2 (numpy model, 151 nodes, identical steps and cuts),
         //      with two sweeps over the basis instead of four.  A single CGS pass WITHOUT the three-term part
-        //      loses orthogonality within dozens of steps (measured in round 1 and again in the model). ----
+        //      loses orthogonality within dozens of steps (measured in round 1 and again in the model); so does a pass
+        //      that leaves alpha v_k to the Gram-Schmidt sweep (1e-3 after 60 steps in the model), which is why alpha has
+        //      its own exchange. ----
         {
             const double bk = (k > 0) ? S.beta[k - 1] : 0.0;
             // own elements of v_k and v_{k-1} (u1 when k = 0: bk = 0)
@@ -993,13 +1025,14 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         }
         __syncthreads();
         CL_PHASE(2);
-        cl_partial_dots(S, yn, B, rows, nr, 1);
+        cl_partial_dots(S, yn, B, rows, nr);
         cl_sync<C>(cl);
-        cl_reduce_h<C>(cl, S, rows, 1);
-        const double a2 = S.hs[rows - 1];
+        const double* hsrc = S.hpart;               // one CTA per node: its partial dots are the coefficients
+        if (C > 1) { cl_reduce_h<C>(cl, S, rows, 1); hsrc = S.hs; }
+        const double a2 = hsrc[rows - 1];
         CL_PHASE(4);
         // ---- update, squared norm, z = S y for the next matvec ----
-        double q = cl_update_norm(S, yn, B, rows, nr);
+        double q = cl_update_norm(hsrc, yn, B, rows, nr);
         // z = S y for the next matvec: every CTA PUSHES its slice into the z vector of all CTAs of the cluster through
         // distributed shared memory (every matvec of this step has ended before the barrier of the Gram-Schmidt exchange
         // above, so the peers' z is free; the barrier of the norm exchange below publishes the stores).  Round 1 went through
@@ -1028,10 +1061,12 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         bprev = beta;
         k += 1;
         { double* t_ = yc; yc = yn; yn = t_; }
-        __syncthreads();
+        // no barrier here: what the next step reads of this one -- yc, z, alpha / beta -- is separated from its writes by the
+        // barrier of the norm reduction above or by the one that ends the next matvec (S.wred / S.wred2 are separate arrays)
         CL_PHASE(6);
         const bool breakdown = beta < 1e-13;
         if (breakdown || k >= kcap || k == S.next_check) {
+            __syncthreads();                 // alpha[k-1], beta[k-1] of thread 0
             cluster_tridiag_eigs(S, k, th);
             if (prof) { tph[3] += S.tmark - tlast; tlast = S.tmark; }     // slot 3: multisection part of the check
             const double res = cluster_tridiag_vec(S, k, th[0]);
