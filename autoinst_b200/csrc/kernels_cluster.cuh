@@ -297,24 +297,44 @@ struct SliceBasis {
 // (Forming the three-term values inside this pass -- every warp from yraw, v_k, v_{k-1}, no barrier in between -- was built
 // and measured: bit-identical results, 3 % SLOWER: sixteen warps re-read v_k and v_{k-1}, from L2 once the basis has outgrown
 // its shared-memory part.)
-__device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const double* __restrict__ y, const SliceBasis& B,
-                                                int rows, int nr) {
+template <int M>
+__device__ __forceinline__ double cl_dot_row(const double* __restrict__ vr, const double (&yr)[M], int lane, int nr) {
+    // the slice has more than 32 (M - 4) rows: only the last four blocks of 32 need the bound check
+    double t[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) { const int i = lane + 32 * m; t[m] = (m < M - 4 || i < nr) ? vr[i] : 0.0; }
+    double s = 0.0;
+#pragma unroll
+    for (int m = 0; m < M; ++m) s += t[m] * yr[m];
+    return warp_sum(s);
+}
+template <int M>
+__device__ __forceinline__ void cl_partial_dots_m(ClusterShared& S, const double* __restrict__ y, const SliceBasis& B,
+                                                  int rows, int nr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int M = (CL_RPMAX + 31) / 32;
     double yr[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) { int i = lane + 32 * m; yr[m] = (i < nr) ? y[i] : 0.0; }
-    for (int j = warp; j < rows; j += CL_WARPS) {
-        double t[M];
-        const double* vr = B.row(j);
-#pragma unroll
-        for (int m = 0; m < M; ++m) { int i = lane + 32 * m; t[m] = (i < nr) ? vr[i] : 0.0; }
-        double s = 0.0;
-#pragma unroll
-        for (int m = 0; m < M; ++m) s += t[m] * yr[m];
-        s = warp_sum(s);
+    // rows in shared memory, then rows in global memory: two loops, so that the loads are LDS / LDG instead of generic
+    const int rs = min(rows, B.rows_s);
+    int j = warp;
+    for (; j < rs; j += CL_WARPS) {
+        const double s = cl_dot_row<M>(B.smem + (size_t)j * B.nrp, yr, lane, nr);
         if (lane == 0) S.hpart[j] = s;
     }
+    for (; j < rows; j += CL_WARPS) {
+        const double s = cl_dot_row<M>(B.glob + (size_t)j * B.P, yr, lane, nr);
+        if (lane == 0) S.hpart[j] = s;
+    }
+}
+// slices of up to 128 / 256 / 384 / 512 rows: the loads and products beyond the slice (zeros) are not issued; same sums
+__device__ __forceinline__ void cl_partial_dots(ClusterShared& S, const double* __restrict__ y, const SliceBasis& B,
+                                                int rows, int nr) {
+    static_assert(CL_RPMAX == 512, "four tiers of 128 rows");
+    if (nr <= 128) cl_partial_dots_m<4>(S, y, B, rows, nr);
+    else if (nr <= 256) cl_partial_dots_m<8>(S, y, B, rows, nr);
+    else if (nr <= 384) cl_partial_dots_m<12>(S, y, B, rows, nr);
+    else cl_partial_dots_m<16>(S, y, B, rows, nr);
 }
 
 template <int C>
@@ -601,13 +621,17 @@ __device__ __forceinline__ double cl_matvec_ring(ClusterShared& S, const double*
 // A slice that does not fit (dense little nodes far above 100 entries per row) sends the node to the grid-wide path.
 struct SparseSlice {
     const float* val; const unsigned short* col; const int* ptr; int nnz;
+    // col holds the BYTE offset of the entry's z value inside the CTA's z buffer, 8 * (column + pad) <= 8 * 4099: the matvec
+    // adds it to the buffer's address and loads (two integer instructions per entry less than index -> address)
+    __device__ __forceinline__ int column(int q, int pad) const { return (int)(col[q] >> 3) - pad; }
 };
 constexpr int SP_LANES = 4;
 
 // Entries of TWO rows inside the block's aligned window, written by one warp: eight 128-bit loads in flight per lane
 // (512 columns of both rows) before the first use.  Entries of a row keep the column order.  A row pointer may be NULL.
 __device__ __forceinline__ void sp_fill_rows(const float* __restrict__ rowa, const float* __restrict__ rowb, int a0, int c_lo,
-                                             int c_hi, int lane, float* val, unsigned short* col, int basea, int baseb) {
+                                             int c_hi, int lane, float* val, unsigned short* col, int basea, int baseb,
+                                             int pad) {
     for (int c0 = a0; c0 < c_hi; c0 += 512) {
         float4 w[2][4];
 #pragma unroll
@@ -633,7 +657,7 @@ __device__ __forceinline__ void sp_fill_rows(const float* __restrict__ rowa, con
                 int& base = rr ? baseb : basea;
                 int pos = base + incl - cnt;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) if (m & (1u << q)) { val[pos] = in[q]; col[pos] = (unsigned short)(c + q - c_lo); ++pos; }
+                for (int q = 0; q < 4; ++q) if (m & (1u << q)) { val[pos] = in[q]; col[pos] = (unsigned short)((c + q - c_lo + pad) << 3); ++pos; }
                 base += __shfl_sync(0xffffffffu, incl, 31);
             }
         }
@@ -651,7 +675,9 @@ __device__ __forceinline__ double cl_matvec_sparse(ClusterShared& S, const doubl
         double acc = 0.0;
         if (i < nr) {
             const int b = sp.ptr[i], e = sp.ptr[i + 1];
-            for (int q = b + sub; q < e; q += SP_LANES) acc = fma((double)sp.val[q], zs[sp.col[q] + pad], acc);
+            const char* zb = reinterpret_cast<const char*>(zs);
+            for (int q = b + sub; q < e; q += SP_LANES)
+                acc = fma((double)sp.val[q], *reinterpret_cast<const double*>(zb + sp.col[q]), acc);
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -742,7 +768,7 @@ __device__ void cl_fused_cut(cg::cluster_group& cl, ClusterShared& S, const Eng&
             if (i < nr) {
                 const int gi = r0 + i, bi = bk[gi];
                 for (int q = sp.ptr[i] + (tid & (SP_LANES - 1)); q < sp.ptr[i + 1]; q += SP_LANES) {
-                    const int c = sp.col[q];
+                    const int c = sp.column(q, pad);
                     if (c > gi) {
                         const int bj = bk[c];
                         if (bj != bi) {
@@ -832,7 +858,7 @@ __device__ void cl_fused_cut(cg::cluster_group& cl, ClusterShared& S, const Eng&
             const int si = (bk[gi] > best) ? 0 : 1;
             if (S.fdec[2 + si]) {
                 for (int q = sp.ptr[i] + (tid & (SP_LANES - 1)); q < sp.ptr[i + 1]; q += SP_LANES) {
-                    const int c = sp.col[q];
+                    const int c = sp.column(q, pad);
                     if (c > gi && ((bk[c] > best) ? 0 : 1) == si) uf_union(e.parent, v.start + gi, v.start + c);
                 }
             }
@@ -911,7 +937,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
             for (int i = warp; i < nr; i += 2 * CL_WARPS) {
                 const int i2 = i + CL_WARPS;
                 sp_fill_rows(v.W + (size_t)(v.ro + r0 + i) * v.ld, i2 < nr ? v.W + (size_t)(v.ro + r0 + i2) * v.ld : nullptr, a0,
-                             c_lo, c_hi, lane, val, col, ptr[i], i2 < nr ? ptr[i2] : 0);
+                             c_lo, c_hi, lane, val, col, ptr[i], i2 < nr ? ptr[i2] : 0, pad);
             }
             sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total;
             __syncthreads();
