@@ -662,6 +662,12 @@ __device__ __forceinline__ void sp_fill_rows(const float* __restrict__ rowa, con
             }
         }
     }
+    // rows start at even entries (the matvec loads value pairs and column pairs): a row with an odd number of entries ends
+    // with a zero that points at the first z slot
+    if (lane == 0) {
+        if (rowa && (basea & 1)) { val[basea] = 0.0f; col[basea] = 0; }
+        if (rowb && (baseb & 1)) { val[baseb] = 0.0f; col[baseb] = 0; }
+    }
 }
 
 // returns (every lane) the thread's share of alpha = v . (M v), v_i = yin_i * invb; the caller reduces it over the warp
@@ -674,10 +680,18 @@ __device__ __forceinline__ double cl_matvec_sparse(ClusterShared& S, const doubl
         const int i = base + tid / SP_LANES;
         double acc = 0.0;
         if (i < nr) {
+            // two adjacent entries per lane and trip: one 64-bit load for the values, one 32-bit load for the columns (rows
+            // start at even entries), two chains
             const int b = sp.ptr[i], e = sp.ptr[i + 1];
             const char* zb = reinterpret_cast<const char*>(zs);
-            for (int q = b + sub; q < e; q += SP_LANES)
-                acc = fma((double)sp.val[q], *reinterpret_cast<const double*>(zb + sp.col[q]), acc);
+            double acc1 = 0.0;
+            for (int q = b + 2 * sub; q < e; q += 2 * SP_LANES) {
+                const float2 w = *reinterpret_cast<const float2*>(sp.val + q);
+                const unsigned cc = *reinterpret_cast<const unsigned*>(sp.col + q);
+                acc = fma((double)w.x, *reinterpret_cast<const double*>(zb + (cc & 0xffffu)), acc);
+                acc1 = fma((double)w.y, *reinterpret_cast<const double*>(zb + (cc >> 16)), acc1);
+            }
+            acc += acc1;
         }
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -898,7 +912,9 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         // ---- build the CSR slice: entries per row (counted by k_degree on its pass over the block), scan, fill ----
         const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
         __shared__ int sp_wtot[CL_WARPS + 1];
-        const int mine = (tid < nr) ? e.rownnz[g0 + tid] : 0;      // stored entries per row, counted by k_degree
+        const int stored = (tid < nr) ? e.rownnz[g0 + tid] : 0;    // stored entries per row, counted by k_degree
+        const int mine = (stored + 1) & ~1;                        // rows start at even entries (cl_matvec_sparse)
+        const int odd_rows = __syncthreads_count(stored & 1);
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -939,7 +955,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
                 sp_fill_rows(v.W + (size_t)(v.ro + r0 + i) * v.ld, i2 < nr ? v.W + (size_t)(v.ro + r0 + i2) * v.ld : nullptr, a0,
                              c_lo, c_hi, lane, val, col, ptr[i], i2 < nr ? ptr[i2] : 0, pad);
             }
-            sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total;
+            sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total - odd_rows;
             __syncthreads();
         }
     }
@@ -1132,7 +1148,13 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         double xs = 0.0, xq = 0.0, xmn = 1e300, xmx = -1e300;
         for (int i = tid; i < nr; i += CL_THREADS) {
             double x = 0.0;
-            for (int j = 0; j < k; ++j) x += S.yv[j] * B.get(j + 1, i);
+            int j = 0;
+            {   // basis rows 1 .. k: shared-memory part, then global part (stepping pointers, same order of the sum)
+                const double* p = B.smem + (size_t)B.nrp + i;
+                for (; j < k && j + 1 < B.rows_s; ++j) { x += S.yv[j] * *p; p += B.nrp; }
+                p = B.glob + (size_t)(j + 1) * B.P + i;
+                for (; j < k; ++j) { x += S.yv[j] * *p; p += B.P; }
+            }
             e.ev[g0 + i] = x;
             xs += x; xq += x * x; xmn = fmin(xmn, x); xmx = fmax(xmx, x);
             if (fuse) {                               // the whole node's Ritz vector into every CTA's z buffer (no matvec follows)
