@@ -662,11 +662,11 @@ __device__ __forceinline__ void sp_fill_rows(const float* __restrict__ rowa, con
             }
         }
     }
-    // rows start at even entries (the matvec loads value pairs and column pairs): a row with an odd number of entries ends
-    // with a zero that points at the first z slot
-    if (lane == 0) {
-        if (rowa && (basea & 1)) { val[basea] = 0.0f; col[basea] = 0; }
-        if (rowb && (baseb & 1)) { val[baseb] = 0.0f; col[baseb] = 0; }
+    // rows start at multiples of four entries (the matvec loads four values and four columns at once): a row is filled up
+    // with zeros that point at the first z slot
+    if (lane < 3) {
+        if (rowa && lane < ((4 - (basea & 3)) & 3)) { val[basea + lane] = 0.0f; col[basea + lane] = 0; }
+        if (rowb && lane < ((4 - (baseb & 3)) & 3)) { val[baseb + lane] = 0.0f; col[baseb + lane] = 0; }
     }
 }
 
@@ -680,16 +680,18 @@ __device__ __forceinline__ double cl_matvec_sparse(ClusterShared& S, const doubl
         const int i = base + tid / SP_LANES;
         double acc = 0.0;
         if (i < nr) {
-            // two adjacent entries per lane and trip: one 64-bit load for the values, one 32-bit load for the columns (rows
-            // start at even entries), two chains
+            // four adjacent entries per lane and trip: one 128-bit load for the values, one 64-bit load for the columns (rows
+            // start at multiples of four entries), two chains
             const int b = sp.ptr[i], e = sp.ptr[i + 1];
             const char* zb = reinterpret_cast<const char*>(zs);
             double acc1 = 0.0;
-            for (int q = b + 2 * sub; q < e; q += 2 * SP_LANES) {
-                const float2 w = *reinterpret_cast<const float2*>(sp.val + q);
-                const unsigned cc = *reinterpret_cast<const unsigned*>(sp.col + q);
-                acc = fma((double)w.x, *reinterpret_cast<const double*>(zb + (cc & 0xffffu)), acc);
-                acc1 = fma((double)w.y, *reinterpret_cast<const double*>(zb + (cc >> 16)), acc1);
+            for (int q = b + 4 * sub; q < e; q += 4 * SP_LANES) {
+                const float4 w = *reinterpret_cast<const float4*>(sp.val + q);
+                const uint2 cc = *reinterpret_cast<const uint2*>(sp.col + q);
+                acc = fma((double)w.x, *reinterpret_cast<const double*>(zb + (cc.x & 0xffffu)), acc);
+                acc1 = fma((double)w.y, *reinterpret_cast<const double*>(zb + (cc.x >> 16)), acc1);
+                acc = fma((double)w.z, *reinterpret_cast<const double*>(zb + (cc.y & 0xffffu)), acc);
+                acc1 = fma((double)w.w, *reinterpret_cast<const double*>(zb + (cc.y >> 16)), acc1);
             }
             acc += acc1;
         }
@@ -913,8 +915,8 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         const int c_lo = v.ro, c_hi = v.ro + n, a0 = c_lo & ~3;
         __shared__ int sp_wtot[CL_WARPS + 1];
         const int stored = (tid < nr) ? e.rownnz[g0 + tid] : 0;    // stored entries per row, counted by k_degree
-        const int mine = (stored + 1) & ~1;                        // rows start at even entries (cl_matvec_sparse)
-        const int odd_rows = __syncthreads_count(stored & 1);
+        const int mine = (stored + 3) & ~3;                        // rows start at multiples of four entries (cl_matvec_sparse)
+        const int fill = __syncthreads_count((mine - stored) & 1) + 2 * __syncthreads_count((mine - stored) & 2);
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -928,7 +930,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
         __syncthreads();
         const int total = sp_wtot[CL_WARPS];
         int* ptr = reinterpret_cast<int*>(zs + nz);
-        const int ptr_d = (nr + 1 + 1) / 2;                                  // doubles
+        const int ptr_d = (((nr + 1 + 1) / 2) + 1) & ~1;                     // doubles; even: the values start 16-byte aligned
         const int val_d = (total + 1) / 2, col_d = (total + 3) / 4;
         sp_doubles = ptr_d + val_d + col_d;
         double misfit = (nz + sp_doubles > dyn_doubles) ? 1.0 : 0.0;
@@ -955,7 +957,7 @@ k_lanczos_cluster(Eng e, int cur, const int* __restrict__ ids, int dyn_doubles) 
                 sp_fill_rows(v.W + (size_t)(v.ro + r0 + i) * v.ld, i2 < nr ? v.W + (size_t)(v.ro + r0 + i2) * v.ld : nullptr, a0,
                              c_lo, c_hi, lane, val, col, ptr[i], i2 < nr ? ptr[i2] : 0, pad);
             }
-            sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total - odd_rows;
+            sp.val = val; sp.col = col; sp.ptr = ptr; sp.nnz = total - fill;
             __syncthreads();
         }
     }
