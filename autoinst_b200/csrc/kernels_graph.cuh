@@ -627,35 +627,58 @@ k_affinity_feats(const PairQ* __restrict__ q, const int* __restrict__ qctr, int 
     // every row read to L2: 147 MB per 8.4 k-point chunk)
     const int per_block = (((total + (int)gridDim.x - 1) / (int)gridDim.x) + 31) & ~31;
     const int b0 = blockIdx.x * per_block, b1 = min(total, b0 + per_block);
-    for (int i0 = b0; i0 < b1; i0 += 32) {
-        const int idx = i0 + (threadIdx.x >> 3);
-        const bool live = idx < b1;
-        int gi = 0, gj = 0;
-        double a = 0.0;
-        if (live) { PairQ e = q[idx]; gi = e.i; gj = e.j; a = e.a; }
-        const int fi = order ? order[gi] : gi, fj = order ? order[gj] : gj;
-        double arg = 0.0;
+    // two pairs per 8-lane group and trip, written as two independent instruction streams: a pair is a chain of six
+    // dependent global-memory round trips (queue entry, order table, feature rows, position table, range id, range state),
+    // and a thread only makes about ten trips -- with one pair at a time the kernel ran at the latency of that chain
+    for (int i0 = b0; i0 < b1; i0 += 64) {
+        int gi[2], gj[2], fi[2], fj[2];
+        double a[2], arg[2];
+        bool live[2];
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const int idx = i0 + 32 * s + (threadIdx.x >> 3);
+            live[s] = idx < b1;
+            gi[s] = 0; gj[s] = 0; a[s] = 0.0;
+            if (live[s]) { PairQ e = q[idx]; gi[s] = e.i; gj[s] = e.j; a[s] = e.a; }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) { fi[s] = order ? order[gi[s]] : gi[s]; fj[s] = order ? order[gj[s]] : gj[s]; arg[s] = 0.0; }
         if (theta != 0.0 && tarl != nullptr) {
-            double td = feat_dist8(tarl + (size_t)fi * tdim, tarl + (size_t)fj * tdim, tdim, lane8);
-            if (tarl_zero[fi] | tarl_zero[fj]) td = 0.0;                 // ncuts_utils.py:145-146
-            arg += theta * td;
+            double td[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) td[s] = feat_dist8(tarl + (size_t)fi[s] * tdim, tarl + (size_t)fj[s] * tdim, tdim, lane8);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (tarl_zero[fi[s]] | tarl_zero[fj[s]]) td[s] = 0.0;    // ncuts_utils.py:145-146
+                arg[s] += theta * td[s];
+            }
         }
         if (gamma != 0.0 && dino != nullptr) {
-            double dd = feat_dist8(dino + (size_t)fi * ddim, dino + (size_t)fj * ddim, ddim, lane8);
-            arg += gamma * dd;                                           // :129-133
+            double dd[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) dd[s] = feat_dist8(dino + (size_t)fi[s] * ddim, dino + (size_t)fj[s] * ddim, ddim, lane8);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) arg[s] += gamma * dd[s];         // :129-133
         }
-        if (live && lane8 == 0) {
-            float w = (float)exp(-(a + arg));
-            int wi = gi, wj = gj;
-            bool keep = true;
-            if (inv) {
-                const int pi = inv[base + gi], pj = inv[base + gj];
-                keep = r_status[rid[pi]] == ST_ACTIVE;
-                wi = pi - base; wj = pj - base;
+        if (lane8 == 0) {
+            int wi[2], wj[2];
+            bool keep[2];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                wi[s] = gi[s]; wj[s] = gj[s]; keep[s] = live[s];
+                if (inv && live[s]) {
+                    const int pi = inv[base + gi[s]], pj = inv[base + gj[s]];
+                    keep[s] = r_status[rid[pi]] == ST_ACTIVE;
+                    wi[s] = pi - base; wj[s] = pj - base;
+                }
             }
-            if (keep) {
-                W[(size_t)wi * ld + wj] = w;
-                W[(size_t)wj * ld + wi] = w;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                if (keep[s]) {
+                    const float w = (float)exp(-(a[s] + arg[s]));
+                    W[(size_t)wi[s] * ld + wj[s]] = w;
+                    W[(size_t)wj[s] * ld + wi[s]] = w;
+                }
             }
         }
     }
