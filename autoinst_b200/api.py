@@ -713,7 +713,9 @@ class SegmentStream:
             t = torch.empty(src.numel(), dtype=src.dtype, device=device)
         return t
 
-    def submit(self, packed: "PackedChunks"):
+    def submit(self, packed: "PackedChunks", labels=None):
+        """Start the upload of `packed`.  `labels`: optional int32 device tensor the batch's labels are written into (e.g.
+        `sharding.LabelGather.send_view()`, so that the gather needs no copy) instead of the slot's own buffer."""
         if len(self.queue) >= 2:
             raise RuntimeError("SegmentStream: two batches are already in flight; call result() first")
         i = self.next_slot
@@ -725,7 +727,12 @@ class SegmentStream:
             sl["points"] = self._fit(sl["points"], packed.points, self.device)
             sl["tarl"] = self._fit(sl["tarl"], packed.tarl if packed.use_t else None, self.device)
             sl["dino"] = self._fit(sl["dino"], packed.dino if packed.use_d else None, self.device)
-            sl["labels"] = self._fit(sl["labels"], packed.labels, self.device)
+            if labels is not None:
+                assert labels.dtype == torch.int32 and labels.is_contiguous() and labels.numel() >= int(packed.off[-1])
+                sl["labels_ext"] = labels
+            else:
+                sl["labels_ext"] = None
+                sl["labels"] = self._fit(sl["labels"], packed.labels, self.device)
             self.copy_stream.wait_stream(cur)          # the slot's previous batch has been cut (stream order)
             with torch.cuda.stream(self.copy_stream):
                 for key, src in (("points", packed.points), ("tarl", packed.tarl if packed.use_t else None),
@@ -748,7 +755,7 @@ class SegmentStream:
         dc.points = sl["points"][:packed.points.numel()].view(packed.points.shape)
         dc.tarl = sl["tarl"][:packed.tarl.numel()].view(packed.tarl.shape) if packed.use_t else None
         dc.dino = sl["dino"][:packed.dino.numel()].view(packed.dino.shape) if packed.use_d else None
-        dc.labels = sl["labels"][:total]
+        dc.labels = (sl["labels_ext"] if sl.get("labels_ext") is not None else sl["labels"])[:total]
         res = segment_packed(packed, dev_chunks=dc, want_stats=want_stats, lane=self.lane, strict=self.strict, **self.kw)
         packed.labels[:total].copy_(dc.labels, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
