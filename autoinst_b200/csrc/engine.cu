@@ -1342,7 +1342,7 @@ int ancuts_feature_pool(ancuts_handle* h, int num_major, const double* d_major, 
     return ANCUTS_OK;
 }
 
-// Pair stage of the deferred affinity for ALL chunks of the call in four launches (ANCUTS_OPT_PAIR_SEARCH = 1):
+// Pair stage of the deferred affinity for ALL chunks of the call in four launches (ANCUTS_OPT_PAIR_SEARCH = 0, the default):
 // cell sort, tile boxes, tile-pair sweep, root-level unions.  Needs the points only.
 static int run_pairs_batched(ancuts_handle* h, Plan& pl, const double* d_points, const float* d_tarl, const ancuts_params* p,
                              cudaStream_t st) {

@@ -9,7 +9,10 @@
 //   against u1 = D^1/2 1 and every Lanczos vector: each CTA forms the partial dots over its slice, the
 //   partials are exchanged through distributed shared memory (cluster barrier, then every CTA sums the C
 //   partials in rank order, so all CTAs hold bit-identical alpha/beta and take identical decisions); the
-//   squared norm is accumulated by the update pass.  Three cluster barriers and four block barriers per step.
+//   squared norm is accumulated by the update pass.  Three cluster barriers and four block barriers per step
+//   (one CTA per node: four block barriers in all, and the partial dots are the coefficients).
+// MODE 7 (default) keeps the slice as CSR in shared memory instead of streaming W, and a node that converged there also
+// takes its N-cut decision in the epilogue (cl_fused_cut).
 // Every sum is float64 and evaluated in a fixed order: results do not depend on scheduling.
 #pragma once
 #include <cooperative_groups.h>
@@ -611,7 +614,7 @@ __device__ __forceinline__ double cl_matvec_ring(ClusterShared& S, const double*
     return pa;
 }
 
-// ---- shared-memory sparse matvec (MODE 7, ANCUTS_OPT_MATVEC = 1): W is 99.5 % zeros (27-66 stored entries per row
+// ---- shared-memory sparse matvec (MODE 7, ANCUTS_OPT_MATVEC = 0, the default): W is 99.5 % zeros (27-66 stored entries per row
 // against n <= 4096 columns), yet the dense form streams every block from HBM once per Lanczos step.  Here the CTA reads
 // its row slice of the dense block ONCE at the start of the node (the entries per row were counted by k_degree on its own
 // pass) and keeps it as CSR in shared memory (float32 value + uint16 column, rows in slice order, columns ascending) for

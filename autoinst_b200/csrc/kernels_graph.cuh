@@ -335,7 +335,7 @@ __device__ __forceinline__ int pg_cell1(const PairGrid& g, double x, int a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pair search on the CELL-SORTED points (ANCUTS_OPT_PAIR_SEARCH = 1), batched over the chunks of a call:
+// Pair search on the CELL-SORTED points (ANCUTS_OPT_PAIR_SEARCH = 0, the default), batched over the chunks of a call:
 //   k_pair_grid_b   one CTA per chunk: counting sort into cells of pitch >= prox (x fastest), points stored in cell order
 //   k_tile_boxes    bounding box of every run of PS_T consecutive sorted points ("tile")
 //   k_pair_sweep    one CTA per tile pair (ti <= tj) of a chunk: pairs of tiles whose boxes are farther apart than prox
