@@ -343,9 +343,7 @@ __device__ __forceinline__ int pg_cell1(const PairGrid& g, double x, int a) {
 //                   survive), the others take the float32 pre-filter in registers (64 pairs per thread) and the exact
 //                   float64 test of k_affinity_pairs; hits go to the chunk's queue with their CELL-SORTED ranks, which are
 //                   the positions of the points at the root of the tree (k_init_positions takes the sorted order)
-//   k_pair_unions   root-level components: one union per queued pair, visited in a scattered order (in queue order
-//                   neighbouring threads would hook into the same component at the same time: the first cell-grid
-//                   search of round 1 spent 75 % of its stall samples in uf_find for that reason)
+//   k_pair_unions   root-level components: one union per queued pair, in queue order
 // Same pairs, same float64 distances as the shuffled 64 x 64 sweep (k_affinity_pairs walks all N^2 / 2 pairs in 8.7 k
 // CTAs per chunk of 16 pairs per thread and is bound by its per-CTA overhead: 96 us per 8.4 k-point chunk).
 // ---------------------------------------------------------------------------------------------
@@ -591,8 +589,10 @@ k_pair_sweep(const int* __restrict__ c_n, const int* __restrict__ c_base, const 
     }
 }
 
-// grid: (blocks, chunks).  Entry t of the chunk's queue is visited as (t * 2147483629) mod total: a bijection for every
-// total below 2^31 (the multiplier is prime), and neighbouring threads land in unrelated components.
+// grid: (blocks, chunks).  The queue is walked in order.  While it held input indices the entries were visited in a scattered
+// order ((t * 2147483629) mod total), because neighbouring threads hooked into the same component at the same time; since
+// the queue holds cell-sorted ranks (neighbouring entries, neighbouring tree nodes, coalesced loads) the plain order is the
+// faster one: pair stage + feature pass 8.19 -> 7.52 ms per 128 chunks.
 __global__ void __launch_bounds__(256)
 k_pair_unions(const PairQ* __restrict__ q_all, const long long* __restrict__ q_off, const int* __restrict__ q_cap,
               const int* __restrict__ qctr_all, const int* __restrict__ c_base, int* parent) {
@@ -602,8 +602,7 @@ k_pair_unions(const PairQ* __restrict__ q_all, const long long* __restrict__ q_o
     const PairQ* q = q_all + q_off[chunk];
     const int pos0 = c_base[chunk];
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-        const long long idx = (long long)(((unsigned long long)t * 2147483629ull) % (unsigned long long)total);
-        const PairQ e = q[idx];
+        const PairQ e = q[t];
         uf_union(parent, pos0 + e.i, pos0 + e.j);
     }
 }
