@@ -258,8 +258,7 @@ int ancuts_set_option(ancuts_handle* h, int option, int value);
  * Lanczos steps x stored entries (what the sparse lower bound of SURVEY.md §8d multiplies by 8 bytes), out2[1] = entries. */
 int ancuts_last_sparse_accounting(ancuts_handle* h, double* out2);
 
-/* Counters for bench.py: kernels launched by this handle since the last reset, and the per-kernel
- * CUDA-event time of the kernels named by ancuts_timing_select(). */
+/* Counter for bench.py (`gpu_launches`): kernels launched by this handle since the last reset. */
 int64_t ancuts_launch_count(ancuts_handle* h, int reset);
 /* Accounting of the last segment call: algorithmic bytes and event-timed
  * milliseconds per stage: [0]=affinity [1]=degree [2]=matvec [3]=reorth [4]=scan [5]=cc+partition */
@@ -272,7 +271,8 @@ int ancuts_set_stage_timing(ancuts_handle* h, int on);
  * kernels of the level, [3..8] nodes per size bin, [9..14] cluster size used per bin.  Returns the row count. */
 int ancuts_last_levels(ancuts_handle* h, double* out, int cap_rows);
 /* Debug (handle created with ANCUTS_PHASES=1 in the environment): cycles spent by the persistent Lanczos kernel per
- * phase, [cluster size 1,2,4,8][basis write, matvec, dots1, update1, dots2, update2, norm+publish, check]. */
+ * phase, [cluster size 1,2,4,8][basis write, matvec, alpha + three-term, multisection of the check, dots, update + norm, z exchange,
+ * rest of the check]. */
 int ancuts_debug_phases(ancuts_handle* h, double* out32, int reset);
 
 #ifdef __cplusplus
